@@ -1,0 +1,163 @@
+/*
+ * matrel.h -- C ABI of the B200-native block-matrix engine (drop-in for the MatRel/MatFast
+ * block-multiply hot path).  Plain C: opaque handles, pointers and sizes; no C++/torch types.
+ *
+ * Every entry point names the reference interface it replaces.  Paths are relative to
+ * /root/reference/src/main/scala/org/apache/spark/sql/matfast/ ("M/").
+ *
+ * Conventions
+ *   - every function returns mr_status; on failure mr_last_error() (thread-local) holds the
+ *     message, reproducing the reference's `require` text ("requirement failed: ...") so a JNI
+ *     shim can ThrowNew(IllegalArgumentException, msg).  Nothing throws or aborts across the ABI.
+ *   - a "dataset" (mr_matrix) is a bag of (rid, cid, block) rows exactly like the reference's
+ *     Dataset rows (rid Int, cid Int, struct7); absent blocks are implicit zeros.  Matrix
+ *     dimensions are passed per operator call, as in M/Dataset.scala.
+ *   - blocks live in device memory (HBM) behind the handle; operators enqueue CUDA kernels on the
+ *     context stream and return new handles (operators are pure).  There is NO CPU fallback:
+ *     without a usable CUDA device mr_init fails with MR_ECUDA.
+ */
+#ifndef MATREL_H_
+#define MATREL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_API __attribute__((visibility("default")))
+
+typedef int32_t mr_status;
+enum {
+  MR_OK = 0,
+  MR_EINVAL = 1,  /* IllegalArgumentException("requirement failed: ...") */
+  MR_EDIM = 2,    /* dimension `require` of an operator failed (also IllegalArgumentException) */
+  MR_ENOMEM = 3,
+  MR_ECUDA = 4,
+  MR_ENOTSUP = 5, /* SparkException("Unsupported matrix type ...") / out-of-scope dispatch row */
+  MR_ENOTFOUND = 6
+};
+
+typedef struct mr_context mr_context; /* one per process per GPU (replaces MatfastSession) */
+typedef struct mr_matrix mr_matrix;   /* a Dataset of MatrixBlock rows, device resident */
+
+/* The 7-field block struct of MatrixUDT / MLMatrixSerializer
+ * (M/matrix/MLMatrix.scala:176-184, M/util/MLMatrixSerializer.scala:26-48). */
+typedef struct mr_block_desc {
+  uint8_t type;          /* [0] 0 = sparse, 1 = dense */
+  int32_t numRows;       /* [1] */
+  int32_t numCols;       /* [2] */
+  int32_t* colPtrs;      /* [3] NULL for dense; length (isTransposed ? numRows : numCols) + 1 */
+  int32_t* rowIndices;   /* [4] NULL for dense; length nnz */
+  double* values;        /* [5] dense: numRows*numCols, column-major (row-major if isTransposed) */
+  uint8_t isTransposed;  /* [6] */
+  int64_t colPtrsLen;    /* array lengths (JVM arrays carry theirs; C needs them spelled out) */
+  int64_t rowIndicesLen;
+  int64_t valuesLen;
+} mr_block_desc;
+
+typedef struct mr_options {
+  int32_t device;       /* CUDA device ordinal; -1 = current device */
+  int32_t compat_bugs;  /* 1 = reproduce reference defects B3/B4; 0 = intended math */
+  int32_t gemm_algo;    /* 0 = auto, 1 = DMMA fp64 tensor-core kernel, 2 = Ozaki int8 tcgen05 kernel */
+  int32_t ozaki_slices; /* number of int8 slices for gemm_algo 2 (0 = default) */
+  void* stream;         /* cudaStream_t to run on; NULL = a stream owned by the context */
+} mr_options;
+
+/* ---- lifetime: replaces MatfastSession.builder().getOrCreate() (M/MatfastSession.scala:177-234) */
+MR_API mr_status mr_init(const mr_options* opts, mr_context** out);
+MR_API mr_status mr_shutdown(mr_context* ctx);
+MR_API mr_status mr_set_stream(mr_context* ctx, void* cuda_stream);
+MR_API mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value);
+MR_API mr_status mr_sync(mr_context* ctx);
+MR_API const char* mr_last_error(void);
+MR_API const char* mr_version(void);
+
+/* ---- datasets: replaces Seq(MatrixBlock(...)).toDS() (M/example/BasicMatrixOps.scala:115-116)
+ *      and .collect() / .rdd.foreach on the result. */
+MR_API mr_status mr_matrix_create(mr_context* ctx, mr_matrix** out);
+MR_API mr_status mr_matrix_free(mr_matrix* m);
+/* Copies the block to the device (MLMatrixSerializer.deserialize, :50-69, incl. the ctor
+ * `require`s of DenseMatrix :240 and SparseMatrix :533-542).  Host arrays stay caller-owned. */
+MR_API mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_block_desc* blk);
+/* Adopts (borrows) a dense block already resident in device memory; not freed by the library. */
+MR_API mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int32_t numRows,
+                                            int32_t numCols, const double* dvalues, uint8_t isTransposed);
+MR_API mr_status mr_matrix_num_blocks(const mr_matrix* m, int64_t* out);
+/* Fills rids/cids (capacity cap) in ascending (rid, cid) order. */
+MR_API mr_status mr_matrix_block_ids(const mr_matrix* m, int32_t* rids, int32_t* cids, int64_t cap);
+/* Two-call protocol (MLMatrixSerializer.serialize, :26-48): with NULL array pointers only the
+ * scalar fields and *Len fields are filled; with non-NULL pointers the arrays are copied out
+ * (capacity given by the *Len fields on entry). */
+MR_API mr_status mr_matrix_get_block(mr_matrix* m, int32_t rid, int32_t cid, mr_block_desc* inout);
+/* Device pointer of a dense block's values (for zero-copy consumers such as NCCL). */
+MR_API mr_status mr_matrix_block_device_ptr(mr_matrix* m, int32_t rid, int32_t cid, double** dptr);
+/* DenseMatrix.rand(numRows, numCols, new java.util.Random(seed)) generated on the device for
+ * every block of an nrows x ncols matrix (M/matrix/MLMatrix.scala:453-457); per-block seed =
+ * seed0 + rid*ceil(ncols/blk) + cid.  Used for synthetic benchmark inputs. */
+MR_API mr_status mr_matrix_rand(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize,
+                                int64_t seed0, mr_matrix** out);
+
+/* ---- operators: argument-for-argument with M/Dataset.scala:57-152 and the physical operators
+ *      of M/execution/MatfastExecution.scala. */
+/* Dataset.matrixMultiply :134-142 -> MatrixMatrixMultiplicationExecution :688-726 ->
+ * MatfastExecutionHelper.matrixMultiplyGeneral :235-263 / multiplyOuterProductDuplicate* :175-221 */
+MR_API mr_status mr_matrix_multiply(mr_matrix* left, int64_t leftRowNum, int64_t leftColNum,
+                                    mr_matrix* right, int64_t rightRowNum, int64_t rightColNum,
+                                    int32_t blkSize, mr_matrix** out);
+/* Dataset.transpose / t :57-61 -> MatrixTransposeExecution :215-236 (flag flip + index swap) */
+MR_API mr_status mr_transpose(mr_matrix* a, mr_matrix** out);
+/* Dataset.addElement :105-112 -> MatrixElementAddExecution :571-607 (outer join) */
+MR_API mr_status mr_add_element(mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right,
+                                int64_t rightRowNum, int64_t rightColNum, int32_t blkSize, mr_matrix** out);
+/* Dataset.multiplyElement :114-122 -> MatrixElementMultiplyExecution :609-644 (inner join) */
+MR_API mr_status mr_multiply_element(mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right,
+                                     int64_t rightRowNum, int64_t rightColNum, int32_t blkSize, mr_matrix** out);
+/* Dataset.divideElement :124-132 -> MatrixElementDivideExecution :646-686 (inner join) */
+MR_API mr_status mr_divide_element(mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right,
+                                   int64_t rightRowNum, int64_t rightColNum, int32_t blkSize, mr_matrix** out);
+/* Dataset.addScalar :89-91 -> MatrixScalarAddExecution :465-486 -> LocalMatrix.addScalar */
+MR_API mr_status mr_add_scalar(mr_matrix* a, double alpha, mr_matrix** out);
+/* Dataset.multiplyScalar :93-97 -> MatrixScalarMultiplyExecution :488-509 */
+MR_API mr_status mr_multiply_scalar(mr_matrix* a, double alpha, mr_matrix** out);
+/* Dataset.power :99-103 -> MatrixPowerExecution :511-532 */
+MR_API mr_status mr_power(mr_matrix* a, double alpha, mr_matrix** out);
+/* Dataset.matrixRankOneUpdate :144-152 -> RankOneUpdateExecution :728-747 */
+MR_API mr_status mr_rank_one_update(mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right,
+                                    int64_t rightRowNum, int64_t rightColNum, int32_t blkSize, mr_matrix** out);
+/* Materialise every dense block as column-major, isTransposed = false (DenseMatrix.toArray,
+ * M/matrix/MLMatrix.scala:55-61, as a device transpose kernel). */
+MR_API mr_status mr_materialize(mr_matrix* a, mr_matrix** out);
+
+/* ---- placement: bit-exact restatement of M/partitioner/*.scala (pure integer, host side) */
+/* RowPartitioner.getPartition (RowPartitioner.scala:32-38) */
+MR_API mr_status mr_row_partition(int32_t rid, int32_t cid, int32_t partitions, int32_t* out);
+/* ColumnPartitioner.getPartition (ColumnPartitioner.scala:32-38) */
+MR_API mr_status mr_column_partition(int32_t rid, int32_t cid, int32_t partitions, int32_t* out);
+/* IndexPartitioner.getPartition (IndexPartitioner.scala:29-34) */
+MR_API mr_status mr_index_partition(int32_t key, int32_t partitions, int32_t* out);
+/* MatfastExecutionHelper.genBlockCyclicPartitioner (MatfastExecutionHelper.scala:46-62):
+ * out = {ROW_BLK_NUM, COL_BLK_NUM, ROW_BLKS_PER_PARTITION, COL_BLKS_PER_PARTITION} */
+MR_API mr_status mr_gen_block_cyclic(int64_t nrows, int64_t ncols, int32_t blkSize, int32_t out[4]);
+/* BlockCyclicPartitioner.getPartition / numPartitions (BlockCyclicPartitioner.scala:31-62) */
+MR_API mr_status mr_block_cyclic_partition(const int32_t params[4], int32_t rid, int32_t cid, int32_t* out);
+MR_API mr_status mr_block_cyclic_num_partitions(const int32_t params[4], int32_t* out);
+
+/* ---- introspection used by bench/tests (not part of the reference surface) */
+typedef struct mr_stats {
+  int64_t kernel_launches;  /* CUDA kernels launched by this library since mr_init / reset */
+  int64_t gemm_launches;
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  double last_gemm_ms;      /* CUDA-event duration of the most recent GEMM kernel launch(es) */
+  double gemm_ms_total;     /* sum of CUDA-event GEMM durations since reset (timing enabled only) */
+  int64_t last_gemm_flops;
+} mr_stats;
+MR_API mr_status mr_get_stats(mr_context* ctx, mr_stats* out);
+MR_API mr_status mr_reset_stats(mr_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATREL_H_ */

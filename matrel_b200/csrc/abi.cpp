@@ -1,0 +1,1127 @@
+// C-ABI host layer of the B200 block-matrix engine (see include/matrel.h).
+//
+// This file is the replacement for the reference's L2 physical operators and their helpers:
+//   MatfastExecution.scala   (MatrixMatrixMultiplicationExecution :688-726, MatrixTransposeExecution
+//                             :215-236, MatrixElement*Execution :571-686, MatrixScalar*/Power :465-532,
+//                             RankOneUpdateExecution :728-747)
+//   MatfastExecutionHelper.scala (matrixMultiplyGeneral :235-263, multiplyOuterProductDuplicate* :175-221,
+//                             add/multiply/divideWithPartitioner :64-173, matrixRankOneUpdate :265-285,
+//                             genBlockCyclicPartitioner :46-62)
+//   LocalMatrix.scala        (matrixMultiplication dispatch :889-914 and the per-block kernels)
+//   MLMatrixSerializer.scala (block <-> 7-field struct, :26-69)
+// The Spark shuffles (groupByKey / join / reduceByKey / zipPartitions) become index arithmetic over a
+// device-resident block table; every arithmetic step is a CUDA kernel (gemm_f64.cu, ew.cu).
+// There is no CPU compute path in this file: host code only validates, builds descriptor tables
+// and launches.
+#include "../../include/matrel.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace matrel;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_last_error;
+
+struct MrError {
+  mr_status code;
+  std::string msg;
+};
+
+[[noreturn]] void fail(mr_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw MrError{code, buf};
+}
+
+// Scala `require(cond, msg)` -> IllegalArgumentException("requirement failed: " + msg)
+#define MR_REQUIRE(cond, code, ...)                                           \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      char _b[900];                                                           \
+      snprintf(_b, sizeof(_b), __VA_ARGS__);                                  \
+      fail((code), "requirement failed: %s", _b);                             \
+    }                                                                         \
+  } while (0)
+
+#define CUDA_CHECK(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) fail(MR_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                                cudaGetErrorString(_e));                                         \
+  } while (0)
+
+template <typename F>
+mr_status guarded(F&& f) {
+  try {
+    f();
+    return MR_OK;
+  } catch (const MrError& e) {
+    g_last_error = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "out of host memory";
+    return MR_ENOMEM;
+  } catch (const std::exception& e) {
+    g_last_error = std::string("internal error: ") + e.what();
+    return MR_EINVAL;
+  } catch (...) {
+    g_last_error = "unknown internal error";
+    return MR_EINVAL;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context, device buffers, blocks
+// ------------------------------------------------------------------------------------------------
+struct mr_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int compat_bugs = 1;
+  int gemm_algo = 0;
+  int ozaki_slices = 0;
+  int time_kernels = 0;
+  int force_variant = -1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  mr_stats stats{};
+  std::mutex mu;
+};
+
+namespace {
+
+struct DevBuf {
+  mr_context* ctx;
+  void* p = nullptr;
+  size_t bytes = 0;
+  bool owned = true;
+  DevBuf(mr_context* c, size_t n) : ctx(c), bytes(n) {
+    if (n == 0) return;
+    cudaError_t e = cudaMallocAsync(&p, n, ctx->stream);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      fail(e == cudaErrorMemoryAllocation ? MR_ENOMEM : MR_ECUDA, "cudaMallocAsync(%zu bytes) failed: %s", n,
+           cudaGetErrorString(e));
+    }
+  }
+  DevBuf(mr_context* c, void* borrowed, size_t n) : ctx(c), p(borrowed), bytes(n), owned(false) {}
+  ~DevBuf() {
+    if (owned && p) cudaFreeAsync(p, ctx->stream);
+  }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+using Buf = std::shared_ptr<DevBuf>;
+
+struct Span {  // a typed window into a (possibly shared) device buffer
+  Buf buf;
+  size_t off = 0;  // bytes
+  template <typename T>
+  T* ptr() const {
+    return buf ? reinterpret_cast<T*>(static_cast<char*>(buf->p) + off) : nullptr;
+  }
+};
+
+struct Block {
+  uint8_t type = 1;  // 0 sparse, 1 dense (MLMatrixSerializer.scala:31,40)
+  int32_t numRows = 0, numCols = 0;
+  bool isT = false;
+  Span values;
+  int64_t valuesLen = 0;
+  Span colPtrs, rowIndices;  // sparse only
+  int64_t colPtrsLen = 0;
+  bool dense() const { return type == 1; }
+};
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+}  // namespace
+
+struct mr_matrix {
+  mr_context* ctx;
+  std::map<std::pair<int32_t, int32_t>, Block> blocks;
+};
+
+namespace {
+
+void note_launch(mr_context* ctx, int n = 1) { ctx->stats.kernel_launches += n; }
+
+template <typename T>
+Buf upload(mr_context* ctx, const std::vector<T>& v) {
+  Buf b = std::make_shared<DevBuf>(ctx, std::max<size_t>(v.size() * sizeof(T), 16));
+  if (!v.empty()) {
+    CUDA_CHECK(cudaMemcpyAsync(b->p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += static_cast<int64_t>(v.size() * sizeof(T));
+  }
+  return b;
+}
+
+// A slab allocator for operator results: one device allocation, blocks are windows into it.
+struct Slab {
+  Buf buf;
+  size_t used = 0;
+  Slab(mr_context* ctx, size_t total) : buf(std::make_shared<DevBuf>(ctx, std::max<size_t>(total, kAlign))) {}
+  Span take(size_t bytes) {
+    Span s{buf, used};
+    used += align_up(bytes);
+    return s;
+  }
+};
+
+Block dense_block(int32_t rows, int32_t cols, Span values, bool isT = false) {
+  Block b;
+  b.type = 1;
+  b.numRows = rows;
+  b.numCols = cols;
+  b.isT = isT;
+  b.values = std::move(values);
+  b.valuesLen = static_cast<int64_t>(rows) * cols;
+  return b;
+}
+
+// SparseMatrix.toDense (MLMatrix.scala:669-671) on the device: zero fill + scatter.
+Block densify(mr_context* ctx, const Block& s) {
+  const size_t bytes = static_cast<size_t>(s.numRows) * s.numCols * sizeof(double);
+  Span v{std::make_shared<DevBuf>(ctx, std::max<size_t>(bytes, 16)), 0};
+  if (bytes) CUDA_CHECK(cudaMemsetAsync(v.ptr<double>(), 0, bytes, ctx->stream));
+  if (s.valuesLen > 0) {
+    CUDA_CHECK(launch_sparse_to_dense(s.colPtrs.ptr<int32_t>(), s.rowIndices.ptr<int32_t>(), s.values.ptr<double>(),
+                                      s.isT, v.ptr<double>(), s.numRows, s.numCols, ctx->stream));
+    note_launch(ctx);
+  }
+  return dense_block(s.numRows, s.numCols, v, false);
+}
+
+const char* type_name(const Block& b) { return b.dense() ? "DenseMatrix" : "SparseMatrix"; }
+
+// ------------------------------------------------------------------------------------------------
+// block product planning (LocalMatrix.matrixMultiplication, LocalMatrix.scala:889-914)
+// ------------------------------------------------------------------------------------------------
+struct OutPlan {
+  int32_t rid, cid;
+  int32_t m = -1, n = -1;
+  std::vector<GemmPair> gemm;                            // dense x dense (possibly densified) pairs
+  std::vector<std::pair<const Block*, const Block*>> spmm;  // sparse x dense pairs
+};
+
+struct MultiplyPlanner {
+  mr_context* ctx;
+  std::vector<Block> temps;  // densified sparse operands kept alive until the launches are enqueued
+  std::map<const Block*, size_t> densified;
+
+  const Block& dense_of(const Block& b) {
+    if (b.dense()) return b;
+    auto it = densified.find(&b);
+    if (it == densified.end()) {
+      temps.push_back(densify(ctx, b));
+      it = densified.emplace(&b, temps.size() - 1).first;
+    }
+    return temps[it->second];
+  }
+
+  void add_pair(OutPlan& o, const Block& a, const Block& b) {
+    // shape checks: BLAS.gemmddd / gemmsdd `require`s (BLAS.scala:338-343, 363-366)
+    MR_REQUIRE(a.numCols == b.numRows, MR_EDIM, "The columns of A don't match the rows of B. A: %d, B: %d", a.numCols,
+               b.numRows);
+    if (o.m < 0) {
+      o.m = a.numRows;
+      o.n = b.numCols;
+    } else {
+      // LocalMatrix.add `require`s on the partial products (LocalMatrix.scala:36-41)
+      MR_REQUIRE(o.m == a.numRows, MR_EDIM,
+                 "Matrix A and B must have the same number of rows. But found A.numRows = %d, B.numRows = %d", o.m,
+                 a.numRows);
+      MR_REQUIRE(o.n == b.numCols, MR_EDIM,
+                 "Matrix A and B must have the same number of cols. But found A.numCols = %d, B.numCols = %d", o.n,
+                 b.numCols);
+    }
+    if (a.dense()) {
+      push_gemm(o, a, dense_of(b));  // dense x dense, dense x sparse.toDense (:891-892)
+    } else if (b.dense()) {
+      o.spmm.emplace_back(&a, &b);   // sparse x dense (:893-899; the n == 1 SpMV case is the same kernel)
+    } else {
+      const double s1 = a.valuesLen * 1.0 / (static_cast<double>(a.numRows) * a.numCols);
+      const double s2 = b.valuesLen * 1.0 / (static_cast<double>(b.numRows) * b.numCols);
+      if (s1 > 0.1) {
+        push_gemm(o, dense_of(a), dense_of(b));  // :903-904
+      } else if (s2 > 0.1) {
+        o.spmm.emplace_back(&a, &dense_of(b));   // :906-907
+      } else {
+        fail(MR_ENOTSUP,
+             "sparse x sparse block product with both densities <= 0.1 (LocalMatrix.multiplySparseSparse) is "
+             "outside the B200 hot-path scope");
+      }
+    }
+  }
+
+  void push_gemm(OutPlan& o, const Block& a, const Block& b) {
+    GemmPair p{};
+    p.A = a.values.ptr<double>();
+    p.B = b.values.ptr<double>();
+    p.aT = a.isT;
+    p.bT = b.isT;
+    p.lda = a.isT ? a.numCols : a.numRows;  // BLAS.scala:335
+    p.ldb = b.isT ? b.numCols : b.numRows;  // BLAS.scala:336
+    p.kdim = a.numCols;
+    o.gemm.push_back(p);
+  }
+};
+
+void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner& planner, int32_t blkSize,
+                  mr_matrix* result) {
+  // allocate all output blocks from one slab
+  size_t total = 0;
+  for (auto& o : plans) total += align_up(static_cast<size_t>(o.m) * o.n * sizeof(double));
+  Slab slab(ctx, total);
+  std::vector<double*> cptr(plans.size());
+  for (size_t i = 0; i < plans.size(); ++i) {
+    auto& o = plans[i];
+    Span s = slab.take(static_cast<size_t>(o.m) * o.n * sizeof(double));
+    cptr[i] = s.ptr<double>();
+    result->blocks[{o.rid, o.cid}] = dense_block(o.m, o.n, s, false);  // product is never transposed (MLMatrix.scala:101)
+  }
+
+  // ---- fused GEMM launch over every output block that has dense pairs
+  std::vector<GemmOut> outs;
+  std::vector<GemmPair> pairs;
+  std::vector<size_t> out_plan;
+  int64_t flops = 0;
+  for (size_t i = 0; i < plans.size(); ++i) {
+    auto& o = plans[i];
+    if (o.gemm.empty() || o.m == 0 || o.n == 0) continue;
+    GemmOut go{};
+    go.C = cptr[i];
+    go.m = o.m;
+    go.n = o.n;
+    go.pair_begin = static_cast<int32_t>(pairs.size());
+    go.pair_count = static_cast<int32_t>(o.gemm.size());
+    for (auto& p : o.gemm) {
+      pairs.push_back(p);
+      flops += 2ll * o.m * o.n * p.kdim;
+    }
+    outs.push_back(go);
+    out_plan.push_back(i);
+  }
+  if (!outs.empty()) {
+    // tile shape: large tiles unless they cannot fill the 148 SMs
+    int64_t tiles128 = 0;
+    for (auto& go : outs) tiles128 += static_cast<int64_t>((go.m + 127) / 128) * ((go.n + 127) / 128);
+    int variant = tiles128 >= 2 * 148 ? GEMM_128x128 : GEMM_64x64;
+    if (ctx->force_variant >= 0) variant = ctx->force_variant;
+    const int BM = gemm_tile_m(variant), BN = gemm_tile_n(variant);
+    const int tpbm = std::max(1, (blkSize + BM - 1) / BM), tpbn = std::max(1, (blkSize + BN - 1) / BN);
+    struct Keyed {
+      int64_t band, gm, gn;
+      GemmTile t;
+    };
+    std::vector<Keyed> keyed;
+    constexpr int kBand = 12;  // ~12 x 12 tiles resident across 148 SMs share A row- and B column-panels in L2
+    for (size_t oi = 0; oi < outs.size(); ++oi) {
+      const OutPlan& o = plans[out_plan[oi]];
+      const int tm = (outs[oi].m + BM - 1) / BM, tn = (outs[oi].n + BN - 1) / BN;
+      for (int a = 0; a < tm; ++a)
+        for (int b = 0; b < tn; ++b) {
+          const int64_t gm = static_cast<int64_t>(o.rid) * tpbm + a, gn = static_cast<int64_t>(o.cid) * tpbn + b;
+          keyed.push_back({gn / kBand, gm, gn, GemmTile{static_cast<int32_t>(oi), a, b, 0}});
+        }
+    }
+    std::sort(keyed.begin(), keyed.end(), [](const Keyed& x, const Keyed& y) {
+      if (x.band != y.band) return x.band < y.band;
+      if (x.gm != y.gm) return x.gm < y.gm;
+      return x.gn < y.gn;
+    });
+    std::vector<GemmTile> tiles(keyed.size());
+    for (size_t i = 0; i < keyed.size(); ++i) tiles[i] = keyed[i].t;
+    Buf d_outs = upload(ctx, outs), d_pairs = upload(ctx, pairs), d_tiles = upload(ctx, tiles);
+    if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_CHECK(launch_gemm_f64(static_cast<const GemmOut*>(d_outs->p), static_cast<const GemmPair*>(d_pairs->p),
+                               static_cast<const GemmTile*>(d_tiles->p), static_cast<int>(tiles.size()), variant,
+                               ctx->stream));
+    note_launch(ctx);
+    ctx->stats.gemm_launches += 1;
+    ctx->stats.last_gemm_flops = flops;
+    if (ctx->time_kernels) {
+      CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+      CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      ctx->stats.last_gemm_ms = ms;
+      ctx->stats.gemm_ms_total += ms;
+    }
+  }
+
+  // ---- sparse x dense partial products accumulate onto the GEMM result (LocalMatrix.add of partials)
+  for (size_t i = 0; i < plans.size(); ++i) {
+    auto& o = plans[i];
+    bool have = !o.gemm.empty();
+    if (o.m == 0 || o.n == 0) continue;
+    for (auto& sp : o.spmm) {
+      const Block& s = *sp.first;
+      const Block& b = *sp.second;
+      CUDA_CHECK(launch_spmm(s.colPtrs.ptr<int32_t>(), s.rowIndices.ptr<int32_t>(), s.values.ptr<double>(), s.isT,
+                             b.values.ptr<double>(), b.isT, cptr[i], s.numRows, s.numCols, b.numCols, have, ctx->stream));
+      note_launch(ctx);
+      have = true;
+    }
+    if (!have) CUDA_CHECK(cudaMemsetAsync(cptr[i], 0, static_cast<size_t>(o.m) * o.n * sizeof(double), ctx->stream));
+  }
+  (void)planner;
+}
+
+int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// element-wise operator plumbing
+// ------------------------------------------------------------------------------------------------
+void check_same_dims(int64_t lr, int64_t lc, int64_t rr, int64_t rc) {
+  // MatfastExecution.scala:584-587 (and :621-624, :658-661)
+  MR_REQUIRE(lr == rr, MR_EDIM, "Row number not match, leftRowNum = %lld, rightRowNum = %lld", (long long)lr,
+             (long long)rr);
+  MR_REQUIRE(lc == rc, MR_EDIM, "Col number not match, leftColNum = %lld, rightColNum = %lld", (long long)lc,
+             (long long)rc);
+}
+
+struct EwBatch {
+  mr_context* ctx;
+  int op;
+  std::vector<EwDesc> descs;
+  std::vector<Block> keep;  // densified temporaries
+  std::vector<std::pair<std::pair<int32_t, int32_t>, std::pair<int32_t, int32_t>>> shapes;  // key -> (rows, cols)
+  int max_rows = 0, max_cols = 0;
+  bool any_T = false;
+  size_t total = 0;
+
+  void add(std::pair<int32_t, int32_t> key, const Block* a, const Block* b, const double* y, int rows, int cols) {
+    EwDesc d{};
+    d.A = a ? a->values.ptr<double>() : nullptr;
+    d.B = b ? b->values.ptr<double>() : nullptr;
+    d.Y = y;
+    d.rows = rows;
+    d.cols = cols;
+    d.aT = a ? a->isT : 0;
+    d.bT = (b && op != EW_RANK1 && op != EW_RANK1_COMPAT) ? b->isT : 0;
+    any_T = any_T || d.aT || d.bT;
+    max_rows = std::max(max_rows, rows);
+    max_cols = std::max(max_cols, cols);
+    total += align_up(static_cast<size_t>(rows) * cols * sizeof(double));
+    descs.push_back(d);
+    shapes.push_back({key, {rows, cols}});
+  }
+
+  void run(mr_matrix* result) {
+    if (descs.empty()) return;
+    Slab slab(ctx, total);
+    for (size_t i = 0; i < descs.size(); ++i) {
+      const int rows = shapes[i].second.first, cols = shapes[i].second.second;
+      Span s = slab.take(static_cast<size_t>(rows) * cols * sizeof(double));
+      descs[i].C = s.ptr<double>();
+      result->blocks[shapes[i].first] = dense_block(rows, cols, s, false);  // always column-major (LocalMatrix.scala:62)
+    }
+    Buf d = upload(ctx, descs);
+    CUDA_CHECK(launch_ew_batched(op, static_cast<const EwDesc*>(d->p), static_cast<int>(descs.size()), max_rows,
+                                 max_cols, any_T, ctx->stream));
+    note_launch(ctx);
+  }
+};
+
+void check_block_dims_add(const Block& a, const Block& b) {
+  // LocalMatrix.add (LocalMatrix.scala:36-41)
+  MR_REQUIRE(a.numRows == b.numRows, MR_EDIM,
+             "Matrix A and B must have the same number of rows. But found A.numRows = %d, B.numRows = %d", a.numRows,
+             b.numRows);
+  MR_REQUIRE(a.numCols == b.numCols, MR_EDIM,
+             "Matrix A and B must have the same number of cols. But found A.numCols = %d, B.numCols = %d", a.numCols,
+             b.numCols);
+}
+
+void check_block_dims_ew(const Block& a, const Block& b) {
+  // LocalMatrix.elementWiseMultiply / Divide (LocalMatrix.scala:467-470, 480-483)
+  MR_REQUIRE(a.numRows == b.numRows, MR_EDIM, "mat1.numRows = %d, mat2.numRows = %d", a.numRows, b.numRows);
+  MR_REQUIRE(a.numCols == b.numCols, MR_EDIM, "mat1.numCols = %d, mat2.numCols = %d", a.numCols, b.numCols);
+}
+
+mr_matrix* new_matrix(mr_context* ctx) {
+  auto* m = new mr_matrix;
+  m->ctx = ctx;
+  return m;
+}
+
+void elementwise_join(int op, mr_matrix* left, mr_matrix* right, mr_matrix* result) {
+  mr_context* ctx = left->ctx;
+  EwBatch batch{ctx, op};
+  batch.keep.reserve(2 * (left->blocks.size() + right->blocks.size()) + 2);
+  auto dense_view = [&](const Block& b) -> const Block* {
+    if (b.dense()) return &b;
+    batch.keep.push_back(densify(ctx, b));
+    return &batch.keep.back();
+  };
+  for (auto& kv : left->blocks) {
+    auto it = right->blocks.find(kv.first);
+    if (it == right->blocks.end()) {
+      if (op == EW_ADD) result->blocks[kv.first] = kv.second;  // outer join: one-sided blocks pass through
+      continue;
+    }
+    const Block& a = kv.second;
+    const Block& b = it->second;
+    if (op == EW_ADD) check_block_dims_add(a, b);
+    else check_block_dims_ew(a, b);
+    if (!a.dense() && !b.dense())
+      fail(MR_ENOTSUP, "sparse (op) sparse element-wise block kernels (LocalMatrix.addSparseSparse / "
+                       "elementWiseOpSparseSparse) are outside the B200 hot-path scope");
+    const Block* x = dense_view(a);
+    const Block* y = dense_view(b);
+    // defect B4 (LocalMatrix.scala:474,487): (Sparse, Dense) swaps the operands; visible for divide only
+    if (op == EW_DIV && !a.dense() && b.dense() && ctx->compat_bugs) std::swap(x, y);
+    batch.add(kv.first, x, y, nullptr, a.numRows, a.numCols);
+  }
+  if (op == EW_ADD)
+    for (auto& kv : right->blocks)
+      if (!left->blocks.count(kv.first)) result->blocks[kv.first] = kv.second;
+  batch.run(result);
+}
+
+void map_values(int op, mr_matrix* a, double alpha, mr_matrix* result) {
+  mr_context* ctx = a->ctx;
+  std::vector<MapDesc> descs;
+  size_t total = 0;
+  int64_t max_n = 0;
+  for (auto& kv : a->blocks) total += align_up(static_cast<size_t>(kv.second.valuesLen) * sizeof(double));
+  Slab slab(ctx, total);
+  for (auto& kv : a->blocks) {
+    const Block& b = kv.second;
+    Block o = b;  // same type, dims, flag and (shared) index arrays: the map touches stored values only
+    o.values = slab.take(static_cast<size_t>(b.valuesLen) * sizeof(double));
+    if (b.valuesLen > 0) {
+      descs.push_back(MapDesc{b.values.ptr<double>(), o.values.ptr<double>(), b.valuesLen});
+      max_n = std::max(max_n, b.valuesLen);
+    }
+    result->blocks[kv.first] = std::move(o);
+  }
+  if (descs.empty()) return;
+  Buf d = upload(ctx, descs);
+  CUDA_CHECK(launch_map_batched(op, static_cast<const MapDesc*>(d->p), static_cast<int>(descs.size()), max_n, alpha,
+                                ctx->stream));
+  note_launch(ctx);
+}
+
+void validate_desc(const mr_block_desc* d) {
+  MR_REQUIRE(d != nullptr, MR_EINVAL, "block descriptor is null");
+  MR_REQUIRE(d->numRows >= 0 && d->numCols >= 0, MR_EINVAL, "negative block dimensions %d x %d", d->numRows, d->numCols);
+  if (d->type == 1) {
+    // DenseMatrix ctor (MLMatrix.scala:240)
+    MR_REQUIRE(d->valuesLen == static_cast<int64_t>(d->numRows) * d->numCols, MR_EINVAL,
+               "The number of values supplied doesn't match the size of the matrix! values.length: %lld, "
+               "numRows * numCols: %lld",
+               (long long)d->valuesLen, (long long)(static_cast<int64_t>(d->numRows) * d->numCols));
+    MR_REQUIRE(d->valuesLen == 0 || d->values != nullptr, MR_EINVAL, "values is null");
+  } else if (d->type == 0) {
+    // SparseMatrix ctor (MLMatrix.scala:533-542)
+    MR_REQUIRE(d->valuesLen == d->rowIndicesLen, MR_EINVAL,
+               "The number of row indices and values don't match! values.length: %lld, rowIndices.length: %lld",
+               (long long)d->valuesLen, (long long)d->rowIndicesLen);
+    if (d->isTransposed)
+      MR_REQUIRE(d->colPtrsLen == d->numRows + 1, MR_EINVAL, "Expecting %d colPtrs when numRows = %d but got %lld",
+                 d->numRows + 1, d->numRows, (long long)d->colPtrsLen);
+    else
+      MR_REQUIRE(d->colPtrsLen == d->numCols + 1, MR_EINVAL, "Expecting %d colPtrs when numCols = %d but got %lld",
+                 d->numCols + 1, d->numCols, (long long)d->colPtrsLen);
+    MR_REQUIRE(d->colPtrs != nullptr, MR_EINVAL, "colPtrs is null");
+    MR_REQUIRE(d->valuesLen == d->colPtrs[d->colPtrsLen - 1], MR_EINVAL,
+               "The last value of colPtrs must equal the number of elements. values.length: %lld, colPtrs.last: %d",
+               (long long)d->valuesLen, d->colPtrs[d->colPtrsLen - 1]);
+    MR_REQUIRE(d->valuesLen == 0 || (d->values != nullptr && d->rowIndices != nullptr), MR_EINVAL,
+               "values / rowIndices is null");
+  } else {
+    fail(MR_ENOTSUP, "Unsupported matrix type %d", static_cast<int>(d->type));
+  }
+}
+
+Span upload_raw(mr_context* ctx, const void* host, size_t bytes) {
+  Span s{std::make_shared<DevBuf>(ctx, std::max<size_t>(bytes, 16)), 0};
+  if (bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(s.buf->p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += static_cast<int64_t>(bytes);
+  }
+  return s;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// ABI: lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mr_last_error(void) { return g_last_error.c_str(); }
+const char* mr_version(void) { return "matrel-b200 0.1 (sm_100a)"; }
+
+mr_status mr_init(const mr_options* opts, mr_context** out) {
+  return guarded([&] {
+    MR_REQUIRE(out != nullptr, MR_EINVAL, "out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      (void)cudaGetLastError();
+      fail(MR_ECUDA, "no usable CUDA device (%s): the B200 engine has no CPU fallback",
+           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    auto ctx = std::unique_ptr<mr_context>(new mr_context);
+    int dev = opts ? opts->device : -1;
+    if (dev < 0) CUDA_CHECK(cudaGetDevice(&dev));
+    MR_REQUIRE(dev < count, MR_EINVAL, "device ordinal %d out of range (have %d)", dev, count);
+    CUDA_CHECK(cudaSetDevice(dev));
+    ctx->device = dev;
+    cudaDeviceProp prop{};
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+      fail(MR_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    if (opts) {
+      ctx->compat_bugs = opts->compat_bugs;
+      ctx->gemm_algo = opts->gemm_algo;
+      ctx->ozaki_slices = opts->ozaki_slices;
+    }
+    if (opts && opts->stream) {
+      ctx->stream = static_cast<cudaStream_t>(opts->stream);
+    } else {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    CUDA_CHECK(cudaEventCreate(&ctx->ev0));
+    CUDA_CHECK(cudaEventCreate(&ctx->ev1));
+    // keep freed blocks in the pool: operators allocate result slabs on every call
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = UINT64_MAX;
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = ctx.release();
+  });
+}
+
+mr_status mr_shutdown(mr_context* ctx) {
+  return guarded([&] {
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+  });
+}
+
+mr_status mr_set_stream(mr_context* ctx, void* cuda_stream) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) {
+      cudaStreamDestroy(ctx->stream);
+      ctx->own_stream = false;
+    }
+    if (cuda_stream) {
+      ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+  });
+}
+
+mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && key != nullptr, MR_EINVAL, "ctx/key is null");
+    std::string k(key);
+    if (k == "compat_bugs") ctx->compat_bugs = static_cast<int>(value);
+    else if (k == "gemm_algo") ctx->gemm_algo = static_cast<int>(value);
+    else if (k == "ozaki_slices") ctx->ozaki_slices = static_cast<int>(value);
+    else if (k == "time_kernels") ctx->time_kernels = static_cast<int>(value);
+    else if (k == "gemm_variant") ctx->force_variant = static_cast<int>(value);
+    else fail(MR_EINVAL, "unknown option '%s'", key);
+  });
+}
+
+mr_status mr_sync(mr_context* ctx) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+mr_status mr_get_stats(mr_context* ctx, mr_stats* out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr, MR_EINVAL, "ctx/out is null");
+    *out = ctx->stats;
+  });
+}
+
+mr_status mr_reset_stats(mr_context* ctx) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    ctx->stats = mr_stats{};
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: datasets
+// ------------------------------------------------------------------------------------------------
+mr_status mr_matrix_create(mr_context* ctx, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr, MR_EINVAL, "ctx/out is null");
+    *out = new_matrix(ctx);
+  });
+}
+
+mr_status mr_matrix_free(mr_matrix* m) {
+  return guarded([&] { delete m; });
+}
+
+mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_block_desc* d) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr, MR_EINVAL, "matrix is null");
+    validate_desc(d);
+    mr_context* ctx = m->ctx;
+    Block b;
+    b.type = d->type;
+    b.numRows = d->numRows;
+    b.numCols = d->numCols;
+    b.isT = d->isTransposed != 0;
+    b.valuesLen = d->valuesLen;
+    b.values = upload_raw(ctx, d->values, static_cast<size_t>(d->valuesLen) * sizeof(double));
+    if (d->type == 0) {
+      b.colPtrsLen = d->colPtrsLen;
+      b.colPtrs = upload_raw(ctx, d->colPtrs, static_cast<size_t>(d->colPtrsLen) * sizeof(int32_t));
+      b.rowIndices = upload_raw(ctx, d->rowIndices, static_cast<size_t>(d->rowIndicesLen) * sizeof(int32_t));
+    }
+    m->blocks[{rid, cid}] = std::move(b);
+  });
+}
+
+mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int32_t numRows, int32_t numCols,
+                                     const double* dvalues, uint8_t isTransposed) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr, MR_EINVAL, "matrix is null");
+    MR_REQUIRE(numRows >= 0 && numCols >= 0, MR_EINVAL, "negative block dimensions %d x %d", numRows, numCols);
+    MR_REQUIRE(dvalues != nullptr || static_cast<int64_t>(numRows) * numCols == 0, MR_EINVAL, "device pointer is null");
+    Span s{std::make_shared<DevBuf>(m->ctx, const_cast<double*>(dvalues),
+                                    static_cast<size_t>(numRows) * numCols * sizeof(double)),
+           0};
+    m->blocks[{rid, cid}] = dense_block(numRows, numCols, s, isTransposed != 0);
+  });
+}
+
+mr_status mr_matrix_num_blocks(const mr_matrix* m, int64_t* out) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && out != nullptr, MR_EINVAL, "matrix/out is null");
+    *out = static_cast<int64_t>(m->blocks.size());
+  });
+}
+
+mr_status mr_matrix_block_ids(const mr_matrix* m, int32_t* rids, int32_t* cids, int64_t cap) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && rids != nullptr && cids != nullptr, MR_EINVAL, "null argument");
+    MR_REQUIRE(cap >= static_cast<int64_t>(m->blocks.size()), MR_EINVAL, "capacity %lld < number of blocks %zu",
+               (long long)cap, m->blocks.size());
+    int64_t i = 0;
+    for (auto& kv : m->blocks) {
+      rids[i] = kv.first.first;
+      cids[i] = kv.first.second;
+      ++i;
+    }
+  });
+}
+
+mr_status mr_matrix_get_block(mr_matrix* m, int32_t rid, int32_t cid, mr_block_desc* io) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && io != nullptr, MR_EINVAL, "null argument");
+    auto it = m->blocks.find({rid, cid});
+    if (it == m->blocks.end()) fail(MR_ENOTFOUND, "no block (%d, %d) in this dataset", rid, cid);
+    const Block& b = it->second;
+    mr_context* ctx = m->ctx;
+    const int64_t rowIndicesLen = b.dense() ? 0 : b.valuesLen;
+    if (io->values != nullptr) {
+      MR_REQUIRE(io->valuesLen >= b.valuesLen, MR_EINVAL, "values capacity %lld < %lld", (long long)io->valuesLen,
+                 (long long)b.valuesLen);
+      if (b.valuesLen)
+        CUDA_CHECK(cudaMemcpyAsync(io->values, b.values.ptr<double>(), static_cast<size_t>(b.valuesLen) * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->stats.d2h_bytes += b.valuesLen * 8;
+    }
+    if (!b.dense() && io->colPtrs != nullptr) {
+      MR_REQUIRE(io->colPtrsLen >= b.colPtrsLen, MR_EINVAL, "colPtrs capacity too small");
+      CUDA_CHECK(cudaMemcpyAsync(io->colPtrs, b.colPtrs.ptr<int32_t>(), static_cast<size_t>(b.colPtrsLen) * 4,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->stats.d2h_bytes += b.colPtrsLen * 4;
+    }
+    if (!b.dense() && io->rowIndices != nullptr) {
+      MR_REQUIRE(io->rowIndicesLen >= rowIndicesLen, MR_EINVAL, "rowIndices capacity too small");
+      if (rowIndicesLen)
+        CUDA_CHECK(cudaMemcpyAsync(io->rowIndices, b.rowIndices.ptr<int32_t>(), static_cast<size_t>(rowIndicesLen) * 4,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->stats.d2h_bytes += rowIndicesLen * 4;
+    }
+    if (io->values || io->colPtrs || io->rowIndices) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    io->type = b.type;
+    io->numRows = b.numRows;
+    io->numCols = b.numCols;
+    io->isTransposed = b.isT ? 1 : 0;
+    io->valuesLen = b.valuesLen;
+    io->colPtrsLen = b.dense() ? 0 : b.colPtrsLen;
+    io->rowIndicesLen = rowIndicesLen;
+  });
+}
+
+mr_status mr_matrix_block_device_ptr(mr_matrix* m, int32_t rid, int32_t cid, double** dptr) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && dptr != nullptr, MR_EINVAL, "null argument");
+    auto it = m->blocks.find({rid, cid});
+    if (it == m->blocks.end()) fail(MR_ENOTFOUND, "no block (%d, %d) in this dataset", rid, cid);
+    *dptr = it->second.values.ptr<double>();
+  });
+}
+
+mr_status mr_matrix_rand(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t seed0,
+                         mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr, MR_EINVAL, "ctx/out is null");
+    MR_REQUIRE(nrows > 0 && ncols > 0 && blkSize > 0, MR_EINVAL, "nrows, ncols, blkSize must be positive");
+    // DenseMatrix.rand `require` (MLMatrix.scala:454-455)
+    MR_REQUIRE(static_cast<int64_t>(blkSize) * blkSize <= INT32_MAX, MR_EINVAL,
+               "%d x %d dense matrix is too large to allocate", blkSize, blkSize);
+    const int64_t nbr = ceil_div(nrows, blkSize), nbc = ceil_div(ncols, blkSize);
+    std::unique_ptr<mr_matrix> m(new_matrix(ctx));
+    size_t total = 0;
+    for (int64_t i = 0; i < nbr; ++i)
+      for (int64_t j = 0; j < nbc; ++j) {
+        const int64_t r = std::min<int64_t>(blkSize, nrows - i * blkSize), c = std::min<int64_t>(blkSize, ncols - j * blkSize);
+        total += align_up(static_cast<size_t>(r * c) * sizeof(double));
+      }
+    Slab slab(ctx, total);
+    for (int64_t i = 0; i < nbr; ++i)
+      for (int64_t j = 0; j < nbc; ++j) {
+        const int32_t r = static_cast<int32_t>(std::min<int64_t>(blkSize, nrows - i * blkSize));
+        const int32_t c = static_cast<int32_t>(std::min<int64_t>(blkSize, ncols - j * blkSize));
+        Span s = slab.take(static_cast<size_t>(r) * c * sizeof(double));
+        CUDA_CHECK(launch_java_rand(s.ptr<double>(), static_cast<int64_t>(r) * c, seed0 + i * nbc + j, ctx->stream));
+        note_launch(ctx);
+        m->blocks[{static_cast<int32_t>(i), static_cast<int32_t>(j)}] = dense_block(r, c, s, false);
+      }
+    *out = m.release();
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: operators
+// ------------------------------------------------------------------------------------------------
+mr_status mr_matrix_multiply(mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right,
+                             int64_t rightRowNum, int64_t rightColNum, int32_t blkSize, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(left && right && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(left->ctx == right->ctx, MR_EINVAL, "operands belong to different contexts");
+    MR_REQUIRE(blkSize > 0, MR_EINVAL, "blkSize must be positive, got %d", blkSize);
+    // MatfastExecution.scala:702-703
+    MR_REQUIRE(leftColNum == rightRowNum, MR_EDIM, "Matrix dimension not match, leftColNum = %lld, rightRowNum = %lld",
+               (long long)leftColNum, (long long)rightRowNum);
+    (void)leftRowNum;
+    (void)rightColNum;
+    mr_context* ctx = left->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    MultiplyPlanner planner{ctx};
+    planner.temps.reserve(left->blocks.size() + right->blocks.size() + 1);
+    std::vector<OutPlan> plans;
+    const int64_t leftColBlkNum = ceil_div(leftColNum, blkSize);    // :712
+    const int64_t rightRowBlkNum = ceil_div(rightRowNum, blkSize);  // :713
+    if (leftColBlkNum == 1 && rightRowBlkNum == 1) {
+      // outer-product paths (:714-721 -> helper :175-221): every left block x every right block, no
+      // reduce.  Reference defect B1 (DuplicateLeft throws) is not reproduced; both branches return
+      // what DuplicateRight returns.
+      std::map<std::pair<int32_t, int32_t>, size_t> seen;
+      for (auto& l : left->blocks)
+        for (auto& r : right->blocks) {
+          OutPlan o;
+          o.rid = l.first.first;
+          o.cid = r.first.second;
+          planner.add_pair(o, l.second, r.second);
+          auto key = std::make_pair(o.rid, o.cid);
+          auto it = seen.find(key);
+          if (it == seen.end()) {
+            seen[key] = plans.size();
+            plans.push_back(std::move(o));
+          } else {
+            plans[it->second] = std::move(o);  // duplicate keys: the last row wins when collected into a map
+          }
+        }
+    } else {
+      // matrixMultiplyGeneral (helper :235-263): join on k, then reduce by (i, j) in ascending k.
+      std::map<int32_t, std::vector<std::pair<int32_t, const Block*>>> rights;  // k -> (j, B(k,j))
+      for (auto& r : right->blocks) rights[r.first.first].push_back({r.first.second, &r.second});
+      std::map<std::pair<int32_t, int32_t>, size_t> index;
+      // left->blocks is ordered by (i, k): iterating it visits k ascending within each i
+      for (auto& l : left->blocks) {
+        const int32_t i = l.first.first, k = l.first.second;
+        auto rit = rights.find(k);
+        if (rit == rights.end()) continue;
+        for (auto& jb : rit->second) {
+          auto key = std::make_pair(i, jb.first);
+          auto it = index.find(key);
+          if (it == index.end()) {
+            OutPlan o;
+            o.rid = i;
+            o.cid = jb.first;
+            it = index.emplace(key, plans.size()).first;
+            plans.push_back(std::move(o));
+          }
+          planner.add_pair(plans[it->second], l.second, *jb.second);
+        }
+      }
+    }
+    std::unique_ptr<mr_matrix> result(new_matrix(ctx));
+    run_multiply(ctx, plans, planner, blkSize, result.get());
+    *out = result.release();
+  });
+}
+
+mr_status mr_transpose(mr_matrix* a, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(a && out, MR_EINVAL, "null argument");
+    std::unique_ptr<mr_matrix> r(new_matrix(a->ctx));
+    for (auto& kv : a->blocks) {
+      Block b = kv.second;  // shares the device arrays (DenseMatrix.transpose, MLMatrix.scala:312; Sparse :634-635)
+      std::swap(b.numRows, b.numCols);
+      b.isT = !b.isT;
+      r->blocks[{kv.first.second, kv.first.first}] = std::move(b);  // (rid, cid) -> (cid, rid), MatfastExecution.scala:230-231
+    }
+    *out = r.release();
+  });
+}
+
+static mr_status ew_operator(int op, mr_matrix* left, int64_t lr, int64_t lc, mr_matrix* right, int64_t rr, int64_t rc,
+                             mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(left && right && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(left->ctx == right->ctx, MR_EINVAL, "operands belong to different contexts");
+    check_same_dims(lr, lc, rr, rc);
+    std::lock_guard<std::mutex> lock(left->ctx->mu);
+    std::unique_ptr<mr_matrix> r(new_matrix(left->ctx));
+    elementwise_join(op, left, right, r.get());
+    *out = r.release();
+  });
+}
+
+mr_status mr_add_element(mr_matrix* left, int64_t lr, int64_t lc, mr_matrix* right, int64_t rr, int64_t rc,
+                         int32_t blkSize, mr_matrix** out) {
+  (void)blkSize;
+  return ew_operator(EW_ADD, left, lr, lc, right, rr, rc, out);
+}
+mr_status mr_multiply_element(mr_matrix* left, int64_t lr, int64_t lc, mr_matrix* right, int64_t rr, int64_t rc,
+                              int32_t blkSize, mr_matrix** out) {
+  (void)blkSize;
+  return ew_operator(EW_MUL, left, lr, lc, right, rr, rc, out);
+}
+mr_status mr_divide_element(mr_matrix* left, int64_t lr, int64_t lc, mr_matrix* right, int64_t rr, int64_t rc,
+                            int32_t blkSize, mr_matrix** out) {
+  (void)blkSize;
+  return ew_operator(EW_DIV, left, lr, lc, right, rr, rc, out);
+}
+
+static mr_status map_operator(int op, mr_matrix* a, double alpha, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(a && out, MR_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lock(a->ctx->mu);
+    std::unique_ptr<mr_matrix> r(new_matrix(a->ctx));
+    map_values(op, a, alpha, r.get());
+    *out = r.release();
+  });
+}
+mr_status mr_add_scalar(mr_matrix* a, double alpha, mr_matrix** out) { return map_operator(MAP_ADD_SCALAR, a, alpha, out); }
+mr_status mr_multiply_scalar(mr_matrix* a, double alpha, mr_matrix** out) { return map_operator(MAP_MUL_SCALAR, a, alpha, out); }
+mr_status mr_power(mr_matrix* a, double alpha, mr_matrix** out) { return map_operator(MAP_POW, a, alpha, out); }
+
+mr_status mr_rank_one_update(mr_matrix* left, int64_t lr, int64_t lc, mr_matrix* right, int64_t rr, int64_t rc,
+                             int32_t blkSize, mr_matrix** out) {
+  (void)blkSize;
+  return guarded([&] {
+    MR_REQUIRE(left && right && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(left->ctx == right->ctx, MR_EINVAL, "operands belong to different contexts");
+    mr_context* ctx = left->ctx;
+    if (ctx->compat_bugs) {
+      // the reference's own `require`s (MatfastExecution.scala:741-744), which only admit 1-row matrices
+      MR_REQUIRE(rr == 1, MR_EDIM, "Vector column size is not 1, but #cols = %lld", (long long)rr);
+      MR_REQUIRE(lr == rr, MR_EDIM,
+                 "Dimension not match for matrix addition, A.nrows = %lld, A.ncols = %lld, B.nrows = %lld, B.ncols = %lld",
+                 (long long)lr, (long long)lc, (long long)rr, (long long)rc);
+    } else {
+      // intended semantics: A (n x n) + v v^T with v an n x 1 block column (MatrixOperator.scala:151-152)
+      MR_REQUIRE(rc == 1, MR_EDIM, "Vector column size is not 1, but #cols = %lld", (long long)rc);
+      MR_REQUIRE(lr == rr && lc == rr, MR_EDIM,
+                 "Dimension not match for matrix addition, A.nrows = %lld, A.ncols = %lld, B.nrows = %lld, B.ncols = %lld",
+                 (long long)lr, (long long)lc, (long long)rr, (long long)rc);
+    }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::unique_ptr<mr_matrix> r(new_matrix(ctx));
+    EwBatch batch{ctx, ctx->compat_bugs ? EW_RANK1_COMPAT : EW_RANK1};
+    batch.keep.reserve(left->blocks.size() + 2 * right->blocks.size() + 2);
+    std::map<const Block*, const Block*> dense_cache;
+    auto dense_view = [&](const Block& b) -> const Block* {
+      if (b.dense()) return &b;
+      auto it = dense_cache.find(&b);
+      if (it != dense_cache.end()) return it->second;
+      batch.keep.push_back(densify(ctx, b));
+      return dense_cache[&b] = &batch.keep.back();
+    };
+    for (auto& kv : left->blocks) {
+      const int32_t i = kv.first.first, j = kv.first.second;
+      const Block& a = kv.second;
+      // helper :271-275: x2.rid == i, x3.rid == j (vector blocks are looked up by their row-block id)
+      const Block *x = nullptr, *y = nullptr;
+      for (auto& vb : right->blocks) {
+        if (vb.first.first == i) x = &vb.second;
+        if (vb.first.first == j) y = &vb.second;
+      }
+      if (!x || !y) continue;
+      MR_REQUIRE(static_cast<int64_t>(x->numRows) * x->numCols >= a.numRows &&
+                     static_cast<int64_t>(y->numRows) * y->numCols >= a.numCols,
+                 MR_EDIM, "vector block shorter than matrix block (%d x %d)", a.numRows, a.numCols);
+      if (ctx->compat_bugs && !a.dense())
+        fail(MR_ENOTSUP, "rankOneAdd on a sparse block in compat mode (LocalMatrix.scala:1079-1081 indexes the "
+                         "dense result with the sparse value index) is not reproduced");
+      const Block* xd = dense_view(*x);
+      const Block* yd = dense_view(*y);
+      const Block* ad = ctx->compat_bugs ? &a : dense_view(a);
+      // mat2(i, 0) of an n x 1 (or, transposed, 1 x n flagged) dense block is values[i] either way
+      batch.add(kv.first, ad, xd, yd->values.ptr<double>(), a.numRows, a.numCols);
+    }
+    batch.run(r.get());
+    *out = r.release();
+  });
+}
+
+mr_status mr_materialize(mr_matrix* a, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(a && out, MR_EINVAL, "null argument");
+    mr_context* ctx = a->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::unique_ptr<mr_matrix> r(new_matrix(ctx));
+    EwBatch batch{ctx, EW_COPY};
+    for (auto& kv : a->blocks) {
+      const Block& b = kv.second;
+      if (!b.dense()) {
+        r->blocks[kv.first] = densify(ctx, b);
+      } else if (!b.isT) {
+        r->blocks[kv.first] = b;  // already canonical: share
+      } else {
+        batch.add(kv.first, &b, nullptr, nullptr, b.numRows, b.numCols);
+      }
+    }
+    batch.run(r.get());
+    *out = r.release();
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: placement (pure integer; bit-exact with M/partitioner/*.scala)
+// ------------------------------------------------------------------------------------------------
+mr_status mr_row_partition(int32_t rid, int32_t cid, int32_t partitions, int32_t* out) {
+  return guarded([&] {
+    (void)cid;
+    MR_REQUIRE(out != nullptr, MR_EINVAL, "out is null");
+    MR_REQUIRE(partitions >= 0, MR_EINVAL, "Number of partitions cannot be negative but found %d", partitions);
+    if (partitions == 0) fail(MR_EINVAL, "/ by zero");  // java.lang.ArithmeticException
+    *out = rid % partitions;                            // RowPartitioner.scala:34 (JVM % truncates like C)
+  });
+}
+
+mr_status mr_column_partition(int32_t rid, int32_t cid, int32_t partitions, int32_t* out) {
+  return guarded([&] {
+    (void)rid;
+    MR_REQUIRE(out != nullptr, MR_EINVAL, "out is null");
+    MR_REQUIRE(partitions >= 0, MR_EINVAL, "Number of partitions cannot be negative but found %d", partitions);
+    if (partitions == 0) fail(MR_EINVAL, "/ by zero");
+    *out = cid % partitions;  // ColumnPartitioner.scala:34
+  });
+}
+
+mr_status mr_index_partition(int32_t key, int32_t partitions, int32_t* out) {
+  return guarded([&] {
+    MR_REQUIRE(out != nullptr, MR_EINVAL, "out is null");
+    MR_REQUIRE(partitions >= 0, MR_EINVAL, "Number of partitions cannot be negative but found %d", partitions);
+    *out = key;  // IndexPartitioner.scala:31
+  });
+}
+
+static int32_t java_round(double x) { return static_cast<int32_t>(std::floor(x + 0.5)); }  // math.round
+
+mr_status mr_gen_block_cyclic(int64_t nrows, int64_t ncols, int32_t blkSize, int32_t out[4]) {
+  return guarded([&] {
+    MR_REQUIRE(out != nullptr, MR_EINVAL, "out is null");
+    MR_REQUIRE(blkSize > 0, MR_EINVAL, "blkSize must be positive, got %d", blkSize);
+    // MatfastExecutionHelper.scala:46-62
+    const int32_t R = static_cast<int32_t>(std::ceil(nrows * 1.0 / blkSize));
+    const int32_t C = static_cast<int32_t>(std::ceil(ncols * 1.0 / blkSize));
+    const int numPartitions = 64;
+    const double scale = 1.0 / std::sqrt(static_cast<double>(numPartitions));
+    int32_t r = java_round(std::max(scale * R, 1.0));
+    int32_t c = java_round(std::max(scale * C, 1.0));
+    if (r == 1 || c == 1) {
+      if (r != 1) r = java_round(std::max(r / 8.0, 1.0));
+      if (c != 1) c = java_round(std::max(c / 8.0, 1.0));
+    }
+    out[0] = R;
+    out[1] = C;
+    out[2] = r;
+    out[3] = c;
+  });
+}
+
+static void block_cyclic_derive(const int32_t p[4], int32_t* rpn, int32_t* cpn, int32_t* nrp, int32_t* ncp) {
+  // BlockCyclicPartitioner.scala:36-50
+  MR_REQUIRE(p[0] > 0, MR_EINVAL, "Number of row blocks should be larger than 0, but found %d", p[0]);
+  MR_REQUIRE(p[1] > 0, MR_EINVAL, "Number of col blocks should be larger than 0, but found %d", p[1]);
+  MR_REQUIRE(p[2] > 0, MR_EINVAL, "Number of row blocks per partition should be larger than 0, but found %d", p[2]);
+  MR_REQUIRE(p[3] > 0, MR_EINVAL, "Number of col blocks per partition should be larger than 0, but found %d", p[3]);
+  *rpn = static_cast<int32_t>(std::ceil(p[0] * 1.0 / p[2]));
+  *cpn = static_cast<int32_t>(std::ceil(p[1] * 1.0 / p[3]));
+  *nrp = p[0] / *rpn;
+  *ncp = p[1] / *cpn;
+}
+
+mr_status mr_block_cyclic_partition(const int32_t params[4], int32_t rid, int32_t cid, int32_t* out) {
+  return guarded([&] {
+    MR_REQUIRE(params != nullptr && out != nullptr, MR_EINVAL, "null argument");
+    int32_t rpn, cpn, nrp, ncp;
+    block_cyclic_derive(params, &rpn, &cpn, &nrp, &ncp);
+    const int32_t n = rpn * cpn;
+    *out = ((rid % nrp) * cpn + (cid % ncp)) % n;  // BlockCyclicPartitioner.scala:54-57 (defect B2 kept: bit-exact ids)
+  });
+}
+
+mr_status mr_block_cyclic_num_partitions(const int32_t params[4], int32_t* out) {
+  return guarded([&] {
+    MR_REQUIRE(params != nullptr && out != nullptr, MR_EINVAL, "null argument");
+    int32_t rpn, cpn, nrp, ncp;
+    block_cyclic_derive(params, &rpn, &cpn, &nrp, &ncp);
+    *out = rpn * cpn;
+  });
+}
+
+}  // extern "C"

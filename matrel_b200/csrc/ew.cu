@@ -1,0 +1,360 @@
+// HBM-bound sibling kernels of the block-multiply path, batched over the blocks of a dataset
+// (one launch per operator call, not per block):
+//   element-wise add / mul / div     LocalMatrix.addDense, elementWiseOpDenseDense (LocalMatrix.scala:56-63,493-505)
+//   materialising transpose / copy   DenseMatrix.toArray (MLMatrix.scala:55-61) for isTransposed blocks
+//   scalar add / mul / pow           LocalMatrix.scala:411-426, 931-980 (layout preserving maps)
+//   rank-one update                  LocalMatrix.rankOneAdd (LocalMatrix.scala:1075-1093)
+//   sparse -> dense                  SparseMatrix.toArray (MLMatrix.scala:637-663)
+//   sparse x dense                   BLAS.gemmsdd (BLAS.scala:352-458)
+//   java.util.Random U(0,1) fill     DenseMatrix.rand (MLMatrix.scala:453-457)
+// Flat paths use 128-bit ld/st.global.v2.f64 with 4 independent vectors in flight per thread;
+// layout-mixing paths stage a 32x32 tile through padded shared memory so both the row-major
+// read and the column-major write are fully coalesced.
+#include "kernels.h"
+
+namespace matrel {
+namespace {
+
+template <int OP>
+__device__ __forceinline__ double ew_apply(double a, double b) {
+  if (OP == EW_ADD) return a + b;
+  if (OP == EW_MUL) return a * b;
+  if (OP == EW_DIV) return a / b;
+  return a;  // EW_COPY
+}
+
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(double2* p, double2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+constexpr int FLAT_THREADS = 256;
+constexpr int FLAT_UNROLL = 4;
+
+// Both operands share C's layout: pure streaming.
+template <int OP>
+__global__ void __launch_bounds__(FLAT_THREADS) ew_flat_kernel(const EwDesc* __restrict__ descs) {
+  const EwDesc d = descs[blockIdx.y];
+  const int64_t n = static_cast<int64_t>(d.rows) * d.cols;
+  const bool has_b = (OP != EW_COPY);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(d.A) | reinterpret_cast<uintptr_t>(d.C) |
+                        (has_b ? reinterpret_cast<uintptr_t>(d.B) : 0)) & 15) == 0;
+  const int64_t nvec = vec_ok ? (n >> 1) : 0;
+  const double2* A2 = reinterpret_cast<const double2*>(d.A);
+  const double2* B2 = reinterpret_cast<const double2*>(d.B);
+  double2* C2 = reinterpret_cast<double2*>(d.C);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * FLAT_THREADS;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * FLAT_THREADS + threadIdx.x;
+  for (; i + (FLAT_UNROLL - 1) * stride < nvec; i += FLAT_UNROLL * stride) {
+    double2 a[FLAT_UNROLL], b[FLAT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < FLAT_UNROLL; ++u) a[u] = ld_stream(A2 + i + u * stride);
+    if (has_b) {
+#pragma unroll
+      for (int u = 0; u < FLAT_UNROLL; ++u) b[u] = ld_stream(B2 + i + u * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < FLAT_UNROLL; ++u) {
+      double2 c;
+      c.x = ew_apply<OP>(a[u].x, has_b ? b[u].x : 0.0);
+      c.y = ew_apply<OP>(a[u].y, has_b ? b[u].y : 0.0);
+      st_stream(C2 + i + u * stride, c);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const double2 a = ld_stream(A2 + i);
+    double2 b = make_double2(0.0, 0.0);
+    if (has_b) b = ld_stream(B2 + i);
+    double2 c;
+    c.x = ew_apply<OP>(a.x, b.x);
+    c.y = ew_apply<OP>(a.y, b.y);
+    st_stream(C2 + i, c);
+  }
+  // scalar tail (odd n, or unaligned borrowed pointers)
+  for (int64_t j = 2 * nvec + static_cast<int64_t>(blockIdx.x) * FLAT_THREADS + threadIdx.x; j < n; j += stride)
+    d.C[j] = ew_apply<OP>(d.A[j], has_b ? d.B[j] : 0.0);
+}
+
+// Layout-mixing path: 32x32 tile, 32x8 threads; output (r = r0 + tx, c = c0 + ty + 8j).
+__device__ __forceinline__ void load_tile(const double* __restrict__ X, bool xT, int rows, int cols, int r0, int c0,
+                                          double (&sm)[32][33], double (&v)[4]) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (!xT) {
+    const int r = r0 + tx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + ty + 8 * j;
+      v[j] = (r < rows && c < cols) ? X[r + static_cast<size_t>(rows) * c] : 0.0;
+    }
+  } else {
+    __syncthreads();  // protect sm against the previous operand's readers
+    const int c = c0 + tx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + ty + 8 * j;
+      sm[ty + 8 * j][tx] = (r < rows && c < cols) ? X[c + static_cast<size_t>(cols) * r] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = sm[tx][ty + 8 * j];
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) ew_tiled_kernel(const EwDesc* __restrict__ descs, int tiles_c_max) {
+  __shared__ double sm[32][33];
+  const EwDesc d = descs[blockIdx.y];
+  const int tr = blockIdx.x / tiles_c_max, tc = blockIdx.x % tiles_c_max;
+  const int r0 = tr * 32, c0 = tc * 32;
+  if (r0 >= d.rows || c0 >= d.cols) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  if (OP == EW_RANK1_COMPAT) {
+    // flat C[k] = x_r * y_c with k = A's storage index; A itself is never read (defect B3).
+    // aT: C_flat is row-major -> treat as the column-major (cols x rows) matrix y x^T.
+    const double* x = d.B;
+    const double* y = d.Y;
+    if (!d.aT) {
+      const int r = r0 + tx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j;
+        if (r < d.rows && c < d.cols) d.C[r + static_cast<size_t>(d.rows) * c] = x[r] * y[c];
+      }
+    } else {
+      // iterate the same tile with roles swapped so writes stay coalesced along c
+      const int c = c0 + tx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + ty + 8 * j;
+        if (r < d.rows && c < d.cols) d.C[c + static_cast<size_t>(d.cols) * r] = x[r] * y[c];
+      }
+    }
+    return;
+  }
+  if (d.A != nullptr) load_tile(d.A, d.aT != 0, d.rows, d.cols, r0, c0, sm, a);
+  if (OP == EW_ADD || OP == EW_MUL || OP == EW_DIV) load_tile(d.B, d.bT != 0, d.rows, d.cols, r0, c0, sm, b);
+  const int r = r0 + tx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 8 * j;
+    if (r < d.rows && c < d.cols) {
+      double out;
+      if (OP == EW_RANK1) out = a[j] + d.B[r] * d.Y[c];
+      else out = ew_apply<OP>(a[j], b[j]);
+      d.C[r + static_cast<size_t>(d.rows) * c] = out;
+    }
+  }
+}
+
+template <int OP>
+__device__ __forceinline__ double map_apply(double v, double alpha) {
+  if (OP == MAP_ADD_SCALAR) return v + alpha;
+  if (OP == MAP_MUL_SCALAR) return alpha * v;
+  return pow(v, alpha);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(FLAT_THREADS) map_kernel(const MapDesc* __restrict__ descs, double alpha) {
+  const MapDesc d = descs[blockIdx.y];
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(d.in) | reinterpret_cast<uintptr_t>(d.out)) & 15) == 0;
+  const int64_t nvec = vec_ok ? (d.n >> 1) : 0;
+  const double2* I2 = reinterpret_cast<const double2*>(d.in);
+  double2* O2 = reinterpret_cast<double2*>(d.out);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * FLAT_THREADS;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * FLAT_THREADS + threadIdx.x;
+  for (; i + (FLAT_UNROLL - 1) * stride < nvec; i += FLAT_UNROLL * stride) {
+    double2 a[FLAT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < FLAT_UNROLL; ++u) a[u] = ld_stream(I2 + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < FLAT_UNROLL; ++u) {
+      double2 c;
+      c.x = map_apply<OP>(a[u].x, alpha);
+      c.y = map_apply<OP>(a[u].y, alpha);
+      st_stream(O2 + i + u * stride, c);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const double2 a = ld_stream(I2 + i);
+    double2 c;
+    c.x = map_apply<OP>(a.x, alpha);
+    c.y = map_apply<OP>(a.y, alpha);
+    st_stream(O2 + i, c);
+  }
+  for (int64_t j = 2 * nvec + static_cast<int64_t>(blockIdx.x) * FLAT_THREADS + threadIdx.x; j < d.n; j += stride)
+    d.out[j] = map_apply<OP>(d.in[j], alpha);
+}
+
+// one warp per compressed line (column of CSC / row of CSR)
+__global__ void sparse_to_dense_kernel(const int32_t* __restrict__ ptrs, const int32_t* __restrict__ idx,
+                                       const double* __restrict__ vals, bool isT, double* __restrict__ out, int rows,
+                                       int cols) {
+  const int nlines = isT ? rows : cols;
+  const int line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (line >= nlines) return;
+  const int beg = ptrs[line], end = ptrs[line + 1];
+  for (int i = beg + lane; i < end; i += 32) {
+    const int minor = idx[i];
+    const size_t o = isT ? (static_cast<size_t>(line) + static_cast<size_t>(rows) * minor)
+                         : (static_cast<size_t>(minor) + static_cast<size_t>(rows) * line);
+    out[o] = vals[i];
+  }
+}
+
+__device__ __forceinline__ double dense_at(const double* __restrict__ B, bool bT, int k, int n, int r, int c) {
+  return bT ? B[c + static_cast<size_t>(n) * r] : B[r + static_cast<size_t>(k) * c];
+}
+
+// CSR x dense: thread per (row, column); rows fastest so C writes coalesce and the 32 lanes of a
+// warp gather from one 8*k-byte column of B (L1/L2 resident).  BLAS.scala:375-413.
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const int32_t* __restrict__ ptrs, const int32_t* __restrict__ idx,
+                                                       const double* __restrict__ vals, const double* __restrict__ B,
+                                                       bool bT, double* __restrict__ C, int m, int k, int n,
+                                                       bool accumulate) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r >= m) return;
+  const int beg = ptrs[r], end = ptrs[r + 1];
+  double sum = 0.0;
+  for (int i = beg; i < end; ++i) sum += vals[i] * dense_at(B, bT, k, n, idx[i], c);
+  const size_t o = static_cast<size_t>(r) + static_cast<size_t>(m) * c;
+  C[o] = accumulate ? C[o] + sum : sum;
+}
+
+// CSC x dense: scatter-AXPY (BLAS.scala:414-456).  Warp per (CSC column, output column); C must be
+// initialised (zeros or the running sum) before launch.
+__global__ void __launch_bounds__(256) spmm_csc_kernel(const int32_t* __restrict__ ptrs, const int32_t* __restrict__ idx,
+                                                       const double* __restrict__ vals, const double* __restrict__ B,
+                                                       bool bT, double* __restrict__ C, int m, int k, int n) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.y;
+  if (col >= k) return;
+  const int beg = ptrs[col], end = ptrs[col + 1];
+  if (beg == end) return;
+  const double bval = dense_at(B, bT, k, n, col, c);
+  for (int i = beg + lane; i < end; i += 32)
+    atomicAdd(&C[static_cast<size_t>(idx[i]) + static_cast<size_t>(m) * c], vals[i] * bval);
+}
+
+// java.util.Random: s' = (s * 0x5DEECE66D + 0xB) mod 2^48; nextDouble = ((next(26) << 27) + next(27)) * 2^-53.
+// Thread i jumps straight to draw i with an O(log i) affine-map power, so the fill is parallel and
+// still bit-identical to the JVM's sequential stream.
+__global__ void __launch_bounds__(256) java_rand_kernel(double* __restrict__ out, int64_t n, uint64_t seed0) {
+  const uint64_t MASK = (1ull << 48) - 1;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // affine map x -> a*x + c applied (2*i) times
+  uint64_t a_acc = 1, c_acc = 0;
+  uint64_t a = 0x5DEECE66Dull, c = 0xBull;
+  for (uint64_t e = 2ull * static_cast<uint64_t>(i); e != 0; e >>= 1) {
+    if (e & 1) {
+      a_acc = (a_acc * a) & MASK;
+      c_acc = (c_acc * a + c) & MASK;
+    }
+    c = (c * a + c) & MASK;  // compose the map with itself: x -> a*(a*x + c) + c
+    a = (a * a) & MASK;
+  }
+  uint64_t s = (a_acc * seed0 + c_acc) & MASK;
+  s = (s * 0x5DEECE66Dull + 0xBull) & MASK;
+  const uint64_t hi = s >> 22;  // next(26)
+  s = (s * 0x5DEECE66Dull + 0xBull) & MASK;
+  const uint64_t lo = s >> 21;  // next(27)
+  out[i] = static_cast<double>((hi << 27) + lo) * (1.0 / 9007199254740992.0);
+}
+
+inline int flat_grid_x(int64_t max_n) {
+  int64_t vec = (max_n + 1) / 2;
+  int64_t gx = (vec + static_cast<int64_t>(FLAT_THREADS) * FLAT_UNROLL - 1) / (static_cast<int64_t>(FLAT_THREADS) * FLAT_UNROLL);
+  if (gx < 1) gx = 1;
+  if (gx > 65535) gx = 65535;
+  return static_cast<int>(gx);
+}
+
+}  // namespace
+
+cudaError_t launch_ew_batched(int op, const EwDesc* d_descs, int nblocks, int max_rows, int max_cols,
+                              bool any_transposed, cudaStream_t stream) {
+  if (nblocks <= 0) return cudaSuccess;
+  const bool tiled = any_transposed || op == EW_RANK1 || op == EW_RANK1_COMPAT;
+  if (!tiled) {
+    dim3 grid(flat_grid_x(static_cast<int64_t>(max_rows) * max_cols), nblocks);
+    switch (op) {
+      case EW_ADD: ew_flat_kernel<EW_ADD><<<grid, FLAT_THREADS, 0, stream>>>(d_descs); break;
+      case EW_MUL: ew_flat_kernel<EW_MUL><<<grid, FLAT_THREADS, 0, stream>>>(d_descs); break;
+      case EW_DIV: ew_flat_kernel<EW_DIV><<<grid, FLAT_THREADS, 0, stream>>>(d_descs); break;
+      case EW_COPY: ew_flat_kernel<EW_COPY><<<grid, FLAT_THREADS, 0, stream>>>(d_descs); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
+  const int tiles_r = (max_rows + 31) / 32, tiles_c = (max_cols + 31) / 32;
+  dim3 grid(tiles_r * tiles_c, nblocks), block(32, 8);
+  switch (op) {
+    case EW_ADD: ew_tiled_kernel<EW_ADD><<<grid, block, 0, stream>>>(d_descs, tiles_c); break;
+    case EW_MUL: ew_tiled_kernel<EW_MUL><<<grid, block, 0, stream>>>(d_descs, tiles_c); break;
+    case EW_DIV: ew_tiled_kernel<EW_DIV><<<grid, block, 0, stream>>>(d_descs, tiles_c); break;
+    case EW_COPY: ew_tiled_kernel<EW_COPY><<<grid, block, 0, stream>>>(d_descs, tiles_c); break;
+    case EW_RANK1: ew_tiled_kernel<EW_RANK1><<<grid, block, 0, stream>>>(d_descs, tiles_c); break;
+    case EW_RANK1_COMPAT: ew_tiled_kernel<EW_RANK1_COMPAT><<<grid, block, 0, stream>>>(d_descs, tiles_c); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_map_batched(int op, const MapDesc* d_descs, int nblocks, int64_t max_n, double alpha,
+                               cudaStream_t stream) {
+  if (nblocks <= 0) return cudaSuccess;
+  dim3 grid(flat_grid_x(max_n), nblocks);
+  switch (op) {
+    case MAP_ADD_SCALAR: map_kernel<MAP_ADD_SCALAR><<<grid, FLAT_THREADS, 0, stream>>>(d_descs, alpha); break;
+    case MAP_MUL_SCALAR: map_kernel<MAP_MUL_SCALAR><<<grid, FLAT_THREADS, 0, stream>>>(d_descs, alpha); break;
+    case MAP_POW: map_kernel<MAP_POW><<<grid, FLAT_THREADS, 0, stream>>>(d_descs, alpha); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sparse_to_dense(const int32_t* ptrs, const int32_t* idx, const double* vals, bool isT, double* out,
+                                   int rows, int cols, cudaStream_t stream) {
+  const int nlines = isT ? rows : cols;
+  if (nlines <= 0) return cudaSuccess;
+  const int warps_per_block = 8;
+  const int grid = (nlines + warps_per_block - 1) / warps_per_block;
+  sparse_to_dense_kernel<<<grid, warps_per_block * 32, 0, stream>>>(ptrs, idx, vals, isT, out, rows, cols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_spmm(const int32_t* ptrs, const int32_t* idx, const double* vals, bool sT, const double* B, bool bT,
+                        double* C, int m, int k, int n, bool accumulate, cudaStream_t stream) {
+  if (m <= 0 || n <= 0) return cudaSuccess;
+  if (sT) {
+    dim3 grid((m + 255) / 256, n);
+    spmm_csr_kernel<<<grid, 256, 0, stream>>>(ptrs, idx, vals, B, bT, C, m, k, n, accumulate);
+  } else {
+    if (!accumulate) {
+      cudaError_t e = cudaMemsetAsync(C, 0, static_cast<size_t>(m) * n * sizeof(double), stream);
+      if (e != cudaSuccess) return e;
+    }
+    if (k <= 0) return cudaSuccess;
+    dim3 grid((k + 7) / 8, n);
+    spmm_csc_kernel<<<grid, 256, 0, stream>>>(ptrs, idx, vals, B, bT, C, m, k, n);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_java_rand(double* out, int64_t n, int64_t seed, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const uint64_t seed0 = (static_cast<uint64_t>(seed) ^ 0x5DEECE66Dull) & ((1ull << 48) - 1);
+  const int64_t grid = (n + 255) / 256;
+  java_rand_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(out, n, seed0);
+  return cudaGetLastError();
+}
+
+}  // namespace matrel

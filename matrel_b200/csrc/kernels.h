@@ -1,0 +1,81 @@
+// Internal interface between the C-ABI host layer (abi.cpp) and the sm_100a kernels.
+// Not part of the public ABI (see include/matrel.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace matrel {
+
+// ---- block GEMM ----------------------------------------------------------------------------------
+// One k-block contribution A(i,k) * B(k,j) to an output block; the block-GEMM kernel walks the
+// pair list of an output block inside its K loop, which fuses the reference's
+// reduceByKey(LocalMatrix.add) (MatfastExecutionHelper.scala:255) into the accumulators.
+struct GemmPair {
+  const double* A;  // values of A(i,k): m x kdim, column-major (lda = m) or row-major if aT (lda = kdim)
+  const double* B;  // values of B(k,j): kdim x n, column-major (ldb = kdim) or row-major if bT (ldb = n)
+  int32_t lda, ldb;
+  int32_t kdim;
+  uint8_t aT, bT;   // isTransposed flags (BLAS.gemmddd's "T"/"N", BLAS.scala:333-336)
+  uint8_t pad[2];
+};
+
+struct GemmOut {
+  double* C;        // m x n, column-major, ldc = m (DenseMatrix.zeros(m, n), MLMatrix.scala:101)
+  int32_t m, n;
+  int32_t pair_begin, pair_count;
+};
+
+struct GemmTile {
+  int32_t out;      // index into GemmOut[]
+  int32_t tm, tn;   // tile coordinates inside the output block
+  int32_t pad;
+};
+
+enum GemmVariant { GEMM_128x128 = 0, GEMM_64x64 = 1 };
+int gemm_tile_m(int variant);
+int gemm_tile_n(int variant);
+
+cudaError_t launch_gemm_f64(const GemmOut* d_outs, const GemmPair* d_pairs, const GemmTile* d_tiles,
+                            int ntiles, int variant, cudaStream_t stream);
+
+// ---- element-wise / layout kernels (HBM-bound), batched over blocks ---------------------------------
+enum EwOp { EW_ADD = 0, EW_MUL = 1, EW_DIV = 2, EW_RANK1 = 3, EW_RANK1_COMPAT = 4, EW_COPY = 5 };
+
+// C (column-major rows x cols) = f(A(r,c), B(r,c)); A, B dense with their own isTransposed flag.
+//   EW_ADD/MUL/DIV : LocalMatrix.addDense / elementWiseOpDenseDense (LocalMatrix.scala:56-63,493-505)
+//   EW_COPY        : C = A  (DenseMatrix.toArray, MLMatrix.scala:55-61)            (B unused)
+//   EW_RANK1       : C = A + x y^T with x = B (rows), y = Y (cols)                 (intended rankOneAdd)
+//   EW_RANK1_COMPAT: flat C[k(r,c)] = x_r y_c, k = A's storage index (defect B3 restated, LocalMatrix.scala:1075-1093)
+struct EwDesc {
+  const double* A;
+  const double* B;
+  const double* Y;
+  double* C;
+  int32_t rows, cols;
+  uint8_t aT, bT;
+  uint8_t pad[6];
+};
+cudaError_t launch_ew_batched(int op, const EwDesc* d_descs, int nblocks, int max_rows, int max_cols,
+                              bool any_transposed, cudaStream_t stream);
+
+enum MapOp { MAP_ADD_SCALAR = 0, MAP_MUL_SCALAR = 1, MAP_POW = 2 };
+struct MapDesc {
+  const double* in;
+  double* out;
+  int64_t n;
+};
+// out[i] = f(in[i], alpha) over flat value arrays (layout preserving; LocalMatrix.scala:411-426,931-980)
+cudaError_t launch_map_batched(int op, const MapDesc* d_descs, int nblocks, int64_t max_n, double alpha,
+                               cudaStream_t stream);
+
+// dense col-major rows x cols from CSC / CSR (SparseMatrix.toArray, MLMatrix.scala:55-61,637-663); out pre-zeroed
+cudaError_t launch_sparse_to_dense(const int32_t* ptrs, const int32_t* idx, const double* vals, bool isT,
+                                   double* out, int rows, int cols, cudaStream_t stream);
+// C (col-major m x n) (+)= S (CSR if sT else CSC, m x k) * B (k x n dense, bT flag) ; BLAS.gemmsdd (BLAS.scala:352-458)
+cudaError_t launch_spmm(const int32_t* ptrs, const int32_t* idx, const double* vals, bool sT,
+                        const double* B, bool bT, double* C, int m, int k, int n, bool accumulate,
+                        cudaStream_t stream);
+// java.util.Random-compatible U(0,1) fill: out[i] = i-th nextDouble() of new Random(seed)
+cudaError_t launch_java_rand(double* out, int64_t n, int64_t seed, cudaStream_t stream);
+
+}  // namespace matrel

@@ -1,0 +1,233 @@
+"""Host-side mirror of the reference's operator API for the block-multiply path.
+
+``MatfastSession`` replaces ``MatfastSession.builder().getOrCreate()`` (M/MatfastSession.scala:177-234)
+and ``Dataset`` keeps the method names and argument order of M/Dataset.scala:57-152
+(``matrixMultiply``, ``transpose``/``t``, ``addElement``, ``multiplyElement``, ``divideElement``,
+``addScalar``, ``multiplyScalar``, ``power``, ``matrixRankOneUpdate``), each forwarding to the C ABI
+(include/matrel.h) which launches the sm_100a kernels.  Execution is eager and asynchronous on the
+session's CUDA stream instead of lazy through Catalyst; results are observationally the same
+because operators are pure.
+
+M/ = /root/reference/src/main/scala/org/apache/spark/sql/matfast/
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .matrix import DenseMatrix, MatrixBlock, MLMatrix, SparseMatrix
+
+
+def _i32p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class MatfastSession:
+    """One engine context per process per GPU (``mr_init`` / ``mr_shutdown``)."""
+
+    def __init__(self, device: int = -1, compat_bugs: bool = True, stream: Optional[int] = None,
+                 gemm_algo: int = 0, ozaki_slices: int = 0):
+        opts = N.mr_options(int(device), int(bool(compat_bugs)), int(gemm_algo), int(ozaki_slices),
+                            C.c_void_p(stream) if stream else None)
+        self._ctx = C.c_void_p()
+        N.check(N.lib.mr_init(C.byref(opts), C.byref(self._ctx)))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def stop(self) -> None:
+        if self._ctx:
+            N.check(N.lib.mr_shutdown(self._ctx))
+            self._ctx = C.c_void_p()
+
+    close = stop
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.stop()
+
+    def __del__(self):
+        try:
+            self.stop()
+        except Exception:
+            pass
+
+    def sync(self) -> None:
+        N.check(N.lib.mr_sync(self._ctx))
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        N.check(N.lib.mr_set_stream(self._ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def set_option(self, key: str, value: int) -> None:
+        N.check(N.lib.mr_set_option(self._ctx, key.encode(), int(value)))
+
+    def stats(self) -> dict:
+        s = N.mr_stats()
+        N.check(N.lib.mr_get_stats(self._ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in N.mr_stats._fields_}
+
+    def reset_stats(self) -> None:
+        N.check(N.lib.mr_reset_stats(self._ctx))
+
+    # -- dataset construction ---------------------------------------------------------------
+    def createDataset(self, blocks: Iterable[MatrixBlock]) -> "Dataset":
+        """``Seq(MatrixBlock(...)).toDS()`` (M/example/BasicMatrixOps.scala:115-116)."""
+        ds = Dataset._new(self)
+        for b in blocks:
+            ds._put(b.rid, b.cid, b.matrix)
+        return ds
+
+    toDS = createDataset
+
+    def emptyDataset(self) -> "Dataset":
+        return Dataset._new(self)
+
+    def rand(self, nrows: int, ncols: int, blkSize: int, seed0: int) -> "Dataset":
+        """Every block ``DenseMatrix.rand(r, c, new java.util.Random(seed0 + rid*nbc + cid))``
+        (M/matrix/MLMatrix.scala:453-457), generated on the device."""
+        h = C.c_void_p()
+        N.check(N.lib.mr_matrix_rand(self._ctx, nrows, ncols, blkSize, seed0, C.byref(h)))
+        return Dataset(self, h)
+
+
+class Dataset:
+    """A bag of ``(rid, cid, block)`` rows resident in HBM (an ``mr_matrix`` handle)."""
+
+    def __init__(self, session: MatfastSession, handle: C.c_void_p):
+        self.matfastSession = session
+        self._h = handle
+
+    @staticmethod
+    def _new(session: MatfastSession) -> "Dataset":
+        h = C.c_void_p()
+        N.check(N.lib.mr_matrix_create(session._ctx, C.byref(h)))
+        return Dataset(session, h)
+
+    def __del__(self):
+        try:
+            if self._h and self.matfastSession._ctx:
+                N.lib.mr_matrix_free(self._h)
+            self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # -- block ingest / egress (MLMatrixSerializer.deserialize / serialize) -------------------
+    def _put(self, rid: int, cid: int, m: MLMatrix) -> None:
+        d = N.mr_block_desc()
+        d.numRows, d.numCols = m.numRows, m.numCols
+        d.isTransposed = 1 if m.isTransposed else 0
+        d.values = _f64p(m.values)
+        d.valuesLen = m.values.size
+        if isinstance(m, SparseMatrix):
+            d.type = 0
+            d.colPtrs, d.colPtrsLen = _i32p(m.colPtrs), m.colPtrs.size
+            d.rowIndices, d.rowIndicesLen = _i32p(m.rowIndices), m.rowIndices.size
+        else:
+            d.type = 1
+        N.check(N.lib.mr_matrix_put_block(self._h, rid, cid, C.byref(d)))
+
+    def put_block(self, rid: int, cid: int, m: MLMatrix) -> None:
+        self._put(rid, cid, m)
+
+    def put_block_device(self, rid: int, cid: int, numRows: int, numCols: int, device_ptr: int,
+                         isTransposed: bool = False) -> None:
+        """Adopt a dense block that already lives in device memory (not freed by the engine)."""
+        N.check(N.lib.mr_matrix_put_block_device(self._h, rid, cid, numRows, numCols,
+                                                 C.c_void_p(device_ptr), 1 if isTransposed else 0))
+
+    def block_ids(self) -> List[tuple]:
+        n = C.c_int64()
+        N.check(N.lib.mr_matrix_num_blocks(self._h, C.byref(n)))
+        rids = np.empty(n.value, dtype=np.int32)
+        cids = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            N.check(N.lib.mr_matrix_block_ids(self._h, _i32p(rids), _i32p(cids), n.value))
+        return list(zip(rids.tolist(), cids.tolist()))
+
+    def get_block(self, rid: int, cid: int, out: Optional[np.ndarray] = None) -> MLMatrix:
+        d = N.mr_block_desc()
+        N.check(N.lib.mr_matrix_get_block(self._h, rid, cid, C.byref(d)))  # sizes only
+        values = out if out is not None else np.empty(d.valuesLen, dtype=np.float64)
+        assert values.size >= d.valuesLen and values.dtype == np.float64
+        d.values = _f64p(values)
+        if d.type == 0:
+            colPtrs = np.empty(d.colPtrsLen, dtype=np.int32)
+            rowIndices = np.empty(d.rowIndicesLen, dtype=np.int32)
+            d.colPtrs, d.rowIndices = _i32p(colPtrs), _i32p(rowIndices)
+        N.check(N.lib.mr_matrix_get_block(self._h, rid, cid, C.byref(d)))
+        if d.type == 0:
+            return SparseMatrix(d.numRows, d.numCols, colPtrs, rowIndices, values[:d.valuesLen],
+                                bool(d.isTransposed))
+        return DenseMatrix(d.numRows, d.numCols, values[:d.valuesLen], bool(d.isTransposed))
+
+    def block_device_ptr(self, rid: int, cid: int) -> int:
+        p = C.c_void_p()
+        N.check(N.lib.mr_matrix_block_device_ptr(self._h, rid, cid, C.byref(p)))
+        return p.value or 0
+
+    def collect(self) -> List[MatrixBlock]:
+        """``.collect()`` / ``.rdd.foreach``: every row back on the host, ordered by (rid, cid)."""
+        return [MatrixBlock(r, c, self.get_block(r, c)) for r, c in self.block_ids()]
+
+    # -- operators: signatures of M/Dataset.scala:57-152 ----------------------------------------
+    def _binary(self, fn, leftRowNum, leftColNum, right, rightRowNum, rightColNum, blkSize) -> "Dataset":
+        h = C.c_void_p()
+        N.check(fn(self._h, int(leftRowNum), int(leftColNum), right._h, int(rightRowNum), int(rightColNum),
+                   int(blkSize), C.byref(h)))
+        return Dataset(self.matfastSession, h)
+
+    def matrixMultiply(self, leftRowNum, leftColNum, right: "Dataset", rightRowNum, rightColNum, blkSize) -> "Dataset":
+        """M/Dataset.scala:134-142."""
+        return self._binary(N.lib.mr_matrix_multiply, leftRowNum, leftColNum, right, rightRowNum, rightColNum, blkSize)
+
+    def addElement(self, leftRowNum, leftColNum, right: "Dataset", rightRowNum, rightColNum, blkSize) -> "Dataset":
+        """M/Dataset.scala:105-112."""
+        return self._binary(N.lib.mr_add_element, leftRowNum, leftColNum, right, rightRowNum, rightColNum, blkSize)
+
+    def multiplyElement(self, leftRowNum, leftColNum, right: "Dataset", rightRowNum, rightColNum, blkSize) -> "Dataset":
+        """M/Dataset.scala:114-122."""
+        return self._binary(N.lib.mr_multiply_element, leftRowNum, leftColNum, right, rightRowNum, rightColNum, blkSize)
+
+    def divideElement(self, leftRowNum, leftColNum, right: "Dataset", rightRowNum, rightColNum, blkSize) -> "Dataset":
+        """M/Dataset.scala:124-132."""
+        return self._binary(N.lib.mr_divide_element, leftRowNum, leftColNum, right, rightRowNum, rightColNum, blkSize)
+
+    def matrixRankOneUpdate(self, leftRowNum, leftColNum, right: "Dataset", rightRowNum, rightColNum, blkSize) -> "Dataset":
+        """M/Dataset.scala:144-152."""
+        return self._binary(N.lib.mr_rank_one_update, leftRowNum, leftColNum, right, rightRowNum, rightColNum, blkSize)
+
+    def _unary(self, fn, *args) -> "Dataset":
+        h = C.c_void_p()
+        N.check(fn(self._h, *args, C.byref(h)))
+        return Dataset(self.matfastSession, h)
+
+    def transpose(self) -> "Dataset":
+        """M/Dataset.scala:59-61."""
+        return self._unary(N.lib.mr_transpose)
+
+    def t(self) -> "Dataset":
+        """M/Dataset.scala:57."""
+        return self.transpose()
+
+    def addScalar(self, alpha: float) -> "Dataset":
+        """M/Dataset.scala:89-91."""
+        return self._unary(N.lib.mr_add_scalar, float(alpha))
+
+    def multiplyScalar(self, alpha: float) -> "Dataset":
+        """M/Dataset.scala:93-97."""
+        return self._unary(N.lib.mr_multiply_scalar, float(alpha))
+
+    def power(self, alpha: float) -> "Dataset":
+        """M/Dataset.scala:99-103."""
+        return self._unary(N.lib.mr_power, float(alpha))
+
+    def materialize(self) -> "Dataset":
+        """Every dense block rewritten column-major (``toArray``, M/matrix/MLMatrix.scala:55-61)."""
+        return self._unary(N.lib.mr_materialize)
