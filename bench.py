@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- fp64 block-matmul GFLOP/s at N=16384 (BASELINE.json metric), 1..8 B200.
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N ...            reference arm: the reference algorithm
+                                                           restated on the box's host cores (oracle/)
+
+A "step" is one full C = A * B over the whole block matrix.  `value` is measured with the inputs
+resident in HBM; `e2e` is the same multiply through the public Dataset API with HOST buffers
+(host->device copies of every A and B block and device->host copies of every C block inside the
+timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DEFAULT, BLK_DEFAULT = 16384, 1024
+METRIC = "fp64 block-matmul GFLOP/s at N=16384"
+UNIT = "GFLOP/s"
+
+
+def fp64_peak_tflops():
+    """Roofline denominator for the fp64 tensor pipe: MEASURED_PEAKS.json has no fp64 entry, so the
+    measured DMMA peak of tools/fp64_peak.cu (profiles/fp64_peaks_r01.jsonl) is used."""
+    path = os.path.join(ROOT, "profiles", "fp64_peaks_r01.jsonl")
+    best, src = None, None
+    try:
+        for line in open(path):
+            d = json.loads(line)
+            if d.get("bench") == "dmma_sustained":
+                best, src = d["tflops"], "profiles/fp64_peaks_r01.jsonl dmma_sustained (measured on this pool's B200; MEASURED_PEAKS.json has no fp64 entry)"
+    except OSError:
+        pass
+    if best is None:
+        best, src = 37.2, "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz (fallback: no measured file)"
+    return best, src
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference ALGORITHM restated on host cores (oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n: int, blk: int, budget_s: float = 20.0):
+    """matrixMultiplyGeneral restated with numpy (OpenBLAS dgemm, all host threads): for the output
+    blocks of ONE block row -- every k: deserialize copies of A(i,k), B(k,j), a fresh C per pair
+    (MLMatrix.multiply), pairwise LocalMatrix.add, serialize copy.  Bounded sample of the N x N
+    workload; GFLOP/s = sample flops / sample seconds.  Upper bound on the reference's speed: no
+    Spark scheduling, shuffle or GC is modelled."""
+    import numpy as np
+    from oracle import matrel_oracle as O
+    nb = n // blk
+    rngA = [O.DenseMatrix.rand(blk, blk, O.JavaRandom(42 + k)) for k in range(nb)]        # A(0, k)
+    cols = []
+    done_flops, t_total, ncols = 0.0, 0.0, 0
+    for _ in range(10):                                      # wake the BLAS thread pool (untimed)
+        O.matrixMultiplication(rngA[0], rngA[-1])
+    for j in range(nb):
+        Bj = [O.DenseMatrix.rand(blk, blk, O.JavaRandom(43 + k * nb + j)) for k in range(nb)]  # B(k, j)
+        t0 = time.perf_counter()
+        acc = None
+        for k in range(nb):
+            a = O.deserialize(O.serialize(rngA[k]))          # MLMatrixSerializer copy-in (:50-69)
+            b = O.deserialize(O.serialize(Bj[k]))
+            p = O.matrixMultiplication(a, b)                 # fresh C + dgemm
+            acc = p if acc is None else O.add(acc, p)        # reduceByKey(LocalMatrix.add)
+        out = O.serialize(acc)                               # copy-out (:26-48)
+        t_total += time.perf_counter() - t0
+        done_flops += 2.0 * blk * blk * blk * nb
+        ncols += 1
+        cols.append(float(out[5][0]))
+        if t_total > budget_s:
+            break
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    return {"value": done_flops / t_total / 1e9, "unit": UNIT, "cores": int(threads), "kind": "port",
+            "sample": f"{ncols} of {nb * nb} output blocks of the {n}x{n}/{blk} multiply (block row 0), "
+                      f"{t_total:.1f} s; numpy/OpenBLAS dgemm per block pair + LocalMatrix.add + "
+                      "serialize/deserialize copies; host cpu_count=%d" % (os.cpu_count() or 1),
+            "seconds": t_total, "flops": done_flops}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, blk = args.n, args.blk
+    vals = []
+    last = None
+    per_step_budget = max(2.0, 120.0 / max(1, args.steps + args.warmup))
+    for s in range(args.warmup + args.steps):
+        r = cpu_reference_sample(n, blk, budget_s=per_step_budget)
+        if s >= args.warmup:
+            vals.append(r)
+        last = r
+    tot_f = sum(r["flops"] for r in vals)
+    tot_t = sum(r["seconds"] for r in vals)
+    v = tot_f / tot_t / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * (2.0 * n ** 3 / (v * 1e9)), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{n}x{n} fp64 dense multiply, {blk}-block (reference algorithm on host cores)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import matrel_b200 as mb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    n, blk = args.n, args.blk
+    nb = n // blk
+    flops = 2.0 * n ** 3
+
+    if world > 1:
+        from matrel_b200 import distributed as dist_mm
+        return dist_mm.bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample)
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        s = mb.MatfastSession(device=local_rank, stream=stream.cuda_stream)
+        A = s.rand(n, n, blk, 42)
+        B = s.rand(n, n, blk, 43)
+        s.sync()
+
+        # ---- device-resident: value + roofline (CUDA events on the launching stream)
+        for _ in range(args.warmup):
+            C = A.matrixMultiply(n, n, B, n, n, blk)
+            del C
+        s.sync()
+        s.reset_stats()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        torch.cuda.synchronize()
+        t_wall0 = time.perf_counter()
+        for e0, e1 in evs:
+            e0.record(stream)
+            C = A.matrixMultiply(n, n, B, n, n, blk)
+            e1.record(stream)
+            del C
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop()
+        ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+        ms_per_step = sum(ms) / len(ms)
+        st = s.stats()
+        launches_per_step = st["kernel_launches"] / args.steps
+        gemm_launches_per_step = st["gemm_launches"] / args.steps
+
+        # GEMM kernel alone (events inside the library, around the launch)
+        s.set_option("time_kernels", 1)
+        s.reset_stats()
+        for _ in range(max(3, args.steps)):
+            C = A.matrixMultiply(n, n, B, n, n, blk)
+            del C
+        st2 = s.stats()
+        s.set_option("time_kernels", 0)
+        kern_ms = st2["gemm_ms_total"] / st2["gemm_launches"]
+        peak, peak_src = fp64_peak_tflops()
+        achieved = flops / (kern_ms * 1e-3) / 1e12
+
+        # ---- end to end through the public API with pinned HOST buffers
+        hostA = {k: A.get_block(*k) for k in A.block_ids()}
+        hostB = {k: B.get_block(*k) for k in B.block_ids()}
+        pin = lambda m: torch.from_numpy(m.values).pin_memory().numpy()  # noqa: E731
+        pA = [mb.MatrixBlock(i, j, mb.DenseMatrix(m.numRows, m.numCols, pin(m), m.isTransposed)) for (i, j), m in hostA.items()]
+        pB = [mb.MatrixBlock(i, j, mb.DenseMatrix(m.numRows, m.numCols, pin(m), m.isTransposed)) for (i, j), m in hostB.items()]
+        outbuf = {(i, j): torch.empty(blk * blk, dtype=torch.float64).pin_memory().numpy() for i in range(nb) for j in range(nb)}
+        del hostA, hostB
+        h2d = sum(b.matrix.values.nbytes for b in pA) + sum(b.matrix.values.nbytes for b in pB)
+        d2h = sum(v.nbytes for v in outbuf.values())
+
+        def e2e_step():
+            dA = s.createDataset(pA)
+            dB = s.createDataset(pB)
+            dC = dA.matrixMultiply(n, n, dB, n, n, blk)
+            for (i, j) in dC.block_ids():
+                dC.get_block(i, j, out=outbuf[(i, j)])
+            return dC
+
+        e2e_warm = min(args.warmup, 2)
+        for _ in range(e2e_warm):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        checksum = float(outbuf[(0, 0)][0])
+        s.stop()
+
+    cpu = cpu_reference_sample(n, blk, budget_s=args.cpu_budget)
+    cpu.pop("seconds", None); cpu.pop("flops", None)
+    line = {
+        "metric": METRIC, "value": flops / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n}x{n} fp64 dense multiply, {blk}-block, 1xB200 (BASELINE metric size)",
+                   "inputs": "U(0,1) java.util.Random streams, every block present, column-major",
+                   "l2": f"inputs 2 x {n * n * 8 / 2**30:.0f} GiB + output {n * n * 8 / 2**30:.0f} GiB >> 126 MB L2; no flush needed",
+                   "gemm_algo": "dmma_fp64", "wall_ms_per_step": t_wall / args.steps * 1e3, "c00": checksum},
+        "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps},
+        "gpu_launches": int(round(launches_per_step * args.steps)),
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "gemm_f64_dmma_kernel<128,128,2,4,4>", "kernel_ms": kern_ms,
+                     "launches_per_step": gemm_launches_per_step,
+                     "algorithmic": f"2*N^3 = {flops:.4g} flop per launch (whole block multiply, K reduction fused)",
+                     "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--blk", type=int, default=BLK_DEFAULT)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/matrel.h
+declares, the ctypes binding covers the same set, the integer placement functions are bit-exact
+against the golden tables, and the engine refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "matrel.h")).read()
+    return sorted(set(re.findall(r"MR_API\s+[\w\s\*]+?\b(mr_\w+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    import matrel_b200._native as N
+    syms = header_symbols()
+    assert len(syms) >= 30
+    out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    for s in syms:
+        assert s in exported, f"{s} declared in matrel.h but not exported by the .so"
+        assert hasattr(N.lib, s)
+    bound = set(N.SIGNATURES) | set(N._STR_FUNCS)
+    assert bound == set(syms), (bound ^ set(syms))
+    # nothing but the ABI (and nothing torch / C++-mangled) is exported
+    extra = {e for e in exported if not e.startswith("mr_")}
+    assert not extra, extra
+    assert N.lib.mr_version().startswith(b"matrel-b200")
+
+
+def test_so_contains_blackwell_native_sass():
+    """UBLKCP = TMA bulk copy, DMMA = fp64 tensor pipe, SYNCS = mbarrier (B200_PROFILING.md table)."""
+    import matrel_b200._native as N
+    sass = subprocess.run(["cuobjdump", "-sass", N.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", N.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("DMMA") >= 128 and "UBLKCP" in sass and "SYNCS" in sass
+
+
+def test_partitioners_bit_exact():
+    import matrel_b200 as mb
+    g = json.load(open(os.path.join(G, "partitioners.json")))
+    for c in g["cases"]:
+        p = mb.genBlockCyclicPartitioner(c["nrows"], c["ncols"], c["blkSize"])
+        assert list(p) == c["params"]
+        bc = mb.BlockCyclicPartitioner(*p)
+        assert bc.numPartitions == c["numPartitions"]
+        used = set()
+        for i in range(p[0]):
+            for j in range(p[1]):
+                v = bc.getPartition((i, j))
+                used.add(v)
+                if c["table"] is not None:
+                    assert v == c["table"][i][j]
+        assert sorted(used) == c["used"]
+    for name, k in g["known"].items():
+        n, blk = map(int, name.split("/"))
+        assert list(mb.genBlockCyclicPartitioner(n, n, blk)) == k["params"]
+    for i, p, want in g["row"]:
+        assert mb.RowPartitioner(p).getPartition((i, 5)) == want
+        assert mb.RowPartitioner(p).getPartition((i, 5, 9)) == want
+    for j, p, want in g["col"]:
+        assert mb.ColumnPartitioner(p).getPartition((5, j)) == want
+    assert mb.IndexPartitioner(8).getPartition(5) == 5
+    with pytest.raises(ValueError, match="Unrecognized key"):
+        mb.RowPartitioner(4).getPartition("x")
+    with pytest.raises(mb.IllegalArgumentException, match="Number of partitions cannot be negative but found -1"):
+        mb.RowPartitioner(-1).getPartition((1, 1))
+    with pytest.raises(mb.IllegalArgumentException, match="Number of row blocks should be larger than 0, but found 0"):
+        mb.BlockCyclicPartitioner(0, 4, 1, 1)
+
+
+def test_partitioners_match_oracle_exhaustively():
+    import matrel_b200 as mb
+    from oracle import matrel_oracle as O
+    for R in range(1, 20):
+        for Cc in (1, 2, 5, 16, 33):
+            for r in (1, 2, 3, 8):
+                for c in (1, 2, 4):
+                    a, b = mb.BlockCyclicPartitioner(R, Cc, r, c), O.BlockCyclicPartitioner(R, Cc, r, c)
+                    assert a.numPartitions == b.numPartitions
+                    for i in range(R):
+                        for j in range(Cc):
+                            assert a.getPartition((i, j)) == b.getPartition(i, j)
+    for nr in (1, 7, 100, 1000, 4096, 12345, 65536):
+        for nc in (1, 9, 512, 3000, 65536):
+            for blk in (1, 3, 100, 256, 1024):
+                if nr // blk > 5000 or nc // blk > 5000:
+                    continue
+                assert tuple(mb.genBlockCyclicPartitioner(nr, nc, blk)) == O.gen_block_cyclic_partitioner(nr, nc, blk)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a CUDA device the engine must fail loudly, never compute on the host."""
+    import torch
+    import matrel_b200 as mb
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mb.CudaError, match="no CPU fallback"):
+        mb.MatfastSession()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "matrel_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the CPU oracle", ""), f
+
+
+def test_cpp_facade_compiles():
+    """include/matrel.hpp (C++ mirror of the Dataset API) compiles against the C ABI."""
+    hpp = os.path.join(ROOT, "include", "matrel.hpp")
+    if not os.path.exists(hpp):
+        pytest.skip("no C++ facade yet")
+    src = '#include "matrel.hpp"\nint main() { return 0; }\n'
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-"],
+                       input=src, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
