@@ -26,6 +26,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -286,6 +287,7 @@ struct MultiplyPlanner {
     p.lda = a.isT ? a.numCols : a.numRows;  // BLAS.scala:335
     p.ldb = b.isT ? b.numCols : b.numRows;  // BLAS.scala:336
     p.kdim = a.numCols;
+    p.tmA = p.tmB = -1;
     o.gemm.push_back(p);
   }
 };
@@ -355,11 +357,34 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     });
     std::vector<GemmTile> tiles(keyed.size());
     for (size_t i = 0; i < keyed.size(); ++i) tiles[i] = keyed[i].t;
-    Buf d_outs = upload(ctx, outs), d_pairs = upload(ctx, pairs), d_tiles = upload(ctx, tiles);
+    // TMA descriptors of the K-contiguous operand blocks (row-major A blocks, column-major B blocks)
+    struct TmapBytes { unsigned char b[128]; };
+    std::vector<TmapBytes> tmaps;
+    std::map<std::tuple<const double*, int64_t, int64_t, int64_t>, int32_t> tmap_index;
+    auto tmap_of = [&](const double* base, int64_t kdim, int64_t rows, int64_t ld, int tile) -> int32_t {
+      auto key = std::make_tuple(base, kdim, rows, ld);
+      auto it = tmap_index.find(key);
+      if (it != tmap_index.end()) return it->second;
+      TmapBytes t;
+      int32_t idx = -1;
+      if (encode_kcontig_tmap(t.b, base, kdim, rows, ld, tile)) {
+        idx = static_cast<int32_t>(tmaps.size());
+        tmaps.push_back(t);
+      }
+      tmap_index.emplace(key, idx);
+      return idx;
+    };
+    for (auto& go : outs)
+      for (int p = go.pair_begin; p < go.pair_begin + go.pair_count; ++p) {
+        GemmPair& pr = pairs[p];
+        if (pr.aT) pr.tmA = tmap_of(pr.A, pr.kdim, go.m, pr.lda, BM);
+        if (!pr.bT) pr.tmB = tmap_of(pr.B, pr.kdim, go.n, pr.ldb, BN);
+      }
+    Buf d_outs = upload(ctx, outs), d_pairs = upload(ctx, pairs), d_tiles = upload(ctx, tiles), d_tmaps = upload(ctx, tmaps);
     if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
     CUDA_CHECK(launch_gemm_f64(static_cast<const GemmOut*>(d_outs->p), static_cast<const GemmPair*>(d_pairs->p),
-                               static_cast<const GemmTile*>(d_tiles->p), static_cast<int>(tiles.size()), variant,
-                               ctx->stream));
+                               static_cast<const GemmTile*>(d_tiles->p), static_cast<int>(tiles.size()), d_tmaps->p,
+                               variant, ctx->stream));
     note_launch(ctx);
     ctx->stats.gemm_launches += 1;
     ctx->stats.last_gemm_flops = flops;

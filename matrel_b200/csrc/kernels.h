@@ -15,6 +15,7 @@ struct GemmPair {
   const double* B;  // values of B(k,j): kdim x n, column-major (ldb = kdim) or row-major if bT (ldb = n)
   int32_t lda, ldb;
   int32_t kdim;
+  int32_t tmA, tmB; // index of the operand's K-contiguous CUtensorMap in the launch's table, -1 = none
   uint8_t aT, bT;   // isTransposed flags (BLAS.gemmddd's "T"/"N", BLAS.scala:333-336)
   uint8_t pad[2];
 };
@@ -35,8 +36,12 @@ enum GemmVariant { GEMM_128x128 = 0, GEMM_64x64 = 1 };
 int gemm_tile_m(int variant);
 int gemm_tile_n(int variant);
 
+// Encodes the 128-byte CUtensorMap of a K-contiguous operand block (rows x kdim, line stride ld doubles,
+// box {16, tile_rows}, SWIZZLE_128B).  Returns false when TMA cannot address it (odd ld / unaligned base).
+bool encode_kcontig_tmap(void* out128, const double* base, int64_t kdim, int64_t rows, int64_t ld, int tile_rows);
+
 cudaError_t launch_gemm_f64(const GemmOut* d_outs, const GemmPair* d_pairs, const GemmTile* d_tiles,
-                            int ntiles, int variant, cudaStream_t stream);
+                            int ntiles, const void* d_tmaps, int variant, cudaStream_t stream);
 
 // ---- element-wise / layout kernels (HBM-bound), batched over blocks ---------------------------------
 enum EwOp { EW_ADD = 0, EW_MUL = 1, EW_DIV = 2, EW_RANK1 = 3, EW_RANK1_COMPAT = 4, EW_COPY = 5 };

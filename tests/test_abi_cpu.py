@@ -42,7 +42,7 @@ def test_so_contains_blackwell_native_sass():
     if not sass:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", N.LIB_PATH], capture_output=True, text=True).stdout
-    assert sass.count("DMMA") >= 128 and "UBLKCP" in sass and "SYNCS" in sass
+    assert sass.count("DMMA") >= 128 and "UBLKCP" in sass and "UTMALDG" in sass and "SYNCS" in sass
 
 
 def test_partitioners_bit_exact():
