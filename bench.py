@@ -98,45 +98,68 @@ class ClockSampler:
 # reference arm / cpu_baseline: the reference ALGORITHM restated on host cores (oracle/)
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_sample(n: int, blk: int, budget_s: float = 20.0):
-    """matrixMultiplyGeneral restated with numpy (OpenBLAS dgemm, all host threads): for the output
-    blocks of ONE block row -- every k: deserialize copies of A(i,k), B(k,j), a fresh C per pair
-    (MLMatrix.multiply), pairwise LocalMatrix.add, serialize copy.  Bounded sample of the N x N
-    workload; GFLOP/s = sample flops / sample seconds.  Upper bound on the reference's speed: no
-    Spark scheduling, shuffle or GC is modelled."""
+    """matrixMultiplyGeneral restated on the host cores the way Spark local[*] runs it: one task per
+    output block (i, j), `cpu_count` tasks in flight, each task single-threaded -- for every k:
+    MLMatrixSerializer copy-in of A(i,k), B(k,j), a fresh C + dgemm per pair (MLMatrix.multiply,
+    OpenBLAS 0.3.30 = the best case a netlib-native install reaches), pairwise LocalMatrix.add,
+    serializer copy-out.  Bounded sample of the N x N workload (as many output blocks as fit the
+    time budget); GFLOP/s = sample flops / wall seconds.  Upper bound on the reference's speed: no
+    Spark scheduling, shuffle, Kryo or GC is modelled."""
     import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from threadpoolctl import threadpool_limits
     from oracle import matrel_oracle as O
     nb = n // blk
-    rngA = [O.DenseMatrix.rand(blk, blk, O.JavaRandom(42 + k)) for k in range(nb)]        # A(0, k)
-    cols = []
-    done_flops, t_total, ncols = 0.0, 0.0, 0
-    for _ in range(10):                                      # wake the BLAS thread pool (untimed)
-        O.matrixMultiplication(rngA[0], rngA[-1])
-    for j in range(nb):
-        Bj = [O.DenseMatrix.rand(blk, blk, O.JavaRandom(43 + k * nb + j)) for k in range(nb)]  # B(k, j)
-        t0 = time.perf_counter()
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(42)
+    # timing inputs: U(0,1) like DenseMatrix.rand (values do not change dgemm's speed)
+    Arow = {}
+    Bcol = {}
+
+    def getA(i, k):
+        if (i, k) not in Arow:
+            Arow[(i, k)] = O.DenseMatrix(blk, blk, rng.random(blk * blk))
+        return Arow[(i, k)]
+
+    def getB(k, j):
+        if (k, j) not in Bcol:
+            Bcol[(k, j)] = O.DenseMatrix(blk, blk, rng.random(blk * blk))
+        return Bcol[(k, j)]
+
+    def task(ij):
+        i, j = ij
         acc = None
         for k in range(nb):
-            a = O.deserialize(O.serialize(rngA[k]))          # MLMatrixSerializer copy-in (:50-69)
-            b = O.deserialize(O.serialize(Bj[k]))
+            a = O.deserialize(O.serialize(Arow[(i, k)]))     # MLMatrixSerializer copy-in (:50-69)
+            b = O.deserialize(O.serialize(Bcol[(k, j)]))
             p = O.matrixMultiplication(a, b)                 # fresh C + dgemm
             acc = p if acc is None else O.add(acc, p)        # reduceByKey(LocalMatrix.add)
-        out = O.serialize(acc)                               # copy-out (:26-48)
-        t_total += time.perf_counter() - t0
-        done_flops += 2.0 * blk * blk * blk * nb
-        ncols += 1
-        cols.append(float(out[5][0]))
-        if t_total > budget_s:
-            break
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    return {"value": done_flops / t_total / 1e9, "unit": UNIT, "cores": int(threads), "kind": "port",
-            "sample": f"{ncols} of {nb * nb} output blocks of the {n}x{n}/{blk} multiply (block row 0), "
-                      f"{t_total:.1f} s; numpy/OpenBLAS dgemm per block pair + LocalMatrix.add + "
-                      "serialize/deserialize copies; host cpu_count=%d" % (os.cpu_count() or 1),
-            "seconds": t_total, "flops": done_flops}
+        return float(O.serialize(acc)[5][0])                 # copy-out (:26-48)
+
+    task_flops = 2.0 * blk * blk * blk * nb
+    with threadpool_limits(limits=1, user_api="blas"):
+        for k in range(nb):
+            getA(0, k), getB(k, 0)
+        task((0, 0))                                         # warm-up (untimed)
+        t0 = time.perf_counter()
+        task((0, 0))
+        t1 = time.perf_counter() - t0                        # one single-threaded task
+        waves = max(1, int(budget_s / max(t1 * 1.5, 1e-3)))
+        ntasks = min(nb * nb, cores * waves)
+        todo = [(t // nb, t % nb) for t in range(ntasks)]
+        for (i, j) in todo:
+            for k in range(nb):
+                getA(i, k), getB(k, j)
+        with ThreadPoolExecutor(max_workers=min(cores, ntasks)) as pool:
+            t0 = time.perf_counter()
+            res = list(pool.map(task, todo))
+            wall = time.perf_counter() - t0
+    return {"value": ntasks * task_flops / wall / 1e9, "unit": UNIT, "cores": int(min(cores, ntasks)), "kind": "port",
+            "sample": f"{ntasks} of {nb * nb} output blocks of the {n}x{n}/{blk} multiply in {wall:.1f} s: one "
+                      f"single-threaded task per output block, {min(cores, ntasks)} tasks in flight (host cpu_count={cores}); "
+                      "per pair: serializer copy-in, fresh C + OpenBLAS dgemm, LocalMatrix.add; single task = "
+                      f"{t1:.2f} s ({task_flops / t1 / 1e9:.1f} GFLOP/s/core)",
+            "seconds": wall, "flops": ntasks * task_flops, "checksum": res[0]}
 
 
 def run_reference(args):
@@ -264,7 +287,7 @@ def run_ours(args):
         s.stop()
 
     cpu = cpu_reference_sample(n, blk, budget_s=args.cpu_budget)
-    cpu.pop("seconds", None); cpu.pop("flops", None)
+    cpu.pop("seconds", None); cpu.pop("flops", None); cpu.pop("checksum", None)
     line = {
         "metric": METRIC, "value": flops / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

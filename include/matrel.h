@@ -84,6 +84,10 @@ MR_API mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, con
 /* Adopts (borrows) a dense block already resident in device memory; not freed by the library. */
 MR_API mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int32_t numRows,
                                             int32_t numCols, const double* dvalues, uint8_t isTransposed);
+/* Batched form of mr_matrix_put_block_device (count blocks; arrays of length count). */
+MR_API mr_status mr_matrix_put_blocks_device(mr_matrix* m, int64_t count, const int32_t* rids, const int32_t* cids,
+                                             const int32_t* numRows, const int32_t* numCols,
+                                             const double* const* dvalues, const uint8_t* isTransposed);
 MR_API mr_status mr_matrix_num_blocks(const mr_matrix* m, int64_t* out);
 /* Fills rids/cids (capacity cap) in ascending (rid, cid) order. */
 MR_API mr_status mr_matrix_block_ids(const mr_matrix* m, int32_t* rids, int32_t* cids, int64_t cap);
@@ -98,6 +102,14 @@ MR_API mr_status mr_matrix_block_device_ptr(mr_matrix* m, int32_t rid, int32_t c
  * seed0 + rid*ceil(ncols/blk) + cid.  Used for synthetic benchmark inputs. */
 MR_API mr_status mr_matrix_rand(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize,
                                 int64_t seed0, mr_matrix** out);
+
+/* Same generator restricted to the blocks a rank of a pr x pc process grid owns
+ * (rid % pr == r, RowPartitioner.scala:34; cid % pc == c, ColumnPartitioner.scala:34), written into a
+ * caller-provided device slab: block (rid, cid) starts at dslab + ((rid / pr) * ceil(nbc / pc) + cid / pc) * slotElems.
+ * The returned dataset borrows the slab. */
+MR_API mr_status mr_matrix_rand_partition(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t seed0,
+                                          int32_t pr, int32_t pc, int32_t r, int32_t c, double* dslab,
+                                          int64_t slotElems, mr_matrix** out);
 
 /* ---- operators: argument-for-argument with M/Dataset.scala:57-152 and the physical operators
  *      of M/execution/MatfastExecution.scala. */

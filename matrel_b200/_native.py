@@ -86,11 +86,14 @@ SIGNATURES = {
     "mr_matrix_free": [_P],
     "mr_matrix_put_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
     "mr_matrix_put_block_device": [_P, _i32, _i32, _i32, _i32, _P, C.c_uint8],
+    "mr_matrix_put_blocks_device": [_P, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_uint8)],
     "mr_matrix_num_blocks": [_P, C.POINTER(_i64)],
     "mr_matrix_block_ids": [_P, C.POINTER(_i32), C.POINTER(_i32), _i64],
     "mr_matrix_get_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
     "mr_matrix_block_device_ptr": [_P, _i32, _i32, _PP],
     "mr_matrix_rand": [_P, _i64, _i64, _i32, _i64, _PP],
+    "mr_matrix_rand_partition": [_P, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _i32, _P, _i64, _PP],
     "mr_matrix_multiply": _BIN,
     "mr_transpose": [_P, _PP],
     "mr_add_element": _BIN,

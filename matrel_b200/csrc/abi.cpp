@@ -755,6 +755,22 @@ mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int
   });
 }
 
+mr_status mr_matrix_put_blocks_device(mr_matrix* m, int64_t count, const int32_t* rids, const int32_t* cids,
+                                      const int32_t* numRows, const int32_t* numCols, const double* const* dvalues,
+                                      const uint8_t* isTransposed) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr, MR_EINVAL, "matrix is null");
+    MR_REQUIRE(count == 0 || (rids && cids && numRows && numCols && dvalues), MR_EINVAL, "null argument");
+    for (int64_t i = 0; i < count; ++i) {
+      MR_REQUIRE(numRows[i] >= 0 && numCols[i] >= 0, MR_EINVAL, "negative block dimensions %d x %d", numRows[i], numCols[i]);
+      Span s{std::make_shared<DevBuf>(m->ctx, const_cast<double*>(dvalues[i]),
+                                      static_cast<size_t>(numRows[i]) * numCols[i] * sizeof(double)),
+             0};
+      m->blocks[{rids[i], cids[i]}] = dense_block(numRows[i], numCols[i], s, isTransposed ? isTransposed[i] != 0 : false);
+    }
+  });
+}
+
 mr_status mr_matrix_num_blocks(const mr_matrix* m, int64_t* out) {
   return guarded([&] {
     MR_REQUIRE(m != nullptr && out != nullptr, MR_EINVAL, "matrix/out is null");
@@ -842,15 +858,59 @@ mr_status mr_matrix_rand(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t 
         total += align_up(static_cast<size_t>(r * c) * sizeof(double));
       }
     Slab slab(ctx, total);
+    std::vector<RandDesc> descs;
+    int64_t max_n = 0;
     for (int64_t i = 0; i < nbr; ++i)
       for (int64_t j = 0; j < nbc; ++j) {
         const int32_t r = static_cast<int32_t>(std::min<int64_t>(blkSize, nrows - i * blkSize));
         const int32_t c = static_cast<int32_t>(std::min<int64_t>(blkSize, ncols - j * blkSize));
         Span s = slab.take(static_cast<size_t>(r) * c * sizeof(double));
-        CUDA_CHECK(launch_java_rand(s.ptr<double>(), static_cast<int64_t>(r) * c, seed0 + i * nbc + j, ctx->stream));
-        note_launch(ctx);
+        descs.push_back(RandDesc{s.ptr<double>(), static_cast<int64_t>(r) * c, seed0 + i * nbc + j});
+        max_n = std::max<int64_t>(max_n, static_cast<int64_t>(r) * c);
         m->blocks[{static_cast<int32_t>(i), static_cast<int32_t>(j)}] = dense_block(r, c, s, false);
       }
+    // gridDim.y limit: launch in chunks of 65535 blocks
+    for (size_t off = 0; off < descs.size(); off += 65535) {
+      std::vector<RandDesc> chunk(descs.begin() + off, descs.begin() + std::min(descs.size(), off + 65535));
+      Buf d = upload(ctx, chunk);
+      CUDA_CHECK(launch_java_rand_batched(static_cast<const RandDesc*>(d->p), static_cast<int>(chunk.size()), max_n, ctx->stream));
+      note_launch(ctx);
+    }
+    *out = m.release();
+  });
+}
+
+mr_status mr_matrix_rand_partition(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t seed0,
+                                   int32_t pr, int32_t pc, int32_t r, int32_t c, double* dslab, int64_t slotElems,
+                                   mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr && dslab != nullptr, MR_EINVAL, "null argument");
+    MR_REQUIRE(nrows > 0 && ncols > 0 && blkSize > 0, MR_EINVAL, "nrows, ncols, blkSize must be positive");
+    MR_REQUIRE(pr > 0 && pc > 0 && r >= 0 && r < pr && c >= 0 && c < pc, MR_EINVAL, "bad process grid %d x %d / (%d, %d)",
+               pr, pc, r, c);
+    MR_REQUIRE(slotElems >= static_cast<int64_t>(blkSize) * blkSize, MR_EINVAL, "slotElems %lld < blkSize^2",
+               (long long)slotElems);
+    const int64_t nbr = ceil_div(nrows, blkSize), nbc = ceil_div(ncols, blkSize);
+    const int64_t slots_c = ceil_div(nbc, pc);
+    std::unique_ptr<mr_matrix> m(new_matrix(ctx));
+    std::vector<RandDesc> descs;
+    int64_t max_n = 0;
+    for (int64_t i = r; i < nbr; i += pr)
+      for (int64_t j = c; j < nbc; j += pc) {
+        const int32_t br = static_cast<int32_t>(std::min<int64_t>(blkSize, nrows - i * blkSize));
+        const int32_t bc = static_cast<int32_t>(std::min<int64_t>(blkSize, ncols - j * blkSize));
+        double* p = dslab + ((i / pr) * slots_c + (j / pc)) * slotElems;
+        descs.push_back(RandDesc{p, static_cast<int64_t>(br) * bc, seed0 + i * nbc + j});
+        max_n = std::max<int64_t>(max_n, static_cast<int64_t>(br) * bc);
+        Span s{std::make_shared<DevBuf>(ctx, p, static_cast<size_t>(br) * bc * sizeof(double)), 0};
+        m->blocks[{static_cast<int32_t>(i), static_cast<int32_t>(j)}] = dense_block(br, bc, s, false);
+      }
+    for (size_t off = 0; off < descs.size(); off += 65535) {
+      std::vector<RandDesc> chunk(descs.begin() + off, descs.begin() + std::min(descs.size(), off + 65535));
+      Buf d = upload(ctx, chunk);
+      CUDA_CHECK(launch_java_rand_batched(static_cast<const RandDesc*>(d->p), static_cast<int>(chunk.size()), max_n, ctx->stream));
+      note_launch(ctx);
+    }
     *out = m.release();
   });
 }

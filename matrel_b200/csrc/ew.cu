@@ -245,28 +245,31 @@ __global__ void __launch_bounds__(256) spmm_csc_kernel(const int32_t* __restrict
 
 // java.util.Random: s' = (s * 0x5DEECE66D + 0xB) mod 2^48; nextDouble = ((next(26) << 27) + next(27)) * 2^-53.
 // Thread i jumps straight to draw i with an O(log i) affine-map power, so the fill is parallel and
-// still bit-identical to the JVM's sequential stream.
-__global__ void __launch_bounds__(256) java_rand_kernel(double* __restrict__ out, int64_t n, uint64_t seed0) {
+// still bit-identical to the JVM's sequential stream.  Batched: blockIdx.y selects the block/stream.
+__global__ void __launch_bounds__(256) java_rand_kernel(const RandDesc* __restrict__ descs) {
   const uint64_t MASK = (1ull << 48) - 1;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  // affine map x -> a*x + c applied (2*i) times
-  uint64_t a_acc = 1, c_acc = 0;
-  uint64_t a = 0x5DEECE66Dull, c = 0xBull;
-  for (uint64_t e = 2ull * static_cast<uint64_t>(i); e != 0; e >>= 1) {
-    if (e & 1) {
-      a_acc = (a_acc * a) & MASK;
-      c_acc = (c_acc * a + c) & MASK;
+  const RandDesc d = descs[blockIdx.y];
+  const uint64_t seed0 = (static_cast<uint64_t>(d.seed) ^ 0x5DEECE66Dull) & MASK;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < d.n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // affine map x -> a*x + c applied (2*i) times
+    uint64_t a_acc = 1, c_acc = 0;
+    uint64_t a = 0x5DEECE66Dull, c = 0xBull;
+    for (uint64_t e = 2ull * static_cast<uint64_t>(i); e != 0; e >>= 1) {
+      if (e & 1) {
+        a_acc = (a_acc * a) & MASK;
+        c_acc = (c_acc * a + c) & MASK;
+      }
+      c = (c * a + c) & MASK;  // compose the map with itself: x -> a*(a*x + c) + c
+      a = (a * a) & MASK;
     }
-    c = (c * a + c) & MASK;  // compose the map with itself: x -> a*(a*x + c) + c
-    a = (a * a) & MASK;
+    uint64_t s = (a_acc * seed0 + c_acc) & MASK;
+    s = (s * 0x5DEECE66Dull + 0xBull) & MASK;
+    const uint64_t hi = s >> 22;  // next(26)
+    s = (s * 0x5DEECE66Dull + 0xBull) & MASK;
+    const uint64_t lo = s >> 21;  // next(27)
+    d.out[i] = static_cast<double>((hi << 27) + lo) * (1.0 / 9007199254740992.0);
   }
-  uint64_t s = (a_acc * seed0 + c_acc) & MASK;
-  s = (s * 0x5DEECE66Dull + 0xBull) & MASK;
-  const uint64_t hi = s >> 22;  // next(26)
-  s = (s * 0x5DEECE66Dull + 0xBull) & MASK;
-  const uint64_t lo = s >> 21;  // next(27)
-  out[i] = static_cast<double>((hi << 27) + lo) * (1.0 / 9007199254740992.0);
 }
 
 inline int flat_grid_x(int64_t max_n) {
@@ -283,6 +286,14 @@ cudaError_t launch_ew_batched(int op, const EwDesc* d_descs, int nblocks, int ma
                               bool any_transposed, cudaStream_t stream) {
   if (nblocks <= 0) return cudaSuccess;
   const bool tiled = any_transposed || op == EW_RANK1 || op == EW_RANK1_COMPAT;
+  if (nblocks > 65535) {  // gridDim.y limit
+    for (int off = 0; off < nblocks; off += 65535) {
+      cudaError_t e = launch_ew_batched(op, d_descs + off, nblocks - off < 65535 ? nblocks - off : 65535, max_rows, max_cols,
+                                        any_transposed, stream);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   if (!tiled) {
     dim3 grid(flat_grid_x(static_cast<int64_t>(max_rows) * max_cols), nblocks);
     switch (op) {
@@ -311,6 +322,13 @@ cudaError_t launch_ew_batched(int op, const EwDesc* d_descs, int nblocks, int ma
 cudaError_t launch_map_batched(int op, const MapDesc* d_descs, int nblocks, int64_t max_n, double alpha,
                                cudaStream_t stream) {
   if (nblocks <= 0) return cudaSuccess;
+  if (nblocks > 65535) {  // gridDim.y limit
+    for (int off = 0; off < nblocks; off += 65535) {
+      cudaError_t e = launch_map_batched(op, d_descs + off, nblocks - off < 65535 ? nblocks - off : 65535, max_n, alpha, stream);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   dim3 grid(flat_grid_x(max_n), nblocks);
   switch (op) {
     case MAP_ADD_SCALAR: map_kernel<MAP_ADD_SCALAR><<<grid, FLAT_THREADS, 0, stream>>>(d_descs, alpha); break;
@@ -349,11 +367,12 @@ cudaError_t launch_spmm(const int32_t* ptrs, const int32_t* idx, const double* v
   return cudaGetLastError();
 }
 
-cudaError_t launch_java_rand(double* out, int64_t n, int64_t seed, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  const uint64_t seed0 = (static_cast<uint64_t>(seed) ^ 0x5DEECE66Dull) & ((1ull << 48) - 1);
-  const int64_t grid = (n + 255) / 256;
-  java_rand_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(out, n, seed0);
+cudaError_t launch_java_rand_batched(const RandDesc* d_descs, int nblocks, int64_t max_n, cudaStream_t stream) {
+  if (nblocks <= 0 || max_n <= 0) return cudaSuccess;
+  int64_t gx = (max_n + 255) / 256;
+  if (gx > 65535) gx = 65535;
+  dim3 grid(static_cast<unsigned>(gx), nblocks);
+  java_rand_kernel<<<grid, 256, 0, stream>>>(d_descs);
   return cudaGetLastError();
 }
 

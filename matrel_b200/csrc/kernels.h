@@ -80,7 +80,12 @@ cudaError_t launch_sparse_to_dense(const int32_t* ptrs, const int32_t* idx, cons
 cudaError_t launch_spmm(const int32_t* ptrs, const int32_t* idx, const double* vals, bool sT,
                         const double* B, bool bT, double* C, int m, int k, int n, bool accumulate,
                         cudaStream_t stream);
-// java.util.Random-compatible U(0,1) fill: out[i] = i-th nextDouble() of new Random(seed)
-cudaError_t launch_java_rand(double* out, int64_t n, int64_t seed, cudaStream_t stream);
+// java.util.Random-compatible U(0,1) fill: out[i] = i-th nextDouble() of new Random(seed), batched over blocks
+struct RandDesc {
+  double* out;
+  int64_t n;
+  int64_t seed;
+};
+cudaError_t launch_java_rand_batched(const RandDesc* d_descs, int nblocks, int64_t max_n, cudaStream_t stream);
 
 }  // namespace matrel

@@ -97,6 +97,15 @@ class MatfastSession:
         return Dataset(self, h)
 
 
+def rand_partition(session: "MatfastSession", nrows: int, ncols: int, blkSize: int, seed0: int, pr: int, pc: int,
+                   r: int, c: int, slab_ptr: int, slot_elems: int) -> "Dataset":
+    """The blocks rank (r, c) of a pr x pc grid owns, generated into a caller-owned device slab."""
+    h = C.c_void_p()
+    N.check(N.lib.mr_matrix_rand_partition(session._ctx, nrows, ncols, blkSize, seed0, pr, pc, r, c,
+                                           C.c_void_p(slab_ptr), slot_elems, C.byref(h)))
+    return Dataset(session, h)
+
+
 class Dataset:
     """A bag of ``(rid, cid, block)`` rows resident in HBM (an ``mr_matrix`` handle)."""
 
@@ -141,6 +150,19 @@ class Dataset:
         """Adopt a dense block that already lives in device memory (not freed by the engine)."""
         N.check(N.lib.mr_matrix_put_block_device(self._h, rid, cid, numRows, numCols,
                                                  C.c_void_p(device_ptr), 1 if isTransposed else 0))
+
+    def put_blocks_device(self, rids, cids, numRows, numCols, device_ptrs, isTransposed=None) -> None:
+        """Batched :meth:`put_block_device` (one ABI call for a whole gathered panel)."""
+        n = len(rids)
+        rids = np.ascontiguousarray(rids, dtype=np.int32)
+        cids = np.ascontiguousarray(cids, dtype=np.int32)
+        nr = np.ascontiguousarray(numRows, dtype=np.int32)
+        nc = np.ascontiguousarray(numCols, dtype=np.int32)
+        ptrs = (C.c_void_p * n)(*[int(p) for p in device_ptrs])
+        flags = None
+        if isTransposed is not None:
+            flags = np.ascontiguousarray(isTransposed, dtype=np.uint8).ctypes.data_as(C.POINTER(C.c_uint8))
+        N.check(N.lib.mr_matrix_put_blocks_device(self._h, n, _i32p(rids), _i32p(cids), _i32p(nr), _i32p(nc), ptrs, flags))
 
     def block_ids(self) -> List[tuple]:
         n = C.c_int64()

@@ -1,0 +1,313 @@
+"""Grid-partitioned block multiply across the GPUs of one box: one process per GPU,
+``torch.distributed`` (NCCL over NVLink 5 / NVSwitch) for the exchange, the engine's own sm_100a
+kernels for the arithmetic.
+
+What it replaces in the reference (M/ = /root/reference/src/main/scala/org/apache/spark/sql/matfast/):
+  * the 2 x groupByKey + join that co-locate A(:, k) with B(k, :) (M/execution/MatfastExecutionHelper.scala:236-249)
+    -> ONE all-gather of A along the grid row and ONE all-gather of B along the grid column;
+  * reduceByKey(LocalMatrix.add) (:255) -> nothing: the layout is C-stationary, every rank owns whole
+    output blocks and keeps the full K reduction inside the GEMM kernel's accumulators;
+  * RowPartitioner / ColumnPartitioner placement (M/partitioner/RowPartitioner.scala:34,
+    ColumnPartitioner.scala:34): rank (r, c) of the pr x pc grid owns blocks with rid % pr == r and
+    cid % pc == c, for A, B and C alike.
+
+Nothing in the planning half of this module needs a GPU (``GridPlan``, ``gather_panels`` work on CPU
+tensors over gloo), which is how tests/test_distributed_cpu.py covers the N > 1 path.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+GRID_SHAPES = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+
+
+def grid_shape(world: int) -> Tuple[int, int]:
+    if world in GRID_SHAPES:
+        return GRID_SHAPES[world]
+    pr = int(world ** 0.5)
+    while world % pr:
+        pr -= 1
+    return pr, world // pr
+
+
+@dataclass
+class GridPlan:
+    """Placement arithmetic of an nrows x ncols block matrix on a pr x pc process grid."""
+    world: int
+    nrows: int
+    ncols: int
+    blk: int
+    pr: int = 0
+    pc: int = 0
+
+    def __post_init__(self):
+        if not self.pr:
+            self.pr, self.pc = grid_shape(self.world)
+        assert self.pr * self.pc == self.world
+        self.nbr = -(-self.nrows // self.blk)
+        self.nbc = -(-self.ncols // self.blk)
+        self.slots_r = -(-self.nbr // self.pr)
+        self.slots_c = -(-self.nbc // self.pc)
+        self.slot_elems = self.blk * self.blk
+
+    def coords(self, rank: int) -> Tuple[int, int]:
+        return rank // self.pc, rank % self.pc
+
+    def rank_of(self, r: int, c: int) -> int:
+        return r * self.pc + c
+
+    def owner(self, rid: int, cid: int) -> int:
+        """RowPartitioner x ColumnPartitioner: (rid % pr, cid % pc)."""
+        return self.rank_of(rid % self.pr, cid % self.pc)
+
+    def slot(self, rid: int, cid: int) -> int:
+        """Index of block (rid, cid) inside its owner's slab."""
+        return (rid // self.pr) * self.slots_c + (cid // self.pc)
+
+    @property
+    def local_slots(self) -> int:
+        return self.slots_r * self.slots_c
+
+    def block_shape(self, rid: int, cid: int) -> Tuple[int, int]:
+        return (min(self.blk, self.nrows - rid * self.blk), min(self.blk, self.ncols - cid * self.blk))
+
+    def owned(self, rank: int) -> List[Tuple[int, int]]:
+        r, c = self.coords(rank)
+        return [(i, j) for i in range(r, self.nbr, self.pr) for j in range(c, self.nbc, self.pc)]
+
+    def row_group_ranks(self, rank: int) -> List[int]:
+        r, _ = self.coords(rank)
+        return [self.rank_of(r, c) for c in range(self.pc)]
+
+    def col_group_ranks(self, rank: int) -> List[int]:
+        _, c = self.coords(rank)
+        return [self.rank_of(r, c) for r in range(self.pr)]
+
+
+class GridGroups:
+    """Row / column sub-communicators (every rank must construct this collectively)."""
+
+    def __init__(self, plan: GridPlan, rank: int):
+        import torch.distributed as dist
+        self.plan, self.rank = plan, rank
+        self.row_group = self.col_group = None
+        for r in range(plan.pr):
+            ranks = [plan.rank_of(r, c) for c in range(plan.pc)]
+            g = dist.new_group(ranks) if len(ranks) > 1 else None
+            if rank in ranks:
+                self.row_group = g
+        for c in range(plan.pc):
+            ranks = [plan.rank_of(r, c) for r in range(plan.pr)]
+            g = dist.new_group(ranks) if len(ranks) > 1 else None
+            if rank in ranks:
+                self.col_group = g
+
+
+def gather_panels(local_slab, group, nranks: int):
+    """All-gather equal-sized slabs [local_slots, slot_elems] -> [nranks, local_slots, slot_elems].
+    (The reference moves the same blocks through groupByKey + join.)"""
+    import torch
+    import torch.distributed as dist
+    if nranks == 1 or group is None:
+        return local_slab.unsqueeze(0)
+    flat = torch.empty((nranks * local_slab.shape[0],) + tuple(local_slab.shape[1:]), dtype=local_slab.dtype,
+                       device=local_slab.device)
+    dist.all_gather_into_tensor(flat, local_slab.contiguous(), group=group)
+    return flat.view((nranks,) + tuple(local_slab.shape))
+
+
+def panel_blocks_A(plan: GridPlan, rank: int):
+    """(rid, k, source index in the row group, slot) for every A block this rank needs: all k of its rows."""
+    r, _ = plan.coords(rank)
+    kplan = GridPlan(plan.world, plan.nrows, plan.ncols, plan.blk, plan.pr, plan.pc)
+    return [(i, k, k % plan.pc, kplan.slot(i, k)) for i in range(r, plan.nbr, plan.pr) for k in range(plan.nbc)]
+
+
+def panel_blocks_B(plan: GridPlan, rank: int):
+    """(k, cid, source index in the column group, slot) for every B block this rank needs: all k of its columns."""
+    _, c = plan.coords(rank)
+    return [(k, j, k % plan.pr, plan.slot(k, j)) for k in range(plan.nbr) for j in range(c, plan.nbc, plan.pc)]
+
+
+class ShardedMatrix:
+    """The blocks of one matrix that this rank owns, in one contiguous device slab (torch tensor)."""
+
+    def __init__(self, plan: GridPlan, rank: int, slab, dataset=None):
+        self.plan, self.rank, self.slab, self.dataset = plan, rank, slab, dataset
+
+    @staticmethod
+    def rand(session, plan: GridPlan, rank: int, seed0: int, device) -> "ShardedMatrix":
+        import torch
+        from .dataset import rand_partition
+        slab = torch.zeros((plan.local_slots, plan.slot_elems), dtype=torch.float64, device=device)
+        r, c = plan.coords(rank)
+        ds = rand_partition(session, plan.nrows, plan.ncols, plan.blk, seed0, plan.pr, plan.pc, r, c,
+                            slab.data_ptr(), plan.slot_elems)
+        return ShardedMatrix(plan, rank, slab, ds)
+
+
+def sharded_multiply(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMatrix, planA: GridPlan, planB: GridPlan):
+    """C = A * B, C-stationary on the process grid.  Returns (local C Dataset, keep-alive tensors).
+
+    planA describes A (n x k), planB describes B (k x m); both share blk and the grid."""
+    from .dataset import Dataset
+    rank = groups.rank
+    pr, pc = planA.pr, planA.pc
+    gA = gather_panels(A.slab, groups.row_group, pc)      # [pc, slots, elems]: A(i, :) for my rows
+    gB = gather_panels(B.slab, groups.col_group, pr)      # [pr, slots, elems]: B(:, j) for my columns
+    esz = 8
+    baseA, strideA0, strideA1 = gA.data_ptr(), gA.stride(0) * esz, gA.stride(1) * esz
+    baseB, strideB0, strideB1 = gB.data_ptr(), gB.stride(0) * esz, gB.stride(1) * esz
+    dA = session.emptyDataset()
+    blocks = panel_blocks_A(planA, rank)
+    shapes = [planA.block_shape(i, k) for i, k, _, _ in blocks]
+    dA.put_blocks_device([b[0] for b in blocks], [b[1] for b in blocks], [s[0] for s in shapes], [s[1] for s in shapes],
+                         [baseA + src * strideA0 + slot * strideA1 for _, _, src, slot in blocks])
+    dB = session.emptyDataset()
+    blocks = panel_blocks_B(planB, rank)
+    shapes = [planB.block_shape(k, j) for k, j, _, _ in blocks]
+    dB.put_blocks_device([b[0] for b in blocks], [b[1] for b in blocks], [s[0] for s in shapes], [s[1] for s in shapes],
+                         [baseB + src * strideB0 + slot * strideB1 for _, _, src, slot in blocks])
+    dC = dA.matrixMultiply(planA.nrows, planA.ncols, dB, planB.nrows, planB.ncols, planA.blk)
+    return dC, (gA, gB, dA, dB)
+
+
+# --------------------------------------------------------------------------------------------------
+# bench.py's N > 1 arm
+# --------------------------------------------------------------------------------------------------
+def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample):
+    import json
+    import time
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from .dataset import MatfastSession
+    from .matrix import DenseMatrix, MatrixBlock
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=device)
+    n, blk = args.n, args.blk
+    plan = GridPlan(world, n, n, blk)
+    groups = GridGroups(plan, rank)
+    flops = 2.0 * n ** 3
+
+    stream = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(stream):
+        s = MatfastSession(device=local_rank, stream=stream.cuda_stream)
+        A = ShardedMatrix.rand(s, plan, rank, 42, device)
+        B = ShardedMatrix.rand(s, plan, rank, 43, device)
+        s.sync()
+
+        def step():
+            dC, keep = sharded_multiply(s, groups, A, B, plan, plan)
+            return dC, keep
+
+        for _ in range(args.warmup):
+            out = step()
+            del out
+        torch.cuda.synchronize()
+        dist.barrier()
+        s.reset_stats()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            out = step()
+            del out
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1) / args.steps
+        st = s.stats()
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+
+        # GEMM kernel alone on this rank (library-side CUDA events)
+        s.set_option("time_kernels", 1)
+        s.reset_stats()
+        for _ in range(3):
+            out = step()
+            del out
+        st2 = s.stats()
+        s.set_option("time_kernels", 0)
+        kern_ms = st2["gemm_ms_total"] / max(1, st2["gemm_launches"])
+        kt = torch.tensor([kern_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+        kern_ms = float(kt.item())
+
+        # ---- end to end: each rank feeds its own A/B blocks from pinned host memory and reads its C blocks back
+        hostA = [(k, A.dataset.get_block(*k)) for k in A.dataset.block_ids()]
+        hostB = [(k, B.dataset.get_block(*k)) for k in B.dataset.block_ids()]
+        pin = lambda v: torch.from_numpy(v).pin_memory()  # noqa: E731
+        pA = [(k, pin(m.values)) for k, m in hostA]
+        pB = [(k, pin(m.values)) for k, m in hostB]
+        outbuf = {k: torch.empty(blk * blk, dtype=torch.float64).pin_memory().numpy() for k in plan.owned(rank)}
+        h2d = sum(v.numel() * 8 for _, v in pA) + sum(v.numel() * 8 for _, v in pB)
+        d2h = sum(v.nbytes for v in outbuf.values())
+        slabA = torch.zeros_like(A.slab)
+        slabB = torch.zeros_like(B.slab)
+
+        def e2e_step():
+            for (i, j), v in pA:
+                slabA[plan.slot(i, j), :v.numel()].copy_(v, non_blocking=True)
+            for (i, j), v in pB:
+                slabB[plan.slot(i, j), :v.numel()].copy_(v, non_blocking=True)
+            dC, keep = sharded_multiply(s, groups, ShardedMatrix(plan, rank, slabA), ShardedMatrix(plan, rank, slabB), plan, plan)
+            for k in dC.block_ids():
+                dC.get_block(*k, out=outbuf[k])
+            return dC, keep
+
+        for _ in range(min(2, args.warmup)):
+            e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        et = torch.tensor([e2e_ms, float(h2d), float(d2h)], dtype=torch.float64, device=device)
+        emax = et.clone()
+        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(et, op=dist.ReduceOp.SUM)
+        e2e_ms = float(emax[0].item())
+        h2d_total, d2h_total = int(et[1].item()), int(et[2].item())
+        launches = torch.tensor([float(st["kernel_launches"])], dtype=torch.float64, device=device)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        s.stop()
+
+    if rank == 0:
+        peak, peak_src = fp64_peak_tflops()
+        achieved = (flops / world) / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": flops / (ms_max * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{n}x{n} fp64 dense multiply, {blk}-block, grid-partitioned {plan.pr}x{plan.pc} over {world}xB200",
+                       "parallelism": f"C-stationary {plan.pr}x{plan.pc} block-cyclic grid; all-gather A along grid rows, B along grid columns (NCCL), no reduction",
+                       "inputs": "U(0,1) java.util.Random streams, every block present, column-major",
+                       "l2": "per-rank operands after all-gather >> 126 MB L2; no flush needed", "gemm_algo": "dmma_fp64"},
+            "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
+                    "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": int(launches.item()), "gpu_launches_per_step_per_rank": st["kernel_launches"] / args.steps,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "gemm_f64_dmma_kernel<128,128,2,4,5>", "kernel_ms": kern_ms,
+                         "algorithmic": f"2*N^3/{world} = {flops / world:.4g} flop per launch per rank (max-over-ranks kernel time)",
+                         "peak_source": peak_src},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,50 @@
+"""Worker for tests/test_gpu_distributed.py: N ranks over NCCL, sharded multiply vs the oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import matrel_b200 as mb  # noqa: E402
+from matrel_b200.distributed import GridGroups, GridPlan, ShardedMatrix, sharded_multiply  # noqa: E402
+from oracle import matrel_oracle as O  # noqa: E402
+
+
+def main():
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    dist.init_process_group("nccl", device_id=device)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    for (n, k, m, blk) in [(1024, 1024, 1024, 128), (7 * 64 - 6, 5 * 64, 6 * 64 - 10, 64)]:
+        planA, planB, planC = GridPlan(world, n, k, blk), GridPlan(world, k, m, blk), GridPlan(world, n, m, blk)
+        groups = GridGroups(planA, rank)
+        stream = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(stream):
+            s = mb.MatfastSession(device=local_rank, stream=stream.cuda_stream)
+            A = ShardedMatrix.rand(s, planA, rank, 42, device)
+            B = ShardedMatrix.rand(s, planB, rank, 43, device)
+            dC, keep = sharded_multiply(s, groups, A, B, planA, planB)
+            got = {(b.rid, b.cid): b.matrix for b in dC.collect()}
+            s.stop()
+        want = O.matrix_multiply(O.rand_dense_dataset(n, k, blk, 42), n, k, O.rand_dense_dataset(k, m, blk, 43), k, m, blk)
+        assert sorted(got) == sorted(planC.owned(rank)), (rank, sorted(got))
+        for key, g in got.items():
+            w = want[key]
+            assert (g.numRows, g.numCols, g.isTransposed) == (w.numRows, w.numCols, False)
+            err = float(np.max(np.abs(g.values - w.values)) / np.max(np.abs(w.values)))
+            assert err <= 1e-12, (key, err)
+        cnt = torch.tensor([len(got)], dtype=torch.int64, device=device)
+        dist.all_reduce(cnt)
+        assert int(cnt.item()) == len(want)
+    dist.barrier()
+    if rank == 0:
+        print(f"OK world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
