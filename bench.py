@@ -162,6 +162,34 @@ def cpu_reference_sample(n: int, blk: int, budget_s: float = 20.0):
             "seconds": wall, "flops": ntasks * task_flops, "checksum": res[0]}
 
 
+def cpu_f2j_sample(n: int, blk: int, budget_s: float = 8.0):
+    """Same algorithm with the pure-loop reference-BLAS dgemm (what netlib-java's F2jBLAS runs when no
+    native BLAS is installed = stock Spark 2.1.0), oracle/oracle.c, OpenMP threads = host cores; one wave
+    of output blocks."""
+    import numpy as np
+    from oracle import c_port
+    if not c_port.available():
+        return None
+    nb = n // blk
+    threads = c_port.max_threads()
+    ntasks = min(nb * nb, threads)
+    rng = np.random.default_rng(7)
+    uniq = [rng.random(blk * blk) for _ in range(2 * nb)]          # block values do not change dgemm's speed
+    A = [uniq[(i + k) % nb] for i in range(nb) for k in range(nb)]
+    B = [uniq[nb + (k + j) % nb] for k in range(nb) for j in range(nb)]
+    t0 = time.perf_counter()
+    c_port.block_multiply_f2j(A, B, nb, blk, 1, 1, 1)              # calibrate: one block pair, one thread
+    t_pair = time.perf_counter() - t0
+    nk = max(1, min(nb, int(budget_s / max(t_pair * 2.0, 1e-3))))
+    t0 = time.perf_counter()
+    c_port.block_multiply_f2j(A, B, nb, blk, ntasks, threads, nk)
+    wall = time.perf_counter() - t0
+    fl = ntasks * 2.0 * blk ** 3 * nk
+    return {"value": fl / wall / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{ntasks} of {nb * nb} output blocks x first {nk} of {nb} k-blocks in {wall:.1f} s, reference-BLAS "
+                      f"(F2J-equivalent) dgemm loop nest, {threads} OpenMP threads (oracle/oracle.c)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -288,6 +316,10 @@ def run_ours(args):
 
     cpu = cpu_reference_sample(n, blk, budget_s=args.cpu_budget)
     cpu.pop("seconds", None); cpu.pop("flops", None); cpu.pop("checksum", None)
+    try:
+        cpu["f2j"] = cpu_f2j_sample(n, blk)
+    except Exception as e:  # the secondary baseline must never take the bench line down
+        cpu["f2j"] = {"error": str(e)}
     line = {
         "metric": METRIC, "value": flops / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -179,3 +179,21 @@ def test_oracle_requires_and_compat():
     t = O.DenseMatrix(2, 3, np.arange(6.0), True)
     assert O.multiplyScalar(2.0, t).isTransposed and O.addScalar(t, 1.0).values.tolist() == (np.arange(6.0) + 1).tolist()
     assert O.addScalar(s, 1.0).to_numpy().tolist() == [[3.0, 0.0], [0.0, 5.0]]
+
+
+def test_c_port_matches_numpy_oracle():
+    """oracle/oracle.c (F2J-style dgemm restatement used for the timed CPU baseline) == numpy oracle."""
+    from oracle import c_port
+    if not c_port.available():
+        import __graft_entry__ as g
+        g.build()
+    assert c_port.rand_block(1000, 42).tolist() == O.JavaRandom(42).next_doubles(1000).tolist()
+    nb, blk = 3, 40
+    A = O.rand_dense_dataset(nb * blk, nb * blk, blk, 42)
+    B = O.rand_dense_dataset(nb * blk, nb * blk, blk, 43)
+    got = c_port.block_multiply_f2j([A[(i, j)].values for i in range(nb) for j in range(nb)],
+                                    [B[(i, j)].values for i in range(nb) for j in range(nb)], nb, blk, nb * nb, 2)
+    want = O.matrix_multiply(A, nb * blk, nb * blk, B, nb * blk, nb * blk, blk)
+    for t, c in enumerate(got):
+        w = want[(t // nb, t % nb)].values
+        assert np.max(np.abs(c - w)) / np.max(np.abs(w)) < 1e-14
