@@ -49,7 +49,12 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.mark_at = index, None, [], 0
+
+    def mark(self):
+        """Call at the start of the timed region: only samples from here on are reported (the sampler is
+        started earlier so that nvidia-smi is already streaming when a short timed region begins)."""
+        self.mark_at = len(self.lines)
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -78,7 +83,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[self.mark_at:]
+        note = None
+        if not lines and self.lines:   # timed region shorter than one sampling period: report the closest samples
+            lines, note = self.lines[-3:], "timed region shorter than the 100 ms sampling period; last warm-up samples reported"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -90,8 +99,11 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+               "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -246,15 +258,16 @@ def run_ours(args):
         s.sync()
 
         # ---- device-resident: value + roofline (CUDA events on the launching stream)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(args.warmup):
             C = A.matrixMultiply(n, n, B, n, n, blk)
             del C
         s.sync()
         s.reset_stats()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         torch.cuda.synchronize()
+        sampler.mark()
         t_wall0 = time.perf_counter()
         for e0, e1 in evs:
             e0.record(stream)

@@ -207,17 +207,18 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
             dC, keep = sharded_multiply(s, groups, A, B, plan, plan)
             return dC, keep
 
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(args.warmup):
             out = step()
             del out
         torch.cuda.synchronize()
         dist.barrier()
         s.reset_stats()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         dist.barrier()
+        sampler.mark()
         e0.record(stream)
         for _ in range(args.steps):
             out = step()
