@@ -218,13 +218,22 @@ Block densify(mr_context* ctx, const Block& s) {
 
 const char* type_name(const Block& b) { return b.dense() ? "DenseMatrix" : "SparseMatrix"; }
 
+int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
 // ------------------------------------------------------------------------------------------------
 // block product planning (LocalMatrix.matrixMultiplication, LocalMatrix.scala:889-914)
 // ------------------------------------------------------------------------------------------------
+struct GemmSrc {
+  const Block* a;
+  const Block* b;
+  int32_t k;
+};
+
 struct OutPlan {
   int32_t rid, cid;
   int32_t m = -1, n = -1;
   std::vector<GemmPair> gemm;                            // dense x dense (possibly densified) pairs
+  std::vector<GemmSrc> src;                              // the blocks behind each gemm pair (+ its k-block id)
   std::vector<std::pair<const Block*, const Block*>> spmm;  // sparse x dense pairs
 };
 
@@ -243,7 +252,7 @@ struct MultiplyPlanner {
     return temps[it->second];
   }
 
-  void add_pair(OutPlan& o, const Block& a, const Block& b) {
+  void add_pair(OutPlan& o, const Block& a, const Block& b, int32_t k) {
     // shape checks: BLAS.gemmddd / gemmsdd `require`s (BLAS.scala:338-343, 363-366)
     MR_REQUIRE(a.numCols == b.numRows, MR_EDIM, "The columns of A don't match the rows of B. A: %d, B: %d", a.numCols,
                b.numRows);
@@ -260,14 +269,14 @@ struct MultiplyPlanner {
                  b.numCols);
     }
     if (a.dense()) {
-      push_gemm(o, a, dense_of(b));  // dense x dense, dense x sparse.toDense (:891-892)
+      push_gemm(o, a, dense_of(b), k);  // dense x dense, dense x sparse.toDense (:891-892)
     } else if (b.dense()) {
       o.spmm.emplace_back(&a, &b);   // sparse x dense (:893-899; the n == 1 SpMV case is the same kernel)
     } else {
       const double s1 = a.valuesLen * 1.0 / (static_cast<double>(a.numRows) * a.numCols);
       const double s2 = b.valuesLen * 1.0 / (static_cast<double>(b.numRows) * b.numCols);
       if (s1 > 0.1) {
-        push_gemm(o, dense_of(a), dense_of(b));  // :903-904
+        push_gemm(o, dense_of(a), dense_of(b), k);  // :903-904
       } else if (s2 > 0.1) {
         o.spmm.emplace_back(&a, &dense_of(b));   // :906-907
       } else {
@@ -278,7 +287,7 @@ struct MultiplyPlanner {
     }
   }
 
-  void push_gemm(OutPlan& o, const Block& a, const Block& b) {
+  void push_gemm(OutPlan& o, const Block& a, const Block& b, int32_t k) {
     GemmPair p{};
     p.A = a.values.ptr<double>();
     p.B = b.values.ptr<double>();
@@ -289,11 +298,66 @@ struct MultiplyPlanner {
     p.kdim = a.numCols;
     p.tmA = p.tmB = -1;
     o.gemm.push_back(p);
+    o.src.push_back(GemmSrc{&a, &b, k});
   }
 };
 
+// gemm_algo 2: the dense pairs of every output block through the tcgen05 int8 Ozaki pipeline (gemm_ozaki.cu).
+// Returns false when the problem does not fit its regular-grid assumptions or holds Inf/NaN (caller uses DMMA).
+bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<double*>& cptr, int32_t blkSize, int64_t M,
+               int64_t K, int64_t N, bool outer) {
+  if (M <= 0 || K <= 0 || N <= 0 || M > INT32_MAX || N > INT32_MAX || K > (1 << 17)) return false;  // s32 accumulator bound
+  const int64_t nbr = ceil_div(M, blkSize), nbc = ceil_div(N, blkSize);
+  if (nbr * nbc > (1 << 24)) return false;
+  std::vector<double*> ctab(static_cast<size_t>(nbr * nbc), nullptr);
+  std::map<const Block*, int> ia, ib;
+  std::vector<OzakiOperand> va, vb;
+  for (size_t i = 0; i < plans.size(); ++i) {
+    const OutPlan& o = plans[i];
+    if (o.gemm.empty()) continue;
+    if (o.rid < 0 || o.rid >= nbr || o.cid < 0 || o.cid >= nbc) return false;
+    if (o.m != std::min<int64_t>(blkSize, M - static_cast<int64_t>(o.rid) * blkSize) ||
+        o.n != std::min<int64_t>(blkSize, N - static_cast<int64_t>(o.cid) * blkSize))
+      return false;
+    if (!o.spmm.empty()) return false;  // mixed dense / sparse partial sums stay on the exact path
+    ctab[static_cast<size_t>(o.rid) * nbc + o.cid] = cptr[i];
+    for (const GemmSrc& g : o.src) {
+      const int64_t k0 = outer ? 0 : static_cast<int64_t>(g.k) * blkSize;
+      if (k0 + g.a->numCols > K || g.a->numCols != g.b->numRows) return false;
+      if (!ia.count(g.a)) {
+        ia[g.a] = 1;
+        va.push_back(OzakiOperand{g.a->values.ptr<double>(), g.a->numRows, g.a->numCols, o.rid * blkSize, static_cast<int32_t>(k0),
+                                  static_cast<uint8_t>(g.a->isT)});
+      }
+      if (!ib.count(g.b)) {
+        ib[g.b] = 1;
+        vb.push_back(OzakiOperand{g.b->values.ptr<double>(), g.b->numRows, g.b->numCols, static_cast<int32_t>(k0), o.cid * blkSize,
+                                  static_cast<uint8_t>(g.b->isT)});
+      }
+    }
+  }
+  if (va.empty() || vb.empty()) return false;
+  int launches = 0, nonfinite = 0;
+  if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CUDA_CHECK(ozaki_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), M, K, N,
+                            ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7, ctab.data(), blkSize, static_cast<int>(nbr),
+                            static_cast<int>(nbc), false, &launches, &nonfinite, ctx->stream));
+  note_launch(ctx, launches);
+  if (nonfinite) return false;
+  ctx->stats.gemm_launches += 1;
+  if (ctx->time_kernels) {
+    CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.last_gemm_ms = ms;
+    ctx->stats.gemm_ms_total += ms;
+  }
+  return true;
+}
+
 void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner& planner, int32_t blkSize,
-                  mr_matrix* result) {
+                  mr_matrix* result, int64_t M, int64_t K, int64_t N, bool outer) {
   // allocate all output blocks from one slab
   size_t total = 0;
   for (auto& o : plans) total += align_up(static_cast<size_t>(o.m) * o.n * sizeof(double));
@@ -327,7 +391,12 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     outs.push_back(go);
     out_plan.push_back(i);
   }
-  if (!outs.empty()) {
+  bool ozaki_done = false;
+  if (!outs.empty() && ctx->gemm_algo == 2) {
+    ozaki_done = try_ozaki(ctx, plans, cptr, blkSize, M, K, N, outer);
+    if (ozaki_done) ctx->stats.last_gemm_flops = flops;
+  }
+  if (!outs.empty() && !ozaki_done) {
     // tile shape: large tiles unless they cannot fill the 148 SMs
     int64_t tiles128 = 0;
     for (auto& go : outs) tiles128 += static_cast<int64_t>((go.m + 127) / 128) * ((go.n + 127) / 128);
@@ -416,7 +485,6 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
   (void)planner;
 }
 
-int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------------
 // element-wise operator plumbing
@@ -946,7 +1014,7 @@ mr_status mr_matrix_multiply(mr_matrix* left, int64_t leftRowNum, int64_t leftCo
           OutPlan o;
           o.rid = l.first.first;
           o.cid = r.first.second;
-          planner.add_pair(o, l.second, r.second);
+          planner.add_pair(o, l.second, r.second, 0);
           auto key = std::make_pair(o.rid, o.cid);
           auto it = seen.find(key);
           if (it == seen.end()) {
@@ -976,12 +1044,13 @@ mr_status mr_matrix_multiply(mr_matrix* left, int64_t leftRowNum, int64_t leftCo
             it = index.emplace(key, plans.size()).first;
             plans.push_back(std::move(o));
           }
-          planner.add_pair(plans[it->second], l.second, *jb.second);
+          planner.add_pair(plans[it->second], l.second, *jb.second, k);
         }
       }
     }
     std::unique_ptr<mr_matrix> result(new_matrix(ctx));
-    run_multiply(ctx, plans, planner, blkSize, result.get());
+    run_multiply(ctx, plans, planner, blkSize, result.get(), leftRowNum, leftColNum, rightColNum,
+                 leftColBlkNum == 1 && rightRowBlkNum == 1);
     *out = result.release();
   });
 }

@@ -1,0 +1,484 @@
+// fp64 block-GEMM on the 5th-generation tensor cores (tcgen05, kind::i8) through Ozaki splitting.
+//
+// tcgen05.mma has no fp64 kind, so the north-star's "block multiply as tcgen05 tiles" is only reachable for
+// fp64 data by error-free integer slicing (Ozaki scheme I, the technique behind vendor "fp64 emulation"):
+//   a_ik = 2^(e_i+2) * sum_{s=1..S} A_s[i,k] * 2^(-8s)      A_s in [-128,127]  (balanced base-256 digits, |a_ik| < 2^e_i)
+//   b_kj = 2^(f_j+2) * sum_{t=1..S} B_t[k,j] * 2^(-8t)
+//   c_ij ~= sum_{d=2..S+1} 2^(e_i+f_j+4-8d) * sum_{s+t=d} (A_s B_t)_ij     (products with s+t > S+1 dropped)
+// e_i / f_j = exponent of the largest |a| in row i of A / column j of B (over ALL k-blocks), every slice
+// product is an exact s32 GEMM on the tensor cores (|digit product| <= 2^14, K*|pairs| <= 2^17 per
+// accumulator), and the only roundings are the final digit (2^-(8S-2) relative to the row/column maximum)
+// and S fp64 additions per element.  S = 7 gives errors at the level of fp64 dgemm's own rounding for
+// data of moderate dynamic range per row/column; the exact DMMA kernel (gemm_f64.cu) stays the default.
+//
+// Pipeline per multiply (replaces the same reference code as gemm_f64.cu: BLAS.scala:327-346,
+// MLMatrix.scala:100-104, MatfastExecutionHelper.scala:255):
+//   1. absmax pass over the blocks of A (per global row) and B (per global column)      -- HBM-bound
+//   2. slice pass: S int8 matrices A_s [M x K] and B_t^T [N x K], K contiguous            -- HBM-bound
+//   3. for each diagonal d: ONE tcgen05 GEMM launch: TMA (SWIZZLE_128B tensor maps) -> 4-stage smem ring ->
+//      tcgen05.mma.kind::i8 (one elected thread, 128x256 s32 accumulator in TMEM) over all (s, d-s) pairs and
+//      all k -> tcgen05.ld epilogue: scale by 2^(e_i+f_j+4-8d) and accumulate into the fp64 output blocks.
+#include <cuda.h>
+
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+
+namespace matrel {
+namespace {
+
+constexpr int BM = 128, BN = 256, BKB = 128 /* bytes (= int8 elements) of K per stage */, UMMA_K = 32, STAGES = 4;
+constexpr int A_BYTES = BM * BKB, B_BYTES = BN * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 256;
+constexpr int TMEM_COLS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+// UMMA shared-memory descriptor, K-major operand tile, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart
+// (start >> 4 @ [0,14), LBO = 1 @ [16,30), SBO = 1024 >> 4 @ [32,46), version 1 @ [46,48), layout SWIZZLE_128B = 2 @ [61,64))
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+               "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+#define TMEM_LD16(taddr, r)                                                                                             \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"   \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                  \
+               : "r"(taddr))
+
+struct OzakiGemmParams {
+  const unsigned char* tmaps;  // 2*S CUtensorMaps (128 B each): A_1..A_S then B_1..B_S
+  const int32_t* row_exp;      // e_i per global row of A      (|a_ik| < 2^e_i)
+  const int32_t* col_exp;      // f_j per global column of B   (|b_kj| < 2^f_j)
+  double* const* ctab;         // [nbr * nbc] output block pointers (nullptr = block absent)
+  int32_t M, N, Kpad;          // logical output dims, padded K (multiple of 128)
+  int32_t blk, nbr, nbc;       // block size and block-grid extent of C
+  int32_t S, d;                // slices, diagonal of this launch (pairs (s, d - s))
+  int32_t accumulate;          // 0: C = term, 1: C += term
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) ozaki_gemm_i8_kernel(const OzakiGemmParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[STAGES], empty[STAGES], acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nk = p.Kpad / BKB;
+  const int s_lo = max(1, p.d - p.S), s_hi = min(p.S, p.d - 1);
+  const int total = (s_hi - s_lo + 1) * nk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[STAGES + s]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one elected lane) =====
+    if (lane == 0) {
+      int it = 0;
+      for (int s = s_lo; s <= s_hi; ++s) {
+        const void* tmA = p.tmaps + static_cast<size_t>(s - 1) * 128;
+        const void* tmB = p.tmaps + static_cast<size_t>(p.S + (p.d - s) - 1) * 128;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&bars[STAGES + st]), ph ^ 1);
+          const uint32_t full = smem_u32(&bars[st]);
+          mbar_arrive_expect_tx(full, STAGE_BYTES);
+          tma_2d(smem_u32(smem + st * STAGE_BYTES), tmA, kc * BKB, m0, full);
+          tma_2d(smem_u32(smem + st * STAGE_BYTES + A_BYTES), tmB, kc * BKB, n0, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane): every (s, d-s) pair and every k accumulates into one s32 tile =====
+    if (lane == 0) {
+      // D = S32 (2 @ bit 4); A, B = signed 8-bit (1 @ bits 7 and 10); both K-major; N >> 3 @ 17; M >> 4 @ 24
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                             (static_cast<uint32_t>(BM >> 4) << 24);
+      for (int it = 0; it < total; ++it) {
+        const int st = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(smem_u32(&bars[st]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(smem + st * STAGE_BYTES), b0 = a0 + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BKB / UMMA_K; ++k)
+          umma_i8(tmem_base, umma_desc_k_sw128(a0 + k * UMMA_K), umma_desc_k_sw128(b0 + k * UMMA_K), idesc, (it | k) != 0);
+        umma_commit(smem_u32(&bars[STAGES + st]));  // stage is free once these MMAs retire
+      }
+      umma_commit(smem_u32(&bars[2 * STAGES]));     // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> fp64 scale -> accumulate into the column-major output blocks =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const int rid = row_ok ? row / p.blk : 0;
+    const int lr = row - rid * p.blk;
+    const int brows = min(p.blk, p.M - rid * p.blk);
+    const int ebase = (row_ok ? p.row_exp[row] : 0) + 4 - 8 * p.d;
+    mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t r[16];
+      TMEM_LD16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = n0 + c + j;
+          if (col < p.N) {
+            const int cid = col / p.blk;
+            double* blkp = p.ctab[rid * p.nbc + cid];
+            if (blkp != nullptr) {
+              double* dst = blkp + lr + static_cast<size_t>(brows) * (col - cid * p.blk);
+              const double term = scalbn(static_cast<double>(static_cast<int32_t>(r[j])), ebase + p.col_exp[col]);
+              *dst = p.accumulate ? *dst + term : term;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// ---- pass 1: per-row / per-column maximum magnitude (as the IEEE bit pattern, which orders like the value) -------
+struct OzBlock {
+  const double* v;
+  int32_t rows, cols;  // logical dims of the block
+  int32_t row0, col0;  // global offsets of its (0,0) element in the operand matrix
+  uint8_t isT;
+  uint8_t pad[7];
+};
+
+__device__ __forceinline__ double blk_at(const OzBlock& b, int r, int c) {
+  return b.isT ? b.v[c + static_cast<size_t>(b.cols) * r] : b.v[r + static_cast<size_t>(b.rows) * c];
+}
+
+// by_row = true: out[row0 + r] = max_c |b(r,c)|; false: out[col0 + c] = max_r |b(r,c)|.  32x32 tiles, 256 threads;
+// tx runs along the block's contiguous dimension (rows for column-major, columns for row-major blocks).
+__global__ void __launch_bounds__(256) absmax_kernel(const OzBlock* __restrict__ blocks, unsigned long long* __restrict__ out,
+                                                     int by_row, int tiles_c_max) {
+  __shared__ unsigned long long sm[8][32];
+  const OzBlock b = blocks[blockIdx.y];
+  const int tr = blockIdx.x / tiles_c_max, tc = blockIdx.x % tiles_c_max;
+  const int r0 = tr * 32, c0 = tc * 32;
+  if (r0 >= b.rows || c0 >= b.cols) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool kept_is_fast = (by_row != 0) == (b.isT == 0);  // kept index == the one tx runs along
+  unsigned long long best = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = b.isT ? r0 + ty + 8 * j : r0 + tx;
+    const int c = b.isT ? c0 + tx : c0 + ty + 8 * j;
+    unsigned long long bits = 0;
+    if (r < b.rows && c < b.cols) bits = static_cast<unsigned long long>(__double_as_longlong(fabs(blk_at(b, r, c))));
+    if (kept_is_fast) {
+      best = max(best, bits);  // reduce over the slow index: per-thread, then across ty below
+    } else {
+      // reduce over the fast index (the 32 lanes of this warp share one slow index)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+      const int slow = by_row ? r : c;
+      const int lim = by_row ? b.rows : b.cols;
+      if (tx == 0 && slow < lim) atomicMax(&out[(by_row ? b.row0 : b.col0) + slow], bits);
+    }
+  }
+  if (kept_is_fast) {
+    sm[ty][tx] = best;
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+      for (int k = 1; k < 8; ++k) best = max(best, sm[k][tx]);
+      const int kept = (by_row ? r0 : c0) + tx;
+      const int lim = by_row ? b.rows : b.cols;
+      if (kept < lim) atomicMax(&out[(by_row ? b.row0 : b.col0) + kept], best);
+    }
+  }
+}
+
+// exponent table: e = ilogb(max) + 1 (so |x| * 2^-e < 1), 0 for all-zero lines; flags non-finite input
+__global__ void exp_kernel(const unsigned long long* __restrict__ maxbits, int32_t* __restrict__ e, int n, int* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = __longlong_as_double(static_cast<long long>(maxbits[i]));
+  if (!isfinite(m)) {
+    *bad = 1;
+    e[i] = 0;
+  } else {
+    e[i] = (m == 0.0) ? 0 : ilogb(m) + 1;
+  }
+}
+
+// ---- pass 2: balanced base-256 digits.  out_s[line * Kpad + k], line = row of A (transpose_out = 0) or column of B --
+// One CTA = 32 lines x 128 k of one block, staged through shared memory so global reads follow the block's
+// contiguous dimension and the int8 writes are 128-byte rows.
+__global__ void __launch_bounds__(256) slice_kernel(const OzBlock* __restrict__ blocks, const int32_t* __restrict__ line_exp,
+                                                    int8_t* __restrict__ out, size_t slice_stride, int Kpad, int S,
+                                                    int lines_are_rows, int tiles_k_max) {
+  __shared__ double sm[32][129];
+  const OzBlock b = blocks[blockIdx.y];
+  const int tl = blockIdx.x / tiles_k_max, tk = blockIdx.x % tiles_k_max;
+  // "line" = kept index (row of A / column of B), "k" = reduction index (column of A / row of B)
+  const int nlines = lines_are_rows ? b.rows : b.cols;
+  const int nks = lines_are_rows ? b.cols : b.rows;
+  const int l0 = tl * 32, k0 = tk * 128;
+  if (l0 >= nlines || k0 >= nks) return;
+  const int tid = threadIdx.x;
+  // element (line l, k) lives at: lines_are_rows ? blk(l, k) : blk(k, l).  Memory-contiguous index:
+  //   column-major block (isT = 0): row index fastest;  row-major (isT = 1): column index fastest.
+  const bool k_fast = lines_are_rows ? (b.isT != 0) : (b.isT == 0);
+  if (k_fast) {
+    for (int idx = tid; idx < 32 * 128; idx += 256) {
+      const int l = idx / 128, k = idx % 128;
+      double v = 0.0;
+      if (l0 + l < nlines && k0 + k < nks) v = lines_are_rows ? blk_at(b, l0 + l, k0 + k) : blk_at(b, k0 + k, l0 + l);
+      sm[l][k] = v;
+    }
+  } else {
+    for (int idx = tid; idx < 32 * 128; idx += 256) {
+      const int k = idx / 32, l = idx % 32;
+      double v = 0.0;
+      if (l0 + l < nlines && k0 + k < nks) v = lines_are_rows ? blk_at(b, l0 + l, k0 + k) : blk_at(b, k0 + k, l0 + l);
+      sm[l][k] = v;
+    }
+  }
+  __syncthreads();
+  const int gl_base = (lines_are_rows ? b.row0 : b.col0) + l0;
+  const int gk_base = (lines_are_rows ? b.col0 : b.row0) + k0;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int l = warp; l < 32; l += 8) {
+    if (l0 + l >= nlines) continue;
+    const int e = line_exp[gl_base + l];
+    long long X[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double x = scalbn(sm[l][lane * 4 + j], 8 * S - 2 - e);  // |x| < 2^(8S-2): exact power-of-two scaling
+      X[j] = __double2ll_rn(x);
+    }
+    // least-significant digit first; digit in [-128, 127], carry folded into the next one
+    for (int s = S; s >= 1; --s) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long dgt = ((X[j] + 128) & 255) - 128;
+        X[j] = (X[j] - dgt) >> 8;
+        packed |= (static_cast<uint32_t>(dgt) & 0xffu) << (8 * j);
+      }
+      const int kq = k0 + lane * 4;  // first k of this quad inside the block
+      const int gk = gk_base + lane * 4;
+      int8_t* dst = out + static_cast<size_t>(s - 1) * slice_stride + static_cast<size_t>(gl_base + l) * Kpad + gk;
+      if (kq + 3 < nks && (gk & 3) == 0) {
+        *reinterpret_cast<uint32_t*>(dst) = packed;
+      } else {  // block edge / unaligned block offset: never touch a neighbouring block's bytes
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (kq + j < nks) dst[j] = static_cast<int8_t>((packed >> (8 * j)) & 0xffu);
+      }
+    }
+  }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn encode_fn() {
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  return fn;
+}
+
+bool make_i8_map(unsigned char* out128, void* base, uint64_t Kpad, uint64_t rows, uint32_t box_rows) {
+  EncodeFn fn = encode_fn();
+  if (!fn) return false;
+  alignas(64) CUtensorMap m;
+  const cuuint64_t gdim[2] = {Kpad, rows};
+  const cuuint64_t gstr[1] = {Kpad};
+  const cuuint32_t box[2] = {BKB, box_rows};
+  const cuuint32_t est[2] = {1, 1};
+  if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  memcpy(out128, &m, 128);
+  return true;
+}
+
+#define OZ_CHECK(x)                      \
+  do {                                   \
+    cudaError_t e_ = (x);                \
+    if (e_ != cudaSuccess) return e_;    \
+  } while (0)
+
+struct AsyncBuf {  // stream-ordered scratch
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit AsyncBuf(cudaStream_t st) : s(st) {}
+  cudaError_t alloc(size_t n) { return cudaMallocAsync(&p, n ? n : 16, s); }
+  ~AsyncBuf() {
+    if (p) cudaFreeAsync(p, s);
+  }
+};
+
+}  // namespace
+
+cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K,
+                           int64_t N, int slices, double* const* h_ctab, int blk, int nbr, int nbc, bool accumulate,
+                           int* launches, int* nonfinite, cudaStream_t stream) {
+  *nonfinite = 0;
+  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  const int S = slices < 2 ? 2 : (slices > 7 ? 7 : slices);
+  const int64_t Mpad = (M + BM - 1) / BM * BM, Npad = (N + BN - 1) / BN * BN, Kpad = (K + BKB - 1) / BKB * BKB;
+  static bool configured = false;
+  const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
+  if (!configured) {
+    OZ_CHECK(cudaFuncSetAttribute(ozaki_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+    configured = true;
+  }
+  // block descriptor tables
+  std::vector<OzBlock> ha(na), hb(nb);
+  int max_ar = 1, max_ac = 1, max_br = 1, max_bc = 1;
+  for (int i = 0; i < na; ++i) {
+    ha[i] = OzBlock{a_blocks[i].v, a_blocks[i].rows, a_blocks[i].cols, a_blocks[i].row0, a_blocks[i].col0, a_blocks[i].isT, {0}};
+    max_ar = std::max(max_ar, a_blocks[i].rows);
+    max_ac = std::max(max_ac, a_blocks[i].cols);
+  }
+  for (int i = 0; i < nb; ++i) {
+    hb[i] = OzBlock{b_blocks[i].v, b_blocks[i].rows, b_blocks[i].cols, b_blocks[i].row0, b_blocks[i].col0, b_blocks[i].isT, {0}};
+    max_br = std::max(max_br, b_blocks[i].rows);
+    max_bc = std::max(max_bc, b_blocks[i].cols);
+  }
+  AsyncBuf d_ab(stream), d_bb(stream), d_max(stream), d_exp(stream), d_bad(stream), d_As(stream), d_Bs(stream), d_maps(stream), d_ctab(stream);
+  OZ_CHECK(d_ab.alloc(sizeof(OzBlock) * na));
+  OZ_CHECK(d_bb.alloc(sizeof(OzBlock) * nb));
+  OZ_CHECK(cudaMemcpyAsync(d_ab.p, ha.data(), sizeof(OzBlock) * na, cudaMemcpyHostToDevice, stream));
+  OZ_CHECK(cudaMemcpyAsync(d_bb.p, hb.data(), sizeof(OzBlock) * nb, cudaMemcpyHostToDevice, stream));
+  OZ_CHECK(d_max.alloc(sizeof(unsigned long long) * (Mpad + Npad)));
+  OZ_CHECK(d_exp.alloc(sizeof(int32_t) * (Mpad + Npad)));
+  OZ_CHECK(d_bad.alloc(sizeof(int)));
+  OZ_CHECK(cudaMemsetAsync(d_max.p, 0, sizeof(unsigned long long) * (Mpad + Npad), stream));
+  OZ_CHECK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), stream));
+  unsigned long long* rowmax = static_cast<unsigned long long*>(d_max.p);
+  unsigned long long* colmax = rowmax + Mpad;
+  int32_t* row_exp = static_cast<int32_t*>(d_exp.p);
+  int32_t* col_exp = row_exp + Mpad;
+  // pass 1
+  {
+    const int tc = (max_ac + 31) / 32, tr = (max_ar + 31) / 32;
+    absmax_kernel<<<dim3(tr * tc, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), rowmax, 1, tc);
+    const int tcb = (max_bc + 31) / 32, trb = (max_br + 31) / 32;
+    absmax_kernel<<<dim3(trb * tcb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), colmax, 0, tcb);
+    exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, row_exp, static_cast<int>(Mpad + Npad),
+                                                                                      static_cast<int*>(d_bad.p));
+    *launches += 3;
+  }
+  int h_bad = 0;
+  OZ_CHECK(cudaMemcpyAsync(&h_bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  OZ_CHECK(cudaStreamSynchronize(stream));
+  if (h_bad) {
+    *nonfinite = 1;  // Inf/NaN input: integer slicing is undefined; the caller falls back to the exact DMMA kernel
+    return cudaSuccess;
+  }
+  // pass 2
+  const size_t a_stride = static_cast<size_t>(Mpad) * Kpad, b_stride = static_cast<size_t>(Npad) * Kpad;
+  OZ_CHECK(d_As.alloc(a_stride * S));
+  OZ_CHECK(d_Bs.alloc(b_stride * S));
+  OZ_CHECK(cudaMemsetAsync(d_As.p, 0, a_stride * S, stream));
+  OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * S, stream));
+  {
+    const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
+    slice_kernel<<<dim3(tl * tk, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), row_exp, static_cast<int8_t*>(d_As.p),
+                                                        a_stride, static_cast<int>(Kpad), S, 1, tk);
+    const int tkb = (max_br + 127) / 128, tlb = (max_bc + 31) / 32;
+    slice_kernel<<<dim3(tlb * tkb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), col_exp, static_cast<int8_t*>(d_Bs.p),
+                                                          b_stride, static_cast<int>(Kpad), S, 0, tkb);
+    *launches += 2;
+  }
+  // tensor maps + output block table
+  std::vector<unsigned char> hmaps(static_cast<size_t>(2 * S) * 128);
+  for (int s = 0; s < S; ++s) {
+    if (!make_i8_map(&hmaps[static_cast<size_t>(s) * 128], static_cast<int8_t*>(d_As.p) + a_stride * s, Kpad, Mpad, BM) ||
+        !make_i8_map(&hmaps[static_cast<size_t>(S + s) * 128], static_cast<int8_t*>(d_Bs.p) + b_stride * s, Kpad, Npad, BN))
+      return cudaErrorInvalidValue;
+  }
+  OZ_CHECK(d_maps.alloc(hmaps.size()));
+  OZ_CHECK(cudaMemcpyAsync(d_maps.p, hmaps.data(), hmaps.size(), cudaMemcpyHostToDevice, stream));
+  OZ_CHECK(d_ctab.alloc(sizeof(double*) * nbr * nbc));
+  OZ_CHECK(cudaMemcpyAsync(d_ctab.p, h_ctab, sizeof(double*) * nbr * nbc, cudaMemcpyHostToDevice, stream));
+  // pass 3: smallest terms first (diagonal S+1 down to 2)
+  OzakiGemmParams p{};
+  p.tmaps = static_cast<const unsigned char*>(d_maps.p);
+  p.row_exp = row_exp;
+  p.col_exp = col_exp;
+  p.ctab = static_cast<double* const*>(d_ctab.p);
+  p.M = static_cast<int32_t>(M);
+  p.N = static_cast<int32_t>(N);
+  p.Kpad = static_cast<int32_t>(Kpad);
+  p.blk = blk;
+  p.nbr = nbr;
+  p.nbc = nbc;
+  p.S = S;
+  const dim3 grid(static_cast<unsigned>(Npad / BN), static_cast<unsigned>(Mpad / BM));
+  bool first = !accumulate;
+  for (int d = S + 1; d >= 2; --d) {
+    p.d = d;
+    p.accumulate = first ? 0 : 1;
+    first = false;
+    ozaki_gemm_i8_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+    OZ_CHECK(cudaGetLastError());
+    *launches += 1;
+  }
+  // scratch is freed stream-ordered by the AsyncBuf destructors; pageable staging vectors were consumed synchronously
+  return cudaSuccess;
+}
+
+}  // namespace matrel

@@ -43,6 +43,19 @@ bool encode_kcontig_tmap(void* out128, const double* base, int64_t kdim, int64_t
 cudaError_t launch_gemm_f64(const GemmOut* d_outs, const GemmPair* d_pairs, const GemmTile* d_tiles,
                             int ntiles, const void* d_tmaps, int variant, cudaStream_t stream);
 
+// ---- fp64 block GEMM on tcgen05 (kind::i8) through Ozaki splitting (gemm_ozaki.cu) --------------------------------
+struct OzakiOperand {
+  const double* v;     // dense block values (column-major, row-major if isT)
+  int32_t rows, cols;  // logical block dims
+  int32_t row0, col0;  // global offset of the block inside its operand matrix
+  uint8_t isT;
+};
+// C(blocks in h_ctab, nbr x nbc grid of blk-sized column-major blocks) (+)= A(M x K) * B(K x N); absent blocks are zeros.
+// *nonfinite = 1 (and nothing written) when an operand holds Inf/NaN: the caller must use the exact kernel instead.
+cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K,
+                           int64_t N, int slices, double* const* h_ctab, int blk, int nbr, int nbc, bool accumulate,
+                           int* launches, int* nonfinite, cudaStream_t stream);
+
 // ---- element-wise / layout kernels (HBM-bound), batched over blocks ---------------------------------
 enum EwOp { EW_ADD = 0, EW_MUL = 1, EW_DIV = 2, EW_RANK1 = 3, EW_RANK1_COMPAT = 4, EW_COPY = 5 };
 

@@ -6,7 +6,7 @@ import matrel_b200 as mb
 n, blk = int(sys.argv[1]), int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 with mb.MatfastSession(device=0) as s:
-    if len(sys.argv) > 4:
+    if len(sys.argv) > 4 and int(sys.argv[4]) >= 0:
         s.set_option("gemm_variant", int(sys.argv[4]))
     for kv in sys.argv[5:]:
         k, v = kv.split("=")
