@@ -306,7 +306,9 @@ struct MultiplyPlanner {
 // Returns false when the problem does not fit its regular-grid assumptions or holds Inf/NaN (caller uses DMMA).
 bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<double*>& cptr, int32_t blkSize, int64_t M,
                int64_t K, int64_t N, bool outer) {
-  if (M <= 0 || K <= 0 || N <= 0 || M > INT32_MAX || N > INT32_MAX || K > (1 << 17)) return false;  // s32 accumulator bound
+  const int S_eff = std::min(7, std::max(2, ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7));
+  // s32 accumulator bound: up to S pairs x K terms of |digit product| <= 2^14 land in one accumulator
+  if (M <= 0 || K <= 0 || N <= 0 || M > INT32_MAX || N > INT32_MAX || K * S_eff >= (1 << 17)) return false;
   const int64_t nbr = ceil_div(M, blkSize), nbc = ceil_div(N, blkSize);
   if (nbr * nbc > (1 << 24)) return false;
   std::vector<double*> ctab(static_cast<size_t>(nbr * nbc), nullptr);

@@ -20,6 +20,8 @@
 //      all k -> tcgen05.ld epilogue: scale by 2^(e_i+f_j+4-8d) and accumulate into the fp64 output blocks.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -30,8 +32,8 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BKB = 128 /* bytes (= int8 elements) of K per stage */, UMMA_K = 32, STAGES = 4;
 constexpr int A_BYTES = BM * BKB, B_BYTES = BN * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_THREADS = 256;
-constexpr int TMEM_COLS = 256;
+
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -46,6 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                  : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -75,36 +78,58 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 struct OzakiGemmParams {
   const unsigned char* tmaps;  // 2*S CUtensorMaps (128 B each): A_1..A_S then B_1..B_S
-  const int32_t* row_exp;      // e_i per global row of A      (|a_ik| < 2^e_i)
-  const int32_t* col_exp;      // f_j per global column of B   (|b_kj| < 2^f_j)
+  const double* row_scale;     // 2^e_i per global row of A      (|a_ik| < 2^e_i)
+  const double* col_scale;     // 2^f_j per global column of B   (|b_kj| < 2^f_j)
   double* const* ctab;         // [nbr * nbc] output block pointers (nullptr = block absent)
   int32_t M, N, Kpad;          // logical output dims, padded K (multiple of 128)
   int32_t blk, nbr, nbc;       // block size and block-grid extent of C
   int32_t S, d;                // slices, diagonal of this launch (pairs (s, d - s))
   int32_t accumulate;          // 0: C = term, 1: C += term
+  int32_t tiles_m, tiles_n;    // tile grid (128 x 256 tiles)
+  double diag_scale;           // 2^(4 - 8 d)
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) ozaki_gemm_i8_kernel(const OzakiGemmParams p) {
+constexpr int EPI_WARPS = 8;                       // 2 per TMEM lane quarter (each takes 128 of the 256 columns)
+constexpr int GEMM_THREADS_P = (4 + EPI_WARPS) * 32;
+constexpr int TMEM_COLS_P = 512;                   // two 128 x 256 s32 accumulators: MMA of tile i+1 overlaps epilogue of tile i
+constexpr int TILE_BAND = 8;                       // n-tiles per rasterisation band (L2 reuse of A / B panels)
+
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int band_tiles = TILE_BAND * tiles_m;
+  const int band = t / band_tiles;
+  const int rem = t - band * band_tiles;
+  const int bw = min(TILE_BAND, tiles_n - band * TILE_BAND);
+  tm = rem / bw;
+  tn = band * TILE_BAND + rem % bw;
+}
+
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..11 = epilogue.  One CTA per SM loops over the output tiles of this diagonal.
+__global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const OzakiGemmParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[STAGES], empty[STAGES], acc_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  // barriers: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nk = p.Kpad / BKB;
   const int s_lo = max(1, p.d - p.S), s_hi = min(p.S, p.d - 1);
-  const int total = (s_hi - s_lo + 1) * nk;
+  const int per_tile = (s_hi - s_lo + 1) * nk;
+  const int ntiles = p.tiles_m * p.tiles_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bars[s]), 1);
       mbar_init(smem_u32(&bars[STAGES + s]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars[2 * STAGES + b]), 1);              // acc_full: one tcgen05.commit
+      mbar_init(smem_u32(&bars[2 * STAGES + 2 + b]), EPI_WARPS);  // acc_empty: one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS_P) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -116,17 +141,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ozaki_gemm_i8_kernel(const Oz
     // ===== TMA producer (one elected lane) =====
     if (lane == 0) {
       int it = 0;
-      for (int s = s_lo; s <= s_hi; ++s) {
-        const void* tmA = p.tmaps + static_cast<size_t>(s - 1) * 128;
-        const void* tmB = p.tmaps + static_cast<size_t>(p.S + (p.d - s) - 1) * 128;
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const int st = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(smem_u32(&bars[STAGES + st]), ph ^ 1);
-          const uint32_t full = smem_u32(&bars[st]);
-          mbar_arrive_expect_tx(full, STAGE_BYTES);
-          tma_2d(smem_u32(smem + st * STAGE_BYTES), tmA, kc * BKB, m0, full);
-          tma_2d(smem_u32(smem + st * STAGE_BYTES + A_BYTES), tmB, kc * BKB, n0, full);
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int tm, tn;
+        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        const int m0 = tm * BM, n0 = tn * BN;
+        for (int s = s_lo; s <= s_hi; ++s) {
+          const void* tmA = p.tmaps + static_cast<size_t>(s - 1) * 128;
+          const void* tmB = p.tmaps + static_cast<size_t>(p.S + (p.d - s) - 1) * 128;
+          for (int kc = 0; kc < nk; ++kc, ++it) {
+            const int st = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(smem_u32(&bars[STAGES + st]), ph ^ 1);
+            const uint32_t full = smem_u32(&bars[st]);
+            mbar_arrive_expect_tx(full, STAGE_BYTES);
+            tma_2d(smem_u32(smem + st * STAGE_BYTES), tmA, kc * BKB, m0, full);
+            tma_2d(smem_u32(smem + st * STAGE_BYTES + A_BYTES), tmB, kc * BKB, n0, full);
+          }
         }
       }
     }
@@ -136,46 +166,93 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ozaki_gemm_i8_kernel(const Oz
       // D = S32 (2 @ bit 4); A, B = signed 8-bit (1 @ bits 7 and 10); both K-major; N >> 3 @ 17; M >> 4 @ 24
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                              (static_cast<uint32_t>(BM >> 4) << 24);
-      for (int it = 0; it < total; ++it) {
-        const int st = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(smem_u32(&bars[st]), ph);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(smem_u32(&bars[2 * STAGES + 2 + buf]), aph ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = smem_u32(smem + st * STAGE_BYTES), b0 = a0 + A_BYTES;
+        const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int j = 0; j < per_tile; ++j, ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&bars[st]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = smem_u32(smem + st * STAGE_BYTES), b0 = a0 + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BKB / UMMA_K; ++k)
-          umma_i8(tmem_base, umma_desc_k_sw128(a0 + k * UMMA_K), umma_desc_k_sw128(b0 + k * UMMA_K), idesc, (it | k) != 0);
-        umma_commit(smem_u32(&bars[STAGES + st]));  // stage is free once these MMAs retire
+          for (int k = 0; k < BKB / UMMA_K; ++k)
+            umma_i8(tacc, umma_desc_k_sw128(a0 + k * UMMA_K), umma_desc_k_sw128(b0 + k * UMMA_K), idesc, (j | k) != 0);
+          umma_commit(smem_u32(&bars[STAGES + st]));  // stage is free once these MMAs retire
+        }
+        umma_commit(smem_u32(&bars[2 * STAGES + buf]));  // accumulator complete
       }
-      umma_commit(smem_u32(&bars[2 * STAGES]));     // accumulator complete
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> fp64 scale -> accumulate into the column-major output blocks =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const int rid = row_ok ? row / p.blk : 0;
-    const int lr = row - rid * p.blk;
-    const int brows = min(p.blk, p.M - rid * p.blk);
-    const int ebase = (row_ok ? p.row_exp[row] : 0) + 4 - 8 * p.d;
-    mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ===== epilogue: TMEM -> registers -> scale by 2^(e_i + f_j + 4 - 8d) -> (+)= column-major fp64 output blocks =====
+    const int ew = warp - 4;
+    const int q = ew & 3;          // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = ew >> 2;      // which 128 of the tile's 256 columns
+    int lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      int tm, tn;
+      tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+      const int m0 = tm * BM, n0 = tn * BN;
+      const int buf = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int rid = row_ok ? row / p.blk : 0;
+      const int lr = row - rid * p.blk;
+      const int brows = min(p.blk, p.M - rid * p.blk);
+      const double rs = row_ok ? p.row_scale[row] * p.diag_scale : 0.0;
+      mbar_wait(smem_u32(&bars[2 * STAGES + buf]), aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tsrc = tmem_base + static_cast<uint32_t>(buf * BN) + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t r[16];
-      TMEM_LD16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row_ok) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = n0 + c + j;
-          if (col < p.N) {
-            const int cid = col / p.blk;
-            double* blkp = p.ctab[rid * p.nbc + cid];
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t r[16];
+        TMEM_LD16(tsrc + c, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == 128 - 16) {
+          // all of this warp's accumulator reads are in registers: hand the buffer back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars[2 * STAGES + 2 + buf]));
+        }
+        const int col0 = n0 + half * 128 + c;
+        if (row_ok && col0 < p.N) {
+          const int cid0 = col0 / p.blk;
+          const bool one_block = (col0 + 15 < p.N) && ((col0 + 15) / p.blk == cid0);
+          if (one_block) {
+            double* blkp = p.ctab[rid * p.nbc + cid0];
             if (blkp != nullptr) {
-              double* dst = blkp + lr + static_cast<size_t>(brows) * (col - cid * p.blk);
-              const double term = scalbn(static_cast<double>(static_cast<int32_t>(r[j])), ebase + p.col_exp[col]);
-              *dst = p.accumulate ? *dst + term : term;
+              double* dst = blkp + lr + static_cast<size_t>(brows) * (col0 - cid0 * p.blk);
+              double old[16];
+              if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) old[j] = dst[static_cast<size_t>(brows) * j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) old[j] = 0.0;
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                dst[static_cast<size_t>(brows) * j] =
+                    old[j] + (static_cast<double>(static_cast<int32_t>(r[j])) * rs) * __ldg(p.col_scale + col0 + j);
+            }
+          } else {
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) {
+              const int col = col0 + j;
+              if (col < p.N) {
+                const int cid = col / p.blk;
+                double* blkp = p.ctab[rid * p.nbc + cid];
+                if (blkp != nullptr) {
+                  double* dst = blkp + lr + static_cast<size_t>(brows) * (col - cid * p.blk);
+                  const double term = (static_cast<double>(static_cast<int32_t>(r[j])) * rs) * p.col_scale[col];
+                  *dst = p.accumulate ? *dst + term : term;
+                }
+              }
             }
           }
         }
@@ -184,7 +261,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ozaki_gemm_i8_kernel(const Oz
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_P) : "memory");
 }
 
 // ---- pass 1: per-row / per-column maximum magnitude (as the IEEE bit pattern, which orders like the value) -------
@@ -243,16 +320,16 @@ __global__ void __launch_bounds__(256) absmax_kernel(const OzBlock* __restrict__
 }
 
 // exponent table: e = ilogb(max) + 1 (so |x| * 2^-e < 1), 0 for all-zero lines; flags non-finite input
-__global__ void exp_kernel(const unsigned long long* __restrict__ maxbits, int32_t* __restrict__ e, int n, int* __restrict__ bad) {
+__global__ void exp_kernel(const unsigned long long* __restrict__ maxbits, int32_t* __restrict__ e, double* __restrict__ scale, int n,
+                           int* __restrict__ bad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double m = __longlong_as_double(static_cast<long long>(maxbits[i]));
-  if (!isfinite(m)) {
-    *bad = 1;
-    e[i] = 0;
-  } else {
-    e[i] = (m == 0.0) ? 0 : ilogb(m) + 1;
-  }
+  int ex = 0;
+  if (!isfinite(m)) *bad = 1;
+  else if (m != 0.0) ex = ilogb(m) + 1;
+  e[i] = ex;
+  scale[i] = scalbn(1.0, ex);
 }
 
 // ---- pass 2: balanced base-256 digits.  out_s[line * Kpad + k], line = row of A (transpose_out = 0) or column of B --
@@ -379,7 +456,7 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   const int S = slices < 2 ? 2 : (slices > 7 ? 7 : slices);
   const int64_t Mpad = (M + BM - 1) / BM * BM, Npad = (N + BN - 1) / BN * BN, Kpad = (K + BKB - 1) / BKB * BKB;
   static bool configured = false;
-  const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
+  const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
   if (!configured) {
     OZ_CHECK(cudaFuncSetAttribute(ozaki_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
     configured = true;
@@ -397,13 +474,14 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
     max_br = std::max(max_br, b_blocks[i].rows);
     max_bc = std::max(max_bc, b_blocks[i].cols);
   }
-  AsyncBuf d_ab(stream), d_bb(stream), d_max(stream), d_exp(stream), d_bad(stream), d_As(stream), d_Bs(stream), d_maps(stream), d_ctab(stream);
+  AsyncBuf d_ab(stream), d_bb(stream), d_max(stream), d_exp(stream), d_scale(stream), d_bad(stream), d_As(stream), d_Bs(stream), d_maps(stream), d_ctab(stream);
   OZ_CHECK(d_ab.alloc(sizeof(OzBlock) * na));
   OZ_CHECK(d_bb.alloc(sizeof(OzBlock) * nb));
   OZ_CHECK(cudaMemcpyAsync(d_ab.p, ha.data(), sizeof(OzBlock) * na, cudaMemcpyHostToDevice, stream));
   OZ_CHECK(cudaMemcpyAsync(d_bb.p, hb.data(), sizeof(OzBlock) * nb, cudaMemcpyHostToDevice, stream));
   OZ_CHECK(d_max.alloc(sizeof(unsigned long long) * (Mpad + Npad)));
   OZ_CHECK(d_exp.alloc(sizeof(int32_t) * (Mpad + Npad)));
+  OZ_CHECK(d_scale.alloc(sizeof(double) * (Mpad + Npad)));
   OZ_CHECK(d_bad.alloc(sizeof(int)));
   OZ_CHECK(cudaMemsetAsync(d_max.p, 0, sizeof(unsigned long long) * (Mpad + Npad), stream));
   OZ_CHECK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), stream));
@@ -417,8 +495,8 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
     absmax_kernel<<<dim3(tr * tc, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), rowmax, 1, tc);
     const int tcb = (max_bc + 31) / 32, trb = (max_br + 31) / 32;
     absmax_kernel<<<dim3(trb * tcb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), colmax, 0, tcb);
-    exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, row_exp, static_cast<int>(Mpad + Npad),
-                                                                                      static_cast<int*>(d_bad.p));
+    exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, row_exp, static_cast<double*>(d_scale.p),
+                                                                                      static_cast<int>(Mpad + Npad), static_cast<int*>(d_bad.p));
     *launches += 3;
   }
   int h_bad = 0;
@@ -457,8 +535,8 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   // pass 3: smallest terms first (diagonal S+1 down to 2)
   OzakiGemmParams p{};
   p.tmaps = static_cast<const unsigned char*>(d_maps.p);
-  p.row_exp = row_exp;
-  p.col_exp = col_exp;
+  p.row_scale = static_cast<const double*>(d_scale.p);
+  p.col_scale = p.row_scale + Mpad;
   p.ctab = static_cast<double* const*>(d_ctab.p);
   p.M = static_cast<int32_t>(M);
   p.N = static_cast<int32_t>(N);
@@ -467,13 +545,20 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   p.nbr = nbr;
   p.nbc = nbc;
   p.S = S;
-  const dim3 grid(static_cast<unsigned>(Npad / BN), static_cast<unsigned>(Mpad / BM));
+  p.tiles_m = static_cast<int32_t>(Mpad / BM);
+  p.tiles_n = static_cast<int32_t>(Npad / BN);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ntiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(ntiles, sms));
   bool first = !accumulate;
   for (int d = S + 1; d >= 2; --d) {
     p.d = d;
     p.accumulate = first ? 0 : 1;
+    p.diag_scale = std::ldexp(1.0, 4 - 8 * d);
     first = false;
-    ozaki_gemm_i8_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+    ozaki_gemm_i8_kernel<<<grid, GEMM_THREADS_P, smem_bytes, stream>>>(p);
     OZ_CHECK(cudaGetLastError());
     *launches += 1;
   }
