@@ -192,7 +192,7 @@ def cpu_f2j_sample(n: int, blk: int, budget_s: float = 8.0):
     t0 = time.perf_counter()
     c_port.block_multiply_f2j(A, B, nb, blk, 1, 1, 1)              # calibrate: one block pair, one thread
     t_pair = time.perf_counter() - t0
-    nk = max(1, min(nb, int(budget_s / max(t_pair * 2.0, 1e-3))))
+    nk = max(1, min(nb, int(budget_s / max(t_pair * 6.0, 1e-3))))   # all-core runs are ~3x slower per pair than one thread alone
     t0 = time.perf_counter()
     c_port.block_multiply_f2j(A, B, nb, blk, ntasks, threads, nk)
     wall = time.perf_counter() - t0
