@@ -192,6 +192,8 @@ struct Slab {
   }
 };
 
+Span upload_raw(mr_context* ctx, const void* host, size_t bytes);
+
 Block dense_block(int32_t rows, int32_t cols, Span values, bool isT = false) {
   Block b;
   b.type = 1;
@@ -469,12 +471,40 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     }
   }
 
-  // ---- sparse x dense partial products accumulate onto the GEMM result (LocalMatrix.add of partials)
+  // ---- sparse x dense partial products accumulate onto the GEMM result (LocalMatrix.add of partials).
+  // CSR pairs with block dims <= 1024 go through ONE fused launch (K loop over the pairs inside the kernel);
+  // CSC pairs and oversized blocks use the per-pair kernels.
+  std::vector<SpmmOut> fouts;
+  std::vector<SpmmPair> fpairs;
+  int fused_max_n = 0;
   for (size_t i = 0; i < plans.size(); ++i) {
     auto& o = plans[i];
     bool have = !o.gemm.empty();
     if (o.m == 0 || o.n == 0) continue;
+    std::vector<std::pair<const Block*, const Block*>> slow;
+    SpmmOut fo{};
+    fo.C = cptr[i];
+    fo.m = o.m;
+    fo.n = o.n;
+    fo.pair_begin = static_cast<int32_t>(fpairs.size());
     for (auto& sp : o.spmm) {
+      const Block& s = *sp.first;
+      const Block& b = *sp.second;
+      if (s.isT && o.m <= kSpmmMaxDim && s.numCols <= kSpmmMaxDim) {
+        SpmmPair pr{};
+        pr.ptrs = s.colPtrs.ptr<int32_t>();
+        pr.idx = s.rowIndices.ptr<int32_t>();
+        pr.vals = s.values.ptr<double>();
+        pr.B = b.values.ptr<double>();
+        pr.kdim = s.numCols;
+        pr.bT = b.isT;
+        fpairs.push_back(pr);
+      } else {
+        slow.push_back(sp);
+      }
+    }
+    fo.pair_count = static_cast<int32_t>(fpairs.size()) - fo.pair_begin;
+    for (auto& sp : slow) {  // per-pair kernels first so the fused launch can simply accumulate on top
       const Block& s = *sp.first;
       const Block& b = *sp.second;
       CUDA_CHECK(launch_spmm(s.colPtrs.ptr<int32_t>(), s.rowIndices.ptr<int32_t>(), s.values.ptr<double>(), s.isT,
@@ -482,7 +512,28 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       note_launch(ctx);
       have = true;
     }
+    if (fo.pair_count > 0) {
+      fo.accumulate = have ? 1 : 0;
+      fouts.push_back(fo);
+      fused_max_n = std::max(fused_max_n, o.n);
+      have = true;
+    }
     if (!have) CUDA_CHECK(cudaMemsetAsync(cptr[i], 0, static_cast<size_t>(o.m) * o.n * sizeof(double), ctx->stream));
+  }
+  if (!fouts.empty()) {
+    Buf d_fo = upload(ctx, fouts), d_fp = upload(ctx, fpairs);
+    if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_CHECK(launch_spmm_fused(static_cast<const SpmmOut*>(d_fo->p), static_cast<int>(fouts.size()),
+                                 static_cast<const SpmmPair*>(d_fp->p), fused_max_n, ctx->stream));
+    note_launch(ctx);
+    if (ctx->time_kernels) {
+      CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+      CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      ctx->stats.last_gemm_ms = ms;
+      ctx->stats.gemm_ms_total += ms;
+    }
   }
   (void)planner;
 }
@@ -508,6 +559,7 @@ struct EwBatch {
   int max_rows = 0, max_cols = 0;
   bool any_T = false;
   size_t total = 0;
+  std::vector<size_t> sparse_rule;  // indices of results that follow the sparse (op) sparse output-format rule
 
   void add(std::pair<int32_t, int32_t> key, const Block* a, const Block* b, const double* y, int rows, int cols) {
     EwDesc d{};
@@ -539,6 +591,70 @@ struct EwBatch {
     CUDA_CHECK(launch_ew_batched(op, static_cast<const EwDesc*>(d->p), static_cast<int>(descs.size()), max_rows,
                                  max_cols, any_T, ctx->stream));
     note_launch(ctx);
+    if (!sparse_rule.empty()) apply_sparse_rule(result);
+  }
+
+  // LocalMatrix.addSparseSparse / elementWiseOpSparseSparse output format (LocalMatrix.scala:74-139, 521-602): the
+  // dense result is converted with toSparse (CSC, isTransposed = false) iff rows*cols > 2*nnz + cols + 1, where nnz
+  // counts entries != 0.0 (NaN included).  Both the transposed and the native branch reduce to this rule.
+  void apply_sparse_rule(mr_matrix* result) {
+    std::vector<CscDesc> cd(sparse_rule.size());
+    size_t ncols_total = 0;
+    int maxc = 0;
+    for (size_t i = 0; i < sparse_rule.size(); ++i) ncols_total += static_cast<size_t>(shapes[sparse_rule[i]].second.second);
+    Buf counts = std::make_shared<DevBuf>(ctx, std::max<size_t>(ncols_total * sizeof(int32_t), 16));
+    size_t off = 0;
+    for (size_t i = 0; i < sparse_rule.size(); ++i) {
+      const size_t bi = sparse_rule[i];
+      cd[i] = CscDesc{descs[bi].C, shapes[bi].second.first, shapes[bi].second.second, static_cast<int32_t*>(counts->p) + off,
+                      nullptr, nullptr, nullptr};
+      off += static_cast<size_t>(cd[i].cols);
+      maxc = std::max(maxc, cd[i].cols);
+    }
+    Buf dcd = upload(ctx, cd);
+    CUDA_CHECK(launch_csc_count(static_cast<const CscDesc*>(dcd->p), static_cast<int>(cd.size()), maxc, ctx->stream));
+    note_launch(ctx);
+    std::vector<int32_t> hcounts(ncols_total);
+    if (ncols_total) {
+      CUDA_CHECK(cudaMemcpyAsync(hcounts.data(), counts->p, ncols_total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->stats.d2h_bytes += static_cast<int64_t>(ncols_total * sizeof(int32_t));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    std::vector<CscDesc> fill;
+    std::vector<Block> fresh;
+    std::vector<std::pair<int32_t, int32_t>> keys;
+    int maxc_fill = 0;
+    off = 0;
+    for (size_t i = 0; i < cd.size(); ++i) {
+      const int rows = cd[i].rows, cols = cd[i].cols;
+      std::vector<int32_t> ptrs(static_cast<size_t>(cols) + 1, 0);
+      for (int c = 0; c < cols; ++c) ptrs[c + 1] = ptrs[c] + hcounts[off + c];
+      off += static_cast<size_t>(cols);
+      const int64_t nnz = ptrs[cols];
+      if (static_cast<int64_t>(rows) * cols > 2 * nnz + cols + 1) {
+        Block sb;
+        sb.type = 0;
+        sb.numRows = rows;
+        sb.numCols = cols;
+        sb.isT = false;
+        sb.valuesLen = nnz;
+        sb.colPtrsLen = cols + 1;
+        sb.colPtrs = upload_raw(ctx, ptrs.data(), ptrs.size() * sizeof(int32_t));
+        sb.rowIndices = Span{std::make_shared<DevBuf>(ctx, std::max<size_t>(nnz * sizeof(int32_t), 16)), 0};
+        sb.values = Span{std::make_shared<DevBuf>(ctx, std::max<size_t>(nnz * sizeof(double), 16)), 0};
+        fill.push_back(CscDesc{cd[i].dense, rows, cols, nullptr, sb.colPtrs.ptr<int32_t>(), sb.rowIndices.ptr<int32_t>(),
+                               sb.values.ptr<double>()});
+        maxc_fill = std::max(maxc_fill, cols);
+        fresh.push_back(std::move(sb));
+        keys.push_back(shapes[sparse_rule[i]].first);
+      }
+    }
+    if (!fill.empty()) {
+      Buf dfill = upload(ctx, fill);
+      CUDA_CHECK(launch_csc_fill(static_cast<const CscDesc*>(dfill->p), static_cast<int>(fill.size()), maxc_fill, ctx->stream));
+      note_launch(ctx);
+      for (size_t i = 0; i < fresh.size(); ++i) result->blocks[keys[i]] = std::move(fresh[i]);  // replaces the dense window
+    }
   }
 };
 
@@ -583,14 +699,13 @@ void elementwise_join(int op, mr_matrix* left, mr_matrix* right, mr_matrix* resu
     const Block& b = it->second;
     if (op == EW_ADD) check_block_dims_add(a, b);
     else check_block_dims_ew(a, b);
-    if (!a.dense() && !b.dense())
-      fail(MR_ENOTSUP, "sparse (op) sparse element-wise block kernels (LocalMatrix.addSparseSparse / "
-                       "elementWiseOpSparseSparse) are outside the B200 hot-path scope");
+    const bool both_sparse = !a.dense() && !b.dense();
     const Block* x = dense_view(a);
     const Block* y = dense_view(b);
     // defect B4 (LocalMatrix.scala:474,487): (Sparse, Dense) swaps the operands; visible for divide only
     if (op == EW_DIV && !a.dense() && b.dense() && ctx->compat_bugs) std::swap(x, y);
     batch.add(kv.first, x, y, nullptr, a.numRows, a.numCols);
+    if (both_sparse) batch.sparse_rule.push_back(batch.descs.size() - 1);
   }
   if (op == EW_ADD)
     for (auto& kv : right->blocks)

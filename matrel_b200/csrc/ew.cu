@@ -227,6 +227,55 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const int32_t* __restrict
   C[o] = accumulate ? C[o] + sum : sum;
 }
 
+// Fused CSR SpMM (see kernels.h): grid = (ceil(n_max / 8), output blocks), 256 threads.
+constexpr int SPMM_CW = 8;
+__global__ void __launch_bounds__(256) spmm_fused_kernel(const SpmmOut* __restrict__ outs, const SpmmPair* __restrict__ pairs) {
+  extern __shared__ double spmm_smem[];
+  const SpmmOut o = outs[blockIdx.y];
+  const int c0 = blockIdx.x * SPMM_CW;
+  if (c0 >= o.n) return;
+  const int cw = min(SPMM_CW, o.n - c0);
+  const int ldc = o.m + 4, ldb_max = kSpmmMaxDim + 2;
+  double* sC = spmm_smem;                       // [SPMM_CW][ldc]
+  double* sB = spmm_smem + SPMM_CW * (kSpmmMaxDim + 4);  // [SPMM_CW][kdim + 2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < SPMM_CW * o.m; idx += 256) {
+    const int c = idx / o.m, r = idx % o.m;
+    sC[c * ldc + r] = (o.accumulate && c < cw) ? o.C[r + static_cast<size_t>(o.m) * (c0 + c)] : 0.0;
+  }
+  const int c = lane & 7, q = lane >> 3;
+  for (int p = 0; p < o.pair_count; ++p) {
+    const SpmmPair pr = pairs[o.pair_begin + p];
+    const int ldb = pr.kdim + 2;
+    __syncthreads();  // previous pair's readers of sB are done (and sC init is visible)
+    if (!pr.bT) {
+      for (int idx = tid; idx < SPMM_CW * pr.kdim; idx += 256) {
+        const int cc = idx / pr.kdim, k = idx % pr.kdim;
+        sB[cc * ldb + k] = cc < cw ? pr.B[k + static_cast<size_t>(pr.kdim) * (c0 + cc)] : 0.0;
+      }
+    } else {
+      for (int idx = tid; idx < SPMM_CW * pr.kdim; idx += 256) {
+        const int k = idx / SPMM_CW, cc = idx % SPMM_CW;
+        sB[cc * ldb + k] = cc < cw ? pr.B[c0 + cc + static_cast<size_t>(o.n) * k] : 0.0;
+      }
+    }
+    __syncthreads();
+    // quarter-warp per row: 8 warps x 4 rows per pass
+    for (int r = warp * 4 + q; r < o.m; r += 32) {
+      const int beg = pr.ptrs[r], end = pr.ptrs[r + 1];
+      double acc = 0.0;
+      for (int i = beg; i < end; ++i) acc += pr.vals[i] * sB[c * ldb + pr.idx[i]];  // ascending i: the reference's order
+      sC[c * ldc + r] += acc;  // (r, c) is owned by exactly this lane
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < cw * o.m; idx += 256) {
+    const int cc = idx / o.m, r = idx % o.m;
+    o.C[r + static_cast<size_t>(o.m) * (c0 + cc)] = sC[cc * ldc + r];
+  }
+  (void)ldb_max;
+}
+
 // CSC x dense: scatter-AXPY (BLAS.scala:414-456).  Warp per (CSC column, output column); C must be
 // initialised (zeros or the running sum) before launch.
 __global__ void __launch_bounds__(256) spmm_csc_kernel(const int32_t* __restrict__ ptrs, const int32_t* __restrict__ idx,
@@ -269,6 +318,40 @@ __global__ void __launch_bounds__(256) java_rand_kernel(const RandDesc* __restri
     s = (s * 0x5DEECE66Dull + 0xBull) & MASK;
     const uint64_t lo = s >> 21;  // next(27)
     d.out[i] = static_cast<double>((hi << 27) + lo) * (1.0 / 9007199254740992.0);
+  }
+}
+
+// one warp per column: count entries with v != 0.0 (NaN != 0.0 is true, like the JVM)
+__global__ void __launch_bounds__(256) csc_count_kernel(const CscDesc* __restrict__ descs) {
+  const CscDesc d = descs[blockIdx.y];
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (col >= d.cols) return;
+  const double* c = d.dense + static_cast<size_t>(d.rows) * col;
+  int n = 0;
+  for (int r = lane; r < d.rows; r += 32) n += (c[r] != 0.0) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0) d.counts[col] = n;
+}
+
+// one warp per column: ordered compaction (row indices strictly increasing, as toSparse produces them)
+__global__ void __launch_bounds__(256) csc_fill_kernel(const CscDesc* __restrict__ descs) {
+  const CscDesc d = descs[blockIdx.y];
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (col >= d.cols) return;
+  const double* c = d.dense + static_cast<size_t>(d.rows) * col;
+  int base = d.colPtrs[col];
+  for (int r0 = 0; r0 < d.rows; r0 += 32) {
+    const int r = r0 + lane;
+    const double v = r < d.rows ? c[r] : 0.0;
+    const bool nz = (r < d.rows) && (v != 0.0);
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    if (nz) {
+      const int pos = base + __popc(m & ((1u << lane) - 1));
+      d.rowIndices[pos] = r;
+      d.values[pos] = v;
+    }
+    base += __popc(m);
   }
 }
 
@@ -363,6 +446,40 @@ cudaError_t launch_spmm(const int32_t* ptrs, const int32_t* idx, const double* v
     if (k <= 0) return cudaSuccess;
     dim3 grid((k + 7) / 8, n);
     spmm_csc_kernel<<<grid, 256, 0, stream>>>(ptrs, idx, vals, B, bT, C, m, k, n);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csc_count(const CscDesc* d_descs, int nblocks, int max_cols, cudaStream_t stream) {
+  if (nblocks <= 0 || max_cols <= 0) return cudaSuccess;
+  for (int off = 0; off < nblocks; off += 65535) {
+    const int nb = nblocks - off < 65535 ? nblocks - off : 65535;
+    csc_count_kernel<<<dim3((max_cols + 7) / 8, nb), 256, 0, stream>>>(d_descs + off);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csc_fill(const CscDesc* d_descs, int nblocks, int max_cols, cudaStream_t stream) {
+  if (nblocks <= 0 || max_cols <= 0) return cudaSuccess;
+  for (int off = 0; off < nblocks; off += 65535) {
+    const int nb = nblocks - off < 65535 ? nblocks - off : 65535;
+    csc_fill_kernel<<<dim3((max_cols + 7) / 8, nb), 256, 0, stream>>>(d_descs + off);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* d_pairs, int max_n, cudaStream_t stream) {
+  if (nouts <= 0 || max_n <= 0) return cudaSuccess;
+  const size_t smem = static_cast<size_t>(SPMM_CW) * ((kSpmmMaxDim + 4) + (kSpmmMaxDim + 2)) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(spmm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  for (int off = 0; off < nouts; off += 65535) {
+    const int nb = nouts - off < 65535 ? nouts - off : 65535;
+    spmm_fused_kernel<<<dim3((max_n + SPMM_CW - 1) / SPMM_CW, nb), 256, smem, stream>>>(d_outs + off, d_pairs);
   }
   return cudaGetLastError();
 }

@@ -93,6 +93,41 @@ cudaError_t launch_sparse_to_dense(const int32_t* ptrs, const int32_t* idx, cons
 cudaError_t launch_spmm(const int32_t* ptrs, const int32_t* idx, const double* vals, bool sT,
                         const double* B, bool bT, double* C, int m, int k, int n, bool accumulate,
                         cudaStream_t stream);
+// DenseMatrix.toSparse (MLMatrix.scala:353-374) on the device, batched: (1) per-column count of v != 0.0 (NaN counts,
+// as in the reference's `arr(i) != 0`), (2) ordered per-column compaction into CSC given the column pointers.
+struct CscDesc {
+  const double* dense;   // column-major rows x cols
+  int32_t rows, cols;
+  int32_t* counts;       // [cols] out (pass 1)
+  const int32_t* colPtrs;  // [cols + 1] in (pass 2)
+  int32_t* rowIndices;   // out (pass 2)
+  double* values;        // out (pass 2)
+};
+cudaError_t launch_csc_count(const CscDesc* d_descs, int nblocks, int max_cols, cudaStream_t stream);
+cudaError_t launch_csc_fill(const CscDesc* d_descs, int nblocks, int max_cols, cudaStream_t stream);
+
+// Fused block-row SpMM: for every output block, C (col-major m x n) (+)= sum over its (CSR sparse A(i,k), dense B(k,j)) pairs.
+// One CTA = 8 output columns of one output block: the B column chunk and the C chunk live in shared memory, the K loop
+// over the block pairs is fused (no partial blocks, no adds).  BLAS.gemmsdd CSR branches (BLAS.scala:375-413).
+struct SpmmPair {
+  const int32_t* ptrs;   // CSR row pointers (m + 1)
+  const int32_t* idx;    // column indices
+  const double* vals;
+  const double* B;       // dense kdim x n (column-major, row-major if bT)
+  int32_t kdim;
+  uint8_t bT;
+  uint8_t pad[3];
+};
+struct SpmmOut {
+  double* C;
+  int32_t m, n;
+  int32_t pair_begin, pair_count;
+  int32_t accumulate;    // 1: C already holds the dense-pair sum
+  int32_t pad;
+};
+constexpr int kSpmmMaxDim = 1024;   // m and kdim limit of the shared-memory kernel
+cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* d_pairs, int max_n, cudaStream_t stream);
+
 // java.util.Random-compatible U(0,1) fill: out[i] = i-th nextDouble() of new Random(seed), batched over blocks
 struct RandDesc {
   double* out;

@@ -223,6 +223,30 @@ def test_elementwise_vs_oracle(session, op, pt, ps):
     assert_same_dataset(from_dataset(got), want, tol=1e-15)
 
 
+@pytest.mark.parametrize("op", ["add", "mul", "div"])
+def test_sparse_op_sparse_output_format_rule(session, op):
+    """sparse (op) sparse: dense result turned into CSC iff rows*cols > 2*nnz + cols + 1 (LocalMatrix.scala:74-139,521-602)."""
+    rng = np.random.default_rng({"add": 1, "mul": 2, "div": 3}[op])
+    n, m, blk = 200, 150, 64
+    for dens in (0.02, 0.3, 0.7):
+        A = random_block_dataset(rng, n, m, blk, p_sparse=1.0, sparse_density=dens, lo=0.5, hi=2.0)
+        B = random_block_dataset(rng, n, m, blk, p_sparse=1.0, sparse_density=dens, lo=0.5, hi=2.0)
+        dA, dB = to_dataset(session, A), to_dataset(session, B)
+        if op == "add":
+            want, got = O.add_element(A, n, m, B, n, m, blk), dA.addElement(n, m, dB, n, m, blk)
+        elif op == "mul":
+            want, got = O.multiply_element(A, n, m, B, n, m, blk), dA.multiplyElement(n, m, dB, n, m, blk)
+        else:
+            want, got = O.divide_element(A, n, m, B, n, m, blk), dA.divideElement(n, m, dB, n, m, blk)
+        got = from_dataset(got)
+        kinds = {type(v).__name__ for v in want.values()}
+        assert_same_dataset(got, want, tol=1e-15)       # types (sparse vs dense), colPtrs, rowIndices exact
+        if op == "mul" and dens == 0.02:
+            assert kinds == {"SparseMatrix"}
+        if op == "div":
+            assert kinds == {"DenseMatrix"}             # 0/0 = NaN counts as non-zero everywhere
+
+
 def test_divide_compat_switch(session):
     """Defect B4: (Sparse, Dense) divide = dense/sparse under compat_bugs, sparse/dense otherwise."""
     s = O.SparseMatrix(2, 2, [0, 1, 2], [0, 1], [2.0, 4.0])
