@@ -227,53 +227,73 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const int32_t* __restrict
   C[o] = accumulate ? C[o] + sum : sum;
 }
 
-// Fused CSR SpMM (see kernels.h): grid = (ceil(n_max / 8), output blocks), 256 threads.
+// Fused CSR SpMM (see kernels.h): grid = (ceil(n_max / 8), output blocks), 512 threads.
+// Thread = one (or two) row(s) of the output block x 8 columns held in registers across ALL block pairs; the B chunk
+// (8 columns x kdim) is staged in shared memory per pair, so each CSR entry costs one index/value load and feeds 8 FMAs.
 constexpr int SPMM_CW = 8;
-__global__ void __launch_bounds__(256) spmm_fused_kernel(const SpmmOut* __restrict__ outs, const SpmmPair* __restrict__ pairs) {
+constexpr int SPMM_THREADS = 512;
+constexpr int SPMM_RPT = kSpmmMaxDim / SPMM_THREADS;  // rows per thread (2)
+__global__ void __launch_bounds__(SPMM_THREADS) spmm_fused_kernel(const SpmmOut* __restrict__ outs, const SpmmPair* __restrict__ pairs) {
   extern __shared__ double spmm_smem[];
   const SpmmOut o = outs[blockIdx.y];
   const int c0 = blockIdx.x * SPMM_CW;
   if (c0 >= o.n) return;
   const int cw = min(SPMM_CW, o.n - c0);
-  const int ldc = o.m + 4, ldb_max = kSpmmMaxDim + 2;
-  double* sC = spmm_smem;                       // [SPMM_CW][ldc]
-  double* sB = spmm_smem + SPMM_CW * (kSpmmMaxDim + 4);  // [SPMM_CW][kdim + 2]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int idx = tid; idx < SPMM_CW * o.m; idx += 256) {
-    const int c = idx / o.m, r = idx % o.m;
-    sC[c * ldc + r] = (o.accumulate && c < cw) ? o.C[r + static_cast<size_t>(o.m) * (c0 + c)] : 0.0;
+  double* sB = spmm_smem;  // [SPMM_CW][kdim + 2]
+  const int tid = threadIdx.x;
+  double acc[SPMM_RPT][SPMM_CW];
+#pragma unroll
+  for (int u = 0; u < SPMM_RPT; ++u) {
+    const int r = tid + u * SPMM_THREADS;
+#pragma unroll
+    for (int c = 0; c < SPMM_CW; ++c)
+      acc[u][c] = (o.accumulate && r < o.m && c < cw) ? o.C[r + static_cast<size_t>(o.m) * (c0 + c)] : 0.0;
   }
-  const int c = lane & 7, q = lane >> 3;
   for (int p = 0; p < o.pair_count; ++p) {
     const SpmmPair pr = pairs[o.pair_begin + p];
     const int ldb = pr.kdim + 2;
-    __syncthreads();  // previous pair's readers of sB are done (and sC init is visible)
+    __syncthreads();  // previous pair's readers of sB are done
     if (!pr.bT) {
-      for (int idx = tid; idx < SPMM_CW * pr.kdim; idx += 256) {
-        const int cc = idx / pr.kdim, k = idx % pr.kdim;
-        sB[cc * ldb + k] = cc < cw ? pr.B[k + static_cast<size_t>(pr.kdim) * (c0 + cc)] : 0.0;
+      for (int cc = 0; cc < SPMM_CW; ++cc) {
+        const double* src = pr.B + static_cast<size_t>(pr.kdim) * (c0 + cc);
+        for (int k = tid; k < pr.kdim; k += SPMM_THREADS) sB[cc * ldb + k] = cc < cw ? src[k] : 0.0;
       }
     } else {
-      for (int idx = tid; idx < SPMM_CW * pr.kdim; idx += 256) {
+      for (int idx = tid; idx < SPMM_CW * pr.kdim; idx += SPMM_THREADS) {
         const int k = idx / SPMM_CW, cc = idx % SPMM_CW;
         sB[cc * ldb + k] = cc < cw ? pr.B[c0 + cc + static_cast<size_t>(o.n) * k] : 0.0;
       }
     }
     __syncthreads();
-    // quarter-warp per row: 8 warps x 4 rows per pass
-    for (int r = warp * 4 + q; r < o.m; r += 32) {
-      const int beg = pr.ptrs[r], end = pr.ptrs[r + 1];
-      double acc = 0.0;
-      for (int i = beg; i < end; ++i) acc += pr.vals[i] * sB[c * ldb + pr.idx[i]];  // ascending i: the reference's order
-      sC[c * ldc + r] += acc;  // (r, c) is owned by exactly this lane
+    int beg[SPMM_RPT], len[SPMM_RPT], maxlen = 0;
+#pragma unroll
+    for (int u = 0; u < SPMM_RPT; ++u) {
+      const int r = tid + u * SPMM_THREADS;
+      beg[u] = r < o.m ? pr.ptrs[r] : 0;
+      len[u] = r < o.m ? pr.ptrs[r + 1] - beg[u] : 0;
+      maxlen = max(maxlen, len[u]);
+    }
+    for (int i = 0; i < maxlen; ++i) {  // ascending nonzero order within a row = the reference's summation order
+#pragma unroll
+      for (int u = 0; u < SPMM_RPT; ++u) {
+        if (i < len[u]) {
+          const double v = pr.vals[beg[u] + i];
+          const double* b = sB + pr.idx[beg[u] + i];
+#pragma unroll
+          for (int c = 0; c < SPMM_CW; ++c) acc[u][c] += v * b[c * ldb];
+        }
+      }
     }
   }
-  __syncthreads();
-  for (int idx = tid; idx < cw * o.m; idx += 256) {
-    const int cc = idx / o.m, r = idx % o.m;
-    o.C[r + static_cast<size_t>(o.m) * (c0 + cc)] = sC[cc * ldc + r];
+#pragma unroll
+  for (int u = 0; u < SPMM_RPT; ++u) {
+    const int r = tid + u * SPMM_THREADS;
+    if (r < o.m) {
+#pragma unroll
+      for (int c = 0; c < SPMM_CW; ++c)
+        if (c < cw) o.C[r + static_cast<size_t>(o.m) * (c0 + c)] = acc[u][c];
+    }
   }
-  (void)ldb_max;
 }
 
 // CSC x dense: scatter-AXPY (BLAS.scala:414-456).  Warp per (CSC column, output column); C must be
@@ -470,7 +490,7 @@ cudaError_t launch_csc_fill(const CscDesc* d_descs, int nblocks, int max_cols, c
 
 cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* d_pairs, int max_n, cudaStream_t stream) {
   if (nouts <= 0 || max_n <= 0) return cudaSuccess;
-  const size_t smem = static_cast<size_t>(SPMM_CW) * ((kSpmmMaxDim + 4) + (kSpmmMaxDim + 2)) * sizeof(double);
+  const size_t smem = static_cast<size_t>(SPMM_CW) * (kSpmmMaxDim + 2) * sizeof(double);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(spmm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -479,7 +499,7 @@ cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* 
   }
   for (int off = 0; off < nouts; off += 65535) {
     const int nb = nouts - off < 65535 ? nouts - off : 65535;
-    spmm_fused_kernel<<<dim3((max_n + SPMM_CW - 1) / SPMM_CW, nb), 256, smem, stream>>>(d_outs + off, d_pairs);
+    spmm_fused_kernel<<<dim3((max_n + SPMM_CW - 1) / SPMM_CW, nb), SPMM_THREADS, smem, stream>>>(d_outs + off, d_pairs);
   }
   return cudaGetLastError();
 }

@@ -176,6 +176,25 @@ def test_multiply_with_sparse_blocks(session):
         to_dataset(session, S).matrixMultiply(n, n, to_dataset(session, S), n, n, blk)
 
 
+def test_config5_shape_csr_times_dense(session):
+    """BASELINE configs[4] at reduced N: 1%-sparse CSR blocks x dense, 1024-blocks (fused shared-memory SpMM kernel),
+    against BLAS.gemmsdd restated in the oracle."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(55)
+    n, blk = 2048, 1024
+    A, B = {}, O.rand_dense_dataset(n, n, blk, 43, transposed_mask=lambda i, j: (i + j) % 2 == 1)
+    for i in range(2):
+        for k in range(2):
+            m = sp.random(blk, blk, density=0.01, format="csr", random_state=rng, dtype=np.float64)
+            m.sort_indices()
+            A[(i, k)] = O.SparseMatrix(blk, blk, m.indptr, m.indices, m.data, True)
+    want = O.matrix_multiply(A, n, n, B, n, n, blk)
+    session.reset_stats()
+    got = from_dataset(to_dataset(session, A).matrixMultiply(n, n, to_dataset(session, B), n, n, blk))
+    assert session.stats()["kernel_launches"] == 1          # the whole block multiply is ONE fused SpMM launch
+    assert_same_dataset(got, want, tol=1e-14)
+
+
 def test_multiply_outer_product_paths(session):
     """Inner dimension of one block: multiplyOuterProductDuplicate{Left,Right} (rank-k update);
     defect B1 (Left variant throws in the reference) is intentionally not reproduced."""
