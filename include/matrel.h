@@ -138,6 +138,16 @@ MR_API mr_status mr_power(mr_matrix* a, double alpha, mr_matrix** out);
 /* Dataset.matrixRankOneUpdate :144-152 -> RankOneUpdateExecution :728-747 */
 MR_API mr_status mr_rank_one_update(mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right,
                                     int64_t rightRowNum, int64_t rightColNum, int32_t blkSize, mr_matrix** out);
+/* ---- aggregates.  The mathematically intended reductions; the reference's index defects
+ *      for non-square transposed / sparse blocks (MatfastExecution.scala:262-287, 338-357 = defect B5) are not reproduced. */
+/* Dataset.rowSum :63-66 -> RowSumDirectExecution :239-300: blocks (rid, 0) of shape rows x 1 */
+MR_API mr_status mr_row_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out);
+/* Dataset.colSum :68-71 -> ColumnSumDirectExecution :303-366: blocks (0, cid) of shape 1 x cols */
+MR_API mr_status mr_col_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out);
+/* Dataset.sum :73-76 -> SumDirectExecution :369-398: one 1 x 1 block (0, 0) */
+MR_API mr_status mr_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out);
+/* Dataset.trace :78-82 -> TraceDirectExecution :401-463: one 1 x 1 block (0, 0) from the diagonal blocks */
+MR_API mr_status mr_trace(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out);
 /* Materialise every dense block as column-major, isTransposed = false (DenseMatrix.toArray,
  * M/matrix/MLMatrix.scala:55-61, as a device transpose kernel). */
 MR_API mr_status mr_materialize(mr_matrix* a, mr_matrix** out);

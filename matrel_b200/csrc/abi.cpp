@@ -1287,6 +1287,94 @@ mr_status mr_rank_one_update(mr_matrix* left, int64_t lr, int64_t lc, mr_matrix*
   });
 }
 
+static mr_status aggregate_operator(int op, mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(a && out, MR_EINVAL, "null argument");
+    if (op == AGG_TRACE)  // Dataset.scala:80
+      MR_REQUIRE(nrows == ncols, MR_EDIM, "Cannot perform trace() on a rectangle matrix");
+    mr_context* ctx = a->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::unique_ptr<mr_matrix> r(new_matrix(ctx));
+    // output blocks: one per block-row (rowSum), block-column (colSum), or a single scalar
+    std::map<std::pair<int32_t, int32_t>, int32_t> out_len;
+    for (auto& kv : a->blocks) {
+      const Block& b = kv.second;
+      if (op == AGG_TRACE && kv.first.first != kv.first.second) continue;
+      if (op == AGG_TRACE && b.dense())  // MatfastExecution.scala:428
+        MR_REQUIRE(b.numRows == b.numCols, MR_EDIM, "block is not square, row_num=%d, col_num=%d", b.numRows, b.numCols);
+      std::pair<int32_t, int32_t> key = op == AGG_ROW_SUM ? std::make_pair(kv.first.first, 0)
+                                        : op == AGG_COL_SUM ? std::make_pair(0, kv.first.second)
+                                                            : std::make_pair(0, 0);
+      const int32_t len = op == AGG_ROW_SUM ? b.numRows : op == AGG_COL_SUM ? b.numCols : 1;
+      auto it = out_len.find(key);
+      if (it == out_len.end()) out_len[key] = len;
+      else if (op == AGG_ROW_SUM)  // LocalMatrix.add requires of the reduceByKey (LocalMatrix.scala:36-41)
+        MR_REQUIRE(it->second == len, MR_EDIM,
+                   "Matrix A and B must have the same number of rows. But found A.numRows = %d, B.numRows = %d", it->second, len);
+      else if (op == AGG_COL_SUM)
+        MR_REQUIRE(it->second == len, MR_EDIM,
+                   "Matrix A and B must have the same number of cols. But found A.numCols = %d, B.numCols = %d", it->second, len);
+    }
+    if (out_len.empty()) {
+      *out = r.release();
+      return;
+    }
+    size_t total = 0;
+    for (auto& kv : out_len) total += align_up(static_cast<size_t>(kv.second) * sizeof(double));
+    Slab slab(ctx, total);
+    CUDA_CHECK(cudaMemsetAsync(slab.buf->p, 0, std::max<size_t>(total, kAlign), ctx->stream));
+    std::map<std::pair<int32_t, int32_t>, double*> out_ptr;
+    for (auto& kv : out_len) {
+      Span s = slab.take(static_cast<size_t>(kv.second) * sizeof(double));
+      out_ptr[kv.first] = s.ptr<double>();
+      r->blocks[kv.first] = op == AGG_ROW_SUM ? dense_block(kv.second, 1, s) : op == AGG_COL_SUM ? dense_block(1, kv.second, s)
+                                                                                                  : dense_block(1, 1, s);
+    }
+    std::vector<AggDesc> descs;
+    std::vector<Block> keep;
+    keep.reserve(a->blocks.size() + 1);
+    int max_r = 1, max_c = 1;
+    for (auto& kv : a->blocks) {
+      const Block& b = kv.second;
+      if (op == AGG_TRACE && kv.first.first != kv.first.second) continue;
+      AggDesc d{};
+      if (op == AGG_SUM) {  // values.sum over the STORED values, dense or sparse (:381-384)
+        d.v = b.values.ptr<double>();
+        d.rows = static_cast<int32_t>(std::min<int64_t>(b.valuesLen, INT32_MAX));
+        d.cols = 1;
+        d.isT = 0;
+        if (b.valuesLen == 0) continue;
+      } else {
+        const Block* src = &b;
+        if (!b.dense()) {
+          keep.push_back(densify(ctx, b));
+          src = &keep.back();
+        }
+        d.v = src->values.ptr<double>();
+        d.rows = src->numRows;
+        d.cols = src->numCols;
+        d.isT = src->isT;
+      }
+      d.out = out_ptr[op == AGG_ROW_SUM ? std::make_pair(kv.first.first, 0)
+                      : op == AGG_COL_SUM ? std::make_pair(0, kv.first.second)
+                                          : std::make_pair(0, 0)];
+      max_r = std::max(max_r, d.rows);
+      max_c = std::max(max_c, d.cols);
+      descs.push_back(d);
+    }
+    if (!descs.empty()) {
+      Buf dd = upload(ctx, descs);
+      CUDA_CHECK(launch_aggregate(op, static_cast<const AggDesc*>(dd->p), static_cast<int>(descs.size()), max_r, max_c, ctx->stream));
+      note_launch(ctx);
+    }
+    *out = r.release();
+  });
+}
+mr_status mr_row_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out) { return aggregate_operator(AGG_ROW_SUM, a, nrows, ncols, out); }
+mr_status mr_col_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out) { return aggregate_operator(AGG_COL_SUM, a, nrows, ncols, out); }
+mr_status mr_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out) { return aggregate_operator(AGG_SUM, a, nrows, ncols, out); }
+mr_status mr_trace(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out) { return aggregate_operator(AGG_TRACE, a, nrows, ncols, out); }
+
 mr_status mr_materialize(mr_matrix* a, mr_matrix** out) {
   return guarded([&] {
     MR_REQUIRE(a && out, MR_EINVAL, "null argument");

@@ -375,6 +375,61 @@ __global__ void __launch_bounds__(256) csc_fill_kernel(const CscDesc* __restrict
   }
 }
 
+// Row / column sums: a CTA reduces a 32 (contiguous dimension) x 256 (strided dimension) tile; tx runs along the
+// block's contiguous dimension so global reads are coalesced for both layouts.
+constexpr int AGG_SLOW = 256;
+__global__ void __launch_bounds__(256) axis_sum_kernel(const AggDesc* __restrict__ descs, int by_row, int tiles_slow_max) {
+  __shared__ double sm[8][33];
+  const AggDesc d = descs[blockIdx.y];
+  const int nfast = d.isT ? d.cols : d.rows, nslow = d.isT ? d.rows : d.cols;
+  const int tf = blockIdx.x / tiles_slow_max, ts = blockIdx.x % tiles_slow_max;
+  const int f0 = tf * 32, s0 = ts * AGG_SLOW;
+  if (f0 >= nfast || s0 >= nslow) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool kept_is_fast = (by_row != 0) == (d.isT == 0);  // row sums of a column-major block keep the fast index
+  const int f = f0 + tx;
+  if (kept_is_fast) {
+    double acc = 0.0;
+    if (f < nfast)
+      for (int s = s0 + ty; s < min(nslow, s0 + AGG_SLOW); s += 8) acc += d.v[f + static_cast<size_t>(nfast) * s];
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && f < nfast) {
+#pragma unroll
+      for (int k = 1; k < 8; ++k) acc += sm[k][tx];
+      atomicAdd(&d.out[f], acc);
+    }
+  } else {
+    for (int s = s0 + ty; s < min(nslow, s0 + AGG_SLOW); s += 8) {
+      double v = f < nfast ? d.v[f + static_cast<size_t>(nfast) * s] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (tx == 0) atomicAdd(&d.out[s], v);
+    }
+  }
+}
+
+// AGG_SUM: sum of every stored value; AGG_TRACE: sum of the diagonal (square blocks; same index for both layouts)
+__global__ void __launch_bounds__(256) scalar_sum_kernel(const AggDesc* __restrict__ descs, int trace) {
+  __shared__ double sm[8];
+  const AggDesc d = descs[blockIdx.y];
+  const int64_t n = trace ? min(d.rows, d.cols) : static_cast<int64_t>(d.rows) * d.cols;
+  const int64_t stride = trace ? static_cast<int64_t>(d.isT ? d.cols : d.rows) + 1 : 1;
+  double acc = 0.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256)
+    acc += d.v[i * stride];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k];
+    atomicAdd(d.out, t);
+  }
+}
+
 inline int flat_grid_x(int64_t max_n) {
   int64_t vec = (max_n + 1) / 2;
   int64_t gx = (vec + static_cast<int64_t>(FLAT_THREADS) * FLAT_UNROLL - 1) / (static_cast<int64_t>(FLAT_THREADS) * FLAT_UNROLL);
@@ -500,6 +555,25 @@ cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* 
   for (int off = 0; off < nouts; off += 65535) {
     const int nb = nouts - off < 65535 ? nouts - off : 65535;
     spmm_fused_kernel<<<dim3((max_n + SPMM_CW - 1) / SPMM_CW, nb), SPMM_THREADS, smem, stream>>>(d_outs + off, d_pairs);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_aggregate(int op, const AggDesc* d_descs, int nblocks, int max_rows, int max_cols, cudaStream_t stream) {
+  if (nblocks <= 0) return cudaSuccess;
+  for (int off = 0; off < nblocks; off += 65535) {
+    const int nb = nblocks - off < 65535 ? nblocks - off : 65535;
+    if (op == AGG_ROW_SUM || op == AGG_COL_SUM) {
+      const int mx = max_rows > max_cols ? max_rows : max_cols;
+      const int tiles_fast = (mx + 31) / 32, tiles_slow = (mx + AGG_SLOW - 1) / AGG_SLOW;
+      axis_sum_kernel<<<dim3(tiles_fast * tiles_slow, nb), 256, 0, stream>>>(d_descs + off, op == AGG_ROW_SUM ? 1 : 0, tiles_slow);
+    } else {
+      const int64_t n = op == AGG_TRACE ? max_rows : static_cast<int64_t>(max_rows) * max_cols;
+      int64_t gx = (n + 256 * 16 - 1) / (256 * 16);
+      if (gx < 1) gx = 1;
+      if (gx > 1024) gx = 1024;
+      scalar_sum_kernel<<<dim3(static_cast<unsigned>(gx), nb), 256, 0, stream>>>(d_descs + off, op == AGG_TRACE ? 1 : 0);
+    }
   }
   return cudaGetLastError();
 }

@@ -128,6 +128,19 @@ struct SpmmOut {
 constexpr int kSpmmMaxDim = 1024;   // m and kdim limit of the shared-memory kernel
 cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* d_pairs, int max_n, cudaStream_t stream);
 
+// Aggregates (RowSum / ColumnSum / Sum / TraceDirectExecution, MatfastExecution.scala:239-463), batched over blocks;
+// the cross-block reduceByKey(LocalMatrix.add) is fused in: every block adds straight into its output vector / scalar
+// (fp64 atomics; the reference's reduce order is arbitrary as well).  Outputs must be zeroed before the launch.
+struct AggDesc {
+  const double* v;        // dense values (sparse blocks are densified by the caller)
+  int32_t rows, cols;     // logical dims
+  uint8_t isT;
+  uint8_t pad[7];
+  double* out;            // row sums [rows] / column sums [cols] / scalar
+};
+enum AggOp { AGG_ROW_SUM = 0, AGG_COL_SUM = 1, AGG_SUM = 2, AGG_TRACE = 3 };
+cudaError_t launch_aggregate(int op, const AggDesc* d_descs, int nblocks, int max_rows, int max_cols, cudaStream_t stream);
+
 // java.util.Random-compatible U(0,1) fill: out[i] = i-th nextDouble() of new Random(seed), batched over blocks
 struct RandDesc {
   double* out;

@@ -250,6 +250,22 @@ class Dataset:
         """M/Dataset.scala:99-103."""
         return self._unary(N.lib.mr_power, float(alpha))
 
+    def rowSum(self, nrows, ncols) -> "Dataset":
+        """M/Dataset.scala:63-66."""
+        return self._unary(N.lib.mr_row_sum, int(nrows), int(ncols))
+
+    def colSum(self, nrows, ncols) -> "Dataset":
+        """M/Dataset.scala:68-71."""
+        return self._unary(N.lib.mr_col_sum, int(nrows), int(ncols))
+
+    def sum(self, nrows, ncols) -> "Dataset":
+        """M/Dataset.scala:73-76."""
+        return self._unary(N.lib.mr_sum, int(nrows), int(ncols))
+
+    def trace(self, nrows, ncols) -> "Dataset":
+        """M/Dataset.scala:78-82."""
+        return self._unary(N.lib.mr_trace, int(nrows), int(ncols))
+
     def materialize(self) -> "Dataset":
         """Every dense block rewritten column-major (``toArray``, M/matrix/MLMatrix.scala:55-61)."""
         return self._unary(N.lib.mr_materialize)

@@ -661,6 +661,97 @@ def rank_one_update(left: BlockDict, lr, lc, right: BlockDict, rr, rc, blkSize,
 
 
 # ----------------------------------------------------------------------------------------------
+# Aggregates: RowSum / ColumnSum / Sum / TraceDirectExecution
+# (M/execution/MatfastExecution.scala:239-463).  literal=True restates the reference's index arithmetic
+# as written (it is only correct for square dense blocks: non-square transposed blocks are mis-strided,
+# CSR blocks are summed along the wrong axis, sparse ColumnSum has defect B5); literal=False is the
+# mathematically intended reduction, which is what the B200 engine computes.
+# ----------------------------------------------------------------------------------------------
+
+
+def _row_sum_block(m: MLMatrix, literal: bool) -> DenseMatrix:
+    if not literal:
+        return DenseMatrix(m.numRows, 1, m.to_numpy().sum(axis=1))
+    if isinstance(m, DenseMatrix):
+        if not m.isTransposed:                                   # :254-261
+            arr = np.zeros(m.numRows)
+            np.add.at(arr, np.arange(m.values.size) % m.numRows, m.values)
+            return DenseMatrix(m.numRows, 1, arr)
+        n = m.numCols                                            # :262-271 ("column sum" branch)
+        arr = np.zeros(n)
+        for i in range(n):
+            for j in range(m.numRows):
+                arr[i] += m.values[i * m.numRows + j]
+        return DenseMatrix(n, 1, arr)
+    if not m.isTransposed:                                       # CSC :274-279
+        arr = np.zeros(m.numRows)
+        np.add.at(arr, m.rowIndices, m.values)
+        return DenseMatrix(m.numRows, 1, arr)
+    arr = np.zeros(m.numCols)                                    # CSR :280-287 (sums by column index)
+    np.add.at(arr, m.rowIndices, m.values)
+    return DenseMatrix(m.numCols, 1, arr)
+
+
+def _col_sum_block(m: MLMatrix, literal: bool) -> DenseMatrix:
+    if not literal:
+        return DenseMatrix(1, m.numCols, m.to_numpy().sum(axis=0))
+    if isinstance(m, DenseMatrix):
+        if not m.isTransposed:                                   # :318-327
+            n = m.numCols
+            arr = np.array([m.values[i * m.numRows:(i + 1) * m.numRows].sum() for i in range(n)])
+            return DenseMatrix(1, n, arr)
+        mm = m.numRows                                           # :328-336
+        arr = np.zeros(mm)
+        np.add.at(arr, np.arange(m.values.size) % mm, m.values)
+        return DenseMatrix(1, mm, arr)
+    nlines = m.colPtrs.size - 1                                  # :338-357, defect B5: values(i + j)
+    arr = np.zeros(nlines)
+    for i in range(nlines):
+        for j in range(int(m.colPtrs[i + 1] - m.colPtrs[i])):
+            arr[i] += m.values[i + j]
+    return DenseMatrix(1, nlines, arr)
+
+
+def row_sum(ds: BlockDict, nrows: int, ncols: int, literal: bool = False) -> BlockDict:
+    """Dataset.rowSum (M/Dataset.scala:63-66) -> RowSumDirectExecution: per-block sums, reduceByKey(add) on rid."""
+    out: BlockDict = {}
+    for (rid, _), m in sorted(ds.items()):
+        v = _row_sum_block(m, literal)
+        out[(rid, 0)] = v if (rid, 0) not in out else add(out[(rid, 0)], v)
+    return out
+
+
+def col_sum(ds: BlockDict, nrows: int, ncols: int, literal: bool = False) -> BlockDict:
+    """Dataset.colSum (M/Dataset.scala:68-71) -> ColumnSumDirectExecution: reduceByKey(add) on cid."""
+    out: BlockDict = {}
+    for (_, cid), m in sorted(ds.items()):
+        v = _col_sum_block(m, literal)
+        out[(0, cid)] = v if (0, cid) not in out else add(out[(0, cid)], v)
+    return out
+
+
+def total_sum(ds: BlockDict, nrows: int, ncols: int) -> BlockDict:
+    """Dataset.sum (M/Dataset.scala:73-76) -> SumDirectExecution (:377-391): values.sum per block (stored values)."""
+    if not ds:
+        return {}
+    return {(0, 0): DenseMatrix(1, 1, [float(sum(float(m.values.sum()) for _, m in sorted(ds.items())))])}
+
+
+def trace(ds: BlockDict, nrows: int, ncols: int) -> BlockDict:
+    """Dataset.trace (M/Dataset.scala:78-82) -> TraceDirectExecution (:412-452): diagonal blocks only."""
+    require(nrows == ncols, "Cannot perform trace() on a rectangle matrix")
+    tr, seen = 0.0, False
+    for (rid, cid), m in sorted(ds.items()):
+        if rid != cid:
+            continue
+        seen = True
+        if isinstance(m, DenseMatrix):
+            require(m.numRows == m.numCols, f"block is not square, row_num={m.numRows}, col_num={m.numCols}")
+        tr += float(np.trace(m.to_numpy()))
+    return {(0, 0): DenseMatrix(1, 1, [tr])} if seen else {}
+
+
+# ----------------------------------------------------------------------------------------------
 # helpers for tests / bench
 # ----------------------------------------------------------------------------------------------
 

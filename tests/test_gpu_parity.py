@@ -401,3 +401,55 @@ def test_full_size_16384_properties(session):
     Be = [sum(B.get_block(k, j).to_numpy().sum(axis=1) for j in range(nb)) for k in range(nb)]
     want = sum(hostA[(0, k)].to_numpy() @ Be[k] for k in range(nb))
     assert rel_err(rowsum_C, want) <= 1e-12
+
+
+# ---------------------------------------------------------------------------------- aggregates (section 8f-2)
+def test_aggregates_golden_and_oracle(session):
+    g = load("basic_matrix_ops")
+    e = g["expected"]
+    blocks = {k: mk(v) for k, v in g["blocks"].items()}
+    A = {(r, c): blocks[n] for r, c, n in g["mat1"]}
+    B = {(r, c): blocks[n] for r, c, n in g["mat2"]}
+    mat1, mat2 = to_dataset(session, A), to_dataset(session, B)
+    rs = from_dataset(mat1.t().rowSum(4, 4))                       # BasicMatrixOps.scala:159
+    assert sorted(rs) == [(0, 0), (1, 0)]
+    assert [x for k in sorted(rs) for x in rs[k].values.tolist()] == e["rowSum_mat1_t"]
+    assert all((m.numRows, m.numCols) == (2, 1) for m in rs.values())
+    cs = from_dataset(mat2.colSum(4, 4))                           # :166
+    assert sorted(cs) == [(0, 0), (0, 1)]
+    assert [x for k in sorted(cs) for x in cs[k].values.tolist()] == e["colSum_mat2"]
+    tr = from_dataset(mat1.matrixMultiply(4, 4, mat2, 4, 4, 2).trace(4, 4))   # :174
+    assert tr[(0, 0)].values.tolist() == [e["trace"]]
+    with pytest.raises(mb.IllegalArgumentException, match="Cannot perform trace\\(\\) on a rectangle matrix"):
+        mat1.trace(4, 5)
+    # random dense / transposed / sparse blocks vs the oracle's intended reductions
+    rng = np.random.default_rng(8)
+    n, m, blk = 300, 260, 64
+    D = random_block_dataset(rng, n, m, blk, density=0.8, p_transposed=0.5, p_sparse=0.3, sparse_density=0.2)
+    dD = to_dataset(session, D)
+    assert_same_dataset(from_dataset(dD.rowSum(n, m)), O.row_sum(D, n, m), tol=1e-14)
+    assert_same_dataset(from_dataset(dD.colSum(n, m)), O.col_sum(D, n, m), tol=1e-14)
+    assert_same_dataset(from_dataset(dD.sum(n, m)), O.total_sum(D, n, m), tol=1e-13)
+    S = random_block_dataset(rng, 256, 256, 64, density=0.7, p_transposed=0.5, p_sparse=0.3, sparse_density=0.2)
+    assert_same_dataset(from_dataset(to_dataset(session, S).trace(256, 256)), O.trace(S, 256, 256), tol=1e-14)
+    # where the reference's literal index arithmetic is sound (square dense blocks) it agrees with the intended sums
+    Q = random_block_dataset(rng, 192, 192, 64, p_transposed=0.5)
+    for key, v in O.row_sum(Q, 192, 192, literal=True).items():
+        assert np.allclose(v.values, O.row_sum(Q, 192, 192)[key].values, rtol=1e-13)
+    for key, v in O.col_sum(Q, 192, 192, literal=True).items():
+        assert np.allclose(v.values, O.col_sum(Q, 192, 192)[key].values, rtol=1e-13)
+
+
+def test_planner_identities_on_device(session):
+    """The rewrites of M/execution/MatfastPlanner.scala hold on the device results:
+    trace(A B) = sum(A^T o B) (:238-241) and sum(A B) = colSum(A) . rowSum(B) (:220-225)."""
+    n, blk = 512, 128
+    A, B = session.rand(n, n, blk, 42), session.rand(n, n, blk, 43)
+    AB = A.matrixMultiply(n, n, B, n, n, blk)
+    tr = AB.trace(n, n).get_block(0, 0).values[0]
+    alt = A.t().multiplyElement(n, n, B, n, n, blk).sum(n, n).get_block(0, 0).values[0]
+    assert abs(tr - alt) / abs(tr) < 1e-13
+    total = AB.sum(n, n).get_block(0, 0).values[0]
+    cs, rs = A.colSum(n, n), B.rowSum(n, n)
+    dot = cs.matrixMultiply(1, n, rs, n, 1, blk).get_block(0, 0).values[0]
+    assert abs(total - dot) / abs(total) < 1e-13
