@@ -453,3 +453,36 @@ def test_planner_identities_on_device(session):
     cs, rs = A.colSum(n, n), B.rowSum(n, n)
     dot = cs.matrixMultiply(1, n, rs, n, 1, blk).get_block(0, 0).values[0]
     assert abs(total - dot) / abs(total) < 1e-13
+
+
+def test_lazy_plan_rewrites_match_direct_execution(session):
+    """the planner's aggregate push-downs (MatfastPlanner.scala:168-244) give the same answers as the
+    un-rewritten plan, and trace(A B) / sum(A B) / rowSum(A B) no longer launch the O(N^3) block GEMM."""
+    from matrel_b200.plan import LazyDataset, Planner
+    n, blk = 512, 128
+    A, B = LazyDataset.of(session.rand(n, n, blk, 42)), LazyDataset.of(session.rand(n, n, blk, 43))
+    queries = {
+        "trace(AB)": A.matrixMultiply(n, n, B, n, n, blk).trace(n, n),
+        "sum(AB)": A.matrixMultiply(n, n, B, n, n, blk).sum(n, n),
+        "rowSum(AB)": A.matrixMultiply(n, n, B, n, n, blk).rowSum(n, n),
+        "colSum(AB)": A.matrixMultiply(n, n, B, n, n, blk).colSum(n, n),
+        "sum(2A+3)": A.multiplyScalar(2.0).addScalar(3.0).sum(n, n),
+        "rowSum(A^T)": A.t().rowSum(n, n),
+        "trace(A+B)": A.addElement(n, n, B, n, n, blk).trace(n, n),
+        "colSum(A+1.5)": A.addScalar(1.5).colSum(n, n),
+    }
+    for name, q in queries.items():
+        p1, p0 = Planner(True), Planner(False)
+        session.reset_stats()
+        got = from_dataset(q.execute(planner=p1))
+        full_gemm_tiles = session.stats()["last_gemm_flops"] if session.stats()["gemm_launches"] else 0
+        want = from_dataset(q.execute(planner=p0))
+        assert sorted(got) == sorted(want), name
+        for key in want:
+            assert (got[key].numRows, got[key].numCols) == (want[key].numRows, want[key].numCols), (name, key)
+            assert rel_err(got[key].to_numpy(), want[key].to_numpy()) <= 1e-12, name
+        if name in ("trace(AB)",):
+            assert "MatrixMatrixMultiplicationExecution" not in p1.trace and "SumDirectExecution" in p1.trace
+        if name in ("sum(AB)", "rowSum(AB)", "colSum(AB)"):
+            assert full_gemm_tiles < 2.0 * n ** 3 / 16          # a matrix-vector sized product, not N^3
+        assert "MatrixMatrixMultiplicationExecution" in p0.trace or "AB" not in name
