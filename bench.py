@@ -341,8 +341,10 @@ def run_ours(args):
         d2h = sum(v.nbytes for v in outbuf.values())
 
         def e2e_step():
-            dA = s.createDataset(pA)
+            # right operand first: the multiply then starts on the row panels of A as they land (per-block events),
+            # and finished block rows of C stream back while later rows are still computing
             dB = s.createDataset(pB)
+            dA = s.createDataset(pA)
             dC = dA.matrixMultiply(n, n, dB, n, n, blk)
             for (i, j) in dC.block_ids():
                 dC.get_block(i, j, out=outbuf[(i, j)])

@@ -106,15 +106,31 @@ struct mr_context {
   int ozaki_slices = 0;
   int time_kernels = 0;
   int force_variant = -1;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr, ev_order = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // ingest / egress overlap with compute on `stream`
+  int pipeline = 1;
   mr_stats stats{};
   std::mutex mu;
 };
 
 namespace {
 
+// Completion event of an asynchronous producer of a block (an H2D copy on the ingest stream, or one chunk of a
+// chunked multiply); consumers on other streams wait on it instead of on whole streams.
+struct Ready {
+  cudaEvent_t ev = nullptr;
+  Ready() { cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); }
+  ~Ready() {
+    if (ev) cudaEventDestroy(ev);
+  }
+  Ready(const Ready&) = delete;
+  Ready& operator=(const Ready&) = delete;
+};
+using ReadyPtr = std::shared_ptr<Ready>;
+
 struct DevBuf {
   mr_context* ctx;
+  ReadyPtr ready;  // set when another stream writes this buffer: the free must be ordered after it
   void* p = nullptr;
   size_t bytes = 0;
   bool owned = true;
@@ -129,7 +145,10 @@ struct DevBuf {
   }
   DevBuf(mr_context* c, void* borrowed, size_t n) : ctx(c), p(borrowed), bytes(n), owned(false) {}
   ~DevBuf() {
-    if (owned && p) cudaFreeAsync(p, ctx->stream);
+    if (owned && p) {
+      if (ready) cudaStreamWaitEvent(ctx->stream, ready->ev, 0);
+      cudaFreeAsync(p, ctx->stream);
+    }
   }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -153,6 +172,7 @@ struct Block {
   int64_t valuesLen = 0;
   Span colPtrs, rowIndices;  // sparse only
   int64_t colPtrsLen = 0;
+  ReadyPtr ready;            // producer still in flight on another stream (nullptr = ordered on the context stream)
   bool dense() const { return type == 1; }
 };
 
@@ -167,8 +187,27 @@ struct mr_matrix {
 };
 
 namespace {
+bool wait_ready(mr_context* ctx, const Block& b);
+}
+
+namespace {
 
 void note_launch(mr_context* ctx, int n = 1) { ctx->stats.kernel_launches += n; }
+
+// Order the context stream after the producer of a block.  Returns true when the producer was still running.
+bool wait_ready(mr_context* ctx, const Block& b) {
+  if (!b.ready) return false;
+  const cudaError_t q = cudaEventQuery(b.ready->ev);
+  if (q == cudaSuccess) return false;
+  (void)cudaGetLastError();
+  cudaStreamWaitEvent(ctx->stream, b.ready->ev, 0);
+  return true;
+}
+bool wait_ready_all(mr_context* ctx, const mr_matrix* m) {
+  bool any = false;
+  for (auto& kv : m->blocks) any = wait_ready(ctx, kv.second) || any;
+  return any;
+}
 
 template <typename T>
 Buf upload(mr_context* ctx, const std::vector<T>& v) {
@@ -395,8 +434,25 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     outs.push_back(go);
     out_plan.push_back(i);
   }
+  // which dense operands are still being produced on another stream (ingest copies)?
+  bool pending = false;
+  for (size_t i = 0; i < plans.size() && !pending; ++i)
+    for (const GemmSrc& g : plans[i].src)
+      if ((g.a->ready && cudaEventQuery(g.a->ready->ev) != cudaSuccess) || (g.b->ready && cudaEventQuery(g.b->ready->ev) != cudaSuccess)) {
+        pending = true;
+        break;
+      }
+  (void)cudaGetLastError();
+  auto wait_all_sources = [&] {
+    for (auto& o : plans)
+      for (const GemmSrc& g : o.src) {
+        wait_ready(ctx, *g.a);
+        wait_ready(ctx, *g.b);
+      }
+  };
   bool ozaki_done = false;
   if (!outs.empty() && ctx->gemm_algo == 2) {
+    wait_all_sources();
     ozaki_done = try_ozaki(ctx, plans, cptr, blkSize, M, K, N, outer);
     if (ozaki_done) ctx->stats.last_gemm_flops = flops;
   }
@@ -423,7 +479,21 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
           keyed.push_back({gn / kBand, gm, gn, GemmTile{static_cast<int32_t>(oi), a, b, 0}});
         }
     }
-    std::sort(keyed.begin(), keyed.end(), [](const Keyed& x, const Keyed& y) {
+    // Chunked launch when operands are still arriving from the host: one launch per block row of C, each waiting
+    // only for the A row panel it reads (and all of B), so compute overlaps the remaining ingest and the egress of
+    // finished rows.  With resident operands it is ONE launch.
+    std::map<int32_t, int> group_of;  // rid -> chunk
+    const bool chunked = pending && ctx->pipeline != 0;
+    if (chunked)
+      for (size_t oi = 0; oi < outs.size(); ++oi) group_of.emplace(plans[out_plan[oi]].rid, 0);
+    {
+      int gidx = 0;
+      for (auto& kv : group_of) kv.second = gidx++;
+    }
+    auto grp = [&](const Keyed& k) { return chunked ? group_of[plans[out_plan[k.t.out]].rid] : 0; };
+    std::sort(keyed.begin(), keyed.end(), [&](const Keyed& x, const Keyed& y) {
+      const int gx = grp(x), gy = grp(y);
+      if (gx != gy) return gx < gy;
       if (x.band != y.band) return x.band < y.band;
       if (x.gm != y.gm) return x.gm < y.gm;
       return x.gn < y.gn;
@@ -455,10 +525,37 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       }
     Buf d_outs = upload(ctx, outs), d_pairs = upload(ctx, pairs), d_tiles = upload(ctx, tiles), d_tmaps = upload(ctx, tmaps);
     if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-    CUDA_CHECK(launch_gemm_f64(static_cast<const GemmOut*>(d_outs->p), static_cast<const GemmPair*>(d_pairs->p),
-                               static_cast<const GemmTile*>(d_tiles->p), static_cast<int>(tiles.size()), d_tmaps->p,
-                               variant, ctx->stream));
-    note_launch(ctx);
+    const int ngroups = chunked ? static_cast<int>(group_of.size()) : 1;
+    size_t t0 = 0;
+    for (int gi = 0; gi < ngroups; ++gi) {
+      size_t t1 = t0;
+      while (t1 < keyed.size() && grp(keyed[t1]) == gi) ++t1;
+      // wait for exactly the operand blocks this chunk reads
+      std::vector<char> seen(outs.size(), 0);
+      for (size_t t = t0; t < t1; ++t) {
+        const int oi = keyed[t].t.out;
+        if (seen[oi]) continue;
+        seen[oi] = 1;
+        for (const GemmSrc& g : plans[out_plan[oi]].src) {
+          wait_ready(ctx, *g.a);
+          wait_ready(ctx, *g.b);
+        }
+      }
+      CUDA_CHECK(launch_gemm_f64(static_cast<const GemmOut*>(d_outs->p), static_cast<const GemmPair*>(d_pairs->p),
+                                 static_cast<const GemmTile*>(d_tiles->p) + t0, static_cast<int>(t1 - t0), d_tmaps->p, variant,
+                                 ctx->stream));
+      note_launch(ctx);
+      if (chunked) {  // consumers on the egress stream wait for this chunk only
+        ReadyPtr r = std::make_shared<Ready>();
+        CUDA_CHECK(cudaEventRecord(r->ev, ctx->stream));
+        for (size_t oi = 0; oi < outs.size(); ++oi)
+          if (seen[oi]) {
+            const OutPlan& o = plans[out_plan[oi]];
+            if (o.spmm.empty()) result->blocks[{o.rid, o.cid}].ready = r;  // blocks with sparse partials finish later
+          }
+      }
+      t0 = t1;
+    }
     ctx->stats.gemm_launches += 1;
     ctx->stats.last_gemm_flops = flops;
     if (ctx->time_kernels) {
@@ -490,6 +587,8 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     for (auto& sp : o.spmm) {
       const Block& s = *sp.first;
       const Block& b = *sp.second;
+      wait_ready(ctx, s);
+      wait_ready(ctx, b);
       if (s.isT && o.m <= kSpmmMaxDim && s.numCols <= kSpmmMaxDim) {
         SpmmPair pr{};
         pr.ptrs = s.colPtrs.ptr<int32_t>();
@@ -821,6 +920,10 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
     }
     CUDA_CHECK(cudaEventCreate(&ctx->ev0));
     CUDA_CHECK(cudaEventCreate(&ctx->ev1));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     // keep freed blocks in the pool: operators allocate result slabs on every call
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -833,7 +936,13 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
 mr_status mr_shutdown(mr_context* ctx) {
   return guarded([&] {
     if (!ctx) return;
+    cudaStreamSynchronize(ctx->h2d_stream);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
+    cudaStreamDestroy(ctx->h2d_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -867,6 +976,7 @@ mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
     else if (k == "ozaki_slices") ctx->ozaki_slices = static_cast<int>(value);
     else if (k == "time_kernels") ctx->time_kernels = static_cast<int>(value);
     else if (k == "gemm_variant") ctx->force_variant = static_cast<int>(value);
+    else if (k == "pipeline") ctx->pipeline = static_cast<int>(value);
     else fail(MR_EINVAL, "unknown option '%s'", key);
   });
 }
@@ -874,7 +984,9 @@ mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
 mr_status mr_sync(mr_context* ctx) {
   return guarded([&] {
     MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->h2d_stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->d2h_stream));
   });
 }
 
@@ -917,11 +1029,47 @@ mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_b
     b.numCols = d->numCols;
     b.isT = d->isTransposed != 0;
     b.valuesLen = d->valuesLen;
-    b.values = upload_raw(ctx, d->values, static_cast<size_t>(d->valuesLen) * sizeof(double));
+    // Ingest on its own stream: the copy of block k+1 overlaps whatever the context stream is computing, and
+    // operators wait per block (Block::ready), so a multiply can start on the row panels that have landed.
+    cudaStream_t cs = ctx->pipeline ? ctx->h2d_stream : ctx->stream;
+    auto put = [&](const void* host, size_t bytes) {
+      Span sp{std::make_shared<DevBuf>(ctx, std::max<size_t>(bytes, 16)), 0};
+      return std::make_pair(sp, bytes ? host : nullptr);
+    };
+    auto vals = put(d->values, static_cast<size_t>(d->valuesLen) * sizeof(double));
+    std::pair<Span, const void*> cp{}, ri{};
     if (d->type == 0) {
       b.colPtrsLen = d->colPtrsLen;
-      b.colPtrs = upload_raw(ctx, d->colPtrs, static_cast<size_t>(d->colPtrsLen) * sizeof(int32_t));
-      b.rowIndices = upload_raw(ctx, d->rowIndices, static_cast<size_t>(d->rowIndicesLen) * sizeof(int32_t));
+      cp = put(d->colPtrs, static_cast<size_t>(d->colPtrsLen) * sizeof(int32_t));
+      ri = put(d->rowIndices, static_cast<size_t>(d->rowIndicesLen) * sizeof(int32_t));
+    }
+    if (ctx->pipeline) {  // allocations are ordered on the context stream: the ingest stream must see them
+      CUDA_CHECK(cudaEventRecord(ctx->ev_alloc, ctx->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_alloc, 0));
+    }
+    auto copy = [&](std::pair<Span, const void*>& x, size_t bytes) {
+      if (x.second && bytes) {
+        CUDA_CHECK(cudaMemcpyAsync(x.first.buf->p, x.second, bytes, cudaMemcpyHostToDevice, cs));
+        ctx->stats.h2d_bytes += static_cast<int64_t>(bytes);
+      }
+    };
+    copy(vals, static_cast<size_t>(d->valuesLen) * sizeof(double));
+    b.values = vals.first;
+    if (d->type == 0) {
+      copy(cp, static_cast<size_t>(d->colPtrsLen) * sizeof(int32_t));
+      copy(ri, static_cast<size_t>(d->rowIndicesLen) * sizeof(int32_t));
+      b.colPtrs = cp.first;
+      b.rowIndices = ri.first;
+    }
+    if (ctx->pipeline) {
+      ReadyPtr r = std::make_shared<Ready>();
+      CUDA_CHECK(cudaEventRecord(r->ev, cs));
+      b.ready = r;
+      b.values.buf->ready = r;
+      if (d->type == 0) {
+        b.colPtrs.buf->ready = r;
+        b.rowIndices.buf->ready = r;
+      }
     }
     m->blocks[{rid, cid}] = std::move(b);
   });
@@ -985,28 +1133,39 @@ mr_status mr_matrix_get_block(mr_matrix* m, int32_t rid, int32_t cid, mr_block_d
     const Block& b = it->second;
     mr_context* ctx = m->ctx;
     const int64_t rowIndicesLen = b.dense() ? 0 : b.valuesLen;
+    // Egress on its own stream, ordered after this block's producer only (one chunk of a chunked multiply, or
+    // everything enqueued on the context stream so far when the block has no event of its own).
+    cudaStream_t rs = ctx->pipeline ? ctx->d2h_stream : ctx->stream;
+    if (ctx->pipeline && (io->values || io->colPtrs || io->rowIndices)) {
+      if (b.ready) {
+        CUDA_CHECK(cudaStreamWaitEvent(rs, b.ready->ev, 0));
+      } else {
+        CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(rs, ctx->ev_order, 0));
+      }
+    }
     if (io->values != nullptr) {
       MR_REQUIRE(io->valuesLen >= b.valuesLen, MR_EINVAL, "values capacity %lld < %lld", (long long)io->valuesLen,
                  (long long)b.valuesLen);
       if (b.valuesLen)
         CUDA_CHECK(cudaMemcpyAsync(io->values, b.values.ptr<double>(), static_cast<size_t>(b.valuesLen) * sizeof(double),
-                                   cudaMemcpyDeviceToHost, ctx->stream));
+                                   cudaMemcpyDeviceToHost, rs));
       ctx->stats.d2h_bytes += b.valuesLen * 8;
     }
     if (!b.dense() && io->colPtrs != nullptr) {
       MR_REQUIRE(io->colPtrsLen >= b.colPtrsLen, MR_EINVAL, "colPtrs capacity too small");
       CUDA_CHECK(cudaMemcpyAsync(io->colPtrs, b.colPtrs.ptr<int32_t>(), static_cast<size_t>(b.colPtrsLen) * 4,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+                                 cudaMemcpyDeviceToHost, rs));
       ctx->stats.d2h_bytes += b.colPtrsLen * 4;
     }
     if (!b.dense() && io->rowIndices != nullptr) {
       MR_REQUIRE(io->rowIndicesLen >= rowIndicesLen, MR_EINVAL, "rowIndices capacity too small");
       if (rowIndicesLen)
         CUDA_CHECK(cudaMemcpyAsync(io->rowIndices, b.rowIndices.ptr<int32_t>(), static_cast<size_t>(rowIndicesLen) * 4,
-                                   cudaMemcpyDeviceToHost, ctx->stream));
+                                   cudaMemcpyDeviceToHost, rs));
       ctx->stats.d2h_bytes += rowIndicesLen * 4;
     }
-    if (io->values || io->colPtrs || io->rowIndices) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (io->values || io->colPtrs || io->rowIndices) CUDA_CHECK(cudaStreamSynchronize(rs));
     io->type = b.type;
     io->numRows = b.numRows;
     io->numCols = b.numCols;
@@ -1116,6 +1275,10 @@ mr_status mr_matrix_multiply(mr_matrix* left, int64_t leftRowNum, int64_t leftCo
     (void)rightColNum;
     mr_context* ctx = left->ctx;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    for (auto& kv : left->blocks)
+      if (!kv.second.dense()) wait_ready(ctx, kv.second);
+    for (auto& kv : right->blocks)
+      if (!kv.second.dense()) wait_ready(ctx, kv.second);
     MultiplyPlanner planner{ctx};
     planner.temps.reserve(left->blocks.size() + right->blocks.size() + 1);
     std::vector<OutPlan> plans;
@@ -1193,6 +1356,8 @@ static mr_status ew_operator(int op, mr_matrix* left, int64_t lr, int64_t lc, mr
     MR_REQUIRE(left->ctx == right->ctx, MR_EINVAL, "operands belong to different contexts");
     check_same_dims(lr, lc, rr, rc);
     std::lock_guard<std::mutex> lock(left->ctx->mu);
+    wait_ready_all(left->ctx, left);
+    wait_ready_all(left->ctx, right);
     std::unique_ptr<mr_matrix> r(new_matrix(left->ctx));
     elementwise_join(op, left, right, r.get());
     *out = r.release();
@@ -1219,6 +1384,7 @@ static mr_status map_operator(int op, mr_matrix* a, double alpha, mr_matrix** ou
   return guarded([&] {
     MR_REQUIRE(a && out, MR_EINVAL, "null argument");
     std::lock_guard<std::mutex> lock(a->ctx->mu);
+    wait_ready_all(a->ctx, a);
     std::unique_ptr<mr_matrix> r(new_matrix(a->ctx));
     map_values(op, a, alpha, r.get());
     *out = r.release();
@@ -1249,6 +1415,8 @@ mr_status mr_rank_one_update(mr_matrix* left, int64_t lr, int64_t lc, mr_matrix*
                  (long long)lr, (long long)lc, (long long)rr, (long long)rc);
     }
     std::lock_guard<std::mutex> lock(ctx->mu);
+    wait_ready_all(ctx, left);
+    wait_ready_all(ctx, right);
     std::unique_ptr<mr_matrix> r(new_matrix(ctx));
     EwBatch batch{ctx, ctx->compat_bugs ? EW_RANK1_COMPAT : EW_RANK1};
     batch.keep.reserve(left->blocks.size() + 2 * right->blocks.size() + 2);
@@ -1294,6 +1462,7 @@ static mr_status aggregate_operator(int op, mr_matrix* a, int64_t nrows, int64_t
       MR_REQUIRE(nrows == ncols, MR_EDIM, "Cannot perform trace() on a rectangle matrix");
     mr_context* ctx = a->ctx;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    wait_ready_all(ctx, a);
     std::unique_ptr<mr_matrix> r(new_matrix(ctx));
     // output blocks: one per block-row (rowSum), block-column (colSum), or a single scalar
     std::map<std::pair<int32_t, int32_t>, int32_t> out_len;
@@ -1380,6 +1549,7 @@ mr_status mr_materialize(mr_matrix* a, mr_matrix** out) {
     MR_REQUIRE(a && out, MR_EINVAL, "null argument");
     mr_context* ctx = a->ctx;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    wait_ready_all(ctx, a);
     std::unique_ptr<mr_matrix> r(new_matrix(ctx));
     EwBatch batch{ctx, EW_COPY};
     for (auto& kv : a->blocks) {

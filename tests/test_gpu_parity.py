@@ -486,3 +486,28 @@ def test_lazy_plan_rewrites_match_direct_execution(session):
         if name in ("sum(AB)", "rowSum(AB)", "colSum(AB)"):
             assert full_gemm_tiles < 2.0 * n ** 3 / 16          # a matrix-vector sized product, not N^3
         assert "MatrixMatrixMultiplicationExecution" in p0.trace or "AB" not in name
+
+
+def test_pipelined_ingest_multiply_egress(session):
+    """Section 8f-4: blocks put from pinned host memory are copied on the ingest stream; a multiply issued while
+    copies are in flight is chunked per block row and must give exactly the resident result; get_block on the
+    egress stream returns finished rows."""
+    import torch
+    n, blk = 2048, 256
+    A = O.rand_dense_dataset(n, n, blk, 42, transposed_mask=lambda i, j: (i * 3 + j) % 4 == 0)
+    B = O.rand_dense_dataset(n, n, blk, 43)
+    ref = from_dataset(to_dataset(session, A).matrixMultiply(n, n, to_dataset(session, B), n, n, blk))
+    pin = lambda m: mb.DenseMatrix(m.numRows, m.numCols, torch.from_numpy(m.values).pin_memory().numpy(), m.isTransposed)  # noqa: E731
+    pA = [mb.MatrixBlock(i, j, pin(m)) for (i, j), m in A.items()]
+    pB = [mb.MatrixBlock(i, j, pin(m)) for (i, j), m in B.items()]
+    for rep in range(3):
+        session.reset_stats()
+        dB = session.createDataset(pB)
+        dA = session.createDataset(pA)
+        dC = dA.matrixMultiply(n, n, dB, n, n, blk)
+        got = from_dataset(dC)
+        assert_same_dataset(got, {k: O.DenseMatrix(v.numRows, v.numCols, v.values) for k, v in ref.items()}, exact_storage=True)
+    with mb.MatfastSession(device=0) as s2:
+        s2.set_option("pipeline", 0)                      # same answer with the overlap machinery off
+        got = from_dataset(to_dataset(s2, A).matrixMultiply(n, n, to_dataset(s2, B), n, n, blk))
+        assert_same_dataset(got, {k: O.DenseMatrix(v.numRows, v.numCols, v.values) for k, v in ref.items()}, exact_storage=True)
