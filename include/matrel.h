@@ -148,6 +148,14 @@ MR_API mr_status mr_col_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matri
 MR_API mr_status mr_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out);
 /* Dataset.trace :78-82 -> TraceDirectExecution :401-463: one 1 x 1 block (0, 0) from the diagonal blocks */
 MR_API mr_status mr_trace(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out);
+/* ---- slicing; intended semantics (the reference's transposed / sparse index defects are not reproduced) */
+/* Dataset.project :38-47 -> Project{Row,Column}DirectExecution :31-150: rowOrCol != 0 -> row `index` as blocks (0, cid) of
+ * shape 1 x cols; rowOrCol == 0 -> column `index` as blocks (rid, 0) of shape rows x 1 */
+MR_API mr_status mr_project(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkSize, int32_t rowOrCol, int64_t index,
+                            mr_matrix** out);
+/* Dataset.selection :49-55 -> SelectDirectExecution :152-213: the element (rowIdx, colIdx) as one 1 x 1 block (0, 0) */
+MR_API mr_status mr_selection(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t rowIdx, int64_t colIdx,
+                              mr_matrix** out);
 /* Materialise every dense block as column-major, isTransposed = false (DenseMatrix.toArray,
  * M/matrix/MLMatrix.scala:55-61, as a device transpose kernel). */
 MR_API mr_status mr_materialize(mr_matrix* a, mr_matrix** out);

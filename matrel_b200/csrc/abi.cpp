@@ -1544,6 +1544,91 @@ mr_status mr_col_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out
 mr_status mr_sum(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out) { return aggregate_operator(AGG_SUM, a, nrows, ncols, out); }
 mr_status mr_trace(mr_matrix* a, int64_t nrows, int64_t ncols, mr_matrix** out) { return aggregate_operator(AGG_TRACE, a, nrows, ncols, out); }
 
+static mr_status slice_operator(mr_matrix* a, int32_t blkSize, bool take_row, int64_t index, int64_t index2, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(blkSize > 0, MR_EINVAL, "blkSize must be positive, got %d", blkSize);
+    mr_context* ctx = a->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    wait_ready_all(ctx, a);
+    std::unique_ptr<mr_matrix> r(new_matrix(ctx));
+    const int32_t blkid = static_cast<int32_t>(index / blkSize), offset = static_cast<int32_t>(index % blkSize);  // :40-41
+    const int32_t blkid2 = index2 >= 0 ? static_cast<int32_t>(index2 / blkSize) : -1;
+    const int32_t offset2 = index2 >= 0 ? static_cast<int32_t>(index2 % blkSize) : -1;
+    std::vector<LineDesc> descs;
+    std::vector<std::pair<std::pair<int32_t, int32_t>, std::pair<int32_t, int32_t>>> outs;  // key -> (rows, cols)
+    std::vector<Block> keep;
+    keep.reserve(a->blocks.size() + 1);
+    size_t total = 0;
+    int max_len = 1;
+    for (auto& kv : a->blocks) {
+      const int32_t rid = kv.first.first, cid = kv.first.second;
+      if ((take_row ? rid : cid) != blkid) continue;                       // filter(tuple => tuple._1 == rowblkID), :48
+      if (index2 >= 0 && (take_row ? cid : rid) != blkid2) continue;
+      const Block* src = &kv.second;
+      if (!src->dense()) {
+        keep.push_back(densify(ctx, *src));
+        src = &keep.back();
+      }
+      if (offset >= (take_row ? src->numRows : src->numCols)) continue;
+      if (index2 >= 0 && offset2 >= (take_row ? src->numCols : src->numRows)) continue;
+      LineDesc d{};
+      d.v = src->values.ptr<double>();
+      d.rows = src->numRows;
+      d.cols = src->numCols;
+      d.offset = offset;
+      d.offset2 = offset2;
+      d.len = index2 >= 0 ? 1 : (take_row ? src->numCols : src->numRows);
+      d.isT = src->isT;
+      d.take_row = take_row;
+      descs.push_back(d);
+      if (index2 >= 0) outs.push_back({{0, 0}, {1, 1}});
+      else if (take_row) outs.push_back({{0, cid}, {1, d.len}});
+      else outs.push_back({{rid, 0}, {d.len, 1}});
+      total += align_up(static_cast<size_t>(d.len) * sizeof(double));
+      max_len = std::max(max_len, d.len);
+    }
+    if (!descs.empty()) {
+      Slab slab(ctx, total);
+      for (size_t i = 0; i < descs.size(); ++i) {
+        Span sp = slab.take(static_cast<size_t>(descs[i].len) * sizeof(double));
+        descs[i].out = sp.ptr<double>();
+        r->blocks[outs[i].first] = dense_block(outs[i].second.first, outs[i].second.second, sp);
+      }
+      Buf dd = upload(ctx, descs);
+      CUDA_CHECK(launch_extract_lines(static_cast<const LineDesc*>(dd->p), static_cast<int>(descs.size()), max_len, ctx->stream));
+      note_launch(ctx);
+    }
+    *out = r.release();
+  });
+}
+
+mr_status mr_project(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkSize, int32_t rowOrCol, int64_t index, mr_matrix** out) {
+  mr_status st = guarded([&] {
+    MR_REQUIRE(a && out, MR_EINVAL, "null argument");
+    if (rowOrCol)  // Dataset.scala:42,44
+      MR_REQUIRE(index >= 0 && index < nrows, MR_EINVAL, "row index should be smaller than #rows, index=%lld, #rows=%lld",
+                 (long long)index, (long long)nrows);
+    else
+      MR_REQUIRE(index >= 0 && index < ncols, MR_EINVAL, "col index should be smaller than #cols, index=%lld, #cols=%lld",
+                 (long long)index, (long long)ncols);
+  });
+  if (st != MR_OK) return st;
+  return slice_operator(a, blkSize, rowOrCol != 0, index, -1, out);
+}
+
+mr_status mr_selection(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t rowIdx, int64_t colIdx, mr_matrix** out) {
+  mr_status st = guarded([&] {
+    MR_REQUIRE(a && out, MR_EINVAL, "null argument");
+    // Dataset.scala:52-53
+    MR_REQUIRE(rowIdx >= 0 && rowIdx < nrows, MR_EINVAL, "row index should be smaller than #rows, rid=%lld, #rows=%lld",
+               (long long)rowIdx, (long long)nrows);
+    MR_REQUIRE(colIdx >= 0 && colIdx < ncols, MR_EINVAL, "col index should be smaller than #cols, cid=%lld, #cols=%lld",
+               (long long)colIdx, (long long)ncols);
+  });
+  if (st != MR_OK) return st;
+  return slice_operator(a, blkSize, true, rowIdx, colIdx, out);
+}
+
 mr_status mr_materialize(mr_matrix* a, mr_matrix** out) {
   return guarded([&] {
     MR_REQUIRE(a && out, MR_EINVAL, "null argument");

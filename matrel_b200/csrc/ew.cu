@@ -430,6 +430,15 @@ __global__ void __launch_bounds__(256) scalar_sum_kernel(const AggDesc* __restri
   }
 }
 
+__global__ void __launch_bounds__(256) extract_lines_kernel(const LineDesc* __restrict__ descs) {
+  const LineDesc d = descs[blockIdx.y];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < d.len; i += gridDim.x * 256) {
+    const int j = d.offset2 >= 0 ? d.offset2 : i;
+    const int r = d.take_row ? d.offset : j, c = d.take_row ? j : d.offset;
+    d.out[i] = d.isT ? d.v[c + static_cast<size_t>(d.cols) * r] : d.v[r + static_cast<size_t>(d.rows) * c];
+  }
+}
+
 inline int flat_grid_x(int64_t max_n) {
   int64_t vec = (max_n + 1) / 2;
   int64_t gx = (vec + static_cast<int64_t>(FLAT_THREADS) * FLAT_UNROLL - 1) / (static_cast<int64_t>(FLAT_THREADS) * FLAT_UNROLL);
@@ -574,6 +583,15 @@ cudaError_t launch_aggregate(int op, const AggDesc* d_descs, int nblocks, int ma
       if (gx > 1024) gx = 1024;
       scalar_sum_kernel<<<dim3(static_cast<unsigned>(gx), nb), 256, 0, stream>>>(d_descs + off, op == AGG_TRACE ? 1 : 0);
     }
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_extract_lines(const LineDesc* d_descs, int nblocks, int max_len, cudaStream_t stream) {
+  if (nblocks <= 0 || max_len <= 0) return cudaSuccess;
+  for (int off = 0; off < nblocks; off += 65535) {
+    const int nb = nblocks - off < 65535 ? nblocks - off : 65535;
+    extract_lines_kernel<<<dim3((max_len + 255) / 256, nb), 256, 0, stream>>>(d_descs + off);
   }
   return cudaGetLastError();
 }

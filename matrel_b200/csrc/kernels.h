@@ -141,6 +141,20 @@ struct AggDesc {
 enum AggOp { AGG_ROW_SUM = 0, AGG_COL_SUM = 1, AGG_SUM = 2, AGG_TRACE = 3 };
 cudaError_t launch_aggregate(int op, const AggDesc* d_descs, int nblocks, int max_rows, int max_cols, cudaStream_t stream);
 
+// Project{Row,Column}DirectExecution / SelectDirectExecution (MatfastExecution.scala:31-213): one row or column of a dense
+// block copied into a 1 x cols / rows x 1 block (a single element for selection), batched over blocks.
+struct LineDesc {
+  const double* v;
+  int32_t rows, cols;
+  int32_t offset;       // row (take_row) or column index inside the block
+  int32_t len;          // elements to copy (cols / rows; 1 for selection with offset2)
+  int32_t offset2;      // selection: the other index (-1 = whole line)
+  uint8_t isT, take_row;
+  uint8_t pad[2];
+  double* out;
+};
+cudaError_t launch_extract_lines(const LineDesc* d_descs, int nblocks, int max_len, cudaStream_t stream);
+
 // java.util.Random-compatible U(0,1) fill: out[i] = i-th nextDouble() of new Random(seed), batched over blocks
 struct RandDesc {
   double* out;

@@ -250,6 +250,14 @@ class Dataset:
         """M/Dataset.scala:99-103."""
         return self._unary(N.lib.mr_power, float(alpha))
 
+    def project(self, nrows, ncols, blkSize, rowOrCol: bool, index) -> "Dataset":
+        """M/Dataset.scala:38-47."""
+        return self._unary(N.lib.mr_project, int(nrows), int(ncols), int(blkSize), 1 if rowOrCol else 0, int(index))
+
+    def selection(self, nrows, ncols, blkSize, rowIdx, colIdx) -> "Dataset":
+        """M/Dataset.scala:49-55."""
+        return self._unary(N.lib.mr_selection, int(nrows), int(ncols), int(blkSize), int(rowIdx), int(colIdx))
+
     def rowSum(self, nrows, ncols) -> "Dataset":
         """M/Dataset.scala:63-66."""
         return self._unary(N.lib.mr_row_sum, int(nrows), int(ncols))

@@ -9,7 +9,6 @@ nodes, ``execute()`` walks them with the same case analysis and runs the chosen 
 eagerly through ``matrel_b200.dataset.Dataset`` (i.e. the sm_100a kernels).
 
 M/ = /root/reference/src/main/scala/org/apache/spark/sql/matfast/
-(The project / selection push-downs of :44-163 need the slicing operators and are not restated yet.)
 """
 from __future__ import annotations
 
@@ -23,6 +22,26 @@ from .dataset import Dataset
 @dataclass
 class Leaf:
     ds: Dataset
+
+
+@dataclass
+class ProjectOperator:              # :25-33
+    child: object
+    nrows: int
+    ncols: int
+    blkSize: int
+    rowOrCol: bool
+    index: int
+
+
+@dataclass
+class SelectOperator:               # :35-41
+    child: object
+    nrows: int
+    ncols: int
+    blkSize: int
+    rowIdx: int
+    colIdx: int
 
 
 @dataclass
@@ -122,6 +141,62 @@ class Planner:
         R = self.run
         if isinstance(n, Leaf):
             return n.ds
+        if isinstance(n, ProjectOperator):                                     # :44-124
+            c = n.child
+            P = lambda ch, nr, nc: ProjectOperator(ch, nr, nc, n.blkSize, n.rowOrCol, n.index)  # noqa: E731
+            if self.rewrite:
+                if isinstance(c, TransposeOperator):      # a row of A^T is a column of A (the reference emits it un-transposed)
+                    self._phys("ProjectColumnDirectExecution" if n.rowOrCol else "ProjectRowDirectExecution")
+                    return R(c.child).project(n.ncols, n.nrows, n.blkSize, not n.rowOrCol, n.index).transpose()
+                if isinstance(c, MatrixScalarAddOperator):
+                    self._phys("MatrixScalarAddExecution")
+                    return R(P(c.child, n.nrows, n.ncols)).addScalar(c.alpha)
+                if isinstance(c, MatrixScalarMultiplyOperator):
+                    self._phys("MatrixScalarMultiplyExecution")
+                    return R(P(c.child, n.nrows, n.ncols)).multiplyScalar(c.alpha)
+                if isinstance(c, (MatrixElementAddOperator, MatrixElementMultiplyOperator, MatrixElementDivideOperator)):
+                    fn = {MatrixElementAddOperator: "addElement", MatrixElementMultiplyOperator: "multiplyElement",
+                          MatrixElementDivideOperator: "divideElement"}[type(c)]
+                    self._phys(type(c).__name__.replace("Operator", "Execution"))
+                    lr, lc = (1, c.leftColNum) if n.rowOrCol else (c.leftRowNum, 1)
+                    rr, rc = (1, c.rightColNum) if n.rowOrCol else (c.rightRowNum, 1)
+                    return getattr(R(P(c.left, c.leftRowNum, c.leftColNum)), fn)(
+                        lr, lc, R(P(c.right, c.rightRowNum, c.rightColNum)), rr, rc, c.blkSize)
+                if isinstance(c, MatrixMatrixMultiplicationOperator):          # row_i(A B) = row_i(A) B ; col_j(A B) = A col_j(B)
+                    self._phys("MatrixMatrixMultiplicationExecution")
+                    if n.rowOrCol:
+                        return R(P(c.left, c.leftRowNum, c.leftColNum)).matrixMultiply(
+                            1, c.leftColNum, R(c.right), c.rightRowNum, c.rightColNum, c.blkSize)
+                    return R(c.left).matrixMultiply(c.leftRowNum, c.leftColNum, R(P(c.right, c.rightRowNum, c.rightColNum)),
+                                                    c.rightRowNum, 1, c.blkSize)
+            self._phys("ProjectRowDirectExecution" if n.rowOrCol else "ProjectColumnDirectExecution")
+            return R(c).project(n.nrows, n.ncols, n.blkSize, n.rowOrCol, n.index)
+        if isinstance(n, SelectOperator):                                      # :125-166
+            c = n.child
+            S = lambda ch, nr, nc: SelectOperator(ch, nr, nc, n.blkSize, n.rowIdx, n.colIdx)  # noqa: E731
+            if self.rewrite:
+                if isinstance(c, TransposeOperator):
+                    self._phys("SelectDirectExecution")
+                    return R(c.child).selection(n.ncols, n.nrows, n.blkSize, n.colIdx, n.rowIdx)
+                if isinstance(c, MatrixScalarAddOperator):
+                    self._phys("MatrixScalarAddExecution")
+                    return R(S(c.child, n.nrows, n.ncols)).addScalar(c.alpha)
+                if isinstance(c, MatrixScalarMultiplyOperator):
+                    self._phys("MatrixScalarMultiplyExecution")
+                    return R(S(c.child, n.nrows, n.ncols)).multiplyScalar(c.alpha)
+                if isinstance(c, (MatrixElementAddOperator, MatrixElementMultiplyOperator, MatrixElementDivideOperator)):
+                    fn = {MatrixElementAddOperator: "addElement", MatrixElementMultiplyOperator: "multiplyElement",
+                          MatrixElementDivideOperator: "divideElement"}[type(c)]
+                    self._phys(type(c).__name__.replace("Operator", "Execution"))
+                    return getattr(R(S(c.left, c.leftRowNum, c.leftColNum)), fn)(
+                        1, 1, R(S(c.right, c.rightRowNum, c.rightColNum)), 1, 1, c.blkSize)
+                if isinstance(c, MatrixMatrixMultiplicationOperator):          # (A B)_ij = row_i(A) . col_j(B)
+                    self._phys("MatrixMatrixMultiplicationExecution")
+                    row = ProjectOperator(c.left, c.leftRowNum, c.leftColNum, n.blkSize, True, n.rowIdx)
+                    col = ProjectOperator(c.right, c.rightRowNum, c.rightColNum, n.blkSize, False, n.colIdx)
+                    return R(row).matrixMultiply(1, c.leftColNum, R(col), c.rightRowNum, 1, c.blkSize)
+            self._phys("SelectDirectExecution")
+            return R(c).selection(n.nrows, n.ncols, n.blkSize, n.rowIdx, n.colIdx)
         if isinstance(n, TransposeOperator):                                   # :167
             self._phys("MatrixTransposeExecution")
             return R(n.child).transpose()
@@ -279,6 +354,12 @@ class LazyDataset:
 
     def power(self, alpha):
         return LazyDataset(MatrixPowerOperator(self.node, float(alpha)))
+
+    def project(self, nrows, ncols, blkSize, rowOrCol, index):
+        return LazyDataset(ProjectOperator(self.node, int(nrows), int(ncols), int(blkSize), bool(rowOrCol), int(index)))
+
+    def selection(self, nrows, ncols, blkSize, rowIdx, colIdx):
+        return LazyDataset(SelectOperator(self.node, int(nrows), int(ncols), int(blkSize), int(rowIdx), int(colIdx)))
 
     def rowSum(self, nrows, ncols):
         return LazyDataset(RowSumOperator(self.node, int(nrows), int(ncols)))

@@ -751,6 +751,34 @@ def trace(ds: BlockDict, nrows: int, ncols: int) -> BlockDict:
     return {(0, 0): DenseMatrix(1, 1, [tr])} if seen else {}
 
 
+def project(ds: BlockDict, nrows: int, ncols: int, blkSize: int, rowOrCol: bool, index: int) -> BlockDict:
+    """Dataset.project (M/Dataset.scala:38-47) -> Project{Row,Column}DirectExecution (MatfastExecution.scala:31-150),
+    intended semantics: row `index` as 1 x cols blocks (0, cid) / column `index` as rows x 1 blocks (rid, 0)."""
+    if rowOrCol:
+        require(index < nrows, f"row index should be smaller than #rows, index={index}, #rows={nrows}")
+    else:
+        require(index < ncols, f"col index should be smaller than #cols, index={index}, #cols={ncols}")
+    bid, off = index // blkSize, index % blkSize
+    out: BlockDict = {}
+    for (rid, cid), m in ds.items():
+        a = m.to_numpy()
+        if rowOrCol and rid == bid and off < m.numRows:
+            out[(0, cid)] = DenseMatrix(1, m.numCols, a[off, :].copy())
+        if not rowOrCol and cid == bid and off < m.numCols:
+            out[(rid, 0)] = DenseMatrix(m.numRows, 1, a[:, off].copy())
+    return out
+
+
+def selection(ds: BlockDict, nrows: int, ncols: int, blkSize: int, rowIdx: int, colIdx: int) -> BlockDict:
+    """Dataset.selection (M/Dataset.scala:49-55) -> SelectDirectExecution (MatfastExecution.scala:152-213)."""
+    require(rowIdx < nrows, f"row index should be smaller than #rows, rid={rowIdx}, #rows={nrows}")
+    require(colIdx < ncols, f"col index should be smaller than #cols, cid={colIdx}, #cols={ncols}")
+    key = (rowIdx // blkSize, colIdx // blkSize)
+    if key not in ds:
+        return {}
+    return {(0, 0): DenseMatrix(1, 1, [ds[key].apply(rowIdx % blkSize, colIdx % blkSize)])}
+
+
 # ----------------------------------------------------------------------------------------------
 # helpers for tests / bench
 # ----------------------------------------------------------------------------------------------

@@ -511,3 +511,43 @@ def test_pipelined_ingest_multiply_egress(session):
         s2.set_option("pipeline", 0)                      # same answer with the overlap machinery off
         got = from_dataset(to_dataset(s2, A).matrixMultiply(n, n, to_dataset(s2, B), n, n, blk))
         assert_same_dataset(got, {k: O.DenseMatrix(v.numRows, v.numCols, v.values) for k, v in ref.items()}, exact_storage=True)
+
+
+def test_project_selection_golden_and_pushdown(session):
+    """Section 8f-4 slicing ops + their planner push-downs: BasicMatrixOps.scala:212 (column 3 of mat1*mat2) and
+    :234 (element (0,3)) from the golden file; select(A B) runs as a 1 x k by k x 1 product."""
+    from matrel_b200.plan import LazyDataset, Planner
+    g = load("basic_matrix_ops")
+    e = g["expected"]
+    blocks = {k: mk(v) for k, v in g["blocks"].items()}
+    A = {(r, c): blocks[n] for r, c, n in g["mat1"]}
+    B = {(r, c): blocks[n] for r, c, n in g["mat2"]}
+    mat1, mat2 = to_dataset(session, A), to_dataset(session, B)
+    prod = mat1.matrixMultiply(4, 4, mat2, 4, 4, 2)
+    col3 = from_dataset(prod.project(4, 4, 2, False, 3))
+    assert sorted(col3) == [(0, 0), (1, 0)]
+    assert [x for k in sorted(col3) for x in col3[k].values.tolist()] == e["column_3"]
+    assert from_dataset(prod.selection(4, 4, 2, 0, 3))[(0, 0)].values.tolist() == [e["selection_0_3"]]
+    for rewrite in (True, False):
+        q = LazyDataset.of(mat1).matrixMultiply(4, 4, LazyDataset.of(mat2), 4, 4, 2)
+        assert from_dataset(q.selection(4, 4, 2, 0, 3).execute(rewrite))[(0, 0)].values.tolist() == [e["selection_0_3"]]
+        c3 = from_dataset(q.project(4, 4, 2, False, 3).execute(rewrite))
+        assert [x for k in sorted(c3) for x in c3[k].values.tolist()] == e["column_3"]
+    with pytest.raises(mb.IllegalArgumentException, match="row index should be smaller than #rows, index=9, #rows=4"):
+        mat1.project(4, 4, 2, True, 9)
+    # random blocks vs the oracle, and the O(N) selection push-down on a large product
+    rng = np.random.default_rng(31)
+    D = random_block_dataset(rng, 300, 200, 64, density=0.8, p_transposed=0.5, p_sparse=0.2, sparse_density=0.3)
+    dD = to_dataset(session, D)
+    assert_same_dataset(from_dataset(dD.project(300, 200, 64, True, 137)), O.project(D, 300, 200, 64, True, 137), exact_storage=True)
+    assert_same_dataset(from_dataset(dD.project(300, 200, 64, False, 99)), O.project(D, 300, 200, 64, False, 99), exact_storage=True)
+    assert_same_dataset(from_dataset(dD.selection(300, 200, 64, 250, 131)), O.selection(D, 300, 200, 64, 250, 131), exact_storage=True)
+    n, blk = 1024, 256
+    X, Y = session.rand(n, n, blk, 1), session.rand(n, n, blk, 2)
+    q = LazyDataset.of(X).matrixMultiply(n, n, LazyDataset.of(Y), n, n, blk).selection(n, n, blk, 700, 300)
+    p1 = Planner(True)
+    session.reset_stats()
+    fast = from_dataset(q.execute(planner=p1))[(0, 0)].values[0]
+    assert session.stats()["last_gemm_flops"] <= 2 * n                      # one dot product, not 2 N^3
+    slow = from_dataset(q.execute(False))[(0, 0)].values[0]
+    assert abs(fast - slow) / abs(slow) < 1e-13
