@@ -350,31 +350,50 @@ bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<d
   const int S_eff = std::min(7, std::max(2, ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7));
   // s32 accumulator bound: up to S pairs x K terms of |digit product| <= 2^14 land in one accumulator
   if (M <= 0 || K <= 0 || N <= 0 || M > INT32_MAX || N > INT32_MAX || K * S_eff >= (1 << 17)) return false;
-  const int64_t nbr = ceil_div(M, blkSize), nbc = ceil_div(N, blkSize);
+  // Compact the block rows / columns that actually have output blocks (a rank of the process grid owns every pr-th
+  // block row and pc-th block column: slicing and multiplying the absent ones would only produce zeros).
+  std::map<int32_t, int32_t> crow, ccol;
+  for (const OutPlan& o : plans)
+    if (!o.gemm.empty()) {
+      crow.emplace(o.rid, 0);
+      ccol.emplace(o.cid, 0);
+    }
+  if (crow.empty()) return false;
+  {
+    int32_t i = 0;
+    for (auto& kv : crow) kv.second = i++;
+    i = 0;
+    for (auto& kv : ccol) kv.second = i++;
+  }
+  const int64_t nbr = static_cast<int64_t>(crow.size()), nbc = static_cast<int64_t>(ccol.size());
   if (nbr * nbc > (1 << 24)) return false;
+  const int64_t last_r = crow.rbegin()->first, last_c = ccol.rbegin()->first;
+  if (last_r * static_cast<int64_t>(blkSize) >= M || last_c * static_cast<int64_t>(blkSize) >= N) return false;
+  const int64_t Mc = (nbr - 1) * blkSize + std::min<int64_t>(blkSize, M - last_r * blkSize);
+  const int64_t Nc = (nbc - 1) * blkSize + std::min<int64_t>(blkSize, N - last_c * blkSize);
   std::vector<double*> ctab(static_cast<size_t>(nbr * nbc), nullptr);
   std::map<const Block*, int> ia, ib;
   std::vector<OzakiOperand> va, vb;
   for (size_t i = 0; i < plans.size(); ++i) {
     const OutPlan& o = plans[i];
     if (o.gemm.empty()) continue;
-    if (o.rid < 0 || o.rid >= nbr || o.cid < 0 || o.cid >= nbc) return false;
-    if (o.m != std::min<int64_t>(blkSize, M - static_cast<int64_t>(o.rid) * blkSize) ||
-        o.n != std::min<int64_t>(blkSize, N - static_cast<int64_t>(o.cid) * blkSize))
+    const int32_t cr = crow[o.rid], cc = ccol[o.cid];
+    // every block row / column but the last must be a full blkSize tall / wide (the kernel finds blocks by division)
+    if (o.m != ((o.rid == last_r) ? Mc - (nbr - 1) * blkSize : blkSize) || o.n != ((o.cid == last_c) ? Nc - (nbc - 1) * blkSize : blkSize))
       return false;
     if (!o.spmm.empty()) return false;  // mixed dense / sparse partial sums stay on the exact path
-    ctab[static_cast<size_t>(o.rid) * nbc + o.cid] = cptr[i];
+    ctab[static_cast<size_t>(cr) * nbc + cc] = cptr[i];
     for (const GemmSrc& g : o.src) {
       const int64_t k0 = outer ? 0 : static_cast<int64_t>(g.k) * blkSize;
       if (k0 + g.a->numCols > K || g.a->numCols != g.b->numRows) return false;
       if (!ia.count(g.a)) {
         ia[g.a] = 1;
-        va.push_back(OzakiOperand{g.a->values.ptr<double>(), g.a->numRows, g.a->numCols, o.rid * blkSize, static_cast<int32_t>(k0),
+        va.push_back(OzakiOperand{g.a->values.ptr<double>(), g.a->numRows, g.a->numCols, cr * blkSize, static_cast<int32_t>(k0),
                                   static_cast<uint8_t>(g.a->isT)});
       }
       if (!ib.count(g.b)) {
         ib[g.b] = 1;
-        vb.push_back(OzakiOperand{g.b->values.ptr<double>(), g.b->numRows, g.b->numCols, static_cast<int32_t>(k0), o.cid * blkSize,
+        vb.push_back(OzakiOperand{g.b->values.ptr<double>(), g.b->numRows, g.b->numCols, static_cast<int32_t>(k0), cc * blkSize,
                                   static_cast<uint8_t>(g.b->isT)});
       }
     }
@@ -382,7 +401,7 @@ bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<d
   if (va.empty() || vb.empty()) return false;
   int launches = 0, nonfinite = 0;
   if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-  CUDA_CHECK(ozaki_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), M, K, N,
+  CUDA_CHECK(ozaki_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc,
                             ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7, ctab.data(), blkSize, static_cast<int>(nbr),
                             static_cast<int>(nbc), false, &launches, &nonfinite, ctx->stream));
   note_launch(ctx, launches);

@@ -246,6 +246,34 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
         kern_ms = float(kt.item())
 
+        # ---- the same sharded multiply with the tcgen05 Ozaki kernel on every rank (reported beside the headline)
+        ozaki = None
+        try:
+            s.set_option("gemm_algo", 2)
+            s.set_option("ozaki_slices", getattr(args, "ozaki_slices", 7))
+            for _ in range(2):
+                out = step()
+                del out
+            torch.cuda.synchronize()
+            dist.barrier()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record(stream)
+            for _ in range(args.steps):
+                out = step()
+                del out
+            o1.record(stream)
+            torch.cuda.synchronize()
+            ot = torch.tensor([o0.elapsed_time(o1) / args.steps], dtype=torch.float64, device=device)
+            dist.all_reduce(ot, op=dist.ReduceOp.MAX)
+            oz_ms = float(ot.item())
+            ozaki = {"algo": "Ozaki-I, %d int8 slices, tcgen05 kind::i8 on every rank" % getattr(args, "ozaki_slices", 7),
+                     "value": flops / (oz_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": oz_ms}
+        except Exception as e:
+            ozaki = {"error": str(e)}
+        finally:
+            s.set_option("gemm_algo", 0)
+        dist.barrier()
+
         # ---- end to end: each rank feeds its own A/B blocks from pinned host memory and reads its C blocks back
         hostA = [(k, A.dataset.get_block(*k)) for k in A.dataset.block_ids()]
         hostB = [(k, B.dataset.get_block(*k)) for k in B.dataset.block_ids()]
@@ -308,6 +336,7 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
                          "algorithmic": f"2*N^3/{world} = {flops / world:.4g} flop per launch per rank (max-over-ranks kernel time)",
                          "peak_source": peak_src},
             "clocks": clocks,
+            "tcgen05_ozaki": ozaki,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -24,11 +24,13 @@ def main():
         groups = GridGroups(planA, rank)
         stream = torch.cuda.Stream(device=device)
         with torch.cuda.stream(stream):
-            s = mb.MatfastSession(device=local_rank, stream=stream.cuda_stream)
+            algo = int(os.environ.get("MATREL_GEMM_ALGO", "0"))
+            s = mb.MatfastSession(device=local_rank, stream=stream.cuda_stream, gemm_algo=algo)
             A = ShardedMatrix.rand(s, planA, rank, 42, device)
             B = ShardedMatrix.rand(s, planB, rank, 43, device)
             dC, keep = sharded_multiply(s, groups, A, B, planA, planB)
             got = {(b.rid, b.cid): b.matrix for b in dC.collect()}
+            s_launches = s.stats()["kernel_launches"]
             s.stop()
         want = O.matrix_multiply(O.rand_dense_dataset(n, k, blk, 42), n, k, O.rand_dense_dataset(k, m, blk, 43), k, m, blk)
         assert sorted(got) == sorted(planC.owned(rank)), (rank, sorted(got))
@@ -37,6 +39,8 @@ def main():
             assert (g.numRows, g.numCols, g.isTransposed) == (w.numRows, w.numCols, False)
             err = float(np.max(np.abs(g.values - w.values)) / np.max(np.abs(w.values)))
             assert err <= 1e-12, (key, err)
+        if algo == 2:
+            assert s_launches >= 8, s_launches     # absmax/slice passes + one GEMM per diagonal: the tcgen05 path really ran
         cnt = torch.tensor([len(got)], dtype=torch.int64, device=device)
         dist.all_reduce(cnt)
         assert int(cnt.item()) == len(want)
