@@ -347,9 +347,11 @@ struct MultiplyPlanner {
 // Returns false when the problem does not fit its regular-grid assumptions or holds Inf/NaN (caller uses DMMA).
 bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<double*>& cptr, int32_t blkSize, int64_t M,
                int64_t K, int64_t N, bool outer) {
+  const bool tf32 = ctx->gemm_algo == 3;
   const int S_eff = std::min(7, std::max(2, ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7));
   // s32 accumulator bound: up to S pairs x K terms of |digit product| <= 2^14 land in one accumulator
-  if (M <= 0 || K <= 0 || N <= 0 || M > INT32_MAX || N > INT32_MAX || K * S_eff >= (1 << 17)) return false;
+  if (M <= 0 || K <= 0 || N <= 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX / 2) return false;
+  if (!tf32 && K * S_eff >= (1 << 17)) return false;
   // Compact the block rows / columns that actually have output blocks (a rank of the process grid owns every pr-th
   // block row and pc-th block column: slicing and multiplying the absent ones would only produce zeros).
   std::map<int32_t, int32_t> crow, ccol;
@@ -401,9 +403,13 @@ bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<d
   if (va.empty() || vb.empty()) return false;
   int launches = 0, nonfinite = 0;
   if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-  CUDA_CHECK(ozaki_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc,
-                            ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7, ctab.data(), blkSize, static_cast<int>(nbr),
-                            static_cast<int>(nbc), false, &launches, &nonfinite, ctx->stream));
+  if (tf32)
+    CUDA_CHECK(tf32x3_gemm(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc, ctab.data(),
+                           blkSize, static_cast<int>(nbr), static_cast<int>(nbc), &launches, ctx->stream));
+  else
+    CUDA_CHECK(ozaki_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc,
+                              ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7, ctab.data(), blkSize, static_cast<int>(nbr),
+                              static_cast<int>(nbc), false, &launches, &nonfinite, ctx->stream));
   note_launch(ctx, launches);
   if (nonfinite) return false;
   ctx->stats.gemm_launches += 1;
@@ -470,7 +476,7 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       }
   };
   bool ozaki_done = false;
-  if (!outs.empty() && ctx->gemm_algo == 2) {
+  if (!outs.empty() && (ctx->gemm_algo == 2 || ctx->gemm_algo == 3)) {
     wait_all_sources();
     ozaki_done = try_ozaki(ctx, plans, cptr, blkSize, M, K, N, outer);
     if (ozaki_done) ctx->stats.last_gemm_flops = flops;

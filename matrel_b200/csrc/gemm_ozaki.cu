@@ -67,6 +67,11 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t da, uint64_t d
                "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
                : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+               "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -87,6 +92,13 @@ struct OzakiGemmParams {
   int32_t accumulate;          // 0: C = term, 1: C += term
   int32_t tiles_m, tiles_n;    // tile grid (128 x 256 tiles)
   double diag_scale;           // 2^(4 - 8 d)
+  // generalisation used by the fp32 path (tf32x3): explicit (A slice, B slice) tensor-map index pairs, the K extent of
+  // one 128-byte stage row in elements, the UMMA instruction descriptor and the accumulator type
+  int32_t npairs;
+  int32_t pair_a[8], pair_b[8];
+  int32_t kstep;               // elements of K per stage (128 int8 / 32 tf32)
+  uint32_t idesc;
+  int32_t f32_acc;             // 0: s32 accumulator scaled by the Ozaki exponents; 1: f32 accumulator written as is
 };
 
 constexpr int EPI_WARPS = 8;                       // 2 per TMEM lane quarter (each takes 128 of the 256 columns)
@@ -112,9 +124,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = p.Kpad / BKB;
-  const int s_lo = max(1, p.d - p.S), s_hi = min(p.S, p.d - 1);
-  const int per_tile = (s_hi - s_lo + 1) * nk;
+  const int nk = p.Kpad / p.kstep;
+  const int per_tile = p.npairs * nk;
   const int ntiles = p.tiles_m * p.tiles_n;
 
   if (threadIdx.x == 0) {
@@ -145,17 +156,17 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
         int tm, tn;
         tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
-        for (int s = s_lo; s <= s_hi; ++s) {
-          const void* tmA = p.tmaps + static_cast<size_t>(s - 1) * 128;
-          const void* tmB = p.tmaps + static_cast<size_t>(p.S + (p.d - s) - 1) * 128;
+        for (int s = 0; s < p.npairs; ++s) {
+          const void* tmA = p.tmaps + static_cast<size_t>(p.pair_a[s]) * 128;
+          const void* tmB = p.tmaps + static_cast<size_t>(p.pair_b[s]) * 128;
           for (int kc = 0; kc < nk; ++kc, ++it) {
             const int st = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(smem_u32(&bars[STAGES + st]), ph ^ 1);
             const uint32_t full = smem_u32(&bars[st]);
             mbar_arrive_expect_tx(full, STAGE_BYTES);
-            tma_2d(smem_u32(smem + st * STAGE_BYTES), tmA, kc * BKB, m0, full);
-            tma_2d(smem_u32(smem + st * STAGE_BYTES + A_BYTES), tmB, kc * BKB, n0, full);
+            tma_2d(smem_u32(smem + st * STAGE_BYTES), tmA, kc * p.kstep, m0, full);
+            tma_2d(smem_u32(smem + st * STAGE_BYTES + A_BYTES), tmB, kc * p.kstep, n0, full);
           }
         }
       }
@@ -163,9 +174,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane): every (s, d-s) pair and every k accumulates into one s32 tile =====
     if (lane == 0) {
-      // D = S32 (2 @ bit 4); A, B = signed 8-bit (1 @ bits 7 and 10); both K-major; N >> 3 @ 17; M >> 4 @ 24
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
-                             (static_cast<uint32_t>(BM >> 4) << 24);
+      const uint32_t idesc = p.idesc;
       int it = 0, lt = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
         const int buf = lt & 1;
@@ -180,8 +189,11 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a0 = smem_u32(smem + st * STAGE_BYTES), b0 = a0 + A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BKB / UMMA_K; ++k)
-            umma_i8(tacc, umma_desc_k_sw128(a0 + k * UMMA_K), umma_desc_k_sw128(b0 + k * UMMA_K), idesc, (j | k) != 0);
+          for (int k = 0; k < BKB / UMMA_K; ++k) {  // 4 MMAs of 32 bytes of K each (32 int8 / 8 tf32)
+            const uint64_t da = umma_desc_k_sw128(a0 + k * UMMA_K), db = umma_desc_k_sw128(b0 + k * UMMA_K);
+            if (p.f32_acc) umma_tf32(tacc, da, db, idesc, (j | k) != 0);
+            else umma_i8(tacc, da, db, idesc, (j | k) != 0);
+          }
           umma_commit(smem_u32(&bars[STAGES + st]));  // stage is free once these MMAs retire
         }
         umma_commit(smem_u32(&bars[2 * STAGES + buf]));  // accumulator complete
@@ -204,7 +216,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
       const int rid = row_ok ? row / p.blk : 0;
       const int lr = row - rid * p.blk;
       const int brows = min(p.blk, p.M - rid * p.blk);
-      const double rs = row_ok ? p.row_scale[row] * p.diag_scale : 0.0;
+      const double rs = p.f32_acc ? 1.0 : (row_ok ? p.row_scale[row] * p.diag_scale : 0.0);
       mbar_wait(smem_u32(&bars[2 * STAGES + buf]), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tsrc = tmem_base + static_cast<uint32_t>(buf * BN) + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
@@ -238,7 +250,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 dst[static_cast<size_t>(brows) * j] =
-                    old[j] + (static_cast<double>(static_cast<int32_t>(r[j])) * rs) * __ldg(p.col_scale + col0 + j);
+                    p.f32_acc ? static_cast<double>(__uint_as_float(r[j]))
+                              : old[j] + (static_cast<double>(static_cast<int32_t>(r[j])) * rs) * __ldg(p.col_scale + col0 + j);
             }
           } else {
 #pragma unroll 1
@@ -249,8 +262,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
                 double* blkp = p.ctab[rid * p.nbc + cid];
                 if (blkp != nullptr) {
                   double* dst = blkp + lr + static_cast<size_t>(brows) * (col - cid * p.blk);
-                  const double term = (static_cast<double>(static_cast<int32_t>(r[j])) * rs) * p.col_scale[col];
-                  *dst = p.accumulate ? *dst + term : term;
+                  const double term = p.f32_acc ? static_cast<double>(__uint_as_float(r[j]))
+                                                : (static_cast<double>(static_cast<int32_t>(r[j])) * rs) * p.col_scale[col];
+                  *dst = (p.accumulate && !p.f32_acc) ? *dst + term : term;
                 }
               }
             }
@@ -401,6 +415,46 @@ __global__ void __launch_bounds__(256) slice_kernel(const OzBlock* __restrict__ 
   }
 }
 
+// ---- fp32 path (BASELINE configs[3]): 3xTF32 split.  hi = tf32(a), lo = tf32(a - hi); A B ~= hi hi' + hi lo' + lo hi'
+// with fp32 accumulation in TMEM.  out_hi/out_lo[line * Kpad + k] (fp32, K contiguous), same staging as slice_kernel.
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(256) slice_tf32_kernel(const OzBlock* __restrict__ blocks, float* __restrict__ out_hi,
+                                                         float* __restrict__ out_lo, int Kpad, int lines_are_rows, int tiles_k_max) {
+  __shared__ double sm[32][129];
+  const OzBlock b = blocks[blockIdx.y];
+  const int tl = blockIdx.x / tiles_k_max, tk = blockIdx.x % tiles_k_max;
+  const int nlines = lines_are_rows ? b.rows : b.cols;
+  const int nks = lines_are_rows ? b.cols : b.rows;
+  const int l0 = tl * 32, k0 = tk * 128;
+  if (l0 >= nlines || k0 >= nks) return;
+  const int tid = threadIdx.x;
+  const bool k_fast = lines_are_rows ? (b.isT != 0) : (b.isT == 0);
+  for (int idx = tid; idx < 32 * 128; idx += 256) {
+    const int l = k_fast ? idx / 128 : idx % 32, k = k_fast ? idx % 128 : idx / 32;
+    double v = 0.0;
+    if (l0 + l < nlines && k0 + k < nks) v = lines_are_rows ? blk_at(b, l0 + l, k0 + k) : blk_at(b, k0 + k, l0 + l);
+    sm[l][k] = v;
+  }
+  __syncthreads();
+  const int gl_base = (lines_are_rows ? b.row0 : b.col0) + l0;
+  const int gk_base = (lines_are_rows ? b.col0 : b.row0) + k0;
+  for (int idx = tid; idx < 32 * 128; idx += 256) {
+    const int l = idx / 128, k = idx % 128;
+    if (l0 + l < nlines && k0 + k < nks) {
+      const float a = static_cast<float>(sm[l][k]);
+      const float hi = to_tf32(a);
+      const float lo = to_tf32(a - hi);
+      const size_t o = static_cast<size_t>(gl_base + l) * Kpad + gk_base + k;
+      out_hi[o] = hi;
+      out_lo[o] = lo;
+    }
+  }
+}
+
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -424,6 +478,21 @@ bool make_i8_map(unsigned char* out128, void* base, uint64_t Kpad, uint64_t rows
   const cuuint32_t box[2] = {BKB, box_rows};
   const cuuint32_t est[2] = {1, 1};
   if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  memcpy(out128, &m, 128);
+  return true;
+}
+
+bool make_f32_map(unsigned char* out128, void* base, uint64_t Kpad, uint64_t rows, uint32_t box_rows) {
+  EncodeFn fn = encode_fn();
+  if (!fn) return false;
+  alignas(64) CUtensorMap m;
+  const cuuint64_t gdim[2] = {Kpad, rows};
+  const cuuint64_t gstr[1] = {Kpad * 4};
+  const cuuint32_t box[2] = {32, box_rows};  // 32 fp32 = one 128-byte swizzle row
+  const cuuint32_t est[2] = {1, 1};
+  if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
   memcpy(out128, &m, 128);
@@ -545,6 +614,10 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   p.nbr = nbr;
   p.nbc = nbc;
   p.S = S;
+  p.kstep = BKB;
+  p.f32_acc = 0;
+  // D = S32 (2 @ bit 4); A, B = signed 8-bit (1 @ bits 7 and 10); both K-major; N >> 3 @ 17; M >> 4 @ 24
+  p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
   p.tiles_m = static_cast<int32_t>(Mpad / BM);
   p.tiles_n = static_cast<int32_t>(Npad / BN);
   int dev = 0, sms = 148;
@@ -557,12 +630,103 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
     p.d = d;
     p.accumulate = first ? 0 : 1;
     p.diag_scale = std::ldexp(1.0, 4 - 8 * d);
+    p.npairs = 0;
+    for (int sl = std::max(1, d - S); sl <= std::min(S, d - 1); ++sl) {  // pairs (s, d - s)
+      p.pair_a[p.npairs] = sl - 1;
+      p.pair_b[p.npairs] = S + (d - sl) - 1;
+      ++p.npairs;
+    }
     first = false;
     ozaki_gemm_i8_kernel<<<grid, GEMM_THREADS_P, smem_bytes, stream>>>(p);
     OZ_CHECK(cudaGetLastError());
     *launches += 1;
   }
   // scratch is freed stream-ordered by the AsyncBuf destructors; pageable staging vectors were consumed synchronously
+  return cudaSuccess;
+}
+
+// fp32 multiply on tcgen05 kind::tf32 with the 3xTF32 split (gemm_algo = 3).  Inputs are rounded to fp32, products are
+// accumulated in fp32 in TMEM, the result is stored into the fp64 output blocks.
+cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K, int64_t N,
+                        double* const* h_ctab, int blk, int nbr, int nbc, int* launches, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  const int64_t Mpad = (M + BM - 1) / BM * BM, Npad = (N + BN - 1) / BN * BN, Kpad = (K + 31) / 32 * 32;
+  static bool configured = false;
+  const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+  if (!configured) {
+    OZ_CHECK(cudaFuncSetAttribute(ozaki_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+    configured = true;
+  }
+  std::vector<OzBlock> ha(na), hb(nb);
+  int max_ar = 1, max_ac = 1, max_br = 1, max_bc = 1;
+  for (int i = 0; i < na; ++i) {
+    ha[i] = OzBlock{a_blocks[i].v, a_blocks[i].rows, a_blocks[i].cols, a_blocks[i].row0, a_blocks[i].col0, a_blocks[i].isT, {0}};
+    max_ar = std::max(max_ar, a_blocks[i].rows);
+    max_ac = std::max(max_ac, a_blocks[i].cols);
+  }
+  for (int i = 0; i < nb; ++i) {
+    hb[i] = OzBlock{b_blocks[i].v, b_blocks[i].rows, b_blocks[i].cols, b_blocks[i].row0, b_blocks[i].col0, b_blocks[i].isT, {0}};
+    max_br = std::max(max_br, b_blocks[i].rows);
+    max_bc = std::max(max_bc, b_blocks[i].cols);
+  }
+  AsyncBuf d_ab(stream), d_bb(stream), d_A(stream), d_B(stream), d_maps(stream), d_ctab(stream);
+  OZ_CHECK(d_ab.alloc(sizeof(OzBlock) * na));
+  OZ_CHECK(d_bb.alloc(sizeof(OzBlock) * nb));
+  OZ_CHECK(cudaMemcpyAsync(d_ab.p, ha.data(), sizeof(OzBlock) * na, cudaMemcpyHostToDevice, stream));
+  OZ_CHECK(cudaMemcpyAsync(d_bb.p, hb.data(), sizeof(OzBlock) * nb, cudaMemcpyHostToDevice, stream));
+  const size_t a_elems = static_cast<size_t>(Mpad) * Kpad, b_elems = static_cast<size_t>(Npad) * Kpad;
+  OZ_CHECK(d_A.alloc(a_elems * 2 * sizeof(float)));
+  OZ_CHECK(d_B.alloc(b_elems * 2 * sizeof(float)));
+  OZ_CHECK(cudaMemsetAsync(d_A.p, 0, a_elems * 2 * sizeof(float), stream));
+  OZ_CHECK(cudaMemsetAsync(d_B.p, 0, b_elems * 2 * sizeof(float), stream));
+  float* Ahi = static_cast<float*>(d_A.p);
+  float* Alo = Ahi + a_elems;
+  float* Bhi = static_cast<float*>(d_B.p);
+  float* Blo = Bhi + b_elems;
+  {
+    const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
+    slice_tf32_kernel<<<dim3(tl * tk, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), Ahi, Alo, static_cast<int>(Kpad), 1, tk);
+    const int tkb = (max_br + 127) / 128, tlb = (max_bc + 31) / 32;
+    slice_tf32_kernel<<<dim3(tlb * tkb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), Bhi, Blo, static_cast<int>(Kpad), 0, tkb);
+    *launches += 2;
+  }
+  std::vector<unsigned char> hmaps(4 * 128);
+  if (!make_f32_map(&hmaps[0], Ahi, Kpad, Mpad, BM) || !make_f32_map(&hmaps[128], Alo, Kpad, Mpad, BM) ||
+      !make_f32_map(&hmaps[256], Bhi, Kpad, Npad, BN) || !make_f32_map(&hmaps[384], Blo, Kpad, Npad, BN))
+    return cudaErrorInvalidValue;
+  OZ_CHECK(d_maps.alloc(hmaps.size()));
+  OZ_CHECK(cudaMemcpyAsync(d_maps.p, hmaps.data(), hmaps.size(), cudaMemcpyHostToDevice, stream));
+  OZ_CHECK(d_ctab.alloc(sizeof(double*) * nbr * nbc));
+  OZ_CHECK(cudaMemcpyAsync(d_ctab.p, h_ctab, sizeof(double*) * nbr * nbc, cudaMemcpyHostToDevice, stream));
+  OzakiGemmParams p{};
+  p.tmaps = static_cast<const unsigned char*>(d_maps.p);
+  p.ctab = static_cast<double* const*>(d_ctab.p);
+  p.M = static_cast<int32_t>(M);
+  p.N = static_cast<int32_t>(N);
+  p.Kpad = static_cast<int32_t>(Kpad);
+  p.blk = blk;
+  p.nbr = nbr;
+  p.nbc = nbc;
+  p.kstep = 32;
+  p.f32_acc = 1;
+  p.accumulate = 0;
+  p.diag_scale = 1.0;
+  // small terms first: lo*hi, hi*lo, then hi*hi
+  p.npairs = 3;
+  p.pair_a[0] = 1; p.pair_b[0] = 2;
+  p.pair_a[1] = 0; p.pair_b[1] = 3;
+  p.pair_a[2] = 0; p.pair_b[2] = 2;
+  // D = F32 (1 @ bit 4); A, B = TF32 (2 @ bits 7 and 10); both K-major; N >> 3 @ 17; M >> 4 @ 24
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+  p.tiles_m = static_cast<int32_t>(Mpad / BM);
+  p.tiles_n = static_cast<int32_t>(Npad / BN);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ntiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+  ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(ntiles, sms)), GEMM_THREADS_P, smem_bytes, stream>>>(p);
+  OZ_CHECK(cudaGetLastError());
+  *launches += 1;
   return cudaSuccess;
 }
 

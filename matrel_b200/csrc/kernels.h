@@ -56,6 +56,10 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
                            int64_t N, int slices, double* const* h_ctab, int blk, int nbr, int nbc, bool accumulate,
                            int* launches, int* nonfinite, cudaStream_t stream);
 
+// fp32 multiply on tcgen05 kind::tf32 (3xTF32 split, fp32 TMEM accumulation); same operand / output conventions.
+cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K, int64_t N,
+                        double* const* h_ctab, int blk, int nbr, int nbc, int* launches, cudaStream_t stream);
+
 // ---- element-wise / layout kernels (HBM-bound), batched over blocks ---------------------------------
 enum EwOp { EW_ADD = 0, EW_MUL = 1, EW_DIV = 2, EW_RANK1 = 3, EW_RANK1_COMPAT = 4, EW_COPY = 5 };
 
