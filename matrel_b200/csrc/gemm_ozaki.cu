@@ -99,6 +99,7 @@ struct OzakiGemmParams {
   int32_t kstep;               // elements of K per stage (128 int8 / 32 tf32)
   uint32_t idesc;
   int32_t f32_acc;             // 0: s32 accumulator scaled by the Ozaki exponents; 1: f32 accumulator written as is
+  int32_t kc0, nkc;            // K range of this launch in stage units (the fp32 path re-accumulates K chunks in fp64)
 };
 
 constexpr int EPI_WARPS = 8;                       // 2 per TMEM lane quarter (each takes 128 of the 256 columns)
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = p.Kpad / p.kstep;
+  const int nk = p.nkc;
   const int per_tile = p.npairs * nk;
   const int ntiles = p.tiles_m * p.tiles_n;
 
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
         for (int s = 0; s < p.npairs; ++s) {
           const void* tmA = p.tmaps + static_cast<size_t>(p.pair_a[s]) * 128;
           const void* tmB = p.tmaps + static_cast<size_t>(p.pair_b[s]) * 128;
-          for (int kc = 0; kc < nk; ++kc, ++it) {
+          for (int kc = p.kc0; kc < p.kc0 + nk; ++kc, ++it) {
             const int st = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(smem_u32(&bars[STAGES + st]), ph ^ 1);
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 dst[static_cast<size_t>(brows) * j] =
-                    p.f32_acc ? static_cast<double>(__uint_as_float(r[j]))
+                    p.f32_acc ? old[j] + static_cast<double>(__uint_as_float(r[j]))
                               : old[j] + (static_cast<double>(static_cast<int32_t>(r[j])) * rs) * __ldg(p.col_scale + col0 + j);
             }
           } else {
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
                   double* dst = blkp + lr + static_cast<size_t>(brows) * (col - cid * p.blk);
                   const double term = p.f32_acc ? static_cast<double>(__uint_as_float(r[j]))
                                                 : (static_cast<double>(static_cast<int32_t>(r[j])) * rs) * p.col_scale[col];
-                  *dst = (p.accumulate && !p.f32_acc) ? *dst + term : term;
+                  *dst = p.accumulate ? *dst + term : term;
                 }
               }
             }
@@ -616,6 +617,8 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   p.S = S;
   p.kstep = BKB;
   p.f32_acc = 0;
+  p.kc0 = 0;
+  p.nkc = static_cast<int32_t>(Kpad / BKB);
   // D = S32 (2 @ bit 4); A, B = signed 8-bit (1 @ bits 7 and 10); both K-major; N >> 3 @ 17; M >> 4 @ 24
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
   p.tiles_m = static_cast<int32_t>(Mpad / BM);
@@ -724,9 +727,18 @@ cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
-  ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(ntiles, sms)), GEMM_THREADS_P, smem_bytes, stream>>>(p);
-  OZ_CHECK(cudaGetLastError());
-  *launches += 1;
+  // fp32 accumulation in the tensor core drifts with K (measured ~1e-4 at K = 16384 for all-positive data), so K is cut
+  // into chunks of 4096 whose fp32 tile sums are re-accumulated in fp64 by the epilogue (read-modify-write of C).
+  const int stages_total = static_cast<int>(Kpad / 32);
+  const int chunk = 4096 / 32;
+  for (int kc = 0; kc < stages_total; kc += chunk) {
+    p.kc0 = kc;
+    p.nkc = std::min(chunk, stages_total - kc);
+    p.accumulate = kc == 0 ? 0 : 1;
+    ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(ntiles, sms)), GEMM_THREADS_P, smem_bytes, stream>>>(p);
+    OZ_CHECK(cudaGetLastError());
+    *launches += 1;
+  }
   return cudaSuccess;
 }
 

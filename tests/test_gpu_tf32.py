@@ -1,8 +1,8 @@
 """GPU tests of the fp32 multiply on tcgen05 kind::tf32 (gemm_algo = 3, 3xTF32 split) -- BASELINE configs[3] shape.
 
 fp32 is not a reference feature (blocks are Array[Double]); parity is defined as: inputs rounded to fp32, oracle =
-fp64 product of those inputs, tolerance 2e-5 relative to max|C| (fp32 accumulation over K plus the dropped lo*lo term;
-a single-pass TF32 product would be ~1e-3)."""
+fp64 product of those inputs, tolerance 5e-5 relative to max|C| (fp32 tensor-core accumulation inside each 4096-deep K
+chunk -- chunks are re-accumulated in fp64 -- plus the dropped lo*lo term; a single-pass TF32 product would be ~1e-3)."""
 import numpy as np
 import pytest
 
@@ -11,7 +11,7 @@ from oracle import matrel_oracle as O
 from tests.util import assert_same_dataset, from_dataset, random_block_dataset, rel_err, to_dataset
 
 pytestmark = pytest.mark.gpu
-TF32X3_TOL = 2e-5
+TF32X3_TOL = 5e-5
 
 
 def f32_round(ds):
@@ -21,8 +21,20 @@ def f32_round(ds):
     return out
 
 
+def test_tf32x3_positive_data_long_k():
+    """All-positive U(0,1) data at K = 16384: the worst case for fp32 accumulation drift."""
+    n, blk = 16384, 1024
+    with mb.MatfastSession(device=0, gemm_algo=3) as s:
+        A, B = s.rand(n, n, blk, 42), s.rand(n, n, blk, 43)
+        C = A.matrixMultiply(n, n, B, n, n, blk)
+        a = np.concatenate([A.get_block(0, k).to_numpy().astype(np.float32).astype(np.float64) for k in range(n // blk)], axis=1)[:128]
+        b = np.concatenate([B.get_block(k, 0).to_numpy().astype(np.float32).astype(np.float64) for k in range(n // blk)], axis=0)[:, :128]
+        got = C.get_block(0, 0).to_numpy()[:128, :128]
+    assert rel_err(got, a @ b) <= TF32X3_TOL
+
+
 @pytest.mark.parametrize("n,k,m,blk,pt", [(256, 256, 256, 128, 0.0), (512, 640, 384, 128, 0.5), (300, 200, 260, 128, 0.5),
-                                          (2048, 2048, 2048, 512, 0.3)])
+                                          (2048, 2048, 2048, 512, 0.3), (256, 9000, 256, 1000, 0.3)])
 def test_tf32x3_multiply(n, k, m, blk, pt):
     rng = np.random.default_rng(n + k + m)
     A = f32_round(random_block_dataset(rng, n, k, blk, p_transposed=pt))
@@ -30,12 +42,12 @@ def test_tf32x3_multiply(n, k, m, blk, pt):
     want = O.matrix_multiply(A, n, k, B, k, m, blk)
     with mb.MatfastSession(device=0, gemm_algo=3) as s:
         got = from_dataset(to_dataset(s, A).matrixMultiply(n, k, to_dataset(s, B), k, m, blk))
-        assert s.stats()["kernel_launches"] == 3            # two slicing passes + ONE tcgen05 launch
+        assert s.stats()["kernel_launches"] == 2 + -(-k // 4096)   # two slicing passes + one tcgen05 launch per K chunk
     assert_same_dataset(got, want, tol=TF32X3_TOL)          # ids / presence / shapes / flags exact
     full_g = O.assemble({k_: O.DenseMatrix(v.numRows, v.numCols, v.values) for k_, v in got.items()}, n, m, blk)
     err = rel_err(full_g, O.assemble(want, n, m, blk))
     assert err <= TF32X3_TOL, err
     assert err > 0                                           # it really is fp32 arithmetic
-    # every stored result is an fp32 value
-    for v in got.values():
-        assert np.array_equal(v.values, v.values.astype(np.float32).astype(np.float64))
+    if k <= 4096:   # a single K chunk: every stored result is exactly an fp32 accumulator value
+        for v in got.values():
+            assert np.array_equal(v.values, v.values.astype(np.float32).astype(np.float64))
