@@ -174,6 +174,61 @@ def sharded_multiply(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMa
     return dC, (gA, gB, dA, dB)
 
 
+def sharded_multiply_overlapped(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMatrix, planA: GridPlan,
+                                planB: GridPlan, comm_stream, nchunks: int = 4):
+    """Same result as :func:`sharded_multiply`, with the A exchange pipelined against the GEMM: B and the first
+    chunk of A's block rows are gathered up front; while the kernel multiplies chunk c on the compute stream, NCCL
+    gathers chunk c+1 on `comm_stream`.  Returns (list of local C Datasets -- one per chunk --, keep-alive objects)."""
+    import torch
+    rank = groups.rank
+    pr, pc = planA.pr, planA.pc
+    compute = torch.cuda.current_stream()
+    r, _ = planA.coords(rank)
+    my_rows = list(range(r, planA.nbr, pr))
+    nchunks = max(1, min(nchunks, len(my_rows)))
+    bounds = [len(my_rows) * c // nchunks for c in range(nchunks + 1)]
+    esz = 8
+    comm_stream.wait_stream(compute)                       # the slabs were produced on the compute stream
+    events, gathered = [], []
+    with torch.cuda.stream(comm_stream):
+        gB = gather_panels(B.slab, groups.col_group, pr)
+        for c in range(nchunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            # block rows are contiguous in the slab: slots [(i // pr) * slots_c, ...)
+            part = A.slab[lo * planA.slots_c:hi * planA.slots_c]
+            gathered.append(gather_panels(part, groups.row_group, pc))
+            ev = torch.cuda.Event()
+            ev.record(comm_stream)
+            events.append(ev)
+    dB = session.emptyDataset()
+    blocks = panel_blocks_B(planB, rank)
+    shapes = [planB.block_shape(k, j) for k, j, _, _ in blocks]
+    baseB, sB0, sB1 = gB.data_ptr(), gB.stride(0) * esz, gB.stride(1) * esz
+    dB.put_blocks_device([b[0] for b in blocks], [b[1] for b in blocks], [x[0] for x in shapes], [x[1] for x in shapes],
+                         [baseB + src * sB0 + slot * sB1 for _, _, src, slot in blocks])
+    outs, keep = [], [gB, dB]
+    for c in range(nchunks):
+        lo, hi = bounds[c], bounds[c + 1]
+        gA = gathered[c]
+        base, s0, s1 = gA.data_ptr(), gA.stride(0) * esz, gA.stride(1) * esz
+        dA = session.emptyDataset()
+        rids, cids, nr, nc, ptrs = [], [], [], [], []
+        for li in range(lo, hi):
+            i = my_rows[li]
+            for k in range(planA.nbc):
+                rr, cc = planA.block_shape(i, k)
+                rids.append(i); cids.append(k); nr.append(rr); nc.append(cc)
+                ptrs.append(base + (k % pc) * s0 + ((li - lo) * planA.slots_c + k // pc) * s1)
+        dA.put_blocks_device(rids, cids, nr, nc, ptrs)
+        compute.wait_event(events[c])
+        outs.append(dA.matrixMultiply(planA.nrows, planA.ncols, dB, planB.nrows, planB.ncols, planA.blk))
+        keep += [gA, dA]
+    for g in gathered:                                     # the caching allocator must not recycle them under the GEMM
+        g.record_stream(compute)
+    gB.record_stream(compute)
+    return outs, keep
+
+
 # --------------------------------------------------------------------------------------------------
 # bench.py's N > 1 arm
 # --------------------------------------------------------------------------------------------------
@@ -203,9 +258,11 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
         B = ShardedMatrix.rand(s, plan, rank, 43, device)
         s.sync()
 
+        comm_stream = torch.cuda.Stream(device=device)
+
         def step():
-            dC, keep = sharded_multiply(s, groups, A, B, plan, plan)
-            return dC, keep
+            # all-gather of A pipelined in 4 chunks of block rows against the GEMM (NCCL on its own stream)
+            return sharded_multiply_overlapped(s, groups, A, B, plan, plan, comm_stream, nchunks=4)
 
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -241,7 +298,7 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
             del out
         st2 = s.stats()
         s.set_option("time_kernels", 0)
-        kern_ms = st2["gemm_ms_total"] / max(1, st2["gemm_launches"])
+        kern_ms = st2["gemm_ms_total"] / 3.0          # all GEMM launches of one step (one per exchange chunk)
         kt = torch.tensor([kern_ms], dtype=torch.float64, device=device)
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
         kern_ms = float(kt.item())
@@ -325,7 +382,7 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
             "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{n}x{n} fp64 dense multiply, {blk}-block, grid-partitioned {plan.pr}x{plan.pc} over {world}xB200",
-                       "parallelism": f"C-stationary {plan.pr}x{plan.pc} block-cyclic grid; all-gather A along grid rows, B along grid columns (NCCL), no reduction",
+                       "parallelism": f"C-stationary {plan.pr}x{plan.pc} block-cyclic grid; all-gather A along grid rows (4 chunks, overlapped with the GEMM on a side stream), B along grid columns (NCCL), no reduction",
                        "inputs": "U(0,1) java.util.Random streams, every block present, column-major",
                        "l2": "per-rank operands after all-gather >> 126 MB L2; no flush needed", "gemm_algo": "dmma_fp64"},
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_total,

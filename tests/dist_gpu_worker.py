@@ -9,7 +9,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import matrel_b200 as mb  # noqa: E402
-from matrel_b200.distributed import GridGroups, GridPlan, ShardedMatrix, sharded_multiply  # noqa: E402
+from matrel_b200.distributed import (GridGroups, GridPlan, ShardedMatrix, sharded_multiply,  # noqa: E402
+                                     sharded_multiply_overlapped)
 from oracle import matrel_oracle as O  # noqa: E402
 
 
@@ -31,6 +32,12 @@ def main():
             dC, keep = sharded_multiply(s, groups, A, B, planA, planB)
             got = {(b.rid, b.cid): b.matrix for b in dC.collect()}
             s_launches = s.stats()["kernel_launches"]
+            # the overlapped exchange (A gathered in chunks on a side stream) must give the same blocks
+            outs, keep2 = sharded_multiply_overlapped(s, groups, A, B, planA, planB, torch.cuda.Stream(device=device), nchunks=3)
+            got2 = {(b.rid, b.cid): b.matrix for d in outs for b in d.collect()}
+            assert sorted(got2) == sorted(got)
+            for key in got:
+                assert np.array_equal(got2[key].values, got[key].values), key
             s.stop()
         want = O.matrix_multiply(O.rand_dense_dataset(n, k, blk, 42), n, k, O.rand_dense_dataset(k, m, blk, 43), k, m, blk)
         assert sorted(got) == sorted(planC.owned(rank)), (rank, sorted(got))
