@@ -45,6 +45,18 @@ def fp64_peak_tflops():
     return best, src
 
 
+def dram_traffic_per_launch(n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the GEMM kernel at this N from the committed ncu capture
+    (profiles/gemm_traffic_r01.json), or None when no capture exists for this size."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")))
+        e = d.get(str(n))
+        return None if e is None else {"bytes": e["dram_read_bytes"] + e["dram_write_bytes"], "algorithmic_bytes": 3 * n * n * 8,
+                                       "source": e.get("source", "ncu")}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -399,7 +411,7 @@ def run_ours(args):
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "gemm_f64_dmma_kernel<128,128,2,4,4>", "kernel_ms": kern_ms,
+                     "traffic": dram_traffic_per_launch(n), "kernel": "gemm_f64_dmma_kernel<128,128,2,4,5>", "kernel_ms": kern_ms,
                      "launches_per_step": gemm_launches_per_step,
                      "algorithmic": f"2*N^3 = {flops:.4g} flop per launch (whole block multiply, K reduction fused)",
                      "peak_source": peak_src},

@@ -155,6 +155,15 @@ template <int OP>
 __device__ __forceinline__ double map_apply(double v, double alpha) {
   if (OP == MAP_ADD_SCALAR) return v + alpha;
   if (OP == MAP_MUL_SCALAR) return alpha * v;
+  // math.pow (LocalMatrix.scala:931-946).  The common exponents take exact closed forms (the correctly rounded value
+  // of x^2 is x*x, of x^0.5 is sqrt(x)) instead of the ~100-instruction general pow.
+  if (alpha == 2.0) return v * v;
+  if (alpha == 1.0) return v;
+  if (alpha == 0.5) {
+    if (v == 0.0) return 0.0;                       // pow(-0.0, 0.5) = +0.0
+    if (isinf(v) && v < 0.0) return -v;             // pow(-inf, 0.5) = +inf
+    return sqrt(v);
+  }
   return pow(v, alpha);
 }
 

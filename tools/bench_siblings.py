@@ -25,6 +25,13 @@ with torch.cuda.stream(stream):
         ("multiplyScalar", lambda: A.multiplyScalar(2.5), 2 * nn),
         ("addScalar", lambda: A.addScalar(2.5), 2 * nn),
         ("power(2.0)", lambda: A.power(2.0), 2 * nn),
+        ("power(0.37)", lambda: A.power(0.37), 2 * nn),
+        ("rowSum", lambda: A.rowSum(n, n), nn),
+        ("colSum", lambda: A.colSum(n, n), nn),
+        ("rowSum of transposed", lambda: At.rowSum(n, n), nn),
+        ("sum", lambda: A.sum(n, n), nn),
+        ("trace", lambda: A.trace(n, n), 0),
+        ("project row", lambda: A.project(n, n, blk, True, n // 3), 0),
         ("transpose (flag only)", lambda: A.t(), 0),
         ("transpose + materialize", lambda: At.materialize(), 2 * nn),
     ]
