@@ -172,7 +172,9 @@ struct Block {
   int64_t valuesLen = 0;
   Span colPtrs, rowIndices;  // sparse only
   int64_t colPtrsLen = 0;
-  ReadyPtr ready;            // producer still in flight on another stream (nullptr = ordered on the context stream)
+  mutable ReadyPtr ready;    // producer still in flight on another stream (nullptr = ordered on the context stream);
+                             // dropped (under the context mutex) once the event is seen complete
+  mutable bool settled = false;  // the dropped event had completed: the block's data needs no further ordering
   bool dense() const { return type == 1; }
 };
 
@@ -198,10 +200,25 @@ void note_launch(mr_context* ctx, int n = 1) { ctx->stats.kernel_launches += n; 
 bool wait_ready(mr_context* ctx, const Block& b) {
   if (!b.ready) return false;
   const cudaError_t q = cudaEventQuery(b.ready->ev);
-  if (q == cudaSuccess) return false;
+  if (q == cudaSuccess) {
+    b.ready.reset();  // never query this block again
+    b.settled = true;
+    return false;
+  }
   (void)cudaGetLastError();
   cudaStreamWaitEvent(ctx->stream, b.ready->ev, 0);
   return true;
+}
+// true when the block's producer has finished (and forgets the event so it is not queried again)
+bool block_done(const Block& b) {
+  if (!b.ready) return true;
+  if (cudaEventQuery(b.ready->ev) == cudaSuccess) {
+    b.ready.reset();
+    b.settled = true;
+    return true;
+  }
+  (void)cudaGetLastError();
+  return false;
 }
 bool wait_ready_all(mr_context* ctx, const mr_matrix* m) {
   bool any = false;
@@ -463,7 +480,7 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
   bool pending = false;
   for (size_t i = 0; i < plans.size() && !pending; ++i)
     for (const GemmSrc& g : plans[i].src)
-      if ((g.a->ready && cudaEventQuery(g.a->ready->ev) != cudaSuccess) || (g.b->ready && cudaEventQuery(g.b->ready->ev) != cudaSuccess)) {
+      if ((g.a->ready && !block_done(*g.a)) || (g.b->ready && !block_done(*g.b))) {
         pending = true;
         break;
       }
@@ -1157,14 +1174,21 @@ mr_status mr_matrix_get_block(mr_matrix* m, int32_t rid, int32_t cid, mr_block_d
     if (it == m->blocks.end()) fail(MR_ENOTFOUND, "no block (%d, %d) in this dataset", rid, cid);
     const Block& b = it->second;
     mr_context* ctx = m->ctx;
+    ReadyPtr ready;
+    bool settled;
+    {
+      std::lock_guard<std::mutex> lock(ctx->mu);
+      ready = b.ready;  // snapshot: operators on other threads may drop completed events
+      settled = b.settled;
+    }
     const int64_t rowIndicesLen = b.dense() ? 0 : b.valuesLen;
     // Egress on its own stream, ordered after this block's producer only (one chunk of a chunked multiply, or
     // everything enqueued on the context stream so far when the block has no event of its own).
     cudaStream_t rs = ctx->pipeline ? ctx->d2h_stream : ctx->stream;
     if (ctx->pipeline && (io->values || io->colPtrs || io->rowIndices)) {
-      if (b.ready) {
-        CUDA_CHECK(cudaStreamWaitEvent(rs, b.ready->ev, 0));
-      } else {
+      if (ready) {
+        CUDA_CHECK(cudaStreamWaitEvent(rs, ready->ev, 0));
+      } else if (!settled) {
         CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
         CUDA_CHECK(cudaStreamWaitEvent(rs, ctx->ev_order, 0));
       }
