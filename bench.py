@@ -352,13 +352,25 @@ def run_ours(args):
         h2d = sum(b.matrix.values.nbytes for b in pA) + sum(b.matrix.values.nbytes for b in pB)
         d2h = sum(v.nbytes for v in outbuf.values())
 
+        rowsA = {}
+        colsB = {}
+        for b_ in pA:
+            rowsA.setdefault(b_.rid, []).append(b_)
+        for b_ in pB:
+            colsB.setdefault(b_.cid, []).append(b_)
+
         def e2e_step():
-            # right operand first: the multiply then starts on the row panels of A as they land (per-block events),
-            # and finished block rows of C stream back while later rows are still computing
-            dB = s.createDataset(pB)
-            dA = s.createDataset(pA)
+            # block row t of A and block column t of B are uploaded alternately; every put_block is an async copy on
+            # the ingest stream tagged with an event, the multiply launches chunk after chunk as the operands each
+            # chunk needs have landed, and finished blocks of C stream back on the egress stream meanwhile
+            dA, dB = s.emptyDataset(), s.emptyDataset()
+            for t_ in range(nb):
+                for b_ in rowsA[t_]:
+                    dA.put_block(b_.rid, b_.cid, b_.matrix)
+                for b_ in colsB[t_]:
+                    dB.put_block(b_.rid, b_.cid, b_.matrix)
             dC = dA.matrixMultiply(n, n, dB, n, n, blk)
-            for (i, j) in dC.block_ids():
+            for (i, j) in sorted(dC.block_ids(), key=lambda ij: (max(ij), ij)):   # the order the chunks complete in
                 dC.get_block(i, j, out=outbuf[(i, j)])
             return dC
 

@@ -108,6 +108,7 @@ struct mr_context {
   int force_variant = -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr, ev_order = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // ingest / egress overlap with compute on `stream`
+  uint64_t ingest_seq = 0;
   int pipeline = 1;
   mr_stats stats{};
   std::mutex mu;
@@ -174,6 +175,7 @@ struct Block {
   int64_t colPtrsLen = 0;
   mutable ReadyPtr ready;    // producer still in flight on another stream (nullptr = ordered on the context stream);
                              // dropped (under the context mutex) once the event is seen complete
+  uint64_t seq = 0;              // ingest order of the block's H2D copy (0 = not produced by the ingest stream)
   mutable bool settled = false;  // the dropped event had completed: the block's data needs no further ordering
   bool dense() const { return type == 1; }
 };
@@ -524,15 +526,41 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     // Chunked launch when operands are still arriving from the host: one launch per block row of C, each waiting
     // only for the A row panel it reads (and all of B), so compute overlaps the remaining ingest and the egress of
     // finished rows.  With resident operands it is ONE launch.
-    std::map<int32_t, int> group_of;  // rid -> chunk
+    // Chunk key of an output block = ingest sequence number of the LAST operand block it needs that is still in flight
+    // (the ingest stream is in order, so waiting for that one copy implies all earlier ones).  Output blocks are
+    // launched in key order, in chunks of >= ~8 waves of tiles, so whatever has landed is multiplied while the rest of
+    // A and B is still on the wire -- row panels, column panels or an interleaving of both, whatever order the caller
+    // uploaded them in.
     const bool chunked = pending && ctx->pipeline != 0;
-    if (chunked)
-      for (size_t oi = 0; oi < outs.size(); ++oi) group_of.emplace(plans[out_plan[oi]].rid, 0);
-    {
-      int gidx = 0;
-      for (auto& kv : group_of) kv.second = gidx++;
+    std::vector<int> group_of(outs.size(), 0);
+    int ngroups_dyn = 1;
+    if (chunked) {
+      std::vector<std::pair<uint64_t, size_t>> order(outs.size());
+      for (size_t oi = 0; oi < outs.size(); ++oi) {
+        uint64_t key = 0;
+        for (const GemmSrc& g : plans[out_plan[oi]].src) {
+          if (g.a->ready) key = std::max(key, g.a->seq);
+          if (g.b->ready) key = std::max(key, g.b->seq);
+        }
+        order[oi] = {key, oi};
+      }
+      std::sort(order.begin(), order.end());
+      const int64_t min_tiles = 8 * 148;
+      int64_t acc_tiles = 0;
+      int gcur = 0;
+      for (size_t r = 0; r < order.size(); ++r) {
+        const size_t oi = order[r].second;
+        // close the chunk when it is big enough AND the next block waits for a later copy
+        if (acc_tiles >= min_tiles && r > 0 && order[r].first != order[r - 1].first) {
+          ++gcur;
+          acc_tiles = 0;
+        }
+        group_of[oi] = gcur;
+        acc_tiles += static_cast<int64_t>((outs[oi].m + BM - 1) / BM) * ((outs[oi].n + BN - 1) / BN);
+      }
+      ngroups_dyn = gcur + 1;
     }
-    auto grp = [&](const Keyed& k) { return chunked ? group_of[plans[out_plan[k.t.out]].rid] : 0; };
+    auto grp = [&](const Keyed& k) { return group_of[k.t.out]; };
     std::sort(keyed.begin(), keyed.end(), [&](const Keyed& x, const Keyed& y) {
       const int gx = grp(x), gy = grp(y);
       if (gx != gy) return gx < gy;
@@ -567,7 +595,7 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       }
     Buf d_outs = upload(ctx, outs), d_pairs = upload(ctx, pairs), d_tiles = upload(ctx, tiles), d_tmaps = upload(ctx, tmaps);
     if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-    const int ngroups = chunked ? static_cast<int>(group_of.size()) : 1;
+    const int ngroups = ngroups_dyn;
     size_t t0 = 0;
     for (int gi = 0; gi < ngroups; ++gi) {
       size_t t1 = t0;
@@ -1107,6 +1135,7 @@ mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_b
       ReadyPtr r = std::make_shared<Ready>();
       CUDA_CHECK(cudaEventRecord(r->ev, cs));
       b.ready = r;
+      b.seq = ++ctx->ingest_seq;
       b.values.buf->ready = r;
       if (d->type == 0) {
         b.colPtrs.buf->ready = r;
