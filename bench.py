@@ -365,10 +365,8 @@ def run_ours(args):
             # chunk needs have landed, and finished blocks of C stream back on the egress stream meanwhile
             dA, dB = s.emptyDataset(), s.emptyDataset()
             for t_ in range(nb):
-                for b_ in rowsA[t_]:
-                    dA.put_block(b_.rid, b_.cid, b_.matrix)
-                for b_ in colsB[t_]:
-                    dB.put_block(b_.rid, b_.cid, b_.matrix)
+                dA.put_blocks(rowsA[t_])
+                dB.put_blocks(colsB[t_])
             dC = dA.matrixMultiply(n, n, dB, n, n, blk)
             for (i, j) in sorted(dC.block_ids(), key=lambda ij: (max(ij), ij)):   # the order the chunks complete in
                 dC.get_block(i, j, out=outbuf[(i, j)])

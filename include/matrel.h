@@ -81,6 +81,9 @@ MR_API mr_status mr_matrix_free(mr_matrix* m);
 /* Copies the block to the device (MLMatrixSerializer.deserialize, :50-69, incl. the ctor
  * `require`s of DenseMatrix :240 and SparseMatrix :533-542).  Host arrays stay caller-owned. */
 MR_API mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_block_desc* blk);
+/* Batched mr_matrix_put_block: `count` blocks in one call (one ABI crossing per Seq[MatrixBlock], not per row). */
+MR_API mr_status mr_matrix_put_blocks(mr_matrix* m, int64_t count, const int32_t* rids, const int32_t* cids,
+                                      const mr_block_desc* blks);
 /* Adopts (borrows) a dense block already resident in device memory; not freed by the library. */
 MR_API mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int32_t numRows,
                                             int32_t numCols, const double* dvalues, uint8_t isTransposed);

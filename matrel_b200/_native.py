@@ -85,6 +85,7 @@ SIGNATURES = {
     "mr_matrix_create": [_P, _PP],
     "mr_matrix_free": [_P],
     "mr_matrix_put_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
+    "mr_matrix_put_blocks": [_P, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(mr_block_desc)],
     "mr_matrix_put_block_device": [_P, _i32, _i32, _i32, _i32, _P, C.c_uint8],
     "mr_matrix_put_blocks_device": [_P, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_uint8)],

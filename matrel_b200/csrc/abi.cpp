@@ -1146,6 +1146,18 @@ mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_b
   });
 }
 
+mr_status mr_matrix_put_blocks(mr_matrix* m, int64_t count, const int32_t* rids, const int32_t* cids, const mr_block_desc* blks) {
+  if (count < 0 || (count > 0 && (!rids || !cids || !blks))) {
+    g_last_error = "requirement failed: null argument";
+    return MR_EINVAL;
+  }
+  for (int64_t i = 0; i < count; ++i) {
+    const mr_status st = mr_matrix_put_block(m, rids[i], cids[i], &blks[i]);
+    if (st != MR_OK) return st;
+  }
+  return MR_OK;
+}
+
 mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int32_t numRows, int32_t numCols,
                                      const double* dvalues, uint8_t isTransposed) {
   return guarded([&] {

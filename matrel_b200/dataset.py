@@ -80,8 +80,7 @@ class MatfastSession:
     def createDataset(self, blocks: Iterable[MatrixBlock]) -> "Dataset":
         """``Seq(MatrixBlock(...)).toDS()`` (M/example/BasicMatrixOps.scala:115-116)."""
         ds = Dataset._new(self)
-        for b in blocks:
-            ds._put(b.rid, b.cid, b.matrix)
+        ds.put_blocks(blocks)
         return ds
 
     toDS = createDataset
@@ -144,6 +143,31 @@ class Dataset:
 
     def put_block(self, rid: int, cid: int, m: MLMatrix) -> None:
         self._put(rid, cid, m)
+
+    def put_blocks(self, blocks) -> None:
+        """A whole Seq[MatrixBlock] in ONE ABI call (the per-block Python / ctypes overhead would otherwise delay the
+        launch of a multiply that is pipelined against these very copies)."""
+        blocks = list(blocks)
+        n = len(blocks)
+        if n == 0:
+            return
+        descs = (N.mr_block_desc * n)()
+        rids = np.empty(n, dtype=np.int32)
+        cids = np.empty(n, dtype=np.int32)
+        for i, b in enumerate(blocks):
+            m, d = b.matrix, descs[i]
+            rids[i], cids[i] = b.rid, b.cid
+            d.numRows, d.numCols = m.numRows, m.numCols
+            d.isTransposed = 1 if m.isTransposed else 0
+            d.values = _f64p(m.values)
+            d.valuesLen = m.values.size
+            if isinstance(m, SparseMatrix):
+                d.type = 0
+                d.colPtrs, d.colPtrsLen = _i32p(m.colPtrs), m.colPtrs.size
+                d.rowIndices, d.rowIndicesLen = _i32p(m.rowIndices), m.rowIndices.size
+            else:
+                d.type = 1
+        N.check(N.lib.mr_matrix_put_blocks(self._h, n, _i32p(rids), _i32p(cids), descs))
 
     def put_block_device(self, rid: int, cid: int, numRows: int, numCols: int, device_ptr: int,
                          isTransposed: bool = False) -> None:
