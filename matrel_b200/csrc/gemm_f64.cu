@@ -193,7 +193,7 @@ struct GemmCfg {
 template <int BM, int BN, int WM, int WN, int STAGES>
 __global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES>::THREADS, 1)
     gemm_f64_dmma_kernel(const GemmOut* __restrict__ outs, const GemmPair* __restrict__ pairs,
-                         const GemmTile* __restrict__ tiles, const unsigned char* __restrict__ tmaps, int ntiles) {
+                         const GemmTile* __restrict__ tiles, const unsigned char* __restrict__ tmaps) {
   using Cfg = GemmCfg<BM, BN, WM, WN, STAGES>;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B destinations must be 1024-byte aligned
@@ -204,9 +204,11 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES>::THREADS, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // Persistent: CTA b walks tiles b, b + gridDim.x, ... of the band-ordered tile list.  All resident CTAs therefore
-  // work on one compact region of C at the same k phase, so the A row panels / B column panels they share are read
-  // from HBM about once per wave instead of once per CTA, and the producer prefetches the next tile during the epilogue.
+  const GemmTile tile = tiles[blockIdx.x];
+  const GemmOut out = outs[tile.out];
+  const int m0 = tile.tm * BM, n0 = tile.tn * BN;
+  const int mv = min(BM, out.m - m0), nv = min(BN, out.n - n0);
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bars[s]), 1);
@@ -219,11 +221,6 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES>::THREADS, 1)
   if (warp == Cfg::NCW) {
     // ===================== producer warp =====================
     int it = 0;
-    for (int tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
-    const GemmTile tile = tiles[tix];
-    const GemmOut out = outs[tile.out];
-    const int m0 = tile.tm * BM, n0 = tile.tn * BN;
-    const int mv = min(BM, out.m - m0), nv = min(BN, out.n - n0);
     for (int p = 0; p < out.pair_count; ++p) {
       const GemmPair pr = pairs[out.pair_begin + p];
       const bool a_k = pr.aT != 0;  // row-major A block: lines contiguous along k
@@ -259,23 +256,18 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES>::THREADS, 1)
         }
       }
     }
-    }  // tiles
   } else {
     // ===================== consumer warps =====================
     const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, t = lane & 3;
     const int m_base = wm * (Cfg::MI * 8), n_base = wn * (Cfg::NJ * 8);
-    int it = 0;
-    for (int tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
-    const GemmTile tile = tiles[tix];
-    const GemmOut out = outs[tile.out];
-    const int m0 = tile.tm * BM, n0 = tile.tn * BN;
     double acc[Cfg::MI][Cfg::NJ][2];
 #pragma unroll
     for (int i = 0; i < Cfg::MI; ++i)
 #pragma unroll
       for (int j = 0; j < Cfg::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    int it = 0;
     for (int p = 0; p < out.pair_count; ++p) {
       const GemmPair pr = pairs[out.pair_begin + p];
       const bool a_k = pr.aT != 0;
@@ -314,7 +306,6 @@ __global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES>::THREADS, 1)
         }
       }
     }
-    }  // tiles
   }
 }
 
@@ -329,16 +320,7 @@ cudaError_t launch_variant(const GemmOut* d_outs, const GemmPair* d_pairs, const
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  // persistent CTAs: one per SM for the 128x128 variant (~175 KB smem), three per SM for the 64x64 variant (~75 KB)
-  const int resident = sms * (BM >= 128 ? 1 : 3);
-  const int grid = ntiles < resident ? ntiles : resident;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(d_outs, d_pairs, d_tiles, static_cast<const unsigned char*>(d_tmaps), ntiles);
+  kern<<<ntiles, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(d_outs, d_pairs, d_tiles, static_cast<const unsigned char*>(d_tmaps));
   return cudaGetLastError();
 }
 
