@@ -363,13 +363,26 @@ def run_ours(args):
             # block row t of A and block column t of B are uploaded alternately; every put_block is an async copy on
             # the ingest stream tagged with an event, the multiply launches chunk after chunk as the operands each
             # chunk needs have landed, and finished blocks of C stream back on the egress stream meanwhile
+            dbg = os.environ.get("MATREL_E2E_DEBUG")
+            tq = [time.perf_counter()]
             dA, dB = s.emptyDataset(), s.emptyDataset()
             for t_ in range(nb):
                 dA.put_blocks(rowsA[t_])
                 dB.put_blocks(colsB[t_])
+            tq.append(time.perf_counter())
             dC = dA.matrixMultiply(n, n, dB, n, n, blk)
+            tq.append(time.perf_counter())
+            first = True
             for (i, j) in sorted(dC.block_ids(), key=lambda ij: (max(ij), ij)):   # the order the chunks complete in
                 dC.get_block(i, j, out=outbuf[(i, j)])
+                if first:
+                    tq.append(time.perf_counter())
+                    first = False
+            tq.append(time.perf_counter())
+            if dbg:
+                print("e2e host timeline ms: puts %.1f  multiply-call %.1f  first-block %.1f  all-blocks %.1f  launches %d" % (
+                    (tq[1] - tq[0]) * 1e3, (tq[2] - tq[1]) * 1e3, (tq[3] - tq[2]) * 1e3, (tq[4] - tq[2]) * 1e3,
+                    s.stats()["kernel_launches"]), file=sys.stderr, flush=True)
             return dC
 
         e2e_warm = min(args.warmup, 2)
