@@ -109,6 +109,10 @@ struct mr_context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr, ev_order = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // ingest / egress overlap with compute on `stream`
   uint64_t ingest_seq = 0;
+  // mapped pinned staging ring for descriptor tables (see upload())
+  char* stage_host = nullptr;
+  char* stage_dev = nullptr;
+  size_t stage_cap = 0, stage_off = 0;
   int pipeline = 1;
   mr_stats stats{};
   std::mutex mu;
@@ -228,14 +232,32 @@ bool wait_ready_all(mr_context* ctx, const mr_matrix* m) {
   return any;
 }
 
+// Descriptor tables (a few hundred KB per operator) travel through a mapped pinned staging ring and an SM-driven copy
+// kernel instead of cudaMemcpyAsync: on the H2D copy engine they would queue behind every block upload already
+// submitted on the ingest stream, and the first chunk of a pipelined multiply could not start until ALL operands had
+// landed.  Ring regions are only reused after a stream synchronisation (on wrap-around).
+Buf upload_bytes(mr_context* ctx, const void* data, size_t bytes) {
+  Buf b = std::make_shared<DevBuf>(ctx, std::max<size_t>((bytes + 3) / 4 * 4, 16));
+  if (bytes == 0) return b;
+  const size_t need = align_up(bytes);
+  if (ctx->stage_host != nullptr && need <= ctx->stage_cap / 2) {
+    if (ctx->stage_off + need > ctx->stage_cap) {
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      ctx->stage_off = 0;
+    }
+    std::memcpy(ctx->stage_host + ctx->stage_off, data, bytes);
+    CUDA_CHECK(launch_copy_words(b->p, ctx->stage_dev + ctx->stage_off, bytes, ctx->stream));
+    ctx->stage_off += need;
+  } else {
+    CUDA_CHECK(cudaMemcpyAsync(b->p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->stats.h2d_bytes += static_cast<int64_t>(bytes);
+  return b;
+}
+
 template <typename T>
 Buf upload(mr_context* ctx, const std::vector<T>& v) {
-  Buf b = std::make_shared<DevBuf>(ctx, std::max<size_t>(v.size() * sizeof(T), 16));
-  if (!v.empty()) {
-    CUDA_CHECK(cudaMemcpyAsync(b->p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes += static_cast<int64_t>(v.size() * sizeof(T));
-  }
-  return b;
+  return upload_bytes(ctx, v.data(), v.size() * sizeof(T));
 }
 
 // A slab allocator for operator results: one device allocation, blocks are windows into it.
@@ -994,6 +1016,21 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    {
+      void* hp = nullptr;
+      const size_t cap = 16u << 20;
+      if (cudaHostAlloc(&hp, cap, cudaHostAllocMapped) == cudaSuccess) {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+          ctx->stage_host = static_cast<char*>(hp);
+          ctx->stage_dev = static_cast<char*>(dp);
+          ctx->stage_cap = cap;
+        } else {
+          cudaFreeHost(hp);
+        }
+      }
+      (void)cudaGetLastError();
+    }
     // keep freed blocks in the pool: operators allocate result slabs on every call
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -1011,6 +1048,7 @@ mr_status mr_shutdown(mr_context* ctx) {
     cudaStreamSynchronize(ctx->d2h_stream);
     cudaStreamDestroy(ctx->h2d_stream);
     cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
     if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -448,6 +448,10 @@ __global__ void __launch_bounds__(256) extract_lines_kernel(const LineDesc* __re
   }
 }
 
+__global__ void __launch_bounds__(256) copy_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t nwords) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < nwords; i += static_cast<size_t>(gridDim.x) * 256) dst[i] = src[i];
+}
+
 inline int flat_grid_x(int64_t max_n) {
   int64_t vec = (max_n + 1) / 2;
   int64_t gx = (vec + static_cast<int64_t>(FLAT_THREADS) * FLAT_UNROLL - 1) / (static_cast<int64_t>(FLAT_THREADS) * FLAT_UNROLL);
@@ -602,6 +606,15 @@ cudaError_t launch_extract_lines(const LineDesc* d_descs, int nblocks, int max_l
     const int nb = nblocks - off < 65535 ? nblocks - off : 65535;
     extract_lines_kernel<<<dim3((max_len + 255) / 256, nb), 256, 0, stream>>>(d_descs + off);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_copy_words(void* dst, const void* src_mapped, size_t bytes, cudaStream_t stream) {
+  const size_t nwords = (bytes + 3) / 4;
+  if (nwords == 0) return cudaSuccess;
+  size_t grid = (nwords + 255) / 256;
+  if (grid > 64) grid = 64;
+  copy_words_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(src_mapped), nwords);
   return cudaGetLastError();
 }
 

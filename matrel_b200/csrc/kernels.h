@@ -159,6 +159,10 @@ struct LineDesc {
 };
 cudaError_t launch_extract_lines(const LineDesc* d_descs, int nblocks, int max_len, cudaStream_t stream);
 
+// Small table upload that does NOT go through the copy engines: an SM-driven copy from mapped pinned host memory.  The
+// descriptor tables of an operator must not queue behind gigabytes of block ingest on the H2D engine.
+cudaError_t launch_copy_words(void* dst, const void* src_mapped, size_t bytes, cudaStream_t stream);
+
 // java.util.Random-compatible U(0,1) fill: out[i] = i-th nextDouble() of new Random(seed), batched over blocks
 struct RandDesc {
   double* out;
