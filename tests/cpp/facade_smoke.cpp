@@ -1,0 +1,81 @@
+// Compiled-host check of the boundary: the C++ facade (include/matrel.hpp) over the C ABI, linked against the in-tree
+// libmatrel_b200.so, multiplying the reference's own demo fixture (example/BasicMatrixOps.scala:107-118) and a random
+// 3x3-block product checked against a plain triple loop written here.  Built and run by tests/test_gpu_cpp_facade.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "matrel.hpp"
+
+using namespace matfast;
+
+static int fail(const char* what) {
+  std::printf("FAIL: %s\n", what);
+  return 1;
+}
+
+int main() {
+  MatfastSession s(0);
+  // mat1 = {(0,0): b1, (1,1): b2}, mat2 = {(0,0): b3, (0,1): b4, (1,1): s1}
+  Dataset mat1(s), mat2(s);
+  mat1.putBlock(0, 0, DenseMatrix{2, 2, {1, 1, 2, 2}, false});
+  mat1.putBlock(1, 1, DenseMatrix{2, 2, {2, 2, 3, 3}, false});
+  mat2.putBlock(0, 0, DenseMatrix{2, 2, {3, 3, 4, 4}, false});
+  mat2.putBlock(0, 1, DenseMatrix{2, 2, {4, 5, 6, 7}, false});
+  mat2.putBlock(1, 1, SparseMatrix{2, 2, {0, 1, 2}, {1, 0}, {4, 2}, false});
+  Dataset prod = mat1.matrixMultiply(4, 4, mat2, 4, 4, 2);
+  auto ids = prod.blockIds();
+  if (ids.size() != 3) return fail("expected blocks (0,0), (0,1), (1,1)");
+  const double want00[4] = {9, 9, 12, 12}, want01[4] = {14, 14, 20, 20}, want11[4] = {12, 12, 4, 4};
+  auto chk = [&](int r, int c, const double* w) {
+    DenseMatrix m = prod.getDenseBlock(r, c);
+    for (int i = 0; i < 4; ++i)
+      if (m.values[i] != w[i]) return false;
+    return !m.isTransposed;
+  };
+  if (!chk(0, 0, want00) || !chk(0, 1, want01) || !chk(1, 1, want11)) return fail("golden product");
+  // the reference's require message crosses the ABI as an exception
+  try {
+    mat1.matrixMultiply(4, 4, mat2, 6, 4, 2);
+    return fail("dimension mismatch not reported");
+  } catch (const IllegalArgumentException& e) {
+    if (std::string(e.what()) != "requirement failed: Matrix dimension not match, leftColNum = 4, rightRowNum = 6")
+      return fail(e.what());
+  }
+  // random 3 x 3 blocks of 50 x 50 (one operand stored row-major) vs a triple loop
+  const int nb = 3, blk = 50, n = nb * blk;
+  std::vector<double> A(n * n), B(n * n), C(n * n, 0.0);
+  unsigned st = 1234567u;
+  auto rnd = [&] { st = st * 1664525u + 1013904223u; return (st >> 8) * (1.0 / 16777216.0) - 0.5; };
+  for (auto& v : A) v = rnd();
+  for (auto& v : B) v = rnd();
+  Dataset dA(s), dB(s);
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < nb; ++j) {
+      DenseMatrix a{blk, blk, std::vector<double>(blk * blk), true};   // row-major storage
+      DenseMatrix b{blk, blk, std::vector<double>(blk * blk), false};  // column-major storage
+      for (int r = 0; r < blk; ++r)
+        for (int c = 0; c < blk; ++c) {
+          a.values[c + blk * r] = A[(i * blk + r) * n + j * blk + c];
+          b.values[r + blk * c] = B[(i * blk + r) * n + j * blk + c];
+        }
+      dA.putBlock(i, j, a);
+      dB.putBlock(i, j, b);
+    }
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < n; ++k)
+      for (int j = 0; j < n; ++j) C[i * n + j] += A[i * n + k] * B[k * n + j];
+  Dataset dC = dA.matrixMultiply(n, n, dB, n, n, blk).addScalar(1.0).multiplyScalar(2.0);
+  double worst = 0.0;
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < nb; ++j) {
+      DenseMatrix m = dC.getDenseBlock(i, j);
+      for (int r = 0; r < blk; ++r)
+        for (int c = 0; c < blk; ++c)
+          worst = std::fmax(worst, std::fabs(m.values[r + blk * c] - 2.0 * (C[(i * blk + r) * n + j * blk + c] + 1.0)));
+    }
+  if (worst > 1e-12) return fail("random product");
+  std::printf("OK facade_smoke worst=%.3e\n", worst);
+  return 0;
+}
