@@ -159,6 +159,10 @@ MR_API mr_status mr_project(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t 
 /* Dataset.selection :49-55 -> SelectDirectExecution :152-213: the element (rowIdx, colIdx) as one 1 x 1 block (0, 0) */
 MR_API mr_status mr_selection(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t rowIdx, int64_t colIdx,
                               mr_matrix** out);
+/* Dataset.vec :84-87 -> VectorizeExecution :534-569: column t of block (i, j) becomes the rows x 1 block
+ * ((j * blkSize + t) * ceil(nrows / blkSize) + i, 0).  Intended semantics (defect B6 -- the reference strides by numLocalCols --
+ * is not reproduced); the output blocks are zero-copy views of the (column-major) input columns. */
+MR_API mr_status mr_vec(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkSize, mr_matrix** out);
 /* Materialise every dense block as column-major, isTransposed = false (DenseMatrix.toArray,
  * M/matrix/MLMatrix.scala:55-61, as a device transpose kernel). */
 MR_API mr_status mr_materialize(mr_matrix* a, mr_matrix** out);

@@ -105,6 +105,7 @@ SIGNATURES = {
     "mr_power": [_P, _f64, _PP],
     "mr_rank_one_update": _BIN,
     "mr_materialize": [_P, _PP],
+    "mr_vec": [_P, _i64, _i64, _i32, _PP],
     "mr_project": [_P, _i64, _i64, _i32, _i32, _i64, _PP],
     "mr_selection": [_P, _i64, _i64, _i32, _i64, _i64, _PP],
     "mr_row_sum": [_P, _i64, _i64, _PP],

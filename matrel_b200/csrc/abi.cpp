@@ -1757,6 +1757,39 @@ mr_status mr_selection(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkSi
   return slice_operator(a, blkSize, true, rowIdx, colIdx, out);
 }
 
+mr_status mr_vec(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkSize, mr_matrix** out) {
+  (void)ncols;
+  mr_matrix* canon = nullptr;
+  mr_status st = guarded([&] {
+    MR_REQUIRE(a && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(blkSize > 0 && nrows > 0, MR_EINVAL, "nrows and blkSize must be positive");
+  });
+  if (st != MR_OK) return st;
+  st = mr_materialize(a, &canon);  // column-major, non-transposed dense blocks (shares already canonical ones)
+  if (st != MR_OK) return st;
+  st = guarded([&] {
+    mr_context* ctx = a->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::unique_ptr<mr_matrix> r(new_matrix(ctx));
+    const int64_t ROW_BLK_NUM = ceil_div(nrows, blkSize);  // MatfastExecution.scala:543
+    for (auto& kv : canon->blocks) {
+      const Block& b = kv.second;
+      const int64_t i = kv.first.first, j = kv.first.second;
+      for (int32_t t = 0; t < b.numCols; ++t) {
+        const int64_t key = (j * blkSize + t) * ROW_BLK_NUM + i;  // :552 with the block-column offset in elements
+        MR_REQUIRE(key <= INT32_MAX, MR_EINVAL, "vec(): block id %lld does not fit an Int", (long long)key);
+        Span col{b.values.buf, b.values.off + static_cast<size_t>(t) * b.numRows * sizeof(double)};
+        Block v = dense_block(b.numRows, 1, col, false);
+        v.ready = b.ready;
+        r->blocks[{static_cast<int32_t>(key), 0}] = std::move(v);
+      }
+    }
+    *out = r.release();
+  });
+  mr_matrix_free(canon);
+  return st;
+}
+
 mr_status mr_materialize(mr_matrix* a, mr_matrix** out) {
   return guarded([&] {
     MR_REQUIRE(a && out, MR_EINVAL, "null argument");

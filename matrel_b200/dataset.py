@@ -274,6 +274,10 @@ class Dataset:
         """M/Dataset.scala:99-103."""
         return self._unary(N.lib.mr_power, float(alpha))
 
+    def vec(self, nrows, ncols, blkSize) -> "Dataset":
+        """M/Dataset.scala:84-87."""
+        return self._unary(N.lib.mr_vec, int(nrows), int(ncols), int(blkSize))
+
     def project(self, nrows, ncols, blkSize, rowOrCol: bool, index) -> "Dataset":
         """M/Dataset.scala:38-47."""
         return self._unary(N.lib.mr_project, int(nrows), int(ncols), int(blkSize), 1 if rowOrCol else 0, int(index))

@@ -769,6 +769,20 @@ def project(ds: BlockDict, nrows: int, ncols: int, blkSize: int, rowOrCol: bool,
     return out
 
 
+def vec(ds: BlockDict, nrows: int, ncols: int, blkSize: int) -> BlockDict:
+    """Dataset.vec (M/Dataset.scala:84-87) -> VectorizeExecution (MatfastExecution.scala:534-569), intended semantics:
+    column t of block (i, j) -> rows x 1 block keyed ((j*blkSize + t) * ceil(nrows/blkSize) + i, 0).
+    (Defect B6: the reference reads arr(t*numLocalCols + k) and keys with j*ROW_BLK_NUM*blkSize + t*ROW_BLK_NUM + i, which is
+    the same key; only the stride differs and it is wrong for non-square blocks.)"""
+    R = -(-nrows // blkSize)
+    out: BlockDict = {}
+    for (i, j), m in ds.items():
+        a = m.to_numpy()
+        for t in range(m.numCols):
+            out[((j * blkSize + t) * R + i, 0)] = DenseMatrix(m.numRows, 1, a[:, t].copy())
+    return out
+
+
 def selection(ds: BlockDict, nrows: int, ncols: int, blkSize: int, rowIdx: int, colIdx: int) -> BlockDict:
     """Dataset.selection (M/Dataset.scala:49-55) -> SelectDirectExecution (MatfastExecution.scala:152-213)."""
     require(rowIdx < nrows, f"row index should be smaller than #rows, rid={rowIdx}, #rows={nrows}")

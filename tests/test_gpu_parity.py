@@ -551,3 +551,17 @@ def test_project_selection_golden_and_pushdown(session):
     assert session.stats()["last_gemm_flops"] <= 2 * n                      # one dot product, not 2 N^3
     slow = from_dataset(q.execute(False))[(0, 0)].values[0]
     assert abs(fast - slow) / abs(slow) < 1e-13
+
+
+def test_vec_reshape(session):
+    rng = np.random.default_rng(77)
+    n, m, blk = 100, 70, 32
+    D = random_block_dataset(rng, n, m, blk, density=0.8, p_transposed=0.5, p_sparse=0.2, sparse_density=0.3)
+    got = from_dataset(to_dataset(session, D).vec(n, m, blk))
+    assert_same_dataset(got, O.vec(D, n, m, blk), exact_storage=True)
+    # stacking the vector blocks in key order reproduces numpy's column-major flattening block column by block column
+    full = O.assemble(D, n, m, blk)
+    R = -(-n // blk)
+    for (key, _), v in got.items():
+        col, i = divmod(key, R)
+        assert np.array_equal(v.values, full[i * blk:i * blk + v.numRows, col])
