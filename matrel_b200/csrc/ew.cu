@@ -236,64 +236,71 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const int32_t* __restrict
   C[o] = accumulate ? C[o] + sum : sum;
 }
 
-// Fused CSR SpMM (see kernels.h): grid = (ceil(n_max / 16), output blocks), 512 threads.
-// One CTA = 16 output columns of one output block.  The B chunk (kdim x 16) of the current block pair is staged in shared
-// memory row-major ([k][16], stride 17), so a half-warp working on one CSR row reads 16 CONSECUTIVE doubles per nonzero
-// (conflict-free, 16 FMAs per 128-byte wavefront = the shared-memory roof of this algorithm) and the CSR entry itself is
-// a broadcast load.  Each lane keeps its column of 32 rows in registers across ALL block pairs (fused K reduction).
-constexpr int SPMM_CW = 16;
+// Fused CSR SpMM (see kernels.h): grid = (ceil(n_max / 8), output blocks), 512 threads.
+// Thread = one (or two) row(s) of the output block x 8 columns held in registers across ALL block pairs; the B chunk
+// (8 columns x kdim) is staged in shared memory per pair, so each CSR entry costs one index/value load and feeds 8 FMAs.
+constexpr int SPMM_CW = 8;
 constexpr int SPMM_THREADS = 512;
-constexpr int SPMM_LDB = SPMM_CW + 1;
-constexpr int SPMM_ROWS_PER_WARP = kSpmmMaxDim / (SPMM_THREADS / 32);  // 64
-constexpr int SPMM_PASSES = SPMM_ROWS_PER_WARP / 2;                     // two rows (one per half-warp) per pass
+constexpr int SPMM_RPT = kSpmmMaxDim / SPMM_THREADS;  // rows per thread (2)
 __global__ void __launch_bounds__(SPMM_THREADS) spmm_fused_kernel(const SpmmOut* __restrict__ outs, const SpmmPair* __restrict__ pairs) {
   extern __shared__ double spmm_smem[];
   const SpmmOut o = outs[blockIdx.y];
   const int c0 = blockIdx.x * SPMM_CW;
   if (c0 >= o.n) return;
   const int cw = min(SPMM_CW, o.n - c0);
-  double* sB = spmm_smem;  // [kdim][17]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int hw = lane >> 4, c = lane & 15;
-  const int row_base = warp * SPMM_ROWS_PER_WARP + hw;
-  double acc[SPMM_PASSES];
+  double* sB = spmm_smem;  // [SPMM_CW][kdim + 2]
+  const int tid = threadIdx.x;
+  double acc[SPMM_RPT][SPMM_CW];
 #pragma unroll
-  for (int p = 0; p < SPMM_PASSES; ++p) {
-    const int r = row_base + 2 * p;
-    acc[p] = (o.accumulate && r < o.m && c < cw) ? o.C[r + static_cast<size_t>(o.m) * (c0 + c)] : 0.0;
+  for (int u = 0; u < SPMM_RPT; ++u) {
+    const int r = tid + u * SPMM_THREADS;
+#pragma unroll
+    for (int c = 0; c < SPMM_CW; ++c)
+      acc[u][c] = (o.accumulate && r < o.m && c < cw) ? o.C[r + static_cast<size_t>(o.m) * (c0 + c)] : 0.0;
   }
-  for (int pi = 0; pi < o.pair_count; ++pi) {
-    const SpmmPair pr = pairs[o.pair_begin + pi];
+  for (int p = 0; p < o.pair_count; ++p) {
+    const SpmmPair pr = pairs[o.pair_begin + p];
+    const int ldb = pr.kdim + 2;
     __syncthreads();  // previous pair's readers of sB are done
-    if (!pr.bT) {     // column-major B: walk each column contiguously, store transposed
+    if (!pr.bT) {
       for (int cc = 0; cc < SPMM_CW; ++cc) {
         const double* src = pr.B + static_cast<size_t>(pr.kdim) * (c0 + cc);
-        for (int k = tid; k < pr.kdim; k += SPMM_THREADS) sB[k * SPMM_LDB + cc] = cc < cw ? src[k] : 0.0;
+        for (int k = tid; k < pr.kdim; k += SPMM_THREADS) sB[cc * ldb + k] = cc < cw ? src[k] : 0.0;
       }
-    } else {          // row-major B: 16 contiguous doubles per k
+    } else {
       for (int idx = tid; idx < SPMM_CW * pr.kdim; idx += SPMM_THREADS) {
         const int k = idx / SPMM_CW, cc = idx % SPMM_CW;
-        sB[k * SPMM_LDB + cc] = cc < cw ? pr.B[c0 + cc + static_cast<size_t>(o.n) * k] : 0.0;
+        sB[cc * ldb + k] = cc < cw ? pr.B[c0 + cc + static_cast<size_t>(o.n) * k] : 0.0;
       }
     }
     __syncthreads();
-    const double* bcol = sB + c;
+    int beg[SPMM_RPT], len[SPMM_RPT], maxlen = 0;
 #pragma unroll
-    for (int p = 0; p < SPMM_PASSES; ++p) {
-      const int r = row_base + 2 * p;
-      if (r < o.m) {
-        const int beg = pr.ptrs[r], end = pr.ptrs[r + 1];
-        double a = acc[p];
-        for (int i = beg; i < end; ++i) a += pr.vals[i] * bcol[pr.idx[i] * SPMM_LDB];  // ascending i = the reference's order
-        acc[p] = a;
+    for (int u = 0; u < SPMM_RPT; ++u) {
+      const int r = tid + u * SPMM_THREADS;
+      beg[u] = r < o.m ? pr.ptrs[r] : 0;
+      len[u] = r < o.m ? pr.ptrs[r + 1] - beg[u] : 0;
+      maxlen = max(maxlen, len[u]);
+    }
+    for (int i = 0; i < maxlen; ++i) {  // ascending nonzero order within a row = the reference's summation order
+#pragma unroll
+      for (int u = 0; u < SPMM_RPT; ++u) {
+        if (i < len[u]) {
+          const double v = pr.vals[beg[u] + i];
+          const double* b = sB + pr.idx[beg[u] + i];
+#pragma unroll
+          for (int c = 0; c < SPMM_CW; ++c) acc[u][c] += v * b[c * ldb];
+        }
       }
     }
   }
-  if (c < cw) {
 #pragma unroll
-    for (int p = 0; p < SPMM_PASSES; ++p) {
-      const int r = row_base + 2 * p;
-      if (r < o.m) o.C[r + static_cast<size_t>(o.m) * (c0 + c)] = acc[p];
+  for (int u = 0; u < SPMM_RPT; ++u) {
+    const int r = tid + u * SPMM_THREADS;
+    if (r < o.m) {
+#pragma unroll
+      for (int c = 0; c < SPMM_CW; ++c)
+        if (c < cw) o.C[r + static_cast<size_t>(o.m) * (c0 + c)] = acc[u][c];
     }
   }
 }
@@ -560,7 +567,7 @@ cudaError_t launch_csc_fill(const CscDesc* d_descs, int nblocks, int max_cols, c
 
 cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* d_pairs, int max_n, cudaStream_t stream) {
   if (nouts <= 0 || max_n <= 0) return cudaSuccess;
-  const size_t smem = static_cast<size_t>(kSpmmMaxDim) * SPMM_LDB * sizeof(double);
+  const size_t smem = static_cast<size_t>(SPMM_CW) * (kSpmmMaxDim + 2) * sizeof(double);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(spmm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
