@@ -60,7 +60,9 @@ typedef struct mr_block_desc {
 typedef struct mr_options {
   int32_t device;       /* CUDA device ordinal; -1 = current device */
   int32_t compat_bugs;  /* 1 = reproduce reference defects B3/B4; 0 = intended math */
-  int32_t gemm_algo;    /* 0 = auto, 1 = DMMA fp64 tensor-core kernel, 2 = Ozaki int8 tcgen05 kernel */
+  int32_t gemm_algo;    /* 0 = auto (= 1), 1 = DMMA fp64 tensor-core kernel, 2 = Ozaki-I int8 tcgen05 kernel (digit slices),
+                           3 = 3xTF32 tcgen05 kernel (fp32 results), 4 = Ozaki-II int8 tcgen05 kernel (CRT residues;
+                           mr_set_option "crt_moduli" 6..16, default 16) */
   int32_t ozaki_slices; /* number of int8 slices for gemm_algo 2 (0 = default) */
   void* stream;         /* cudaStream_t to run on; NULL = a stream owned by the context */
 } mr_options;

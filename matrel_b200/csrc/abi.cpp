@@ -104,6 +104,7 @@ struct mr_context {
   int compat_bugs = 1;
   int gemm_algo = 0;
   int ozaki_slices = 0;
+  int crt_moduli = 0;
   int time_kernels = 0;
   int force_variant = -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr, ev_order = nullptr;
@@ -389,10 +390,11 @@ struct MultiplyPlanner {
 bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<double*>& cptr, int32_t blkSize, int64_t M,
                int64_t K, int64_t N, bool outer) {
   const bool tf32 = ctx->gemm_algo == 3;
+  const bool crt = ctx->gemm_algo == 4;
   const int S_eff = std::min(7, std::max(2, ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7));
   // s32 accumulator bound: up to S pairs x K terms of |digit product| <= 2^14 land in one accumulator
   if (M <= 0 || K <= 0 || N <= 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX / 2) return false;
-  if (!tf32 && K * S_eff >= (1 << 17)) return false;
+  if (crt ? K >= (1 << 17) : (!tf32 && K * S_eff >= (1 << 17))) return false;
   // Compact the block rows / columns that actually have output blocks (a rank of the process grid owns every pr-th
   // block row and pc-th block column: slicing and multiplying the absent ones would only produce zeros).
   std::map<int32_t, int32_t> crow, ccol;
@@ -447,6 +449,10 @@ bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<d
   if (tf32)
     CUDA_CHECK(tf32x3_gemm(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc, ctab.data(),
                            blkSize, static_cast<int>(nbr), static_cast<int>(nbc), &launches, ctx->stream));
+  else if (crt)
+    CUDA_CHECK(ozaki2_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc,
+                               ctx->crt_moduli > 0 ? ctx->crt_moduli : 16, ctab.data(), blkSize, static_cast<int>(nbr),
+                               static_cast<int>(nbc), &launches, &nonfinite, ctx->stream));
   else
     CUDA_CHECK(ozaki_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc,
                               ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7, ctab.data(), blkSize, static_cast<int>(nbr),
@@ -517,7 +523,7 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       }
   };
   bool ozaki_done = false;
-  if (!outs.empty() && (ctx->gemm_algo == 2 || ctx->gemm_algo == 3)) {
+  if (!outs.empty() && (ctx->gemm_algo >= 2 && ctx->gemm_algo <= 4)) {
     wait_all_sources();
     ozaki_done = try_ozaki(ctx, plans, cptr, blkSize, M, K, N, outer);
     if (ozaki_done) ctx->stats.last_gemm_flops = flops;
@@ -1082,6 +1088,7 @@ mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
     if (k == "compat_bugs") ctx->compat_bugs = static_cast<int>(value);
     else if (k == "gemm_algo") ctx->gemm_algo = static_cast<int>(value);
     else if (k == "ozaki_slices") ctx->ozaki_slices = static_cast<int>(value);
+    else if (k == "crt_moduli") ctx->crt_moduli = static_cast<int>(value);
     else if (k == "time_kernels") ctx->time_kernels = static_cast<int>(value);
     else if (k == "gemm_variant") ctx->force_variant = static_cast<int>(value);
     else if (k == "pipeline") ctx->pipeline = static_cast<int>(value);

@@ -100,6 +100,14 @@ struct OzakiGemmParams {
   uint32_t idesc;
   int32_t f32_acc;             // 0: s32 accumulator scaled by the Ozaki exponents; 1: f32 accumulator written as is
   int32_t kc0, nkc;            // K range of this launch in stage units (the fp32 path re-accumulates K chunks in fp64)
+  // CRT mode (Ozaki scheme II, gemm_algo 4): nmod > 0 makes ONE launch walk nmod x tiles work items; item (t, tile) multiplies
+  // residue matrices A mod p_t (tensor map t) and B mod p_t (tensor map nmod + t) and stores (A_t B_t) mod p_t as int8.
+  int32_t nmod;
+  int32_t npad;                // row pitch of the residue planes (bytes)
+  int8_t* planes;              // [nmod][Mpad][npad]
+  size_t plane_stride;
+  int32_t mod_p[16];
+  double mod_inv[16];          // 1 / p_t
 };
 
 constexpr int EPI_WARPS = 8;                       // 2 per TMEM lane quarter (each takes 128 of the 256 columns)
@@ -128,6 +136,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
   const int nk = p.nkc;
   const int per_tile = p.npairs * nk;
   const int ntiles = p.tiles_m * p.tiles_n;
+  const int nitems = ntiles * (p.nmod ? p.nmod : 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -153,13 +162,14 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
     // ===== TMA producer (one elected lane) =====
     if (lane == 0) {
       int it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+        const int mi = w / ntiles, t = w - mi * ntiles;
         int tm, tn;
         tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
         for (int s = 0; s < p.npairs; ++s) {
-          const void* tmA = p.tmaps + static_cast<size_t>(p.pair_a[s]) * 128;
-          const void* tmB = p.tmaps + static_cast<size_t>(p.pair_b[s]) * 128;
+          const void* tmA = p.tmaps + static_cast<size_t>(p.nmod ? mi : p.pair_a[s]) * 128;
+          const void* tmB = p.tmaps + static_cast<size_t>(p.nmod ? p.nmod + mi : p.pair_b[s]) * 128;
           for (int kc = p.kc0; kc < p.kc0 + nk; ++kc, ++it) {
             const int st = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -177,7 +187,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
     if (lane == 0) {
       const uint32_t idesc = p.idesc;
       int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++lt) {
         const int buf = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(smem_u32(&bars[2 * STAGES + 2 + buf]), aph ^ 1);  // epilogue has drained this accumulator
@@ -206,7 +216,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
     const int q = ew & 3;          // TMEM lane quarter this warp may access (warp id % 4)
     const int half = ew >> 2;      // which 128 of the tile's 256 columns
     int lt = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++lt) {
+      const int mi = w / ntiles, t = w - mi * ntiles;
       int tm, tn;
       tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
       const int m0 = tm * BM, n0 = tn * BN;
@@ -217,7 +228,7 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
       const int rid = row_ok ? row / p.blk : 0;
       const int lr = row - rid * p.blk;
       const int brows = min(p.blk, p.M - rid * p.blk);
-      const double rs = p.f32_acc ? 1.0 : (row_ok ? p.row_scale[row] * p.diag_scale : 0.0);
+      const double rs = (p.f32_acc || p.nmod) ? 1.0 : (row_ok ? p.row_scale[row] * p.diag_scale : 0.0);
       mbar_wait(smem_u32(&bars[2 * STAGES + buf]), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tsrc = tmem_base + static_cast<uint32_t>(buf * BN) + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
@@ -233,7 +244,26 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
           if (lane == 0) mbar_arrive(smem_u32(&bars[2 * STAGES + 2 + buf]));
         }
         const int col0 = n0 + half * 128 + c;
-        if (row_ok && col0 < p.N) {
+        if (p.nmod) {
+          // symmetric residue of the exact s32 dot product: q = rint(c / p) is exact in fp64 (no integer c / p lies within
+          // 1/(2p) of a tie except the true ties of the even modulus 256, where +128 wraps to the congruent -128)
+          const int pm = p.mod_p[mi];
+          const double pinv = p.mod_inv[mi];
+          uint32_t packed[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t wv = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int v = static_cast<int32_t>(r[4 * g + j]);
+              const int res = v - __double2int_rn(static_cast<double>(v) * pinv) * pm;
+              wv |= (static_cast<uint32_t>(res) & 0xffu) << (8 * j);
+            }
+            packed[g] = wv;
+          }
+          int8_t* dst = p.planes + static_cast<size_t>(mi) * p.plane_stride + static_cast<size_t>(row) * p.npad + col0;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);  // padded planes: no guards
+        } else if (row_ok && col0 < p.N) {
           const int cid0 = col0 / p.blk;
           const bool one_block = (col0 + 15 < p.N) && ((col0 + 15) / p.blk == cid0);
           if (one_block) {
@@ -413,6 +443,218 @@ __global__ void __launch_bounds__(256) slice_kernel(const OzBlock* __restrict__ 
           if (kq + j < nks) dst[j] = static_cast<int8_t>((packed >> (8 * j)) & 0xffu);
       }
     }
+  }
+}
+
+// ---- Ozaki scheme II (gemm_algo 4): residues of the scaled integer operands modulo T pairwise-coprime p_t <= 256 ------
+// A' = rint(A * 2^(alpha - e_i)) (|a'| <= 2^alpha <= 2^62), B' likewise per column; C' = A' B' is an exact integer with
+// |c'| < P / 2 (P = prod p_t) by the choice of alpha, so it is recovered from the T int8 GEMMs (A' mod p_t)(B' mod p_t) by the
+// Chinese remainder theorem: T tensor-core GEMMs instead of the S (S + 1) / 2 of the digit-slicing scheme.
+constexpr int CRT_MAX_T = 16;
+constexpr int CRT_MIN_T = 6;
+struct CrtConst {
+  uint32_t p[CRT_MAX_T];       // moduli
+  uint32_t magic[CRT_MAX_T];   // floor(2^32 / p)
+  uint32_t c21[CRT_MAX_T];     // 2^21 mod p
+  uint32_t c42[CRT_MAX_T];     // 2^42 mod p
+  uint32_t w[CRT_MAX_T][4];    // CRT weight (P / p_t) * ((P / p_t)^-1 mod p_t) < P, little-endian 32-bit limbs
+  uint32_t P[4], Phalf[4];     // P and floor(P / 2)
+  double invP;                 // 1 / P (rounded)
+  int32_t T, pad;
+};
+__constant__ CrtConst c_crt[CRT_MAX_T + 1];  // indexed by T, filled once on first use
+
+// out_t[line * Kpad + k] = symmetric residue of a'(line, k) mod p_t, same tiling / staging as slice_kernel
+__global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict__ blocks, const int32_t* __restrict__ line_exp,
+                                                      int8_t* __restrict__ out, size_t slice_stride, int Kpad, int T, int alpha,
+                                                      int lines_are_rows, int tiles_k_max) {
+  __shared__ double sm[32][129];
+  const OzBlock b = blocks[blockIdx.y];
+  const int tl = blockIdx.x / tiles_k_max, tk = blockIdx.x % tiles_k_max;
+  const int nlines = lines_are_rows ? b.rows : b.cols;
+  const int nks = lines_are_rows ? b.cols : b.rows;
+  const int l0 = tl * 32, k0 = tk * 128;
+  if (l0 >= nlines || k0 >= nks) return;
+  const int tid = threadIdx.x;
+  const bool k_fast = lines_are_rows ? (b.isT != 0) : (b.isT == 0);
+  for (int idx = tid; idx < 32 * 128; idx += 256) {
+    const int l = k_fast ? idx / 128 : idx % 32, k = k_fast ? idx % 128 : idx / 32;
+    double v = 0.0;
+    if (l0 + l < nlines && k0 + k < nks) v = lines_are_rows ? blk_at(b, l0 + l, k0 + k) : blk_at(b, k0 + k, l0 + l);
+    sm[l][k] = v;
+  }
+  __syncthreads();
+  const CrtConst& cc = c_crt[T];
+  const int gl_base = (lines_are_rows ? b.row0 : b.col0) + l0;
+  const int gk_base = (lines_are_rows ? b.col0 : b.row0) + k0;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int l = warp; l < 32; l += 8) {
+    if (l0 + l >= nlines) continue;
+    const int e = line_exp[gl_base + l];
+    uint32_t hi[4], mid[4], lo[4];
+    bool neg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long X = __double2ll_rn(scalbn(sm[l][lane * 4 + j], alpha - e));  // exact power-of-two scaling, |X| <= 2^alpha
+      neg[j] = X < 0;
+      const unsigned long long U = static_cast<unsigned long long>(neg[j] ? -X : X);
+      hi[j] = static_cast<uint32_t>(U >> 42);
+      mid[j] = static_cast<uint32_t>(U >> 21) & 0x1FFFFFu;
+      lo[j] = static_cast<uint32_t>(U) & 0x1FFFFFu;
+    }
+    const int kq = k0 + lane * 4;
+    const int gk = gk_base + lane * 4;
+    const bool whole = kq + 3 < nks && (gk & 3) == 0;
+    for (int t = 0; t < T; ++t) {
+      const uint32_t pm = cc.p[t], mg = cc.magic[t], m21 = cc.c21[t], m42 = cc.c42[t];
+      uint32_t packed = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t x = hi[j] * m42 + mid[j] * m21 + lo[j];  // < 2^30, congruent to |X|
+        int r = static_cast<int>(x - __umulhi(x, mg) * pm);      // in [0, 2p)
+        if (r >= static_cast<int>(pm)) r -= pm;
+        if (2 * r >= static_cast<int>(pm)) r -= pm;              // symmetric: [-(p-1)/2, (p-1)/2], [-128, 127] for 256
+        if (neg[j]) r = -r;                                      // +128 (p = 256 only) wraps to the congruent -128
+        packed |= (static_cast<uint32_t>(r) & 0xffu) << (8 * j);
+      }
+      int8_t* dst = out + static_cast<size_t>(t) * slice_stride + static_cast<size_t>(gl_base + l) * Kpad + gk;
+      if (whole) {
+        *reinterpret_cast<uint32_t*>(dst) = packed;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (kq + j < nks) dst[j] = static_cast<int8_t>((packed >> (8 * j)) & 0xffu);
+      }
+    }
+  }
+}
+
+// CRT reconstruction: one CTA = 32 rows x 128 columns of C.  Thread (row, 4 columns) reads its T residue quads (coalesced along
+// the plane rows), accumulates sum_t r_t w_t in 32-bit limbs (IMAD.WIDE into 64-bit lanes), reduces modulo P to the symmetric
+// range, converts to fp64 and scales by 2^(e_i + f_j - 2 alpha); the tile is transposed through shared memory so the stores
+// follow the column-major output blocks.
+__global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ planes, size_t plane_stride, int npad, int T,
+                                                  const int32_t* __restrict__ row_exp, const int32_t* __restrict__ col_exp,
+                                                  int two_alpha, double* const* __restrict__ ctab, int M, int N, int blk, int nbc) {
+  __shared__ double tile[128][33];
+  const CrtConst& cc = c_crt[T];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 128;
+  const int tid = threadIdx.x;
+  const int lr = tid >> 5, lc = (tid & 31) * 4;  // 8 rows per pass, 4 passes
+  for (int pass = 0; pass < 4; ++pass) {
+    const int row = r0 + pass * 8 + lr;
+    unsigned long long acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0ull;
+    const int8_t* src = planes + static_cast<size_t>(row) * npad + c0 + lc;
+    for (int t = 0; t < T; ++t) {
+      const uint32_t quad = *reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(t) * plane_stride);
+      const uint32_t pm = cc.p[t];
+      const uint32_t w0 = cc.w[t][0], w1 = cc.w[t][1], w2 = cc.w[t][2], w3 = cc.w[t][3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = static_cast<int8_t>((quad >> (8 * j)) & 0xffu);
+        const uint32_t ru = r < 0 ? static_cast<uint32_t>(r + static_cast<int>(pm)) : static_cast<uint32_t>(r);
+        acc[j][0] += static_cast<unsigned long long>(ru) * w0;
+        acc[j][1] += static_cast<unsigned long long>(ru) * w1;
+        acc[j][2] += static_cast<unsigned long long>(ru) * w2;
+        acc[j][3] += static_cast<unsigned long long>(ru) * w3;
+      }
+    }
+    const int er = row < M ? row_exp[row] : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // carry-normalise to five 32-bit limbs (value < T * 256 * P < 2^140)
+      uint32_t l[5];
+      unsigned long long c = acc[j][0];
+      l[0] = static_cast<uint32_t>(c);
+      c = (c >> 32) + acc[j][1];
+      l[1] = static_cast<uint32_t>(c);
+      c = (c >> 32) + acc[j][2];
+      l[2] = static_cast<uint32_t>(c);
+      c = (c >> 32) + acc[j][3];
+      l[3] = static_cast<uint32_t>(c);
+      l[4] = static_cast<uint32_t>(c >> 32);
+      // quotient estimate from the top limbs (relative error 2^-52 on a quotient < 2^13): one below, then fix up
+      const double top = (static_cast<double>((static_cast<unsigned long long>(l[4]) << 32) | l[3]) * 4294967296.0 + static_cast<double>(l[2])) *
+                         18446744073709551616.0;  // * 2^64
+      const double qd = floor(top * cc.invP);
+      const uint32_t qq = qd >= 1.0 ? static_cast<uint32_t>(qd) - 1u : 0u;
+      {
+        unsigned long long m = 0;
+        long long bw = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          if (i < 4) m += static_cast<unsigned long long>(qq) * cc.P[i];
+          const long long d = static_cast<long long>(l[i]) - static_cast<long long>(static_cast<uint32_t>(m)) + bw;
+          l[i] = static_cast<uint32_t>(d);
+          bw = d >> 32;
+          m >>= 32;
+        }
+      }
+#pragma unroll 1
+      for (int it = 0; it < 3; ++it) {  // remainder is in [0, 3P): at most two subtractions
+        bool ge = l[4] != 0;
+        if (!ge) {
+          ge = true;
+#pragma unroll
+          for (int i = 3; i >= 0; --i) {
+            if (l[i] != cc.P[i]) {
+              ge = l[i] > cc.P[i];
+              break;
+            }
+          }
+        }
+        if (!ge) break;
+        long long bw = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const long long d = static_cast<long long>(l[i]) - (i < 4 ? static_cast<long long>(cc.P[i]) : 0ll) + bw;
+          l[i] = static_cast<uint32_t>(d);
+          bw = d >> 32;
+        }
+      }
+      // symmetric range: x > floor(P / 2)  ->  x - P (store the magnitude P - x)
+      bool gt = false;
+#pragma unroll
+      for (int i = 3; i >= 0; --i) {
+        if (l[i] != cc.Phalf[i]) {
+          gt = l[i] > cc.Phalf[i];
+          break;
+        }
+      }
+      if (gt) {
+        long long bw = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long d = static_cast<long long>(cc.P[i]) - static_cast<long long>(l[i]) + bw;
+          l[i] = static_cast<uint32_t>(d);
+          bw = d >> 32;
+        }
+      }
+      const double mag = static_cast<double>((static_cast<unsigned long long>(l[3]) << 32) | l[2]) * 18446744073709551616.0 +
+                         static_cast<double>((static_cast<unsigned long long>(l[1]) << 32) | l[0]);
+      const int col = c0 + lc + j;
+      const int ec = col < N ? col_exp[col] : 0;
+      tile[lc + j][pass * 8 + lr] = scalbn(gt ? -mag : mag, er + ec - two_alpha);
+    }
+  }
+  __syncthreads();
+  // store: warp w writes columns w, w + 8, ...; lanes run along the 32 rows (contiguous in the column-major block)
+  const int warp = tid >> 5, lane = tid & 31;
+  const int row = r0 + lane;
+  if (row >= M) return;
+  const int rid = row / blk;
+  const int brows = min(blk, M - rid * blk);
+  const int lrow = row - rid * blk;
+  for (int cidx = warp; cidx < 128; cidx += 8) {
+    const int col = c0 + cidx;
+    if (col >= N) break;
+    const int cid = col / blk;
+    double* blkp = ctab[rid * nbc + cid];
+    if (blkp != nullptr) blkp[lrow + static_cast<size_t>(brows) * (col - cid * blk)] = tile[cidx][lane];
   }
 }
 
@@ -645,6 +887,184 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
     *launches += 1;
   }
   // scratch is freed stream-ordered by the AsyncBuf destructors; pageable staging vectors were consumed synchronously
+  return cudaSuccess;
+}
+
+namespace {
+const int kCrtModuli[CRT_MAX_T] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};  // pairwise coprime
+
+// fills c_crt[T] for every supported T once; returns floor(log2 P) per T through log2P
+cudaError_t crt_constants(int* log2P) {
+  static bool done = false;
+  static int l2[CRT_MAX_T + 1];
+  static cudaError_t status = cudaSuccess;
+  if (!done) {
+    std::vector<CrtConst> all(CRT_MAX_T + 1);
+    for (int T = CRT_MIN_T; T <= CRT_MAX_T; ++T) {
+      CrtConst& c = all[T];
+      memset(&c, 0, sizeof(c));
+      unsigned __int128 P = 1;
+      for (int t = 0; t < T; ++t) P *= static_cast<unsigned>(kCrtModuli[t]);
+      for (int t = 0; t < T; ++t) {
+        const unsigned pm = static_cast<unsigned>(kCrtModuli[t]);
+        c.p[t] = pm;
+        c.magic[t] = static_cast<uint32_t>((1ull << 32) / pm);
+        c.c21[t] = static_cast<uint32_t>((1ull << 21) % pm);
+        c.c42[t] = static_cast<uint32_t>((1ull << 42) % pm);
+        const unsigned __int128 Mt = P / pm;
+        const unsigned mr = static_cast<unsigned>(Mt % pm);
+        unsigned inv = 1;
+        while ((mr * inv) % pm != 1u) ++inv;  // Mt is coprime to pm, the inverse exists below pm
+        const unsigned __int128 w = Mt * inv;
+        for (int i = 0; i < 4; ++i) c.w[t][i] = static_cast<uint32_t>(w >> (32 * i));
+      }
+      const unsigned __int128 H = P >> 1;
+      for (int i = 0; i < 4; ++i) {
+        c.P[i] = static_cast<uint32_t>(P >> (32 * i));
+        c.Phalf[i] = static_cast<uint32_t>(H >> (32 * i));
+      }
+      c.invP = 1.0 / static_cast<double>(P);
+      c.T = T;
+      int lg = 0;
+      while ((P >> (lg + 1)) != 0) ++lg;
+      l2[T] = lg;
+    }
+    status = cudaMemcpyToSymbol(c_crt, all.data(), sizeof(CrtConst) * (CRT_MAX_T + 1));
+    done = status == cudaSuccess;
+  }
+  for (int T = 0; T <= CRT_MAX_T; ++T) log2P[T] = l2[T];
+  return status;
+}
+}  // namespace
+
+// gemm_algo 4: Ozaki scheme II.  Same contract as ozaki_gemm_f64 (C = A B into the fp64 output blocks; non-finite input is
+// reported through *nonfinite and nothing is written).  moduli in [6, 16] sets the operand precision alpha =
+// floor((floor(log2 P) - 1 - ceil(log2 K)) / 2) bits relative to the row / column maximum (16 moduli, K = 16384: 55 bits).
+cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K,
+                            int64_t N, int moduli, double* const* h_ctab, int blk, int nbr, int nbc, int* launches, int* nonfinite,
+                            cudaStream_t stream) {
+  *nonfinite = 0;
+  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  const int T = moduli < CRT_MIN_T ? CRT_MIN_T : (moduli > CRT_MAX_T ? CRT_MAX_T : moduli);
+  int log2P[CRT_MAX_T + 1];
+  OZ_CHECK(crt_constants(log2P));
+  int lgK = 0;
+  while ((1ll << lgK) < K) ++lgK;
+  int alpha = (log2P[T] - 1 - lgK) / 2;  // K * (2^alpha)^2 <= 2^(floor(log2 P) - 1) < P / 2
+  if (alpha > 62) alpha = 62;
+  if (alpha < 8) return cudaErrorInvalidValue;
+  const int64_t Mpad = (M + BM - 1) / BM * BM, Npad = (N + BN - 1) / BN * BN, Kpad = (K + BKB - 1) / BKB * BKB;
+  static bool configured = false;
+  const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+  if (!configured) {
+    OZ_CHECK(cudaFuncSetAttribute(ozaki_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+    configured = true;
+  }
+  std::vector<OzBlock> ha(na), hb(nb);
+  int max_ar = 1, max_ac = 1, max_br = 1, max_bc = 1;
+  for (int i = 0; i < na; ++i) {
+    ha[i] = OzBlock{a_blocks[i].v, a_blocks[i].rows, a_blocks[i].cols, a_blocks[i].row0, a_blocks[i].col0, a_blocks[i].isT, {0}};
+    max_ar = std::max(max_ar, a_blocks[i].rows);
+    max_ac = std::max(max_ac, a_blocks[i].cols);
+  }
+  for (int i = 0; i < nb; ++i) {
+    hb[i] = OzBlock{b_blocks[i].v, b_blocks[i].rows, b_blocks[i].cols, b_blocks[i].row0, b_blocks[i].col0, b_blocks[i].isT, {0}};
+    max_br = std::max(max_br, b_blocks[i].rows);
+    max_bc = std::max(max_bc, b_blocks[i].cols);
+  }
+  AsyncBuf d_ab(stream), d_bb(stream), d_max(stream), d_exp(stream), d_scale(stream), d_bad(stream), d_As(stream), d_Bs(stream),
+      d_maps(stream), d_ctab(stream), d_planes(stream);
+  OZ_CHECK(d_ab.alloc(sizeof(OzBlock) * na));
+  OZ_CHECK(d_bb.alloc(sizeof(OzBlock) * nb));
+  OZ_CHECK(cudaMemcpyAsync(d_ab.p, ha.data(), sizeof(OzBlock) * na, cudaMemcpyHostToDevice, stream));
+  OZ_CHECK(cudaMemcpyAsync(d_bb.p, hb.data(), sizeof(OzBlock) * nb, cudaMemcpyHostToDevice, stream));
+  OZ_CHECK(d_max.alloc(sizeof(unsigned long long) * (Mpad + Npad)));
+  OZ_CHECK(d_exp.alloc(sizeof(int32_t) * (Mpad + Npad)));
+  OZ_CHECK(d_scale.alloc(sizeof(double) * (Mpad + Npad)));
+  OZ_CHECK(d_bad.alloc(sizeof(int)));
+  OZ_CHECK(cudaMemsetAsync(d_max.p, 0, sizeof(unsigned long long) * (Mpad + Npad), stream));
+  OZ_CHECK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), stream));
+  unsigned long long* rowmax = static_cast<unsigned long long*>(d_max.p);
+  unsigned long long* colmax = rowmax + Mpad;
+  int32_t* row_exp = static_cast<int32_t*>(d_exp.p);
+  int32_t* col_exp = row_exp + Mpad;
+  {
+    const int tc = (max_ac + 31) / 32, tr = (max_ar + 31) / 32;
+    absmax_kernel<<<dim3(tr * tc, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), rowmax, 1, tc);
+    const int tcb = (max_bc + 31) / 32, trb = (max_br + 31) / 32;
+    absmax_kernel<<<dim3(trb * tcb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), colmax, 0, tcb);
+    exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, row_exp, static_cast<double*>(d_scale.p),
+                                                                                      static_cast<int>(Mpad + Npad), static_cast<int*>(d_bad.p));
+    *launches += 3;
+  }
+  int h_bad = 0;
+  OZ_CHECK(cudaMemcpyAsync(&h_bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  OZ_CHECK(cudaStreamSynchronize(stream));
+  if (h_bad) {
+    *nonfinite = 1;
+    return cudaSuccess;
+  }
+  const size_t a_stride = static_cast<size_t>(Mpad) * Kpad, b_stride = static_cast<size_t>(Npad) * Kpad;
+  const size_t plane_stride = static_cast<size_t>(Mpad) * Npad;
+  OZ_CHECK(d_As.alloc(a_stride * T));
+  OZ_CHECK(d_Bs.alloc(b_stride * T));
+  OZ_CHECK(d_planes.alloc(plane_stride * T));
+  OZ_CHECK(cudaMemsetAsync(d_As.p, 0, a_stride * T, stream));
+  OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * T, stream));
+  {
+    const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
+    residue_kernel<<<dim3(tl * tk, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), row_exp, static_cast<int8_t*>(d_As.p),
+                                                          a_stride, static_cast<int>(Kpad), T, alpha, 1, tk);
+    const int tkb = (max_br + 127) / 128, tlb = (max_bc + 31) / 32;
+    residue_kernel<<<dim3(tlb * tkb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), col_exp, static_cast<int8_t*>(d_Bs.p),
+                                                            b_stride, static_cast<int>(Kpad), T, alpha, 0, tkb);
+    *launches += 2;
+  }
+  std::vector<unsigned char> hmaps(static_cast<size_t>(2 * T) * 128);
+  for (int t = 0; t < T; ++t) {
+    if (!make_i8_map(&hmaps[static_cast<size_t>(t) * 128], static_cast<int8_t*>(d_As.p) + a_stride * t, Kpad, Mpad, BM) ||
+        !make_i8_map(&hmaps[static_cast<size_t>(T + t) * 128], static_cast<int8_t*>(d_Bs.p) + b_stride * t, Kpad, Npad, BN))
+      return cudaErrorInvalidValue;
+  }
+  OZ_CHECK(d_maps.alloc(hmaps.size()));
+  OZ_CHECK(cudaMemcpyAsync(d_maps.p, hmaps.data(), hmaps.size(), cudaMemcpyHostToDevice, stream));
+  OZ_CHECK(d_ctab.alloc(sizeof(double*) * nbr * nbc));
+  OZ_CHECK(cudaMemcpyAsync(d_ctab.p, h_ctab, sizeof(double*) * nbr * nbc, cudaMemcpyHostToDevice, stream));
+  OzakiGemmParams p{};
+  p.tmaps = static_cast<const unsigned char*>(d_maps.p);
+  p.M = static_cast<int32_t>(M);
+  p.N = static_cast<int32_t>(N);
+  p.Kpad = static_cast<int32_t>(Kpad);
+  p.blk = blk;
+  p.nbr = nbr;
+  p.nbc = nbc;
+  p.kstep = BKB;
+  p.kc0 = 0;
+  p.nkc = static_cast<int32_t>(Kpad / BKB);
+  p.npairs = 1;
+  p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+  p.tiles_m = static_cast<int32_t>(Mpad / BM);
+  p.tiles_n = static_cast<int32_t>(Npad / BN);
+  p.nmod = T;
+  p.npad = static_cast<int32_t>(Npad);
+  p.planes = static_cast<int8_t*>(d_planes.p);
+  p.plane_stride = plane_stride;
+  for (int t = 0; t < T; ++t) {
+    p.mod_p[t] = kCrtModuli[t];
+    p.mod_inv[t] = 1.0 / kCrtModuli[t];
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t nitems = static_cast<int64_t>(p.tiles_m) * p.tiles_n * T;
+  if (nitems > INT32_MAX) return cudaErrorInvalidValue;
+  ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(nitems, sms)), GEMM_THREADS_P, smem_bytes, stream>>>(p);
+  OZ_CHECK(cudaGetLastError());
+  crt_kernel<<<dim3(static_cast<unsigned>((N + 127) / 128), static_cast<unsigned>((M + 31) / 32)), 256, 0, stream>>>(
+      static_cast<const int8_t*>(d_planes.p), plane_stride, static_cast<int>(Npad), T, row_exp, col_exp, 2 * alpha,
+      static_cast<double* const*>(d_ctab.p), static_cast<int>(M), static_cast<int>(N), blk, nbc);
+  OZ_CHECK(cudaGetLastError());
+  *launches += 2;
   return cudaSuccess;
 }
 

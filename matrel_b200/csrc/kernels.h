@@ -56,6 +56,10 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
                            int64_t N, int slices, double* const* h_ctab, int blk, int nbr, int nbc, bool accumulate,
                            int* launches, int* nonfinite, cudaStream_t stream);
 
+// Ozaki scheme II (gemm_algo 4): `moduli` int8 GEMMs of residue matrices + Chinese-remainder reconstruction (gemm_ozaki.cu)
+cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K,
+                            int64_t N, int moduli, double* const* h_ctab, int blk, int nbr, int nbc, int* launches, int* nonfinite,
+                            cudaStream_t stream);
 // fp32 multiply on tcgen05 kind::tf32 (3xTF32 split, fp32 TMEM accumulation); same operand / output conventions.
 cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K, int64_t N,
                         double* const* h_ctab, int blk, int nbr, int nbc, int* launches, cudaStream_t stream);
