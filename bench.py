@@ -28,6 +28,13 @@ METRIC = "fp64 block-matmul GFLOP/s at N=16384"
 UNIT = "GFLOP/s"
 
 
+def tc_algo_name(args):
+    if getattr(args, "tc_algo", 4) == 4:
+        return ("Ozaki-II, %d coprime moduli <= 256: int8 residue GEMMs on tcgen05.mma kind::i8 (exact s32 TMEM accumulators), "
+                "CRT reconstruction to fp64" % getattr(args, "crt_moduli", 16))
+    return "Ozaki-I, %d balanced int8 slices, tcgen05.mma kind::i8 (s32 TMEM accumulators), fp64 epilogue" % getattr(args, "ozaki_slices", 7)
+
+
 def fp64_peak_tflops():
     """Roofline denominator for the fp64 tensor pipe: MEASURED_PEAKS.json has no fp64 entry, so the
     measured DMMA peak of tools/fp64_peak.cu (profiles/fp64_peaks_r01.jsonl) is used."""
@@ -307,13 +314,15 @@ def run_ours(args):
         peak, peak_src = fp64_peak_tflops()
         achieved = flops / (kern_ms * 1e-3) / 1e12
 
-        # ---- the same multiply on the 5th-gen tensor cores: Ozaki int8 slicing on tcgen05 (gemm_algo = 2), reported
-        #      beside the native-fp64 headline together with its measured deviation from the DMMA result
+        # ---- the same multiply on the 5th-gen tensor cores: Ozaki fp64 emulation on tcgen05 kind::i8 (gemm_algo = 4: CRT
+        #      residues, or 2: digit slices), reported beside the native-fp64 headline together with its measured deviation
+        #      from the DMMA result
         ozaki = None
         try:
             Cref = A.matrixMultiply(n, n, B, n, n, blk)
-            s.set_option("gemm_algo", 2)
+            s.set_option("gemm_algo", args.tc_algo)
             s.set_option("ozaki_slices", args.ozaki_slices)
+            s.set_option("crt_moduli", args.crt_moduli)
             for _ in range(2):
                 C2 = A.matrixMultiply(n, n, B, n, n, blk)
                 del C2
@@ -331,9 +340,10 @@ def run_ours(args):
             for key in [(0, 0), (nb // 2, nb // 3), (nb - 1, nb - 1)]:
                 a_, b_ = Cref.get_block(*key).values, C2.get_block(*key).values
                 worst = max(worst, float(np.max(np.abs(a_ - b_)) / np.max(np.abs(a_))))
-            ozaki = {"algo": "Ozaki-I, %d balanced int8 slices, tcgen05.mma kind::i8 (s32 TMEM accumulators), fp64 epilogue" % args.ozaki_slices,
+            ngemm = args.crt_moduli if args.tc_algo == 4 else args.ozaki_slices * (args.ozaki_slices + 1) // 2
+            ozaki = {"algo": tc_algo_name(args),
                      "value": flops / (oz_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": oz_ms,
-                     "int8_tensor_TOPS": (args.ozaki_slices * (args.ozaki_slices + 1) // 2) * flops / (oz_ms * 1e-3) / 1e12,
+                     "int8_gemms_per_multiply": ngemm, "int8_tensor_TOPS": ngemm * flops / (oz_ms * 1e-3) / 1e12,
                      "max_rel_dev_vs_dmma_fp64": worst, "x_dmma_roof": flops / (oz_ms * 1e-3) / 1e12 / fp64_peak_tflops()[0]}
             del C2, Cref
         except Exception as e:  # never take the headline down
@@ -399,7 +409,7 @@ def run_ours(args):
         # the same end-to-end step with the tcgen05 Ozaki kernel (reported inside "tcgen05_ozaki")
         if isinstance(ozaki, dict) and "error" not in ozaki:
             try:
-                s.set_option("gemm_algo", 2)
+                s.set_option("gemm_algo", args.tc_algo)
                 e2e_step()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
@@ -455,6 +465,8 @@ def main():
     ap.add_argument("--blk", type=int, default=BLK_DEFAULT)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ozaki-slices", type=int, default=7)
+    ap.add_argument("--tc-algo", type=int, default=4, choices=(2, 4), help="tcgen05 fp64 emulation reported beside the headline")
+    ap.add_argument("--crt-moduli", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
         }
         const int col0 = n0 + half * 128 + c;
         if (p.nmod) {
-          // symmetric residue of the exact s32 dot product: q = rint(c / p) is exact in fp64 (no integer c / p lies within
-          // 1/(2p) of a tie except the true ties of the even modulus 256, where +128 wraps to the congruent -128)
+          // residue of the exact s32 dot product: q = rint(c / p) is exact in fp64 (no integer c / p lies within 1/(2p) of a
+          // tie except the true ties of the even modulus 256, where either neighbour is a valid representative)
           const int pm = p.mod_p[mi];
           const double pinv = p.mod_inv[mi];
           uint32_t packed[4];
@@ -256,8 +256,9 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int v = static_cast<int32_t>(r[4 * g + j]);
-              const int res = v - __double2int_rn(static_cast<double>(v) * pinv) * pm;
-              wv |= (static_cast<uint32_t>(res) & 0xffu) << (8 * j);
+              int res = v - __double2int_rn(static_cast<double>(v) * pinv) * pm;  // [-p/2, p/2]
+              res += (res >> 31) & pm;                                          // [0, p): the CRT kernel reads unsigned bytes
+              wv |= static_cast<uint32_t>(res) << (8 * j);
             }
             packed[g] = wv;
           }
@@ -454,9 +455,9 @@ constexpr int CRT_MAX_T = 16;
 constexpr int CRT_MIN_T = 6;
 struct CrtConst {
   uint32_t p[CRT_MAX_T];       // moduli
-  uint32_t magic[CRT_MAX_T];   // floor(2^32 / p)
-  uint32_t c21[CRT_MAX_T];     // 2^21 mod p
-  uint32_t c42[CRT_MAX_T];     // 2^42 mod p
+  uint32_t clo[CRT_MAX_T];     // bytes (256^0, 256^1, 256^2, 256^3) mod p
+  uint32_t chi[CRT_MAX_T];     // bytes (256^4, 256^5, 256^6, 256^7) mod p
+  float invpf[CRT_MAX_T];      // 1 / p
   uint32_t w[CRT_MAX_T][4];    // CRT weight (P / p_t) * ((P / p_t)^-1 mod p_t) < P, little-endian 32-bit limbs
   uint32_t P[4], Phalf[4];     // P and floor(P / 2)
   double invP;                 // 1 / P (rounded)
@@ -491,31 +492,31 @@ __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict_
   for (int l = warp; l < 32; l += 8) {
     if (l0 + l >= nlines) continue;
     const int e = line_exp[gl_base + l];
-    uint32_t hi[4], mid[4], lo[4];
-    bool neg[4];
+    uint32_t hi[4], lo[4];
+    int sgn[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const long long X = __double2ll_rn(scalbn(sm[l][lane * 4 + j], alpha - e));  // exact power-of-two scaling, |X| <= 2^alpha
-      neg[j] = X < 0;
-      const unsigned long long U = static_cast<unsigned long long>(neg[j] ? -X : X);
-      hi[j] = static_cast<uint32_t>(U >> 42);
-      mid[j] = static_cast<uint32_t>(U >> 21) & 0x1FFFFFu;
-      lo[j] = static_cast<uint32_t>(U) & 0x1FFFFFu;
+      sgn[j] = X < 0 ? -1 : 1;
+      const unsigned long long U = static_cast<unsigned long long>(X < 0 ? -X : X);
+      hi[j] = static_cast<uint32_t>(U >> 32);
+      lo[j] = static_cast<uint32_t>(U);
     }
     const int kq = k0 + lane * 4;
     const int gk = gk_base + lane * 4;
     const bool whole = kq + 3 < nks && (gk & 3) == 0;
     for (int t = 0; t < T; ++t) {
-      const uint32_t pm = cc.p[t], mg = cc.magic[t], m21 = cc.c21[t], m42 = cc.c42[t];
+      const int pm = static_cast<int>(cc.p[t]);
+      const uint32_t wl = cc.clo[t], wh = cc.chi[t];
+      const float ip = cc.invpf[t];
       uint32_t packed = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t x = hi[j] * m42 + mid[j] * m21 + lo[j];  // < 2^30, congruent to |X|
-        int r = static_cast<int>(x - __umulhi(x, mg) * pm);      // in [0, 2p)
-        if (r >= static_cast<int>(pm)) r -= pm;
-        if (2 * r >= static_cast<int>(pm)) r -= pm;              // symmetric: [-(p-1)/2, (p-1)/2], [-128, 127] for 256
-        if (neg[j]) r = -r;                                      // +128 (p = 256 only) wraps to the congruent -128
-        packed |= (static_cast<uint32_t>(r) & 0xffu) << (8 * j);
+        // |X| = sum_i byte_i 256^i  ->  x = sum_i byte_i (256^i mod p) < 2^19, congruent to |X| and exact in fp32
+        const uint32_t x = __dp4a(lo[j], wl, __dp4a(hi[j], wh, 0u));
+        // nearest multiple of p: the fp32 quotient is off by < 5e-4, so |r| <= p/2 + 0.13 -> |r| <= 128 (p = 256), 127 (odd p)
+        const int r = (static_cast<int>(x) - __float2int_rn(__uint2float_rn(x) * ip) * pm) * sgn[j];
+        packed |= (static_cast<uint32_t>(r) & 0xffu) << (8 * j);  // +-128 (p = 256 only) wrap to the congruent -128
       }
       int8_t* dst = out + static_cast<size_t>(t) * slice_stride + static_cast<size_t>(gl_base + l) * Kpad + gk;
       if (whole) {
@@ -551,12 +552,10 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
     const int8_t* src = planes + static_cast<size_t>(row) * npad + c0 + lc;
     for (int t = 0; t < T; ++t) {
       const uint32_t quad = *reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(t) * plane_stride);
-      const uint32_t pm = cc.p[t];
       const uint32_t w0 = cc.w[t][0], w1 = cc.w[t][1], w2 = cc.w[t][2], w3 = cc.w[t][3];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = static_cast<int8_t>((quad >> (8 * j)) & 0xffu);
-        const uint32_t ru = r < 0 ? static_cast<uint32_t>(r + static_cast<int>(pm)) : static_cast<uint32_t>(r);
+        const uint32_t ru = (quad >> (8 * j)) & 0xffu;
         acc[j][0] += static_cast<unsigned long long>(ru) * w0;
         acc[j][1] += static_cast<unsigned long long>(ru) * w1;
         acc[j][2] += static_cast<unsigned long long>(ru) * w2;
@@ -748,6 +747,14 @@ bool make_f32_map(unsigned char* out128, void* base, uint64_t Kpad, uint64_t row
     if (e_ != cudaSuccess) return e_;    \
   } while (0)
 
+// The slice / residue matrices only need zero-filling where no block writes: K padding (garbage there would enter every dot
+// product) and absent blocks.  Row padding beyond M / N may hold garbage: those accumulator rows are never stored.
+bool covers_operand(const OzakiOperand* blocks, int n, int64_t lines, int64_t K, int64_t Kpad) {
+  if (K != Kpad) return false;
+  int64_t area = 0;
+  for (int i = 0; i < n; ++i) area += static_cast<int64_t>(blocks[i].rows) * blocks[i].cols;
+  return area == lines * K;  // block ids are unique, so equal area means full coverage
+}
 struct AsyncBuf {  // stream-ordered scratch
   void* p = nullptr;
   cudaStream_t s;
@@ -822,8 +829,8 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   const size_t a_stride = static_cast<size_t>(Mpad) * Kpad, b_stride = static_cast<size_t>(Npad) * Kpad;
   OZ_CHECK(d_As.alloc(a_stride * S));
   OZ_CHECK(d_Bs.alloc(b_stride * S));
-  OZ_CHECK(cudaMemsetAsync(d_As.p, 0, a_stride * S, stream));
-  OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * S, stream));
+  if (!covers_operand(a_blocks, na, M, K, Kpad)) OZ_CHECK(cudaMemsetAsync(d_As.p, 0, a_stride * S, stream));
+  if (!covers_operand(b_blocks, nb, N, K, Kpad)) OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * S, stream));
   {
     const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
     slice_kernel<<<dim3(tl * tk, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), row_exp, static_cast<int8_t*>(d_As.p),
@@ -908,9 +915,13 @@ cudaError_t crt_constants(int* log2P) {
       for (int t = 0; t < T; ++t) {
         const unsigned pm = static_cast<unsigned>(kCrtModuli[t]);
         c.p[t] = pm;
-        c.magic[t] = static_cast<uint32_t>((1ull << 32) / pm);
-        c.c21[t] = static_cast<uint32_t>((1ull << 21) % pm);
-        c.c42[t] = static_cast<uint32_t>((1ull << 42) % pm);
+        uint32_t pw = 1;
+        for (int i = 0; i < 8; ++i) {  // 256^i mod p, one byte each
+          if (i < 4) c.clo[t] |= pw << (8 * i);
+          else c.chi[t] |= pw << (8 * (i - 4));
+          pw = (pw * 256u) % pm;
+        }
+        c.invpf[t] = 1.0f / static_cast<float>(pm);
         const unsigned __int128 Mt = P / pm;
         const unsigned mr = static_cast<unsigned>(Mt % pm);
         unsigned inv = 1;
@@ -1009,8 +1020,8 @@ cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOpe
   OZ_CHECK(d_As.alloc(a_stride * T));
   OZ_CHECK(d_Bs.alloc(b_stride * T));
   OZ_CHECK(d_planes.alloc(plane_stride * T));
-  OZ_CHECK(cudaMemsetAsync(d_As.p, 0, a_stride * T, stream));
-  OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * T, stream));
+  if (!covers_operand(a_blocks, na, M, K, Kpad)) OZ_CHECK(cudaMemsetAsync(d_As.p, 0, a_stride * T, stream));
+  if (!covers_operand(b_blocks, nb, N, K, Kpad)) OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * T, stream));
   {
     const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
     residue_kernel<<<dim3(tl * tk, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), row_exp, static_cast<int8_t*>(d_As.p),

@@ -306,8 +306,9 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
         # ---- the same sharded multiply with the tcgen05 Ozaki kernel on every rank (reported beside the headline)
         ozaki = None
         try:
-            s.set_option("gemm_algo", 2)
+            s.set_option("gemm_algo", getattr(args, "tc_algo", 4))
             s.set_option("ozaki_slices", getattr(args, "ozaki_slices", 7))
+            s.set_option("crt_moduli", getattr(args, "crt_moduli", 16))
             for _ in range(2):
                 out = step()
                 del out
@@ -323,7 +324,8 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
             ot = torch.tensor([o0.elapsed_time(o1) / args.steps], dtype=torch.float64, device=device)
             dist.all_reduce(ot, op=dist.ReduceOp.MAX)
             oz_ms = float(ot.item())
-            ozaki = {"algo": "Ozaki-I, %d int8 slices, tcgen05 kind::i8 on every rank" % getattr(args, "ozaki_slices", 7),
+            ozaki = {"algo": ("Ozaki-II, %d moduli" % getattr(args, "crt_moduli", 16) if getattr(args, "tc_algo", 4) == 4 else
+                              "Ozaki-I, %d int8 slices" % getattr(args, "ozaki_slices", 7)) + ", tcgen05 kind::i8 on every rank",
                      "value": flops / (oz_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": oz_ms}
         except Exception as e:
             ozaki = {"error": str(e)}
