@@ -14,13 +14,13 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("algo", [0, 2])
+@pytest.mark.parametrize("algo", [0, 2, 4])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_multiply_nccl(world, algo):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MATREL_GEMM_ALGO=str(algo))
-    port = 29700 + world * 3 + algo + (os.getpid() % 200)
+    port = 29700 + world * 5 + algo + (os.getpid() % 200)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900, cwd=ROOT)
