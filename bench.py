@@ -59,7 +59,7 @@ def dram_traffic_per_launch(n: int):
         d = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")))
         e = d.get(str(n))
         return None if e is None else {"bytes": e["dram_read_bytes"] + e["dram_write_bytes"], "algorithmic_bytes": 3 * n * n * 8,
-                                       "source": e.get("source", "ncu")}
+                                       "unit": "bytes per launch", "source": e.get("source", "ncu")}
     except (OSError, ValueError, KeyError):
         return None
 
@@ -444,7 +444,7 @@ def run_ours(args):
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": dram_traffic_per_launch(n), "kernel": "gemm_f64_dmma_kernel<128,128,2,4,5>", "kernel_ms": kern_ms,
+                     "traffic": (dram_traffic_per_launch(n) or {}).get("bytes"), "traffic_detail": dram_traffic_per_launch(n), "kernel": "gemm_f64_dmma_kernel<128,128,2,4,5>", "kernel_ms": kern_ms,
                      "launches_per_step": gemm_launches_per_step,
                      "algorithmic": f"2*N^3 = {flops:.4g} flop per launch (whole block multiply, K reduction fused)",
                      "peak_source": peak_src},
