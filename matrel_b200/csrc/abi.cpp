@@ -22,6 +22,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -318,11 +319,13 @@ struct OutPlan {
   std::vector<GemmPair> gemm;                            // dense x dense (possibly densified) pairs
   std::vector<GemmSrc> src;                              // the blocks behind each gemm pair (+ its k-block id)
   std::vector<std::pair<const Block*, const Block*>> spmm;  // sparse x dense pairs
+  std::vector<std::pair<const Block*, const Block*>> spsp;  // sparse x sparse, both densities <= 0.1 (ascending k)
 };
 
 struct MultiplyPlanner {
   mr_context* ctx;
-  std::vector<Block> temps;  // densified sparse operands kept alive until the launches are enqueued
+  std::deque<Block> temps;   // densified sparse operands kept alive until the launches are enqueued (deque: the
+                             // plans hold pointers to these blocks, so growth must not move them)
   std::map<const Block*, size_t> densified;
 
   const Block& dense_of(const Block& b) {
@@ -363,9 +366,7 @@ struct MultiplyPlanner {
       } else if (s2 > 0.1) {
         o.spmm.emplace_back(&a, &dense_of(b));   // :906-907
       } else {
-        fail(MR_ENOTSUP,
-             "sparse x sparse block product with both densities <= 0.1 (LocalMatrix.multiplySparseSparse) is "
-             "outside the B200 hot-path scope");
+        o.spsp.emplace_back(&a, &b);  // LocalMatrix.multiplySparseSparse (:909-911, :143-323): see run_sparse_chains
       }
     }
   }
@@ -471,8 +472,235 @@ bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<d
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// dense window -> CSC compaction (DenseMatrix.toSparse, MLMatrix.scala:392-420), batched
+// ------------------------------------------------------------------------------------------------
+struct DenseWin {
+  const double* p;  // column-major rows x cols
+  int32_t rows, cols;
+};
+
+// Per-column counts of entries != 0.0 (NaN counts, as in the reference's `arr(i) != 0`): one launch + one sync.
+std::vector<std::vector<int32_t>> column_counts(mr_context* ctx, const std::vector<DenseWin>& wins) {
+  std::vector<std::vector<int32_t>> out(wins.size());
+  if (wins.empty()) return out;
+  size_t ncols_total = 0;
+  int maxc = 0;
+  for (auto& w : wins) {
+    ncols_total += static_cast<size_t>(w.cols);
+    maxc = std::max(maxc, w.cols);
+  }
+  Buf counts = std::make_shared<DevBuf>(ctx, std::max<size_t>(ncols_total * sizeof(int32_t), 16));
+  std::vector<CscDesc> cd(wins.size());
+  size_t off = 0;
+  for (size_t i = 0; i < wins.size(); ++i) {
+    cd[i] = CscDesc{wins[i].p, wins[i].rows, wins[i].cols, static_cast<int32_t*>(counts->p) + off, nullptr, nullptr, nullptr};
+    off += static_cast<size_t>(wins[i].cols);
+  }
+  Buf dcd = upload(ctx, cd);
+  CUDA_CHECK(launch_csc_count(static_cast<const CscDesc*>(dcd->p), static_cast<int>(cd.size()), maxc, ctx->stream));
+  note_launch(ctx);
+  std::vector<int32_t> h(ncols_total);
+  if (ncols_total) {
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), counts->p, ncols_total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += static_cast<int64_t>(ncols_total * sizeof(int32_t));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  off = 0;
+  for (size_t i = 0; i < wins.size(); ++i) {
+    out[i].assign(h.begin() + static_cast<std::ptrdiff_t>(off), h.begin() + static_cast<std::ptrdiff_t>(off + wins[i].cols));
+    off += static_cast<size_t>(wins[i].cols);
+  }
+  return out;
+}
+
+int64_t total_count(const std::vector<int32_t>& counts) {
+  int64_t n = 0;
+  for (int32_t c : counts) n += c;
+  return n;
+}
+
+// CSC blocks (isTransposed = false) of the windows, given their column counts: one launch.
+std::vector<Block> compact_csc(mr_context* ctx, const std::vector<DenseWin>& wins, const std::vector<std::vector<int32_t>>& counts) {
+  std::vector<Block> out;
+  std::vector<CscDesc> fill;
+  int maxc = 0;
+  for (size_t i = 0; i < wins.size(); ++i) {
+    const int rows = wins[i].rows, cols = wins[i].cols;
+    std::vector<int32_t> ptrs(static_cast<size_t>(cols) + 1, 0);
+    for (int c = 0; c < cols; ++c) ptrs[c + 1] = ptrs[c] + counts[i][c];
+    const int64_t nnz = ptrs[cols];
+    Block sb;
+    sb.type = 0;
+    sb.numRows = rows;
+    sb.numCols = cols;
+    sb.isT = false;
+    sb.valuesLen = nnz;
+    sb.colPtrsLen = cols + 1;
+    sb.colPtrs = upload_raw(ctx, ptrs.data(), ptrs.size() * sizeof(int32_t));
+    sb.rowIndices = Span{std::make_shared<DevBuf>(ctx, std::max<size_t>(nnz * sizeof(int32_t), 16)), 0};
+    sb.values = Span{std::make_shared<DevBuf>(ctx, std::max<size_t>(nnz * sizeof(double), 16)), 0};
+    fill.push_back(CscDesc{wins[i].p, rows, cols, nullptr, sb.colPtrs.ptr<int32_t>(), sb.rowIndices.ptr<int32_t>(),
+                           sb.values.ptr<double>()});
+    maxc = std::max(maxc, cols);
+    out.push_back(std::move(sb));
+  }
+  if (!fill.empty()) {
+    Buf dfill = upload(ctx, fill);
+    CUDA_CHECK(launch_csc_fill(static_cast<const CscDesc*>(dfill->p), static_cast<int>(fill.size()), maxc, ctx->stream));
+    note_launch(ctx);
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output blocks whose partial products are ALL low-density sparse x sparse (LocalMatrix.multiplySparseSparse,
+// LocalMatrix.scala:143-323).  Values: each partial is computed as sparse A x densified B (the same sums in a different
+// order).  Storage format: the reference's four loop nests end in four different rules, and `reduceByKey(LocalMatrix.add)`
+// re-decides the format at every sparse + sparse step, so the chain is replayed partial by partial in ascending k (Spark's
+// own reduce order is arbitrary; the oracle uses ascending k as well):
+//   CSC x CSC (:155-196): CSC iff rows*cols > 2 nnz + cols + 1, else dense      CSR x CSR (:198-239): CSR iff ... + rows + 1
+//   CSR x CSC (:241-286): always CSC (both branches build a SparseMatrix)       CSC x CSR (:288-323): dense iff rows*cols <= 2 nnz + cols
+//   sparse + sparse (:74-139): CSC iff rows*cols > 2 nnz + cols + 1, else dense; anything + dense: dense.
+// ------------------------------------------------------------------------------------------------
+enum ChainFmt { FMT_DENSE = 0, FMT_CSC = 1, FMT_CSR = 2 };
+
+void run_sparse_chains(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<size_t>& chains,
+                       const std::vector<double*>& cptr, MultiplyPlanner& planner, mr_matrix* result) {
+  if (chains.empty()) return;
+  size_t levels = 0;
+  for (size_t i : chains) levels = std::max(levels, plans[i].spsp.size());
+  std::vector<int> fmt(chains.size(), FMT_DENSE);
+  std::vector<Buf> scratch(chains.size());
+  for (size_t lv = 0; lv < levels; ++lv) {
+    std::vector<size_t> act;  // chains that have a partial at this level
+    std::vector<DenseWin> pw;
+    for (size_t c = 0; c < chains.size(); ++c) {
+      OutPlan& o = plans[chains[c]];
+      if (lv >= o.spsp.size() || o.m == 0 || o.n == 0) continue;
+      const Block& a = *o.spsp[lv].first;
+      const Block& b = planner.dense_of(*o.spsp[lv].second);
+      wait_ready(ctx, a);
+      wait_ready(ctx, *o.spsp[lv].second);
+      const size_t bytes = static_cast<size_t>(o.m) * o.n * sizeof(double);
+      double* target = cptr[chains[c]];
+      if (lv > 0) {
+        if (!scratch[c]) scratch[c] = std::make_shared<DevBuf>(ctx, bytes);
+        target = static_cast<double*>(scratch[c]->p);
+      }
+      if (!a.isT) CUDA_CHECK(cudaMemsetAsync(target, 0, bytes, ctx->stream));  // the CSC kernel scatters into zeros
+      CUDA_CHECK(launch_spmm(a.colPtrs.ptr<int32_t>(), a.rowIndices.ptr<int32_t>(), a.values.ptr<double>(), a.isT,
+                             b.values.ptr<double>(), b.isT, target, a.numRows, a.numCols, b.numCols, false, ctx->stream));
+      note_launch(ctx);
+      act.push_back(c);
+      pw.push_back(DenseWin{target, o.m, o.n});
+    }
+    if (act.empty()) continue;
+    const auto pcounts = column_counts(ctx, pw);
+    std::vector<size_t> recount;  // chains whose running sum is sparse + sparse at this level
+    std::vector<EwDesc> adds;
+    int max_rows = 0, max_cols = 0;
+    for (size_t t = 0; t < act.size(); ++t) {
+      const size_t c = act[t];
+      OutPlan& o = plans[chains[c]];
+      const bool aT = o.spsp[lv].first->isT, bT = o.spsp[lv].second->isT;
+      const int64_t cells = static_cast<int64_t>(o.m) * o.n, nnz = total_count(pcounts[t]);
+      int pf;
+      if (!aT && !bT) pf = cells > 2 * nnz + o.n + 1 ? FMT_CSC : FMT_DENSE;
+      else if (aT && bT) pf = cells > 2 * nnz + o.m + 1 ? FMT_CSR : FMT_DENSE;
+      else if (aT && !bT) pf = FMT_CSC;
+      else pf = cells <= 2 * nnz + o.n ? FMT_DENSE : FMT_CSC;
+      if (lv == 0) {
+        fmt[c] = pf;
+        continue;
+      }
+      EwDesc d{};
+      d.A = cptr[chains[c]];
+      d.B = pw[t].p;
+      d.C = cptr[chains[c]];  // in place: every element is read and written by the same thread
+      d.rows = o.m;
+      d.cols = o.n;
+      adds.push_back(d);
+      max_rows = std::max(max_rows, o.m);
+      max_cols = std::max(max_cols, o.n);
+      if (fmt[c] == FMT_DENSE || pf == FMT_DENSE) fmt[c] = FMT_DENSE;
+      else recount.push_back(c);
+    }
+    if (!adds.empty()) {
+      Buf d = upload(ctx, adds);
+      CUDA_CHECK(launch_ew_batched(EW_ADD, static_cast<const EwDesc*>(d->p), static_cast<int>(adds.size()), max_rows, max_cols,
+                                   false, ctx->stream));
+      note_launch(ctx);
+    }
+    if (!recount.empty()) {
+      std::vector<DenseWin> sw;
+      for (size_t c : recount) sw.push_back(DenseWin{cptr[chains[c]], plans[chains[c]].m, plans[chains[c]].n});
+      const auto scounts = column_counts(ctx, sw);
+      for (size_t t = 0; t < recount.size(); ++t) {
+        const OutPlan& o = plans[chains[recount[t]]];
+        fmt[recount[t]] = static_cast<int64_t>(o.m) * o.n > 2 * total_count(scounts[t]) + o.n + 1 ? FMT_CSC : FMT_DENSE;
+      }
+    }
+  }
+  // final storage: dense results stay in their slab window; CSC / CSR results are compacted out of it
+  std::vector<DenseWin> cw;
+  std::vector<size_t> cw_chain;
+  std::vector<Buf> keep;
+  for (size_t c = 0; c < chains.size(); ++c) {
+    const OutPlan& o = plans[chains[c]];
+    if (o.m == 0 || o.n == 0 || fmt[c] == FMT_DENSE) continue;
+    if (fmt[c] == FMT_CSC) {
+      cw.push_back(DenseWin{cptr[chains[c]], o.m, o.n});
+    } else {  // CSR of C = CSC of C^T: materialise the row-major copy (= column-major n x m) first
+      Buf t = std::make_shared<DevBuf>(ctx, static_cast<size_t>(o.m) * o.n * sizeof(double));
+      EwDesc d{};
+      d.A = cptr[chains[c]];
+      d.C = static_cast<double*>(t->p);
+      d.rows = o.n;
+      d.cols = o.m;
+      d.aT = 1;
+      std::vector<EwDesc> one{d};
+      Buf dd = upload(ctx, one);
+      CUDA_CHECK(launch_ew_batched(EW_COPY, static_cast<const EwDesc*>(dd->p), 1, o.n, o.m, true, ctx->stream));
+      note_launch(ctx);
+      cw.push_back(DenseWin{static_cast<const double*>(t->p), o.n, o.m});
+      keep.push_back(t);
+    }
+    cw_chain.push_back(c);
+  }
+  if (!cw.empty()) {
+    const auto counts = column_counts(ctx, cw);
+    std::vector<Block> blocks = compact_csc(ctx, cw, counts);
+    for (size_t t = 0; t < blocks.size(); ++t) {
+      const size_t c = cw_chain[t];
+      const OutPlan& o = plans[chains[c]];
+      Block& b = blocks[t];
+      if (fmt[c] == FMT_CSR) {  // the CSC arrays of C^T are the CSR arrays of C
+        b.numRows = o.m;
+        b.numCols = o.n;
+        b.isT = true;
+      }
+      result->blocks[{o.rid, o.cid}] = std::move(b);
+    }
+  }
+}
+
 void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner& planner, int32_t blkSize,
                   mr_matrix* result, int64_t M, int64_t K, int64_t N, bool outer) {
+  // Low-density sparse x sparse pairs: next to any dense partial the block sum is dense whatever the partial's own format
+  // (LocalMatrix.add), so there they are ordinary sparse x dense products of the densified right operand; an output block
+  // made of such pairs ONLY replays the reference's format rules (run_sparse_chains).
+  std::vector<size_t> chains;
+  for (size_t i = 0; i < plans.size(); ++i) {
+    OutPlan& o = plans[i];
+    if (o.spsp.empty()) continue;
+    if (o.gemm.empty() && o.spmm.empty()) {
+      chains.push_back(i);
+    } else {
+      for (auto& pr : o.spsp) o.spmm.emplace_back(pr.first, &planner.dense_of(*pr.second));
+      o.spsp.clear();
+    }
+  }
   // allocate all output blocks from one slab
   size_t total = 0;
   for (auto& o : plans) total += align_up(static_cast<size_t>(o.m) * o.n * sizeof(double));
@@ -675,7 +903,7 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
   for (size_t i = 0; i < plans.size(); ++i) {
     auto& o = plans[i];
     bool have = !o.gemm.empty();
-    if (o.m == 0 || o.n == 0) continue;
+    if (o.m == 0 || o.n == 0 || !o.spsp.empty()) continue;
     std::vector<std::pair<const Block*, const Block*>> slow;
     SpmmOut fo{};
     fo.C = cptr[i];
@@ -732,7 +960,7 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       ctx->stats.gemm_ms_total += ms;
     }
   }
-  (void)planner;
+  run_sparse_chains(ctx, plans, chains, cptr, planner, result);
 }
 
 
@@ -795,63 +1023,21 @@ struct EwBatch {
   // dense result is converted with toSparse (CSC, isTransposed = false) iff rows*cols > 2*nnz + cols + 1, where nnz
   // counts entries != 0.0 (NaN included).  Both the transposed and the native branch reduce to this rule.
   void apply_sparse_rule(mr_matrix* result) {
-    std::vector<CscDesc> cd(sparse_rule.size());
-    size_t ncols_total = 0;
-    int maxc = 0;
-    for (size_t i = 0; i < sparse_rule.size(); ++i) ncols_total += static_cast<size_t>(shapes[sparse_rule[i]].second.second);
-    Buf counts = std::make_shared<DevBuf>(ctx, std::max<size_t>(ncols_total * sizeof(int32_t), 16));
-    size_t off = 0;
-    for (size_t i = 0; i < sparse_rule.size(); ++i) {
-      const size_t bi = sparse_rule[i];
-      cd[i] = CscDesc{descs[bi].C, shapes[bi].second.first, shapes[bi].second.second, static_cast<int32_t*>(counts->p) + off,
-                      nullptr, nullptr, nullptr};
-      off += static_cast<size_t>(cd[i].cols);
-      maxc = std::max(maxc, cd[i].cols);
-    }
-    Buf dcd = upload(ctx, cd);
-    CUDA_CHECK(launch_csc_count(static_cast<const CscDesc*>(dcd->p), static_cast<int>(cd.size()), maxc, ctx->stream));
-    note_launch(ctx);
-    std::vector<int32_t> hcounts(ncols_total);
-    if (ncols_total) {
-      CUDA_CHECK(cudaMemcpyAsync(hcounts.data(), counts->p, ncols_total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->stats.d2h_bytes += static_cast<int64_t>(ncols_total * sizeof(int32_t));
-    }
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    std::vector<CscDesc> fill;
-    std::vector<Block> fresh;
+    std::vector<DenseWin> wins;
+    for (size_t bi : sparse_rule) wins.push_back(DenseWin{descs[bi].C, shapes[bi].second.first, shapes[bi].second.second});
+    const auto counts = column_counts(ctx, wins);
+    std::vector<DenseWin> chosen;
+    std::vector<std::vector<int32_t>> chosen_counts;
     std::vector<std::pair<int32_t, int32_t>> keys;
-    int maxc_fill = 0;
-    off = 0;
-    for (size_t i = 0; i < cd.size(); ++i) {
-      const int rows = cd[i].rows, cols = cd[i].cols;
-      std::vector<int32_t> ptrs(static_cast<size_t>(cols) + 1, 0);
-      for (int c = 0; c < cols; ++c) ptrs[c + 1] = ptrs[c] + hcounts[off + c];
-      off += static_cast<size_t>(cols);
-      const int64_t nnz = ptrs[cols];
-      if (static_cast<int64_t>(rows) * cols > 2 * nnz + cols + 1) {
-        Block sb;
-        sb.type = 0;
-        sb.numRows = rows;
-        sb.numCols = cols;
-        sb.isT = false;
-        sb.valuesLen = nnz;
-        sb.colPtrsLen = cols + 1;
-        sb.colPtrs = upload_raw(ctx, ptrs.data(), ptrs.size() * sizeof(int32_t));
-        sb.rowIndices = Span{std::make_shared<DevBuf>(ctx, std::max<size_t>(nnz * sizeof(int32_t), 16)), 0};
-        sb.values = Span{std::make_shared<DevBuf>(ctx, std::max<size_t>(nnz * sizeof(double), 16)), 0};
-        fill.push_back(CscDesc{cd[i].dense, rows, cols, nullptr, sb.colPtrs.ptr<int32_t>(), sb.rowIndices.ptr<int32_t>(),
-                               sb.values.ptr<double>()});
-        maxc_fill = std::max(maxc_fill, cols);
-        fresh.push_back(std::move(sb));
+    for (size_t i = 0; i < wins.size(); ++i) {
+      if (static_cast<int64_t>(wins[i].rows) * wins[i].cols > 2 * total_count(counts[i]) + wins[i].cols + 1) {
+        chosen.push_back(wins[i]);
+        chosen_counts.push_back(counts[i]);
         keys.push_back(shapes[sparse_rule[i]].first);
       }
     }
-    if (!fill.empty()) {
-      Buf dfill = upload(ctx, fill);
-      CUDA_CHECK(launch_csc_fill(static_cast<const CscDesc*>(dfill->p), static_cast<int>(fill.size()), maxc_fill, ctx->stream));
-      note_launch(ctx);
-      for (size_t i = 0; i < fresh.size(); ++i) result->blocks[keys[i]] = std::move(fresh[i]);  // replaces the dense window
-    }
+    std::vector<Block> fresh = compact_csc(ctx, chosen, chosen_counts);
+    for (size_t i = 0; i < fresh.size(); ++i) result->blocks[keys[i]] = std::move(fresh[i]);  // replaces the dense window
   }
 };
 
@@ -1415,7 +1601,6 @@ mr_status mr_matrix_multiply(mr_matrix* left, int64_t leftRowNum, int64_t leftCo
     for (auto& kv : right->blocks)
       if (!kv.second.dense()) wait_ready(ctx, kv.second);
     MultiplyPlanner planner{ctx};
-    planner.temps.reserve(left->blocks.size() + right->blocks.size() + 1);
     std::vector<OutPlan> plans;
     const int64_t leftColBlkNum = ceil_div(leftColNum, blkSize);    // :712
     const int64_t rightRowBlkNum = ceil_div(rightRowNum, blkSize);  // :713

@@ -568,12 +568,10 @@ cudaError_t launch_csc_fill(const CscDesc* d_descs, int nblocks, int max_cols, c
 cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* d_pairs, int max_n, cudaStream_t stream) {
   if (nouts <= 0 || max_n <= 0) return cudaSuccess;
   const size_t smem = static_cast<size_t>(SPMM_CW) * (kSpmmMaxDim + 2) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(spmm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  cudaError_t e = configured.run(
+      [&] { return cudaFuncSetAttribute(spmm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); });
+  if (e != cudaSuccess) return e;
   for (int off = 0; off < nouts; off += 65535) {
     const int nb = nouts - off < 65535 ? nouts - off : 65535;
     spmm_fused_kernel<<<dim3((max_n + SPMM_CW - 1) / SPMM_CW, nb), SPMM_THREADS, smem, stream>>>(d_outs + off, d_pairs);

@@ -314,12 +314,10 @@ cudaError_t launch_variant(const GemmOut* d_outs, const GemmPair* d_pairs, const
                            const void* d_tmaps, cudaStream_t stream) {
   using Cfg = GemmCfg<BM, BN, WM, WN, STAGES>;
   auto kern = gemm_f64_dmma_kernel<BM, BN, WM, WN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::SMEM_BYTES));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  cudaError_t e = configured.run(
+      [&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::SMEM_BYTES)); });
+  if (e != cudaSuccess) return e;
   kern<<<ntiles, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(d_outs, d_pairs, d_tiles, static_cast<const unsigned char*>(d_tmaps));
   return cudaGetLastError();
 }

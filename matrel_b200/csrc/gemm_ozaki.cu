@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "kernels.h"
@@ -755,6 +756,13 @@ bool covers_operand(const OzakiOperand* blocks, int n, int64_t lines, int64_t K,
   for (int i = 0; i < n; ++i) area += static_cast<int64_t>(blocks[i].rows) * blocks[i].cols;
   return area == lines * K;  // block ids are unique, so equal area means full coverage
 }
+cudaError_t configure_gemm_kernel(size_t smem_bytes) {
+  static PerDeviceOnce once;
+  return once.run([&] {
+    return cudaFuncSetAttribute(ozaki_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+  });
+}
+
 struct AsyncBuf {  // stream-ordered scratch
   void* p = nullptr;
   cudaStream_t s;
@@ -774,12 +782,8 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   const int S = slices < 2 ? 2 : (slices > 7 ? 7 : slices);
   const int64_t Mpad = (M + BM - 1) / BM * BM, Npad = (N + BN - 1) / BN * BN, Kpad = (K + BKB - 1) / BKB * BKB;
-  static bool configured = false;
   const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
-  if (!configured) {
-    OZ_CHECK(cudaFuncSetAttribute(ozaki_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-    configured = true;
-  }
+  OZ_CHECK(configure_gemm_kernel(smem_bytes));
   // block descriptor tables
   std::vector<OzBlock> ha(na), hb(nb);
   int max_ar = 1, max_ac = 1, max_br = 1, max_bc = 1;
@@ -902,11 +906,11 @@ const int kCrtModuli[CRT_MAX_T] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 
 
 // fills c_crt[T] for every supported T once; returns floor(log2 P) per T through log2P
 cudaError_t crt_constants(int* log2P) {
-  static bool done = false;
+  static PerDeviceOnce uploaded;
+  static std::once_flag built;
   static int l2[CRT_MAX_T + 1];
-  static cudaError_t status = cudaSuccess;
-  if (!done) {
-    std::vector<CrtConst> all(CRT_MAX_T + 1);
+  static std::vector<CrtConst> all(CRT_MAX_T + 1);
+  std::call_once(built, [&] {
     for (int T = CRT_MIN_T; T <= CRT_MAX_T; ++T) {
       CrtConst& c = all[T];
       memset(&c, 0, sizeof(c));
@@ -940,11 +944,9 @@ cudaError_t crt_constants(int* log2P) {
       while ((P >> (lg + 1)) != 0) ++lg;
       l2[T] = lg;
     }
-    status = cudaMemcpyToSymbol(c_crt, all.data(), sizeof(CrtConst) * (CRT_MAX_T + 1));
-    done = status == cudaSuccess;
-  }
+  });
   for (int T = 0; T <= CRT_MAX_T; ++T) log2P[T] = l2[T];
-  return status;
+  return uploaded.run([&] { return cudaMemcpyToSymbol(c_crt, all.data(), sizeof(CrtConst) * (CRT_MAX_T + 1)); });
 }
 }  // namespace
 
@@ -965,12 +967,8 @@ cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOpe
   if (alpha > 62) alpha = 62;
   if (alpha < 8) return cudaErrorInvalidValue;
   const int64_t Mpad = (M + BM - 1) / BM * BM, Npad = (N + BN - 1) / BN * BN, Kpad = (K + BKB - 1) / BKB * BKB;
-  static bool configured = false;
   const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
-  if (!configured) {
-    OZ_CHECK(cudaFuncSetAttribute(ozaki_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-    configured = true;
-  }
+  OZ_CHECK(configure_gemm_kernel(smem_bytes));
   std::vector<OzBlock> ha(na), hb(nb);
   int max_ar = 1, max_ac = 1, max_br = 1, max_bc = 1;
   for (int i = 0; i < na; ++i) {
@@ -1085,12 +1083,8 @@ cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand
                         double* const* h_ctab, int blk, int nbr, int nbc, int* launches, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   const int64_t Mpad = (M + BM - 1) / BM * BM, Npad = (N + BN - 1) / BN * BN, Kpad = (K + 31) / 32 * 32;
-  static bool configured = false;
   const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
-  if (!configured) {
-    OZ_CHECK(cudaFuncSetAttribute(ozaki_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-    configured = true;
-  }
+  OZ_CHECK(configure_gemm_kernel(smem_bytes));
   std::vector<OzBlock> ha(na), hb(nb);
   int max_ar = 1, max_ac = 1, max_br = 1, max_bc = 1;
   for (int i = 0; i < na; ++i) {

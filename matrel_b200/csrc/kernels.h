@@ -2,9 +2,35 @@
 // Not part of the public ABI (see include/matrel.h).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <mutex>
 #include <stdint.h>
 
 namespace matrel {
+
+// Kernel function attributes and __constant__ tables are per DEVICE: "configure once" must be keyed by the current device
+// (one process may drive several GPUs) and be safe against concurrent first calls from different contexts.
+class PerDeviceOnce {
+ public:
+  template <class F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> g(mu_);
+    if (dev < 0 || dev >= kMaxDevices) return f();
+    if (done_[dev]) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess) done_[dev] = true;
+    return e;
+  }
+
+ private:
+  static constexpr int kMaxDevices = 64;
+  std::mutex mu_;
+  bool done_[kMaxDevices] = {};
+};
+
 
 // ---- block GEMM ----------------------------------------------------------------------------------
 // One k-block contribution A(i,k) * B(k,j) to an output block; the block-GEMM kernel walks the

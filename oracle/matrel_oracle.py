@@ -342,7 +342,35 @@ def multiplySparseMatDenseVec(spm: SparseMatrix, dv: DenseMatrix) -> DenseMatrix
     return DenseMatrix(spm.numRows, 1, spm.to_numpy() @ dv.to_numpy()[:, 0])
 
 
-SPARSE_SPARSE_NOT_RESTATED = "multiplySparseSparse (LocalMatrix.scala:143-323) is out of the hot-path scope"
+def multiplySparseSparse(ma: SparseMatrix, mb: SparseMatrix) -> MLMatrix:
+    """LocalMatrix.multiplySparseSparse (M/matrix/LocalMatrix.scala:143-323).  The four loop nests (CSC x CSC :155-196,
+    CSR x CSR :198-239, CSR x CSC :241-286, CSC x CSR :288-323) compute the same product over the STORED entries only and
+    drop results that are exactly 0.0 (`!= 0.0`, so NaN is kept); they differ in the storage format of the result:
+      CSC x CSC: CSC iff rows*cols > 2 nnz + (cols + 1), else that matrix .toDense
+      CSR x CSR: CSR iff rows*cols > 2 nnz + (rows + 1), else .toDense
+      CSR x CSC: always CSC (both branches construct the SparseMatrix, :280-285)
+      CSC x CSR: dense iff rows*cols <= 2 nnz + cols, else DenseMatrix.toSparse (CSC)
+    Summation order inside an entry follows scipy here, not the Scala loops (fp64 tolerance, not bit-exact)."""
+    import scipy.sparse as sp
+    require(ma.numCols == mb.numRows, "Matrix A.numCols must be equals to B.numRows, but found "
+            f"A.numCols = {ma.numCols}, B.numRows = {mb.numRows}")
+
+    def as_scipy(m: SparseMatrix):
+        cls = sp.csr_matrix if m.isTransposed else sp.csc_matrix
+        return cls((m.values, m.rowIndices, m.colPtrs), shape=(m.numRows, m.numCols))
+    arr = np.asarray((as_scipy(ma) @ as_scipy(mb)).toarray(), dtype=np.float64)
+    rows, cols = ma.numRows, mb.numCols
+    nnz = int(np.count_nonzero(arr))
+    dense = DenseMatrix(rows, cols, np.ascontiguousarray(arr.T).reshape(-1))
+    csc = dense.toSparse()
+    if not ma.isTransposed and not mb.isTransposed:
+        return csc if rows * cols > 2 * nnz + cols + 1 else dense
+    if ma.isTransposed and mb.isTransposed:
+        csr = DenseMatrix(cols, rows, np.ascontiguousarray(arr).reshape(-1)).toSparse().transpose()
+        return csr if rows * cols > 2 * nnz + rows + 1 else dense
+    if ma.isTransposed and not mb.isTransposed:
+        return csc
+    return dense if rows * cols <= 2 * nnz + cols else csc
 
 
 def matrixMultiplication(mat1: MLMatrix, mat2: MLMatrix) -> MLMatrix:
@@ -362,7 +390,7 @@ def matrixMultiplication(mat1: MLMatrix, mat2: MLMatrix) -> MLMatrix:
         return gemmddd(mat1.toDense(), mat2.toDense())             # :903-904
     if s2 > 0.1:
         return gemmsdd(mat1, mat2.toDense())                       # :906-907
-    raise NotImplementedError(SPARSE_SPARSE_NOT_RESTATED)
+    return multiplySparseSparse(mat1, mat2)                        # :909-911
 
 
 # ----------------------------------------------------------------------------------------------

@@ -170,10 +170,75 @@ def test_multiply_with_sparse_blocks(session):
     want = O.matrix_multiply(B, n, n, A, n, n, blk)
     got = from_dataset(to_dataset(session, B).matrixMultiply(n, n, to_dataset(session, A), n, n, blk))
     assert_same_dataset(got, want, tol=TIGHT_TOL)
-    # low-density sparse x sparse is outside the hot path: loud, typed failure
-    S = random_block_dataset(rng, n, n, blk, p_sparse=1.0, sparse_density=0.02)
-    with pytest.raises(mb.UnsupportedOperation, match="multiplySparseSparse"):
-        to_dataset(session, S).matrixMultiply(n, n, to_dataset(session, S), n, n, blk)
+
+
+def _sparse_blocks(rng, n, m, blk, density, fmt, presence=1.0):
+    """All blocks sparse: fmt 'csc' / 'csr' / 'mix'."""
+    out = {}
+    for i in range(-(-n // blk)):
+        for j in range(-(-m // blk)):
+            if rng.random() >= presence:
+                continue
+            r, c = min(blk, n - i * blk), min(blk, m - j * blk)
+            a = rng.uniform(0.5, 1.5, (r, c)) * (rng.random((r, c)) < density)
+            csr = fmt == "csr" or (fmt == "mix" and rng.random() < 0.5)
+            if csr:
+                out[(i, j)] = O.DenseMatrix(c, r, np.ascontiguousarray(a).reshape(-1)).toSparse().transpose()
+            else:
+                out[(i, j)] = O.DenseMatrix(r, c, np.ascontiguousarray(a.T).reshape(-1)).toSparse()
+    return out
+
+
+@pytest.mark.parametrize("fa,fb", [("csc", "csc"), ("csr", "csr"), ("csr", "csc"), ("csc", "csr")])
+@pytest.mark.parametrize("density", [0.004, 0.05])
+def test_sparse_times_sparse_single_block_pair_formats(session, fa, fb, density):
+    """LocalMatrix.multiplySparseSparse (LocalMatrix.scala:143-323), one k-block (outer-product path, no reduce): the four
+    loop nests end in four different storage rules -- CSC / CSR / always-CSC / dense-or-CSC -- reproduced exactly
+    (type, isTransposed, index arrays); values to fp64 tolerance."""
+    rng = np.random.default_rng(int(density * 1000) + len(fa + fb))
+    blk, nb = 64, 3
+    A = _sparse_blocks(rng, nb * blk, blk, blk, density, fa)          # nb x 1 blocks
+    B = _sparse_blocks(rng, blk, nb * blk - 7, blk, density, fb)      # 1 x nb blocks, ragged last column block
+    want = O.matrix_multiply(A, nb * blk, blk, B, blk, nb * blk - 7, blk)
+    got = from_dataset(to_dataset(session, A).matrixMultiply(nb * blk, blk, to_dataset(session, B), blk, nb * blk - 7, blk))
+    assert_same_dataset(got, want, tol=TIGHT_TOL)
+    kinds = {(isinstance(w, O.SparseMatrix), w.isTransposed) for w in want.values()}
+    if (fa, fb) == ("csr", "csc"):
+        assert kinds == {(True, False)}                              # always CSC, whatever the density
+    if (fa, fb) == ("csr", "csr") and density < 0.01:
+        assert kinds == {(True, True)}                               # CSR result
+
+
+@pytest.mark.parametrize("fmt", ["csc", "csr", "mix"])
+def test_sparse_times_sparse_chains_follow_the_add_rules(session, fmt):
+    """Several k-blocks: every partial is a multiplySparseSparse result and `reduceByKey(LocalMatrix.add)` re-decides the
+    format at each sparse + sparse step (LocalMatrix.scala:74-139); replayed in ascending k like the oracle."""
+    rng = np.random.default_rng({"csc": 1, "csr": 2, "mix": 3}[fmt])
+    n, blk = 4 * 48 - 5, 48
+    for density, presence in [(0.01, 1.0), (0.06, 1.0), (0.02, 0.6)]:
+        A = _sparse_blocks(rng, n, n, blk, density, fmt, presence)
+        B = _sparse_blocks(rng, n, n, blk, density, fmt, presence)
+        want = O.matrix_multiply(A, n, n, B, n, n, blk)
+        got = from_dataset(to_dataset(session, A).matrixMultiply(n, n, to_dataset(session, B), n, n, blk))
+        assert_same_dataset(got, want, tol=TIGHT_TOL)
+        np.testing.assert_allclose(O.assemble(want, n, n, blk), O.assemble(A, n, n, blk) @ O.assemble(B, n, n, blk), atol=1e-12)
+
+
+def test_sparse_times_sparse_next_to_dense_partials_is_dense(session):
+    """A block sum that contains any dense partial product is dense (LocalMatrix.add), so low-density sparse x sparse pairs
+    in such a sum only contribute values."""
+    rng = np.random.default_rng(9)
+    n, blk = 3 * 40, 40
+    A = _sparse_blocks(rng, n, n, blk, 0.03, "mix")
+    B = _sparse_blocks(rng, n, n, blk, 0.03, "mix")
+    dense = rng.uniform(-1, 1, (blk, blk))
+    A[(0, 1)] = O.DenseMatrix(blk, blk, np.ascontiguousarray(dense.T).reshape(-1))     # dense x sparse -> densify (:892)
+    B[(2, 2)] = O.DenseMatrix(blk, blk, np.ascontiguousarray(dense).reshape(-1), True)  # sparse x dense -> gemmsdd
+    want = O.matrix_multiply(A, n, n, B, n, n, blk)
+    got = from_dataset(to_dataset(session, A).matrixMultiply(n, n, to_dataset(session, B), n, n, blk))
+    assert_same_dataset(got, want, tol=TIGHT_TOL)
+    assert all(isinstance(want[(0, j)], O.DenseMatrix) for j in range(3))
+    assert all(isinstance(want[(i, 2)], O.DenseMatrix) for i in range(3))
 
 
 def test_config5_shape_csr_times_dense(session):

@@ -108,3 +108,34 @@ def test_partitioner_ranges(nr, nc, blk, i, j, p):
     assert 0 <= part.getPartition(i, j) < part.numPartitions
     # periodic in the per-partition block counts (BlockCyclicPartitioner.scala:52-58)
     assert part.getPartition(i, j) == part.getPartition(i + part.num_row_part, j + part.num_col_part)
+
+
+@settings(**SET)
+@given(r=st.integers(1, 14), k=st.integers(1, 14), c=st.integers(1, 14), seed=st.integers(0, 2 ** 20),
+       dens=st.sampled_from([0.02, 0.09]), aT=st.booleans(), bT=st.booleans())
+def test_multiply_sparse_sparse_formats(r, k, c, seed, dens, aT, bT):
+    """LocalMatrix.multiplySparseSparse (LocalMatrix.scala:143-323): the product of the stored entries, in the storage format
+    its four loop nests end with."""
+    rng = np.random.default_rng(seed)
+
+    def sparse(rows, cols, csr):
+        a = rng.uniform(0.5, 1.5, (rows, cols)) * (rng.random((rows, cols)) < dens)
+        if csr:
+            return a, O.DenseMatrix(cols, rows, np.ascontiguousarray(a).reshape(-1)).toSparse().transpose()
+        return a, O.DenseMatrix(rows, cols, np.ascontiguousarray(a.T).reshape(-1)).toSparse()
+    fa, A = sparse(r, k, aT)
+    fb, B = sparse(k, c, bT)
+    C = O.multiplySparseSparse(A, B)
+    np.testing.assert_allclose(C.to_numpy(), fa @ fb, atol=1e-13)
+    nnz = int(np.count_nonzero(fa @ fb))
+    if aT and not bT:
+        assert isinstance(C, O.SparseMatrix) and not C.isTransposed
+    elif aT and bT:
+        assert isinstance(C, O.SparseMatrix) == (r * c > 2 * nnz + r + 1)
+        assert isinstance(C, O.DenseMatrix) or C.isTransposed
+    elif not aT and not bT:
+        assert isinstance(C, O.SparseMatrix) == (r * c > 2 * nnz + c + 1)
+    else:
+        assert isinstance(C, O.DenseMatrix) == (r * c <= 2 * nnz + c)
+    if isinstance(C, O.SparseMatrix):
+        assert int(C.colPtrs[-1]) == nnz == C.values.size                       # exact zeros are not stored
