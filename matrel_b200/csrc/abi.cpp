@@ -110,6 +110,11 @@ struct mr_context {
   int force_variant = -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr, ev_order = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // ingest / egress overlap with compute on `stream`
+  // The chunks of a pipelined multiply are independent launches: issued round-robin on these side streams, the last
+  // (partial) wave of one chunk overlaps the first waves of the next instead of leaving SMs idle between launches.
+  static constexpr int kChunkStreams = 3;
+  cudaStream_t chunk_stream[kChunkStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_join[kChunkStreams] = {nullptr, nullptr, nullptr};
   uint64_t ingest_seq = 0;
   // mapped pinned staging ring for descriptor tables (see upload())
   char* stage_host = nullptr;
@@ -198,6 +203,7 @@ struct mr_matrix {
 
 namespace {
 bool wait_ready(mr_context* ctx, const Block& b);
+bool wait_ready_on(cudaStream_t stream, const Block& b);
 }
 
 namespace {
@@ -215,6 +221,18 @@ bool wait_ready(mr_context* ctx, const Block& b) {
   }
   (void)cudaGetLastError();
   cudaStreamWaitEvent(ctx->stream, b.ready->ev, 0);
+  return true;
+}
+bool wait_ready_on(cudaStream_t stream, const Block& b) {  // same, ordering `stream` instead of the context stream
+  if (!b.ready) return false;
+  const cudaError_t q = cudaEventQuery(b.ready->ev);
+  if (q == cudaSuccess) {
+    b.ready.reset();
+    b.settled = true;
+    return false;
+  }
+  (void)cudaGetLastError();
+  cudaStreamWaitEvent(stream, b.ready->ev, 0);
   return true;
 }
 // true when the block's producer has finished (and forgets the event so it is not queried again)
@@ -801,7 +819,7 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
         order[oi] = {key, oi};
       }
       std::sort(order.begin(), order.end());
-      const int64_t min_tiles = 8 * 148;
+      const int64_t min_tiles = 148;  // >= one wave; the launches overlap on the side streams, so small chunks cost nothing
       int64_t acc_tiles = 0;
       int gcur = 0;
       for (size_t r = 0; r < order.size(); ++r) {
@@ -852,10 +870,16 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     Buf d_outs = upload(ctx, outs), d_pairs = upload(ctx, pairs), d_tiles = upload(ctx, tiles), d_tmaps = upload(ctx, tmaps);
     if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
     const int ngroups = ngroups_dyn;
+    const bool side = chunked && ngroups > 1;
+    if (side) {  // fork: the side streams start after everything enqueued so far (output slab, descriptor tables)
+      CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
+      for (int i = 0; i < mr_context::kChunkStreams; ++i) CUDA_CHECK(cudaStreamWaitEvent(ctx->chunk_stream[i], ctx->ev_order, 0));
+    }
     size_t t0 = 0;
     for (int gi = 0; gi < ngroups; ++gi) {
       size_t t1 = t0;
       while (t1 < keyed.size() && grp(keyed[t1]) == gi) ++t1;
+      cudaStream_t cs = side ? ctx->chunk_stream[gi % mr_context::kChunkStreams] : ctx->stream;
       // wait for exactly the operand blocks this chunk reads
       std::vector<char> seen(outs.size(), 0);
       for (size_t t = t0; t < t1; ++t) {
@@ -863,17 +887,17 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
         if (seen[oi]) continue;
         seen[oi] = 1;
         for (const GemmSrc& g : plans[out_plan[oi]].src) {
-          wait_ready(ctx, *g.a);
-          wait_ready(ctx, *g.b);
+          wait_ready_on(cs, *g.a);
+          wait_ready_on(cs, *g.b);
         }
       }
       CUDA_CHECK(launch_gemm_f64(static_cast<const GemmOut*>(d_outs->p), static_cast<const GemmPair*>(d_pairs->p),
                                  static_cast<const GemmTile*>(d_tiles->p) + t0, static_cast<int>(t1 - t0), d_tmaps->p, variant,
-                                 ctx->stream));
+                                 cs));
       note_launch(ctx);
       if (chunked) {  // consumers on the egress stream wait for this chunk only
         ReadyPtr r = std::make_shared<Ready>();
-        CUDA_CHECK(cudaEventRecord(r->ev, ctx->stream));
+        CUDA_CHECK(cudaEventRecord(r->ev, cs));
         for (size_t oi = 0; oi < outs.size(); ++oi)
           if (seen[oi]) {
             const OutPlan& o = plans[out_plan[oi]];
@@ -881,6 +905,12 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
           }
       }
       t0 = t1;
+    }
+    if (side) {  // join: later work on the context stream (and the release of the descriptor tables) follows every chunk
+      for (int i = 0; i < mr_context::kChunkStreams; ++i) {
+        CUDA_CHECK(cudaEventRecord(ctx->chunk_join[i], ctx->chunk_stream[i]));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_join[i], 0));
+      }
     }
     ctx->stats.gemm_launches += 1;
     ctx->stats.last_gemm_flops = flops;
@@ -1208,6 +1238,10 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < mr_context::kChunkStreams; ++i) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->chunk_stream[i], cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ctx->chunk_join[i], cudaEventDisableTiming));
+    }
     {
       void* hp = nullptr;
       const size_t cap = 16u << 20;
@@ -1240,6 +1274,10 @@ mr_status mr_shutdown(mr_context* ctx) {
     cudaStreamSynchronize(ctx->d2h_stream);
     cudaStreamDestroy(ctx->h2d_stream);
     cudaStreamDestroy(ctx->d2h_stream);
+    for (int i = 0; i < mr_context::kChunkStreams; ++i) {
+      if (ctx->chunk_stream[i]) cudaStreamDestroy(ctx->chunk_stream[i]);
+      if (ctx->chunk_join[i]) cudaEventDestroy(ctx->chunk_join[i]);
+    }
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
     if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
