@@ -576,7 +576,7 @@ std::vector<Block> compact_csc(mr_context* ctx, const std::vector<DenseWin>& win
 // LocalMatrix.scala:143-323).  Values: each partial is computed as sparse A x densified B (the same sums in a different
 // order).  Storage format: the reference's four loop nests end in four different rules, and `reduceByKey(LocalMatrix.add)`
 // re-decides the format at every sparse + sparse step, so the chain is replayed partial by partial in ascending k (Spark's
-// own reduce order is arbitrary; the oracle uses ascending k as well):
+// own reduce order is arbitrary; ascending k is the deterministic choice):
 //   CSC x CSC (:155-196): CSC iff rows*cols > 2 nnz + cols + 1, else dense      CSR x CSR (:198-239): CSR iff ... + rows + 1
 //   CSR x CSC (:241-286): always CSC (both branches build a SparseMatrix)       CSC x CSR (:288-323): dense iff rows*cols <= 2 nnz + cols
 //   sparse + sparse (:74-139): CSC iff rows*cols > 2 nnz + cols + 1, else dense; anything + dense: dense.
