@@ -95,6 +95,9 @@ MR_API mr_status mr_matrix_put_blocks_device(mr_matrix* m, int64_t count, const 
                                              const int32_t* numRows, const int32_t* numCols,
                                              const double* const* dvalues, const uint8_t* isTransposed);
 MR_API mr_status mr_matrix_num_blocks(const mr_matrix* m, int64_t* out);
+/* *out = 1 iff block (rid, cid) is present (absent blocks are implicit zeros: the join semantics of
+ * MatfastExecutionHelper.scala:64-263 depend on presence, not on values) */
+MR_API mr_status mr_matrix_has_block(const mr_matrix* m, int32_t rid, int32_t cid, int32_t* out);
 /* Fills rids/cids (capacity cap) in ascending (rid, cid) order. */
 MR_API mr_status mr_matrix_block_ids(const mr_matrix* m, int32_t* rids, int32_t* cids, int64_t cap);
 /* Two-call protocol (MLMatrixSerializer.serialize, :26-48): with NULL array pointers only the
@@ -183,6 +186,11 @@ MR_API mr_status mr_gen_block_cyclic(int64_t nrows, int64_t ncols, int32_t blkSi
 /* BlockCyclicPartitioner.getPartition / numPartitions (BlockCyclicPartitioner.scala:31-62) */
 MR_API mr_status mr_block_cyclic_partition(const int32_t params[4], int32_t rid, int32_t cid, int32_t* out);
 MR_API mr_status mr_block_cyclic_num_partitions(const int32_t params[4], int32_t* out);
+/* One entry point over the four schemes (Partitioner.getPartition of M/partitioner/*.scala): params[0] = partitions for
+ * MR_PART_ROW / MR_PART_COLUMN / MR_PART_INDEX (INDEX keys on rid), params[0..3] = the mr_gen_block_cyclic tuple for
+ * MR_PART_BLOCK_CYCLIC. */
+typedef enum mr_partition_scheme { MR_PART_ROW = 0, MR_PART_COLUMN = 1, MR_PART_INDEX = 2, MR_PART_BLOCK_CYCLIC = 3 } mr_partition_scheme;
+MR_API mr_status mr_partition_id(int32_t scheme, const int32_t params[4], int32_t rid, int32_t cid, int32_t* out);
 
 /* ---- introspection used by bench/tests (not part of the reference surface) */
 typedef struct mr_stats {

@@ -95,6 +95,11 @@ class Dataset {
     d.isTransposed = m.isTransposed;
     check(mr_matrix_put_block(h_.get(), rid, cid, &d));
   }
+  bool hasBlock(int32_t rid, int32_t cid) const {
+    int32_t present = 0;
+    check(mr_matrix_has_block(h_.get(), rid, cid, &present));
+    return present != 0;
+  }
   std::vector<std::pair<int32_t, int32_t>> blockIds() const {
     int64_t n = 0;
     check(mr_matrix_num_blocks(h_.get(), &n));

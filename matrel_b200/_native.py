@@ -90,6 +90,7 @@ SIGNATURES = {
     "mr_matrix_put_blocks_device": [_P, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_uint8)],
     "mr_matrix_num_blocks": [_P, C.POINTER(_i64)],
+    "mr_matrix_has_block": [_P, _i32, _i32, C.POINTER(_i32)],
     "mr_matrix_block_ids": [_P, C.POINTER(_i32), C.POINTER(_i32), _i64],
     "mr_matrix_get_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
     "mr_matrix_block_device_ptr": [_P, _i32, _i32, _PP],
@@ -118,6 +119,7 @@ SIGNATURES = {
     "mr_gen_block_cyclic": [_i64, _i64, _i32, C.POINTER(_i32)],
     "mr_block_cyclic_partition": [C.POINTER(_i32), _i32, _i32, C.POINTER(_i32)],
     "mr_block_cyclic_num_partitions": [C.POINTER(_i32), C.POINTER(_i32)],
+    "mr_partition_id": [_i32, C.POINTER(_i32), _i32, _i32, C.POINTER(_i32)],
     "mr_get_stats": [_P, C.POINTER(mr_stats)],
     "mr_reset_stats": [_P],
 }

@@ -1463,6 +1463,13 @@ mr_status mr_matrix_num_blocks(const mr_matrix* m, int64_t* out) {
   });
 }
 
+mr_status mr_matrix_has_block(const mr_matrix* m, int32_t rid, int32_t cid, int32_t* out) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && out != nullptr, MR_EINVAL, "matrix/out is null");
+    *out = m->blocks.count({rid, cid}) ? 1 : 0;
+  });
+}
+
 mr_status mr_matrix_block_ids(const mr_matrix* m, int32_t* rids, int32_t* cids, int64_t cap) {
   return guarded([&] {
     MR_REQUIRE(m != nullptr && rids != nullptr && cids != nullptr, MR_EINVAL, "null argument");
@@ -2118,6 +2125,17 @@ mr_status mr_block_cyclic_partition(const int32_t params[4], int32_t rid, int32_
     const int32_t n = rpn * cpn;
     *out = ((rid % nrp) * cpn + (cid % ncp)) % n;  // BlockCyclicPartitioner.scala:54-57 (defect B2 kept: bit-exact ids)
   });
+}
+
+mr_status mr_partition_id(int32_t scheme, const int32_t params[4], int32_t rid, int32_t cid, int32_t* out) {
+  if (params == nullptr || out == nullptr) return guarded([&] { fail(MR_EINVAL, "null argument"); });
+  switch (scheme) {
+    case MR_PART_ROW: return mr_row_partition(rid, cid, params[0], out);
+    case MR_PART_COLUMN: return mr_column_partition(rid, cid, params[0], out);
+    case MR_PART_INDEX: return mr_index_partition(rid, params[0], out);
+    case MR_PART_BLOCK_CYCLIC: return mr_block_cyclic_partition(params, rid, cid, out);
+    default: return guarded([&] { fail(MR_EINVAL, "unknown partition scheme %d", scheme); });
+  }
 }
 
 mr_status mr_block_cyclic_num_partitions(const int32_t params[4], int32_t* out) {

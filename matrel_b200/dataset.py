@@ -188,6 +188,11 @@ class Dataset:
             flags = np.ascontiguousarray(isTransposed, dtype=np.uint8).ctypes.data_as(C.POINTER(C.c_uint8))
         N.check(N.lib.mr_matrix_put_blocks_device(self._h, n, _i32p(rids), _i32p(cids), _i32p(nr), _i32p(nc), ptrs, flags))
 
+    def has_block(self, rid: int, cid: int) -> bool:
+        out = C.c_int32()
+        N.check(N.lib.mr_matrix_has_block(self._h, int(rid), int(cid), C.byref(out)))
+        return bool(out.value)
+
     def block_ids(self) -> List[tuple]:
         n = C.c_int64()
         N.check(N.lib.mr_matrix_num_blocks(self._h, C.byref(n)))

@@ -73,6 +73,17 @@ def genBlockCyclicPartitioner(nrows: int, ncols: int, blkSize: int) -> Tuple[int
     return tuple(out)
 
 
+PART_ROW, PART_COLUMN, PART_INDEX, PART_BLOCK_CYCLIC = 0, 1, 2, 3
+
+
+def partition_id(scheme: int, params, rid: int, cid: int) -> int:
+    """`mr_partition_id`: one entry point over the four schemes (params = (partitions,) or the block-cyclic 4-tuple)."""
+    p = (C.c_int32 * 4)(*(list(params) + [0, 0, 0, 0])[:4])
+    out = C.c_int32()
+    N.check(N.lib.mr_partition_id(int(scheme), p, int(rid), int(cid), C.byref(out)))
+    return out.value
+
+
 def _check_key(key) -> None:
     if not (isinstance(key, tuple) and len(key) in (2, 3) and all(isinstance(k, int) for k in key)):
         raise ValueError(f"Unrecognized key: {key}")  # IllegalArgumentException(s"Unrecognized key: $key")

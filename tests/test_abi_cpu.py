@@ -98,6 +98,22 @@ def test_partitioners_match_oracle_exhaustively():
                 assert tuple(mb.genBlockCyclicPartitioner(nr, nc, blk)) == O.gen_block_cyclic_partitioner(nr, nc, blk)
 
 
+def test_partition_id_covers_the_four_schemes():
+    """mr_partition_id: the single placement entry point agrees with the per-scheme functions and the oracle."""
+    from matrel_b200 import partitioner as P
+    from oracle import matrel_oracle as O
+    for i in range(0, 40, 3):
+        for j in range(0, 40, 7):
+            for p in (1, 2, 7, 8, 64):
+                assert P.partition_id(P.PART_ROW, (p,), i, j) == O.row_partition(i, j, p)
+                assert P.partition_id(P.PART_COLUMN, (p,), i, j) == O.column_partition(i, j, p)
+                assert P.partition_id(P.PART_INDEX, (p,), i, j) == O.index_partition(i)
+            params = O.gen_block_cyclic_partitioner(16384, 16384, 1024)
+            assert P.partition_id(P.PART_BLOCK_CYCLIC, params, i, j) == O.BlockCyclicPartitioner(*params).getPartition(i, j)
+    with pytest.raises(Exception, match="unknown partition scheme"):
+        P.partition_id(9, (1,), 0, 0)
+
+
 def test_no_cpu_fallback_without_gpu():
     """On a box without a CUDA device the engine must fail loudly, never compute on the host."""
     import torch

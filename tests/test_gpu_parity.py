@@ -158,6 +158,19 @@ def test_multiply_block_sparse_presence(session):
     assert from_dataset(empty.matrixMultiply(n, n, to_dataset(session, B), n, n, blk)) == {}
 
 
+def test_has_block_follows_join_presence(session):
+    rng = np.random.default_rng(4)
+    n, blk = 4 * 32, 32
+    A = random_block_dataset(rng, n, n, blk, density=0.5)
+    B = random_block_dataset(rng, n, n, blk, density=0.5)
+    C = to_dataset(session, A).matrixMultiply(n, n, to_dataset(session, B), n, n, blk)
+    want = O.matrix_multiply(A, n, n, B, n, n, blk)
+    for i in range(4):
+        for j in range(4):
+            assert C.has_block(i, j) == ((i, j) in want)
+    assert not C.has_block(7, 0)
+
+
 def test_multiply_with_sparse_blocks(session):
     rng = np.random.default_rng(11)
     n, blk = 4 * 64, 64
