@@ -232,6 +232,117 @@ def sharded_multiply_overlapped(session, groups: GridGroups, A: ShardedMatrix, B
 # --------------------------------------------------------------------------------------------------
 # bench.py's N > 1 arm
 # --------------------------------------------------------------------------------------------------
+# ---- the siblings of the multiply on the same grid -------------------------------------------------------------------
+def sharded_elementwise(op: str, A: ShardedMatrix, B: ShardedMatrix, plan: GridPlan):
+    """add / mul / div of two matrices laid out on the SAME grid.  Both sides are co-partitioned (RowPartitioner x
+    ColumnPartitioner arithmetic on A and B alike), which is the reference's `zipPartitions` fast path
+    (M/execution/MatfastExecutionHelper.scala:64-105 / :107-139 / :141-173 when the partitioners match): no communication, each
+    rank runs the element-wise kernel on its own blocks.  Returns the local result Dataset."""
+    fn = {"add": "addElement", "mul": "multiplyElement", "div": "divideElement"}[op]
+    return getattr(A.dataset, fn)(plan.nrows, plan.ncols, B.dataset, plan.nrows, plan.ncols, plan.blk)
+
+
+def transpose_plan(plan: GridPlan) -> GridPlan:
+    return GridPlan(plan.world, plan.ncols, plan.nrows, plan.blk, plan.pr, plan.pc)
+
+
+def transpose_routes(plan: GridPlan, rank: int):
+    """Block moves of C = A^T on the same grid: block (j, i) of A lives on owner(j, i) = (j % pr, i % pc); as block (i, j) of
+    A^T it belongs to (i % pr, j % pc).  Returns (sends, recvs): sends[dst] = [(src_slot, dst_slot)], recvs[src] = [dst_slot],
+    both in the same deterministic order (sorted by the A^T block id), so one packed message per peer suffices.
+    (The reference's transpose is a flag flip plus a key swap, MatfastExecution.scala:215-236; the re-placement is what its
+    next shuffle would do.)"""
+    pt = transpose_plan(plan)
+    sends: Dict[int, list] = {}
+    recvs: Dict[int, list] = {}
+    for (j, i) in sorted(plan.owned(rank), key=lambda b: (b[1], b[0])):          # my A blocks, ordered by their A^T id (i, j)
+        sends.setdefault(pt.owner(i, j), []).append((plan.slot(j, i), pt.slot(i, j)))
+    for (i, j) in sorted(pt.owned(rank)):                                        # the A^T blocks I will own
+        recvs.setdefault(plan.owner(j, i), []).append(pt.slot(i, j))
+    return sends, recvs
+
+
+def exchange_transpose(slab, plan: GridPlan, rank: int):
+    """Moves the slab's blocks to their owners under the transposed plan (point-to-point, one packed message per peer; works
+    on CPU tensors over gloo and on device tensors over NCCL).  Block payloads are not touched: a column-major block (j, i)
+    of A IS the row-major block (i, j) of A^T."""
+    import torch
+    import torch.distributed as dist
+    pt = transpose_plan(plan)
+    out = torch.zeros((pt.local_slots, pt.slot_elems), dtype=slab.dtype, device=slab.device)
+    sends, recvs = transpose_routes(plan, rank)
+    ops, staged = [], []
+    for dst, moves in sorted(sends.items()):
+        src_idx = torch.tensor([m[0] for m in moves], dtype=torch.long, device=slab.device)
+        if dst == rank:
+            out[torch.tensor([m[1] for m in moves], dtype=torch.long, device=slab.device)] = slab[src_idx]
+        else:
+            buf = slab[src_idx].contiguous()
+            staged.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, dst))
+    inbox = []
+    for src, slots in sorted(recvs.items()):
+        if src == rank:
+            continue
+        buf = torch.empty((len(slots), pt.slot_elems), dtype=slab.dtype, device=slab.device)
+        inbox.append((buf, slots))
+        ops.append(dist.P2POp(dist.irecv, buf, src))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for buf, slots in inbox:
+        out[torch.tensor(slots, dtype=torch.long, device=slab.device)] = buf
+    return out, pt
+
+
+def sharded_transpose(session, A: ShardedMatrix) -> ShardedMatrix:
+    """A^T on the same grid: one packed point-to-point exchange, then the received column-major blocks are registered
+    zero-copy as ROW-major blocks of A^T (isTransposed = true) -- no transpose kernel runs, as in the reference."""
+    slab, pt = exchange_transpose(A.slab, A.plan, A.rank)
+    esz = slab.element_size()
+    ds = session.emptyDataset()
+    blocks = pt.owned(A.rank)
+    shapes = [pt.block_shape(i, j) for i, j in blocks]
+    ds.put_blocks_device([b[0] for b in blocks], [b[1] for b in blocks], [sh[0] for sh in shapes], [sh[1] for sh in shapes],
+                         [slab.data_ptr() + pt.slot(i, j) * pt.slot_elems * esz for i, j in blocks], [1] * len(blocks))
+    return ShardedMatrix(pt, A.rank, slab, ds)
+
+
+def sharded_aggregate(kind: str, groups: GridGroups, A: ShardedMatrix):
+    """rowSum / colSum / sum / trace of a grid-sharded matrix (RowSum/ColumnSum/Sum/TraceDirectExecution,
+    MatfastExecution.scala:239-463): the local reduction kernel per rank, then the reference's reduceByKey(add) across
+    partitions becomes one all-reduce of an O(N) vector inside the grid row (rowSum), grid column (colSum) or world
+    (sum, trace).  Returns a numpy array: the entries of the rows (rowSum) / columns (colSum) this rank's grid row / column
+    owns, in global order, or a scalar."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    plan, ds = A.plan, A.dataset
+    dev = A.slab.device
+
+    def reduce(vec, group, needed):
+        t = torch.from_numpy(vec).to(dev)
+        if needed:
+            dist.all_reduce(t, group=group)
+        return t.cpu().numpy()
+    r, c = plan.coords(A.rank)
+    if kind == "rowSum":
+        loc = {b.rid: b.matrix.to_numpy()[:, 0] for b in ds.rowSum(plan.nrows, plan.ncols).collect()}
+        rows = list(range(r, plan.nbr, plan.pr))
+        vec = np.concatenate([loc.get(i, np.zeros(plan.block_shape(i, 0)[0])) for i in rows]) if rows else np.zeros(0)
+        return reduce(vec, groups.row_group, plan.pc > 1)
+    if kind == "colSum":
+        loc = {b.cid: b.matrix.to_numpy()[0, :] for b in ds.colSum(plan.nrows, plan.ncols).collect()}
+        cols = list(range(c, plan.nbc, plan.pc))
+        vec = np.concatenate([loc.get(j, np.zeros(plan.block_shape(0, j)[1])) for j in cols]) if cols else np.zeros(0)
+        return reduce(vec, groups.col_group, plan.pr > 1)
+    if kind in ("sum", "trace"):
+        res = (ds.sum if kind == "sum" else ds.trace)(plan.nrows, plan.ncols).collect()
+        v = np.array([res[0].matrix.to_numpy()[0, 0] if res else 0.0])
+        return float(reduce(v, None, plan.world > 1)[0])
+    raise ValueError(kind)
+
+
 def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample):
     import json
     import time

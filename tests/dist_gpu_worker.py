@@ -9,9 +9,39 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import matrel_b200 as mb  # noqa: E402
-from matrel_b200.distributed import (GridGroups, GridPlan, ShardedMatrix, sharded_multiply,  # noqa: E402
-                                     sharded_multiply_overlapped)
+from matrel_b200.distributed import (GridGroups, GridPlan, ShardedMatrix, sharded_aggregate,  # noqa: E402
+                                     sharded_elementwise, sharded_multiply, sharded_multiply_overlapped, sharded_transpose)
 from oracle import matrel_oracle as O  # noqa: E402
+
+
+def siblings(s, groups, A, planA, rank, device, n, k, blk):
+    """The multiply's siblings on the same grid: transpose (one packed P2P exchange, flag flip), co-partitioned element-wise
+    ops (no communication), aggregates (local kernel + one O(N) all-reduce)."""
+    Af = O.rand_dense_dataset(n, k, blk, 42)
+    full = O.assemble(Af, n, k, blk)
+    AT = sharded_transpose(s, A)
+    want = O.transpose(Af)
+    got = {(b.rid, b.cid): b.matrix for b in AT.dataset.collect()}
+    assert sorted(got) == sorted(AT.plan.owned(rank))
+    for key, g in got.items():
+        assert g.isTransposed and (g.numRows, g.numCols) == (want[key].numRows, want[key].numCols)
+        assert np.array_equal(g.to_numpy(), want[key].to_numpy()), key
+    A2 = ShardedMatrix.rand(s, planA, rank, 44, device)
+    A2f = O.rand_dense_dataset(n, k, blk, 44)
+    for op, fn in (("add", O.add_element), ("mul", O.multiply_element), ("div", O.divide_element)):
+        w = fn(Af, n, k, A2f, n, k, blk)
+        g = {(b.rid, b.cid): b.matrix for b in sharded_elementwise(op, A, A2, planA).collect()}
+        assert sorted(g) == sorted(planA.owned(rank))
+        for key, m in g.items():
+            assert np.allclose(m.to_numpy(), w[key].to_numpy(), rtol=1e-14, atol=0), (op, key)
+    r, c = planA.coords(rank)
+    rows = np.concatenate([np.arange(i * blk, min(n, (i + 1) * blk)) for i in range(r, planA.nbr, planA.pr)])
+    cols = np.concatenate([np.arange(j * blk, min(k, (j + 1) * blk)) for j in range(c, planA.nbc, planA.pc)])
+    assert np.allclose(sharded_aggregate("rowSum", groups, A), full.sum(axis=1)[rows], rtol=1e-12)
+    assert np.allclose(sharded_aggregate("colSum", groups, A), full.sum(axis=0)[cols], rtol=1e-12)
+    assert abs(sharded_aggregate("sum", groups, A) - full.sum()) <= 1e-12 * full.sum()
+    if n == k:
+        assert abs(sharded_aggregate("trace", groups, A) - np.trace(full)) <= 1e-12 * abs(np.trace(full))
 
 
 def main():
@@ -38,6 +68,8 @@ def main():
             assert sorted(got2) == sorted(got)
             for key in got:
                 assert np.array_equal(got2[key].values, got[key].values), key
+            if algo == 0:
+                siblings(s, groups, A, planA, rank, device, n, k, blk)
             s.stop()
         want = O.matrix_multiply(O.rand_dense_dataset(n, k, blk, 42), n, k, O.rand_dense_dataset(k, m, blk, 43), k, m, blk)
         assert sorted(got) == sorted(planC.owned(rank)), (rank, sorted(got))

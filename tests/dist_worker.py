@@ -11,7 +11,8 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from matrel_b200.distributed import GridGroups, GridPlan, gather_panels, panel_blocks_A, panel_blocks_B  # noqa: E402
+from matrel_b200.distributed import (GridGroups, GridPlan, exchange_transpose, gather_panels, panel_blocks_A,  # noqa: E402
+                                     panel_blocks_B, transpose_routes)
 from oracle import matrel_oracle as O  # noqa: E402
 
 
@@ -55,6 +56,16 @@ def main():
     cnt = torch.tensor([len(mine)], dtype=torch.int64)
     dist.all_reduce(cnt)
     assert int(cnt.item()) == len(full)
+    # transpose on the grid: every block (j, i) of A lands, untouched, in the slot of block (i, j) of A^T on its new owner
+    slabT, planT = exchange_transpose(local_slab(A, planA), planA, rank)
+    assert (planT.nrows, planT.ncols) == (k, n)
+    AT = O.transpose(A)
+    for (i, j) in planT.owned(rank):
+        v = AT[(i, j)].values
+        assert np.array_equal(slabT[planT.slot(i, j), :v.size].numpy(), v), ("A^T", i, j)
+    sends, recvs = transpose_routes(planA, rank)
+    assert sum(len(v) for v in sends.values()) == len(planA.owned(rank))
+    assert sum(len(v) for v in recvs.values()) == len(planT.owned(rank))
     dist.barrier()
     if rank == 0:
         print(f"OK world={world} grid={planA.pr}x{planA.pc} blocks={len(full)}")
