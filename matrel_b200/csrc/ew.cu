@@ -620,8 +620,10 @@ cudaError_t launch_java_rand_batched(const RandDesc* d_descs, int nblocks, int64
   if (nblocks <= 0 || max_n <= 0) return cudaSuccess;
   int64_t gx = (max_n + 255) / 256;
   if (gx > 65535) gx = 65535;
-  dim3 grid(static_cast<unsigned>(gx), nblocks);
-  java_rand_kernel<<<grid, 256, 0, stream>>>(d_descs);
+  for (int off = 0; off < nblocks; off += 65535) {  // gridDim.y limit
+    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(nblocks - off < 65535 ? nblocks - off : 65535));
+    java_rand_kernel<<<grid, 256, 0, stream>>>(d_descs + off);
+  }
   return cudaGetLastError();
 }
 

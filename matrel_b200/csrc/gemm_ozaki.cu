@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
                                                   int two_alpha, double* const* __restrict__ ctab, int M, int N, int blk, int nbc) {
   __shared__ double tile[128][33];
   const CrtConst& cc = c_crt[T];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 128;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 128;  // row tiles on x (no 65535 limit)
   const int tid = threadIdx.x;
   const int lr = tid >> 5, lc = (tid & 31) * 4;  // 8 rows per pass, 4 passes
   for (int pass = 0; pass < 4; ++pass) {
@@ -756,6 +756,18 @@ bool covers_operand(const OzakiOperand* blocks, int n, int64_t lines, int64_t K,
   for (int i = 0; i < n; ++i) area += static_cast<int64_t>(blocks[i].rows) * blocks[i].cols;
   return area == lines * K;  // block ids are unique, so equal area means full coverage
 }
+// gridDim.y carries the block index of the batched passes: split lists longer than its 65535 limit
+constexpr int kMaxGridY = 65535;
+template <class Launch>
+cudaError_t for_block_chunks(int nblocks, Launch&& launch) {
+  for (int off = 0; off < nblocks; off += kMaxGridY) {
+    launch(off, std::min(kMaxGridY, nblocks - off));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t configure_gemm_kernel(size_t smem_bytes) {
   static PerDeviceOnce once;
   return once.run([&] {
@@ -815,9 +827,13 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   // pass 1
   {
     const int tc = (max_ac + 31) / 32, tr = (max_ar + 31) / 32;
-    absmax_kernel<<<dim3(tr * tc, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), rowmax, 1, tc);
+    OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
+      absmax_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, rowmax, 1, tc);
+    }));
     const int tcb = (max_bc + 31) / 32, trb = (max_br + 31) / 32;
-    absmax_kernel<<<dim3(trb * tcb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), colmax, 0, tcb);
+    OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
+      absmax_kernel<<<dim3(trb * tcb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, colmax, 0, tcb);
+    }));
     exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, row_exp, static_cast<double*>(d_scale.p),
                                                                                       static_cast<int>(Mpad + Npad), static_cast<int*>(d_bad.p));
     *launches += 3;
@@ -837,11 +853,15 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   if (!covers_operand(b_blocks, nb, N, K, Kpad)) OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * S, stream));
   {
     const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
-    slice_kernel<<<dim3(tl * tk, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), row_exp, static_cast<int8_t*>(d_As.p),
-                                                        a_stride, static_cast<int>(Kpad), S, 1, tk);
+    OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
+      slice_kernel<<<dim3(tl * tk, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, row_exp, static_cast<int8_t*>(d_As.p),
+                                                           a_stride, static_cast<int>(Kpad), S, 1, tk);
+    }));
     const int tkb = (max_br + 127) / 128, tlb = (max_bc + 31) / 32;
-    slice_kernel<<<dim3(tlb * tkb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), col_exp, static_cast<int8_t*>(d_Bs.p),
-                                                          b_stride, static_cast<int>(Kpad), S, 0, tkb);
+    OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
+      slice_kernel<<<dim3(tlb * tkb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, col_exp, static_cast<int8_t*>(d_Bs.p),
+                                                             b_stride, static_cast<int>(Kpad), S, 0, tkb);
+    }));
     *launches += 2;
   }
   // tensor maps + output block table
@@ -999,9 +1019,13 @@ cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOpe
   int32_t* col_exp = row_exp + Mpad;
   {
     const int tc = (max_ac + 31) / 32, tr = (max_ar + 31) / 32;
-    absmax_kernel<<<dim3(tr * tc, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), rowmax, 1, tc);
+    OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
+      absmax_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, rowmax, 1, tc);
+    }));
     const int tcb = (max_bc + 31) / 32, trb = (max_br + 31) / 32;
-    absmax_kernel<<<dim3(trb * tcb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), colmax, 0, tcb);
+    OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
+      absmax_kernel<<<dim3(trb * tcb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, colmax, 0, tcb);
+    }));
     exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, row_exp, static_cast<double*>(d_scale.p),
                                                                                       static_cast<int>(Mpad + Npad), static_cast<int*>(d_bad.p));
     *launches += 3;
@@ -1022,11 +1046,15 @@ cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOpe
   if (!covers_operand(b_blocks, nb, N, K, Kpad)) OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * T, stream));
   {
     const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
-    residue_kernel<<<dim3(tl * tk, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), row_exp, static_cast<int8_t*>(d_As.p),
-                                                          a_stride, static_cast<int>(Kpad), T, alpha, 1, tk);
+    OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
+      residue_kernel<<<dim3(tl * tk, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, row_exp,
+                                                             static_cast<int8_t*>(d_As.p), a_stride, static_cast<int>(Kpad), T, alpha, 1, tk);
+    }));
     const int tkb = (max_br + 127) / 128, tlb = (max_bc + 31) / 32;
-    residue_kernel<<<dim3(tlb * tkb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), col_exp, static_cast<int8_t*>(d_Bs.p),
-                                                            b_stride, static_cast<int>(Kpad), T, alpha, 0, tkb);
+    OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
+      residue_kernel<<<dim3(tlb * tkb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, col_exp,
+                                                               static_cast<int8_t*>(d_Bs.p), b_stride, static_cast<int>(Kpad), T, alpha, 0, tkb);
+    }));
     *launches += 2;
   }
   std::vector<unsigned char> hmaps(static_cast<size_t>(2 * T) * 128);
@@ -1069,7 +1097,7 @@ cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOpe
   if (nitems > INT32_MAX) return cudaErrorInvalidValue;
   ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(nitems, sms)), GEMM_THREADS_P, smem_bytes, stream>>>(p);
   OZ_CHECK(cudaGetLastError());
-  crt_kernel<<<dim3(static_cast<unsigned>((N + 127) / 128), static_cast<unsigned>((M + 31) / 32)), 256, 0, stream>>>(
+  crt_kernel<<<dim3(static_cast<unsigned>((M + 31) / 32), static_cast<unsigned>((N + 127) / 128)), 256, 0, stream>>>(
       static_cast<const int8_t*>(d_planes.p), plane_stride, static_cast<int>(Npad), T, row_exp, col_exp, 2 * alpha,
       static_cast<double* const*>(d_ctab.p), static_cast<int>(M), static_cast<int>(N), blk, nbc);
   OZ_CHECK(cudaGetLastError());
@@ -1113,9 +1141,13 @@ cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand
   float* Blo = Bhi + b_elems;
   {
     const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
-    slice_tf32_kernel<<<dim3(tl * tk, na), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p), Ahi, Alo, static_cast<int>(Kpad), 1, tk);
+    OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
+      slice_tf32_kernel<<<dim3(tl * tk, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, Ahi, Alo, static_cast<int>(Kpad), 1, tk);
+    }));
     const int tkb = (max_br + 127) / 128, tlb = (max_bc + 31) / 32;
-    slice_tf32_kernel<<<dim3(tlb * tkb, nb), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p), Bhi, Blo, static_cast<int>(Kpad), 0, tkb);
+    OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
+      slice_tf32_kernel<<<dim3(tlb * tkb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, Bhi, Blo, static_cast<int>(Kpad), 0, tkb);
+    }));
     *launches += 2;
   }
   std::vector<unsigned char> hmaps(4 * 128);
