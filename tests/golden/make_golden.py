@@ -71,6 +71,23 @@ def basic_matrix_ops():
             "mul_full_on_common": (M1 * M2).tolist(),
             "mul_present": ["0,0", "1,1"],
             "transpose_mat1_full": M1.T.tolist(),
+            # runMatrixProjection (:196, :204): row 2 of mat1 as 1 x 4, column 3 of mat2 as 4 x 1
+            "project_row_2_mat1": [float(x) for x in M1[2, :]],
+            "project_col_3_mat2": [float(x) for x in M2[:, 3]],
+        },
+        # runMatrixTranspose (:47-64): blocks at ids (0,2) s1, (2,3) b2, (4,5) b3, (6,7) b4; t() swaps the ids and flips flags
+        "transpose_demo": {
+            "blocks": [[0, 2, "s1"], [2, 3, "b2"], [4, 5, "b3"], [6, 7, "b4"]],
+            "expected": {"2,0": np.array([[0, 2], [4, 0]], dtype=float).T.tolist(),     # s1 = [[0,2],[4,0]]
+                         "3,2": np.array([[2, 3], [2, 3]], dtype=float).T.tolist(),
+                         "5,4": np.array([[3, 4], [3, 4]], dtype=float).T.tolist(),
+                         "7,6": np.array([[4, 6], [5, 7]], dtype=float).T.tolist()},
+        },
+        # runMatrixScalar (:66-78): power(2) of b1 at (0,2) and s1 at (1,3); element-wise squares, structure kept
+        "power_demo": {
+            "blocks": [[0, 2, "b1"], [1, 3, "s1"]],
+            "expected": {"0,2": (np.array([[1, 2], [1, 2]], dtype=float) ** 2).tolist(),
+                         "1,3": (np.array([[0, 2], [4, 0]], dtype=float) ** 2).tolist()},
         },
     }
 

@@ -67,6 +67,31 @@ def test_golden_basic_matrix_ops(session):
     assert pf.tolist() == e["mul_full_on_common"]
 
 
+def test_golden_remaining_demos(session):
+    """runMatrixTranspose / runMatrixScalar / runMatrixProjection (example/BasicMatrixOps.scala:47-78, 183-210) on the device."""
+    g = load("basic_matrix_ops")
+    e = g["expected"]
+    blocks = {k: mk(v) for k, v in g["blocks"].items()}
+    t = from_dataset(to_dataset(session, {(r, c): blocks[n] for r, c, n in g["transpose_demo"]["blocks"]}).t())
+    assert sorted(f"{i},{j}" for i, j in t) == sorted(g["transpose_demo"]["expected"])
+    for key, want in g["transpose_demo"]["expected"].items():
+        m = t[tuple(map(int, key.split(",")))]
+        assert m.isTransposed and m.to_numpy().tolist() == want
+        assert isinstance(m, mb.SparseMatrix) == (key == "2,0")
+    p = from_dataset(to_dataset(session, {(r, c): blocks[n] for r, c, n in g["power_demo"]["blocks"]}).power(2.0))
+    for key, want in g["power_demo"]["expected"].items():
+        m = p[tuple(map(int, key.split(",")))]
+        assert m.to_numpy().tolist() == want
+        assert isinstance(m, mb.SparseMatrix) == (key == "1,3")
+    mat1 = to_dataset(session, {(r, c): blocks[n] for r, c, n in g["mat1"]})
+    mat2 = to_dataset(session, {(r, c): blocks[n] for r, c, n in g["mat2"]})
+    row = from_dataset(mat1.project(4, 4, 2, True, 2))
+    assert sorted(row) == [(0, 1)] and row[(0, 1)].to_numpy()[0].tolist() == e["project_row_2_mat1"][2:]
+    col = from_dataset(mat2.project(4, 4, 2, False, 3))
+    assert sorted(col) == [(0, 0), (1, 0)]
+    assert col[(0, 0)].to_numpy()[:, 0].tolist() + col[(1, 0)].to_numpy()[:, 0].tolist() == e["project_col_3_mat2"]
+
+
 def test_golden_test_sparse(session):
     g = load("test_sparse")
     e = g["expected"]

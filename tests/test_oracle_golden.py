@@ -68,6 +68,30 @@ def test_transpose_add_mul_golden(basic):
     assert O.assemble(p, 4, 4, 2).tolist() == e["mul_full_on_common"]
 
 
+def test_remaining_demos_golden(basic):
+    """runMatrixTranspose / runMatrixScalar / runMatrixProjection of example/BasicMatrixOps.scala:47-78, 183-210."""
+    g, mat1, mat2 = basic
+    e = g["expected"]
+    blocks = {k: mk(v) for k, v in g["blocks"].items()}
+    demo = {(r, c): blocks[n] for r, c, n in g["transpose_demo"]["blocks"]}
+    t = O.transpose(demo)
+    assert sorted(f"{i},{j}" for i, j in t) == sorted(g["transpose_demo"]["expected"])
+    for key, want in g["transpose_demo"]["expected"].items():
+        m = t[tuple(map(int, key.split(",")))]
+        assert m.isTransposed and m.to_numpy().tolist() == want
+        assert isinstance(m, O.SparseMatrix) == (key == "2,0")           # the sparse block stays sparse (CSR now)
+    demo = {(r, c): blocks[n] for r, c, n in g["power_demo"]["blocks"]}
+    p = O.power(demo, 2.0)
+    for key, want in g["power_demo"]["expected"].items():
+        m = p[tuple(map(int, key.split(",")))]
+        assert m.to_numpy().tolist() == want
+        assert isinstance(m, O.SparseMatrix) == (key == "1,3")           # map over the stored values only
+    row = O.project(mat1, 4, 4, 2, True, 2)
+    assert sorted(row) == [(0, 1)] and O.assemble(row, 1, 4, 2)[0].tolist() == e["project_row_2_mat1"]
+    col = O.project(mat2, 4, 4, 2, False, 3)
+    assert sorted(col) == [(0, 0), (1, 0)] and O.assemble(col, 4, 1, 2)[:, 0].tolist() == e["project_col_3_mat2"]
+
+
 def test_test_sparse_golden():
     g = load("test_sparse")
     e = g["expected"]
@@ -90,6 +114,10 @@ def test_test_sparse_golden():
     assert O.matrixMultiplication(s1, v).to_numpy()[:, 0].tolist() == e["S1_times_v"]
     assert O.elementWiseMultiply(s1, s2).to_numpy().tolist() == e["S1_hadamard_S2"]
     assert O.add(s1, s2).to_numpy().tolist() == e["S1_plus_S2"]
+    # multiplySparseSparse called directly by the demo (LocalMatrix.scala:1112, :1132): CSC x CSC and CSC x CSR
+    assert O.multiplySparseSparse(s1, s2).to_numpy().tolist() == e["S1_times_S2"]
+    assert O.multiplySparseSparse(s1, s2.transpose()).to_numpy().tolist() == e["S1_times_S2t"]
+    assert isinstance(O.multiplySparseSparse(s1, s2), O.DenseMatrix)        # 9 > 2*7 + 4 is false -> densified
     # sparse+sparse density rule (LocalMatrix.scala:133): 9 > 2*9 + 4 is false -> dense result
     assert isinstance(O.add(s1, s2), O.DenseMatrix)
     assert isinstance(O.elementWiseMultiply(s1, s2), O.SparseMatrix)   # 1 nnz: 9 > 2 + 4
