@@ -1,0 +1,687 @@
+// C-ABI host layer of the B200 block-matrix engine (see include/matrel.h): context lifetime, device memory, block ingest /
+// egress and the helpers shared by the operator files (abi_multiply.cpp, abi_elementwise.cpp, abi_aggregate.cpp,
+// abi_partition.cpp).
+//
+// This file is the replacement for the reference's L2 physical operators and their helpers:
+//   MatfastExecution.scala   (MatrixMatrixMultiplicationExecution :688-726, MatrixTransposeExecution
+//                             :215-236, MatrixElement*Execution :571-686, MatrixScalar*/Power :465-532,
+//                             RankOneUpdateExecution :728-747)
+//   MatfastExecutionHelper.scala (matrixMultiplyGeneral :235-263, multiplyOuterProductDuplicate* :175-221,
+//                             add/multiply/divideWithPartitioner :64-173, matrixRankOneUpdate :265-285,
+//                             genBlockCyclicPartitioner :46-62)
+//   LocalMatrix.scala        (matrixMultiplication dispatch :889-914 and the per-block kernels)
+//   MLMatrixSerializer.scala (block <-> 7-field struct, :26-69)
+// The Spark shuffles (groupByKey / join / reduceByKey / zipPartitions) become index arithmetic over a
+// device-resident block table; every arithmetic step is a CUDA kernel (gemm_f64.cu, ew.cu).
+// There is no CPU compute path in this file: host code only validates, builds descriptor tables
+// and launches.
+#include "host.h"
+
+using namespace matrel;
+using namespace mrhost;
+
+namespace mrhost {
+
+thread_local std::string g_last_error;
+
+[[noreturn]] void fail(mr_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw MrError{code, buf};
+}
+
+void note_launch(mr_context* ctx, int n) { ctx->stats.kernel_launches += n; }
+
+// Order the context stream after the producer of a block.  Returns true when the producer was still running.
+bool wait_ready(mr_context* ctx, const Block& b) {
+  if (!b.ready) return false;
+  const cudaError_t q = cudaEventQuery(b.ready->ev);
+  if (q == cudaSuccess) {
+    b.ready.reset();  // never query this block again
+    b.settled = true;
+    return false;
+  }
+  (void)cudaGetLastError();
+  cudaStreamWaitEvent(ctx->stream, b.ready->ev, 0);
+  return true;
+}
+bool wait_ready_on(cudaStream_t stream, const Block& b) {  // same, ordering `stream` instead of the context stream
+  if (!b.ready) return false;
+  const cudaError_t q = cudaEventQuery(b.ready->ev);
+  if (q == cudaSuccess) {
+    b.ready.reset();
+    b.settled = true;
+    return false;
+  }
+  (void)cudaGetLastError();
+  cudaStreamWaitEvent(stream, b.ready->ev, 0);
+  return true;
+}
+// true when the block's producer has finished (and forgets the event so it is not queried again)
+bool block_done(const Block& b) {
+  if (!b.ready) return true;
+  if (cudaEventQuery(b.ready->ev) == cudaSuccess) {
+    b.ready.reset();
+    b.settled = true;
+    return true;
+  }
+  (void)cudaGetLastError();
+  return false;
+}
+bool wait_ready_all(mr_context* ctx, const mr_matrix* m) {
+  bool any = false;
+  for (auto& kv : m->blocks) any = wait_ready(ctx, kv.second) || any;
+  return any;
+}
+
+// Descriptor tables (a few hundred KB per operator) travel through a mapped pinned staging ring and an SM-driven copy
+// kernel instead of cudaMemcpyAsync: on the H2D copy engine they would queue behind every block upload already
+// submitted on the ingest stream, and the first chunk of a pipelined multiply could not start until ALL operands had
+// landed.  Ring regions are only reused after a stream synchronisation (on wrap-around).
+Buf upload_bytes(mr_context* ctx, const void* data, size_t bytes) {
+  Buf b = std::make_shared<DevBuf>(ctx, std::max<size_t>((bytes + 3) / 4 * 4, 16));
+  if (bytes == 0) return b;
+  const size_t need = align_up(bytes);
+  if (ctx->stage_host != nullptr && need <= ctx->stage_cap / 2) {
+    if (ctx->stage_off + need > ctx->stage_cap) {
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      ctx->stage_off = 0;
+    }
+    std::memcpy(ctx->stage_host + ctx->stage_off, data, bytes);
+    CUDA_CHECK(launch_copy_words(b->p, ctx->stage_dev + ctx->stage_off, bytes, ctx->stream));
+    ctx->stage_off += need;
+  } else {
+    CUDA_CHECK(cudaMemcpyAsync(b->p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->stats.h2d_bytes += static_cast<int64_t>(bytes);
+  return b;
+}
+
+Block dense_block(int32_t rows, int32_t cols, Span values, bool isT) {
+  Block b;
+  b.type = 1;
+  b.numRows = rows;
+  b.numCols = cols;
+  b.isT = isT;
+  b.values = std::move(values);
+  b.valuesLen = static_cast<int64_t>(rows) * cols;
+  return b;
+}
+
+// SparseMatrix.toDense (MLMatrix.scala:669-671) on the device: zero fill + scatter.
+Block densify(mr_context* ctx, const Block& s) {
+  const size_t bytes = static_cast<size_t>(s.numRows) * s.numCols * sizeof(double);
+  Span v{std::make_shared<DevBuf>(ctx, std::max<size_t>(bytes, 16)), 0};
+  if (bytes) CUDA_CHECK(cudaMemsetAsync(v.ptr<double>(), 0, bytes, ctx->stream));
+  if (s.valuesLen > 0) {
+    CUDA_CHECK(launch_sparse_to_dense(s.colPtrs.ptr<int32_t>(), s.rowIndices.ptr<int32_t>(), s.values.ptr<double>(),
+                                      s.isT, v.ptr<double>(), s.numRows, s.numCols, ctx->stream));
+    note_launch(ctx);
+  }
+  return dense_block(s.numRows, s.numCols, v, false);
+}
+
+const char* type_name(const Block& b) { return b.dense() ? "DenseMatrix" : "SparseMatrix"; }
+
+int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// ------------------------------------------------------------------------------------------------
+// dense window -> CSC compaction (DenseMatrix.toSparse, MLMatrix.scala:392-420), batched
+// ------------------------------------------------------------------------------------------------
+// Per-column counts of entries != 0.0 (NaN counts, as in the reference's `arr(i) != 0`): one launch + one sync.
+std::vector<std::vector<int32_t>> column_counts(mr_context* ctx, const std::vector<DenseWin>& wins) {
+  std::vector<std::vector<int32_t>> out(wins.size());
+  if (wins.empty()) return out;
+  size_t ncols_total = 0;
+  int maxc = 0;
+  for (auto& w : wins) {
+    ncols_total += static_cast<size_t>(w.cols);
+    maxc = std::max(maxc, w.cols);
+  }
+  Buf counts = std::make_shared<DevBuf>(ctx, std::max<size_t>(ncols_total * sizeof(int32_t), 16));
+  std::vector<CscDesc> cd(wins.size());
+  size_t off = 0;
+  for (size_t i = 0; i < wins.size(); ++i) {
+    cd[i] = CscDesc{wins[i].p, wins[i].rows, wins[i].cols, static_cast<int32_t*>(counts->p) + off, nullptr, nullptr, nullptr};
+    off += static_cast<size_t>(wins[i].cols);
+  }
+  Buf dcd = upload(ctx, cd);
+  CUDA_CHECK(launch_csc_count(static_cast<const CscDesc*>(dcd->p), static_cast<int>(cd.size()), maxc, ctx->stream));
+  note_launch(ctx);
+  std::vector<int32_t> h(ncols_total);
+  if (ncols_total) {
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), counts->p, ncols_total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += static_cast<int64_t>(ncols_total * sizeof(int32_t));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  off = 0;
+  for (size_t i = 0; i < wins.size(); ++i) {
+    out[i].assign(h.begin() + static_cast<std::ptrdiff_t>(off), h.begin() + static_cast<std::ptrdiff_t>(off + wins[i].cols));
+    off += static_cast<size_t>(wins[i].cols);
+  }
+  return out;
+}
+
+int64_t total_count(const std::vector<int32_t>& counts) {
+  int64_t n = 0;
+  for (int32_t c : counts) n += c;
+  return n;
+}
+
+// CSC blocks (isTransposed = false) of the windows, given their column counts: one launch.
+std::vector<Block> compact_csc(mr_context* ctx, const std::vector<DenseWin>& wins, const std::vector<std::vector<int32_t>>& counts) {
+  std::vector<Block> out;
+  std::vector<CscDesc> fill;
+  int maxc = 0;
+  for (size_t i = 0; i < wins.size(); ++i) {
+    const int rows = wins[i].rows, cols = wins[i].cols;
+    std::vector<int32_t> ptrs(static_cast<size_t>(cols) + 1, 0);
+    for (int c = 0; c < cols; ++c) ptrs[c + 1] = ptrs[c] + counts[i][c];
+    const int64_t nnz = ptrs[cols];
+    Block sb;
+    sb.type = 0;
+    sb.numRows = rows;
+    sb.numCols = cols;
+    sb.isT = false;
+    sb.valuesLen = nnz;
+    sb.colPtrsLen = cols + 1;
+    sb.colPtrs = upload_raw(ctx, ptrs.data(), ptrs.size() * sizeof(int32_t));
+    sb.rowIndices = Span{std::make_shared<DevBuf>(ctx, std::max<size_t>(nnz * sizeof(int32_t), 16)), 0};
+    sb.values = Span{std::make_shared<DevBuf>(ctx, std::max<size_t>(nnz * sizeof(double), 16)), 0};
+    fill.push_back(CscDesc{wins[i].p, rows, cols, nullptr, sb.colPtrs.ptr<int32_t>(), sb.rowIndices.ptr<int32_t>(),
+                           sb.values.ptr<double>()});
+    maxc = std::max(maxc, cols);
+    out.push_back(std::move(sb));
+  }
+  if (!fill.empty()) {
+    Buf dfill = upload(ctx, fill);
+    CUDA_CHECK(launch_csc_fill(static_cast<const CscDesc*>(dfill->p), static_cast<int>(fill.size()), maxc, ctx->stream));
+    note_launch(ctx);
+  }
+  return out;
+}
+mr_matrix* new_matrix(mr_context* ctx) {
+  auto* m = new mr_matrix;
+  m->ctx = ctx;
+  return m;
+}
+
+void validate_desc(const mr_block_desc* d) {
+  MR_REQUIRE(d != nullptr, MR_EINVAL, "block descriptor is null");
+  MR_REQUIRE(d->numRows >= 0 && d->numCols >= 0, MR_EINVAL, "negative block dimensions %d x %d", d->numRows, d->numCols);
+  if (d->type == 1) {
+    // DenseMatrix ctor (MLMatrix.scala:240)
+    MR_REQUIRE(d->valuesLen == static_cast<int64_t>(d->numRows) * d->numCols, MR_EINVAL,
+               "The number of values supplied doesn't match the size of the matrix! values.length: %lld, "
+               "numRows * numCols: %lld",
+               (long long)d->valuesLen, (long long)(static_cast<int64_t>(d->numRows) * d->numCols));
+    MR_REQUIRE(d->valuesLen == 0 || d->values != nullptr, MR_EINVAL, "values is null");
+  } else if (d->type == 0) {
+    // SparseMatrix ctor (MLMatrix.scala:533-542)
+    MR_REQUIRE(d->valuesLen == d->rowIndicesLen, MR_EINVAL,
+               "The number of row indices and values don't match! values.length: %lld, rowIndices.length: %lld",
+               (long long)d->valuesLen, (long long)d->rowIndicesLen);
+    if (d->isTransposed)
+      MR_REQUIRE(d->colPtrsLen == d->numRows + 1, MR_EINVAL, "Expecting %d colPtrs when numRows = %d but got %lld",
+                 d->numRows + 1, d->numRows, (long long)d->colPtrsLen);
+    else
+      MR_REQUIRE(d->colPtrsLen == d->numCols + 1, MR_EINVAL, "Expecting %d colPtrs when numCols = %d but got %lld",
+                 d->numCols + 1, d->numCols, (long long)d->colPtrsLen);
+    MR_REQUIRE(d->colPtrs != nullptr, MR_EINVAL, "colPtrs is null");
+    MR_REQUIRE(d->valuesLen == d->colPtrs[d->colPtrsLen - 1], MR_EINVAL,
+               "The last value of colPtrs must equal the number of elements. values.length: %lld, colPtrs.last: %d",
+               (long long)d->valuesLen, d->colPtrs[d->colPtrsLen - 1]);
+    MR_REQUIRE(d->valuesLen == 0 || (d->values != nullptr && d->rowIndices != nullptr), MR_EINVAL,
+               "values / rowIndices is null");
+  } else {
+    fail(MR_ENOTSUP, "Unsupported matrix type %d", static_cast<int>(d->type));
+  }
+}
+
+Span upload_raw(mr_context* ctx, const void* host, size_t bytes) {
+  Span s{std::make_shared<DevBuf>(ctx, std::max<size_t>(bytes, 16)), 0};
+  if (bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(s.buf->p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += static_cast<int64_t>(bytes);
+  }
+  return s;
+}
+
+}  // namespace mrhost
+
+// ------------------------------------------------------------------------------------------------
+// ABI: lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mr_last_error(void) { return g_last_error.c_str(); }
+const char* mr_version(void) { return "matrel-b200 0.1 (sm_100a)"; }
+
+mr_status mr_init(const mr_options* opts, mr_context** out) {
+  return guarded([&] {
+    MR_REQUIRE(out != nullptr, MR_EINVAL, "out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      (void)cudaGetLastError();
+      fail(MR_ECUDA, "no usable CUDA device (%s): the B200 engine has no CPU fallback",
+           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    auto ctx = std::unique_ptr<mr_context>(new mr_context);
+    int dev = opts ? opts->device : -1;
+    if (dev < 0) CUDA_CHECK(cudaGetDevice(&dev));
+    MR_REQUIRE(dev < count, MR_EINVAL, "device ordinal %d out of range (have %d)", dev, count);
+    CUDA_CHECK(cudaSetDevice(dev));
+    ctx->device = dev;
+    cudaDeviceProp prop{};
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+      fail(MR_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    if (opts) {
+      ctx->compat_bugs = opts->compat_bugs;
+      ctx->gemm_algo = opts->gemm_algo;
+      ctx->ozaki_slices = opts->ozaki_slices;
+    }
+    if (opts && opts->stream) {
+      ctx->stream = static_cast<cudaStream_t>(opts->stream);
+    } else {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    CUDA_CHECK(cudaEventCreate(&ctx->ev0));
+    CUDA_CHECK(cudaEventCreate(&ctx->ev1));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < mr_context::kChunkStreams; ++i) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->chunk_stream[i], cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ctx->chunk_join[i], cudaEventDisableTiming));
+    }
+    {
+      void* hp = nullptr;
+      const size_t cap = 16u << 20;
+      if (cudaHostAlloc(&hp, cap, cudaHostAllocMapped) == cudaSuccess) {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+          ctx->stage_host = static_cast<char*>(hp);
+          ctx->stage_dev = static_cast<char*>(dp);
+          ctx->stage_cap = cap;
+        } else {
+          cudaFreeHost(hp);
+        }
+      }
+      (void)cudaGetLastError();
+    }
+    // keep freed blocks in the pool: operators allocate result slabs on every call
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = UINT64_MAX;
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = ctx.release();
+  });
+}
+
+mr_status mr_shutdown(mr_context* ctx) {
+  return guarded([&] {
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->h2d_stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
+    cudaStreamDestroy(ctx->h2d_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
+    for (int i = 0; i < mr_context::kChunkStreams; ++i) {
+      if (ctx->chunk_stream[i]) cudaStreamDestroy(ctx->chunk_stream[i]);
+      if (ctx->chunk_join[i]) cudaEventDestroy(ctx->chunk_join[i]);
+    }
+    if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+    if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+  });
+}
+
+mr_status mr_set_stream(mr_context* ctx, void* cuda_stream) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) {
+      cudaStreamDestroy(ctx->stream);
+      ctx->own_stream = false;
+    }
+    if (cuda_stream) {
+      ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+  });
+}
+
+mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && key != nullptr, MR_EINVAL, "ctx/key is null");
+    std::string k(key);
+    if (k == "compat_bugs") ctx->compat_bugs = static_cast<int>(value);
+    else if (k == "gemm_algo") ctx->gemm_algo = static_cast<int>(value);
+    else if (k == "ozaki_slices") ctx->ozaki_slices = static_cast<int>(value);
+    else if (k == "crt_moduli") ctx->crt_moduli = static_cast<int>(value);
+    else if (k == "time_kernels") ctx->time_kernels = static_cast<int>(value);
+    else if (k == "gemm_variant") ctx->force_variant = static_cast<int>(value);
+    else if (k == "pipeline") ctx->pipeline = static_cast<int>(value);
+    else fail(MR_EINVAL, "unknown option '%s'", key);
+  });
+}
+
+mr_status mr_sync(mr_context* ctx) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->h2d_stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->d2h_stream));
+  });
+}
+
+mr_status mr_get_stats(mr_context* ctx, mr_stats* out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr, MR_EINVAL, "ctx/out is null");
+    *out = ctx->stats;
+  });
+}
+
+mr_status mr_reset_stats(mr_context* ctx) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    ctx->stats = mr_stats{};
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: datasets
+// ------------------------------------------------------------------------------------------------
+mr_status mr_matrix_create(mr_context* ctx, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr, MR_EINVAL, "ctx/out is null");
+    *out = new_matrix(ctx);
+  });
+}
+
+mr_status mr_matrix_free(mr_matrix* m) {
+  return guarded([&] { delete m; });
+}
+
+mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_block_desc* d) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr, MR_EINVAL, "matrix is null");
+    validate_desc(d);
+    mr_context* ctx = m->ctx;
+    Block b;
+    b.type = d->type;
+    b.numRows = d->numRows;
+    b.numCols = d->numCols;
+    b.isT = d->isTransposed != 0;
+    b.valuesLen = d->valuesLen;
+    // Ingest on its own stream: the copy of block k+1 overlaps whatever the context stream is computing, and
+    // operators wait per block (Block::ready), so a multiply can start on the row panels that have landed.
+    cudaStream_t cs = ctx->pipeline ? ctx->h2d_stream : ctx->stream;
+    auto put = [&](const void* host, size_t bytes) {
+      Span sp{std::make_shared<DevBuf>(ctx, std::max<size_t>(bytes, 16)), 0};
+      return std::make_pair(sp, bytes ? host : nullptr);
+    };
+    auto vals = put(d->values, static_cast<size_t>(d->valuesLen) * sizeof(double));
+    std::pair<Span, const void*> cp{}, ri{};
+    if (d->type == 0) {
+      b.colPtrsLen = d->colPtrsLen;
+      cp = put(d->colPtrs, static_cast<size_t>(d->colPtrsLen) * sizeof(int32_t));
+      ri = put(d->rowIndices, static_cast<size_t>(d->rowIndicesLen) * sizeof(int32_t));
+    }
+    if (ctx->pipeline) {  // allocations are ordered on the context stream: the ingest stream must see them
+      CUDA_CHECK(cudaEventRecord(ctx->ev_alloc, ctx->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_alloc, 0));
+    }
+    auto copy = [&](std::pair<Span, const void*>& x, size_t bytes) {
+      if (x.second && bytes) {
+        CUDA_CHECK(cudaMemcpyAsync(x.first.buf->p, x.second, bytes, cudaMemcpyHostToDevice, cs));
+        ctx->stats.h2d_bytes += static_cast<int64_t>(bytes);
+      }
+    };
+    copy(vals, static_cast<size_t>(d->valuesLen) * sizeof(double));
+    b.values = vals.first;
+    if (d->type == 0) {
+      copy(cp, static_cast<size_t>(d->colPtrsLen) * sizeof(int32_t));
+      copy(ri, static_cast<size_t>(d->rowIndicesLen) * sizeof(int32_t));
+      b.colPtrs = cp.first;
+      b.rowIndices = ri.first;
+    }
+    if (ctx->pipeline) {
+      ReadyPtr r = std::make_shared<Ready>();
+      CUDA_CHECK(cudaEventRecord(r->ev, cs));
+      b.ready = r;
+      b.seq = ++ctx->ingest_seq;
+      b.values.buf->ready = r;
+      if (d->type == 0) {
+        b.colPtrs.buf->ready = r;
+        b.rowIndices.buf->ready = r;
+      }
+    }
+    m->blocks[{rid, cid}] = std::move(b);
+  });
+}
+
+mr_status mr_matrix_put_blocks(mr_matrix* m, int64_t count, const int32_t* rids, const int32_t* cids, const mr_block_desc* blks) {
+  if (count < 0 || (count > 0 && (!rids || !cids || !blks))) {
+    g_last_error = "requirement failed: null argument";
+    return MR_EINVAL;
+  }
+  for (int64_t i = 0; i < count; ++i) {
+    const mr_status st = mr_matrix_put_block(m, rids[i], cids[i], &blks[i]);
+    if (st != MR_OK) return st;
+  }
+  return MR_OK;
+}
+
+mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int32_t numRows, int32_t numCols,
+                                     const double* dvalues, uint8_t isTransposed) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr, MR_EINVAL, "matrix is null");
+    MR_REQUIRE(numRows >= 0 && numCols >= 0, MR_EINVAL, "negative block dimensions %d x %d", numRows, numCols);
+    MR_REQUIRE(dvalues != nullptr || static_cast<int64_t>(numRows) * numCols == 0, MR_EINVAL, "device pointer is null");
+    Span s{std::make_shared<DevBuf>(m->ctx, const_cast<double*>(dvalues),
+                                    static_cast<size_t>(numRows) * numCols * sizeof(double)),
+           0};
+    m->blocks[{rid, cid}] = dense_block(numRows, numCols, s, isTransposed != 0);
+  });
+}
+
+mr_status mr_matrix_put_blocks_device(mr_matrix* m, int64_t count, const int32_t* rids, const int32_t* cids,
+                                      const int32_t* numRows, const int32_t* numCols, const double* const* dvalues,
+                                      const uint8_t* isTransposed) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr, MR_EINVAL, "matrix is null");
+    MR_REQUIRE(count == 0 || (rids && cids && numRows && numCols && dvalues), MR_EINVAL, "null argument");
+    for (int64_t i = 0; i < count; ++i) {
+      MR_REQUIRE(numRows[i] >= 0 && numCols[i] >= 0, MR_EINVAL, "negative block dimensions %d x %d", numRows[i], numCols[i]);
+      Span s{std::make_shared<DevBuf>(m->ctx, const_cast<double*>(dvalues[i]),
+                                      static_cast<size_t>(numRows[i]) * numCols[i] * sizeof(double)),
+             0};
+      m->blocks[{rids[i], cids[i]}] = dense_block(numRows[i], numCols[i], s, isTransposed ? isTransposed[i] != 0 : false);
+    }
+  });
+}
+
+mr_status mr_matrix_num_blocks(const mr_matrix* m, int64_t* out) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && out != nullptr, MR_EINVAL, "matrix/out is null");
+    *out = static_cast<int64_t>(m->blocks.size());
+  });
+}
+
+mr_status mr_matrix_has_block(const mr_matrix* m, int32_t rid, int32_t cid, int32_t* out) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && out != nullptr, MR_EINVAL, "matrix/out is null");
+    *out = m->blocks.count({rid, cid}) ? 1 : 0;
+  });
+}
+
+mr_status mr_matrix_block_ids(const mr_matrix* m, int32_t* rids, int32_t* cids, int64_t cap) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && rids != nullptr && cids != nullptr, MR_EINVAL, "null argument");
+    MR_REQUIRE(cap >= static_cast<int64_t>(m->blocks.size()), MR_EINVAL, "capacity %lld < number of blocks %zu",
+               (long long)cap, m->blocks.size());
+    int64_t i = 0;
+    for (auto& kv : m->blocks) {
+      rids[i] = kv.first.first;
+      cids[i] = kv.first.second;
+      ++i;
+    }
+  });
+}
+
+mr_status mr_matrix_get_block(mr_matrix* m, int32_t rid, int32_t cid, mr_block_desc* io) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && io != nullptr, MR_EINVAL, "null argument");
+    auto it = m->blocks.find({rid, cid});
+    if (it == m->blocks.end()) fail(MR_ENOTFOUND, "no block (%d, %d) in this dataset", rid, cid);
+    const Block& b = it->second;
+    mr_context* ctx = m->ctx;
+    ReadyPtr ready;
+    bool settled;
+    {
+      std::lock_guard<std::mutex> lock(ctx->mu);
+      ready = b.ready;  // snapshot: operators on other threads may drop completed events
+      settled = b.settled;
+    }
+    const int64_t rowIndicesLen = b.dense() ? 0 : b.valuesLen;
+    // Egress on its own stream, ordered after this block's producer only (one chunk of a chunked multiply, or
+    // everything enqueued on the context stream so far when the block has no event of its own).
+    cudaStream_t rs = ctx->pipeline ? ctx->d2h_stream : ctx->stream;
+    if (ctx->pipeline && (io->values || io->colPtrs || io->rowIndices)) {
+      if (ready) {
+        CUDA_CHECK(cudaStreamWaitEvent(rs, ready->ev, 0));
+      } else if (!settled) {
+        CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(rs, ctx->ev_order, 0));
+      }
+    }
+    if (io->values != nullptr) {
+      MR_REQUIRE(io->valuesLen >= b.valuesLen, MR_EINVAL, "values capacity %lld < %lld", (long long)io->valuesLen,
+                 (long long)b.valuesLen);
+      if (b.valuesLen)
+        CUDA_CHECK(cudaMemcpyAsync(io->values, b.values.ptr<double>(), static_cast<size_t>(b.valuesLen) * sizeof(double),
+                                   cudaMemcpyDeviceToHost, rs));
+      ctx->stats.d2h_bytes += b.valuesLen * 8;
+    }
+    if (!b.dense() && io->colPtrs != nullptr) {
+      MR_REQUIRE(io->colPtrsLen >= b.colPtrsLen, MR_EINVAL, "colPtrs capacity too small");
+      CUDA_CHECK(cudaMemcpyAsync(io->colPtrs, b.colPtrs.ptr<int32_t>(), static_cast<size_t>(b.colPtrsLen) * 4,
+                                 cudaMemcpyDeviceToHost, rs));
+      ctx->stats.d2h_bytes += b.colPtrsLen * 4;
+    }
+    if (!b.dense() && io->rowIndices != nullptr) {
+      MR_REQUIRE(io->rowIndicesLen >= rowIndicesLen, MR_EINVAL, "rowIndices capacity too small");
+      if (rowIndicesLen)
+        CUDA_CHECK(cudaMemcpyAsync(io->rowIndices, b.rowIndices.ptr<int32_t>(), static_cast<size_t>(rowIndicesLen) * 4,
+                                   cudaMemcpyDeviceToHost, rs));
+      ctx->stats.d2h_bytes += rowIndicesLen * 4;
+    }
+    if (io->values || io->colPtrs || io->rowIndices) CUDA_CHECK(cudaStreamSynchronize(rs));
+    io->type = b.type;
+    io->numRows = b.numRows;
+    io->numCols = b.numCols;
+    io->isTransposed = b.isT ? 1 : 0;
+    io->valuesLen = b.valuesLen;
+    io->colPtrsLen = b.dense() ? 0 : b.colPtrsLen;
+    io->rowIndicesLen = rowIndicesLen;
+  });
+}
+
+mr_status mr_matrix_block_device_ptr(mr_matrix* m, int32_t rid, int32_t cid, double** dptr) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr && dptr != nullptr, MR_EINVAL, "null argument");
+    auto it = m->blocks.find({rid, cid});
+    if (it == m->blocks.end()) fail(MR_ENOTFOUND, "no block (%d, %d) in this dataset", rid, cid);
+    *dptr = it->second.values.ptr<double>();
+  });
+}
+
+mr_status mr_matrix_rand(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t seed0,
+                         mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr, MR_EINVAL, "ctx/out is null");
+    MR_REQUIRE(nrows > 0 && ncols > 0 && blkSize > 0, MR_EINVAL, "nrows, ncols, blkSize must be positive");
+    // DenseMatrix.rand `require` (MLMatrix.scala:454-455)
+    MR_REQUIRE(static_cast<int64_t>(blkSize) * blkSize <= INT32_MAX, MR_EINVAL,
+               "%d x %d dense matrix is too large to allocate", blkSize, blkSize);
+    const int64_t nbr = ceil_div(nrows, blkSize), nbc = ceil_div(ncols, blkSize);
+    std::unique_ptr<mr_matrix> m(new_matrix(ctx));
+    size_t total = 0;
+    for (int64_t i = 0; i < nbr; ++i)
+      for (int64_t j = 0; j < nbc; ++j) {
+        const int64_t r = std::min<int64_t>(blkSize, nrows - i * blkSize), c = std::min<int64_t>(blkSize, ncols - j * blkSize);
+        total += align_up(static_cast<size_t>(r * c) * sizeof(double));
+      }
+    Slab slab(ctx, total);
+    std::vector<RandDesc> descs;
+    int64_t max_n = 0;
+    for (int64_t i = 0; i < nbr; ++i)
+      for (int64_t j = 0; j < nbc; ++j) {
+        const int32_t r = static_cast<int32_t>(std::min<int64_t>(blkSize, nrows - i * blkSize));
+        const int32_t c = static_cast<int32_t>(std::min<int64_t>(blkSize, ncols - j * blkSize));
+        Span s = slab.take(static_cast<size_t>(r) * c * sizeof(double));
+        descs.push_back(RandDesc{s.ptr<double>(), static_cast<int64_t>(r) * c, seed0 + i * nbc + j});
+        max_n = std::max<int64_t>(max_n, static_cast<int64_t>(r) * c);
+        m->blocks[{static_cast<int32_t>(i), static_cast<int32_t>(j)}] = dense_block(r, c, s, false);
+      }
+    // gridDim.y limit: launch in chunks of 65535 blocks
+    for (size_t off = 0; off < descs.size(); off += 65535) {
+      std::vector<RandDesc> chunk(descs.begin() + off, descs.begin() + std::min(descs.size(), off + 65535));
+      Buf d = upload(ctx, chunk);
+      CUDA_CHECK(launch_java_rand_batched(static_cast<const RandDesc*>(d->p), static_cast<int>(chunk.size()), max_n, ctx->stream));
+      note_launch(ctx);
+    }
+    *out = m.release();
+  });
+}
+
+mr_status mr_matrix_rand_partition(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t seed0,
+                                   int32_t pr, int32_t pc, int32_t r, int32_t c, double* dslab, int64_t slotElems,
+                                   mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr && dslab != nullptr, MR_EINVAL, "null argument");
+    MR_REQUIRE(nrows > 0 && ncols > 0 && blkSize > 0, MR_EINVAL, "nrows, ncols, blkSize must be positive");
+    MR_REQUIRE(pr > 0 && pc > 0 && r >= 0 && r < pr && c >= 0 && c < pc, MR_EINVAL, "bad process grid %d x %d / (%d, %d)",
+               pr, pc, r, c);
+    MR_REQUIRE(slotElems >= static_cast<int64_t>(blkSize) * blkSize, MR_EINVAL, "slotElems %lld < blkSize^2",
+               (long long)slotElems);
+    const int64_t nbr = ceil_div(nrows, blkSize), nbc = ceil_div(ncols, blkSize);
+    const int64_t slots_c = ceil_div(nbc, pc);
+    std::unique_ptr<mr_matrix> m(new_matrix(ctx));
+    std::vector<RandDesc> descs;
+    int64_t max_n = 0;
+    for (int64_t i = r; i < nbr; i += pr)
+      for (int64_t j = c; j < nbc; j += pc) {
+        const int32_t br = static_cast<int32_t>(std::min<int64_t>(blkSize, nrows - i * blkSize));
+        const int32_t bc = static_cast<int32_t>(std::min<int64_t>(blkSize, ncols - j * blkSize));
+        double* p = dslab + ((i / pr) * slots_c + (j / pc)) * slotElems;
+        descs.push_back(RandDesc{p, static_cast<int64_t>(br) * bc, seed0 + i * nbc + j});
+        max_n = std::max<int64_t>(max_n, static_cast<int64_t>(br) * bc);
+        Span s{std::make_shared<DevBuf>(ctx, p, static_cast<size_t>(br) * bc * sizeof(double)), 0};
+        m->blocks[{static_cast<int32_t>(i), static_cast<int32_t>(j)}] = dense_block(br, bc, s, false);
+      }
+    for (size_t off = 0; off < descs.size(); off += 65535) {
+      std::vector<RandDesc> chunk(descs.begin() + off, descs.begin() + std::min(descs.size(), off + 65535));
+      Buf d = upload(ctx, chunk);
+      CUDA_CHECK(launch_java_rand_batched(static_cast<const RandDesc*>(d->p), static_cast<int>(chunk.size()), max_n, ctx->stream));
+      note_launch(ctx);
+    }
+    *out = m.release();
+  });
+}
+
+
+}  // extern "C"

@@ -1,4 +1,4 @@
-// Internal interface between the C-ABI host layer (abi.cpp) and the sm_100a kernels.
+// Internal interface between the C-ABI host layer (abi_*.cpp, host.h) and the sm_100a kernels.
 // Not part of the public ABI (see include/matrel.h).
 #pragma once
 #include <cuda_runtime.h>
