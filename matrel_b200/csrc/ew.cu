@@ -384,20 +384,27 @@ __global__ void __launch_bounds__(256) csc_fill_kernel(const CscDesc* __restrict
   }
 }
 
-// Row / column sums: a CTA reduces a 32 (contiguous dimension) x 256 (strided dimension) tile; tx runs along the
-// block's contiguous dimension so global reads are coalesced for both layouts.
-constexpr int AGG_SLOW = 256;
-__global__ void __launch_bounds__(256) axis_sum_kernel(const AggDesc* __restrict__ descs, int by_row, int tiles_slow_max) {
+// Row / column sums.  tx always runs along the block's contiguous ("fast") dimension so global reads are coalesced for both
+// layouts.  Two CTA shapes, chosen per block:
+//   kept index = fast (rowSum of a column-major block): a CTA reduces a 32 (fast) x 256 (slow) tile, one partial per thread,
+//     8 partials per fast index folded through shared memory, one atomic per fast index;
+//   kept index = slow (colSum of a column-major block): a warp owns ONE slow index and sweeps up to 1024 fast elements in
+//     registers (32 independent 256-byte warp loads) before a single shuffle reduction and one atomic -- the first version
+//     reduced every 32-element row separately and was shuffle/atomic-bound at 3.4 TB/s.
+constexpr int AGG_SLOW = 256;      // slow extent of a "kept fast" tile
+constexpr int AGG_SWEEP = 1024;    // fast extent one warp sweeps in a "kept slow" tile (8 slow indices per CTA)
+__global__ void __launch_bounds__(256) axis_sum_kernel(const AggDesc* __restrict__ descs, int by_row, int tiles_slow_a,
+                                                       int tiles_slow_b) {
   __shared__ double sm[8][33];
   const AggDesc d = descs[blockIdx.y];
   const int nfast = d.isT ? d.cols : d.rows, nslow = d.isT ? d.rows : d.cols;
-  const int tf = blockIdx.x / tiles_slow_max, ts = blockIdx.x % tiles_slow_max;
-  const int f0 = tf * 32, s0 = ts * AGG_SLOW;
-  if (f0 >= nfast || s0 >= nslow) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const bool kept_is_fast = (by_row != 0) == (d.isT == 0);  // row sums of a column-major block keep the fast index
-  const int f = f0 + tx;
   if (kept_is_fast) {
+    const int tf = blockIdx.x / tiles_slow_a, ts = blockIdx.x % tiles_slow_a;
+    const int f0 = tf * 32, s0 = ts * AGG_SLOW;
+    if (f0 >= nfast || s0 >= nslow) return;
+    const int f = f0 + tx;
     double acc = 0.0;
     if (f < nfast)
       for (int s = s0 + ty; s < min(nslow, s0 + AGG_SLOW); s += 8) acc += d.v[f + static_cast<size_t>(nfast) * s];
@@ -409,12 +416,24 @@ __global__ void __launch_bounds__(256) axis_sum_kernel(const AggDesc* __restrict
       atomicAdd(&d.out[f], acc);
     }
   } else {
-    for (int s = s0 + ty; s < min(nslow, s0 + AGG_SLOW); s += 8) {
-      double v = f < nfast ? d.v[f + static_cast<size_t>(nfast) * s] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (tx == 0) atomicAdd(&d.out[s], v);
+    const int tf = blockIdx.x / tiles_slow_b, ts = blockIdx.x % tiles_slow_b;
+    const int f0 = tf * AGG_SWEEP, s = ts * 8 + ty;
+    if (f0 >= nfast || s >= nslow) return;
+    const double* __restrict__ line = d.v + static_cast<size_t>(nfast) * s;
+    const int f1 = min(nfast, f0 + AGG_SWEEP);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int f = f0 + tx;
+    for (; f + 96 < f1; f += 128) {  // four independent loads in flight per lane
+      a0 += line[f];
+      a1 += line[f + 32];
+      a2 += line[f + 64];
+      a3 += line[f + 96];
     }
+    for (; f < f1; f += 32) a0 += line[f];
+    double v = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tx == 0) atomicAdd(&d.out[s], v);
   }
 }
 
@@ -585,8 +604,11 @@ cudaError_t launch_aggregate(int op, const AggDesc* d_descs, int nblocks, int ma
     const int nb = nblocks - off < 65535 ? nblocks - off : 65535;
     if (op == AGG_ROW_SUM || op == AGG_COL_SUM) {
       const int mx = max_rows > max_cols ? max_rows : max_cols;
-      const int tiles_fast = (mx + 31) / 32, tiles_slow = (mx + AGG_SLOW - 1) / AGG_SLOW;
-      axis_sum_kernel<<<dim3(tiles_fast * tiles_slow, nb), 256, 0, stream>>>(d_descs + off, op == AGG_ROW_SUM ? 1 : 0, tiles_slow);
+      // grid.x covers whichever of the two CTA shapes needs more tiles (a batch may mix layouts); extra CTAs return at once
+      const int tiles_a = ((mx + 31) / 32) * ((mx + AGG_SLOW - 1) / AGG_SLOW);
+      const int tiles_b = ((mx + AGG_SWEEP - 1) / AGG_SWEEP) * ((mx + 7) / 8);
+      axis_sum_kernel<<<dim3(tiles_a > tiles_b ? tiles_a : tiles_b, nb), 256, 0, stream>>>(
+          d_descs + off, op == AGG_ROW_SUM ? 1 : 0, (mx + AGG_SLOW - 1) / AGG_SLOW, (mx + 7) / 8);
     } else {
       const int64_t n = op == AGG_TRACE ? max_rows : static_cast<int64_t>(max_rows) * max_cols;
       int64_t gx = (n + 256 * 16 - 1) / (256 * 16);
