@@ -1,0 +1,38 @@
+"""The committed bench lines (profiles/bench_r01_n*.json, written by bench.py on the B200 box) carry every key of the
+measurement contract, with consistent arithmetic."""
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
+def test_committed_bench_line(n_gpus):
+    path = os.path.join(ROOT, "profiles", f"bench_r01_n{n_gpus}.json")
+    d = json.load(open(path))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == n_gpus and d["higher_is_better"] is True and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["metric"].split(",")[0] in BASE["metric"] and d["unit"] == "GFLOP/s"
+    assert "workload" in d["config"] and "16384" in d["config"]["workload"] and "model" not in d["config"]
+    assert d["steps"] >= 1 and d["warmup"] >= 3
+    flops = 2.0 * 16384 ** 3
+    assert abs(d["value"] - flops / (d["ms_per_step"] * 1e-3) / 1e9) / d["value"] < 1e-6       # whole-job GFLOP/s
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 2 * 16384 * 16384 * 8 and e["d2h_bytes_per_step"] == 16384 * 16384 * 8
+    assert 0 < e["value"] < d["value"]                                                         # copies are inside the timed region
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert 0.5 < r["frac"] <= 1.0 and (r["traffic"] is None or r["traffic"] > 0)
+    assert d["gpu_launches"] >= d["steps"]
+    c = d["clocks"]
+    assert c["sm_mhz"] > 0.8 * c["sm_max_mhz"]
+    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if n_gpus == 1:
+        b = d["cpu_baseline"]
+        assert b["kind"] in ("port", "reference") and b["cores"] >= 1 and b["value"] > 0 and b["sample"]
+        assert d["value"] / b["value"] > 10
