@@ -173,7 +173,7 @@ MR_API mr_status mr_vec(mr_matrix* a, int64_t nrows, int64_t ncols, int32_t blkS
  * M/matrix/MLMatrix.scala:55-61, as a device transpose kernel). */
 MR_API mr_status mr_materialize(mr_matrix* a, mr_matrix** out);
 
-/* ---- placement: bit-exact restatement of M/partitioner/*.scala (pure integer, host side) */
+/* ---- placement: bit-exact restatement of M/partitioner/{Row,Column,Index,BlockCyclic}Partitioner.scala (pure integer, host side) */
 /* RowPartitioner.getPartition (RowPartitioner.scala:32-38) */
 MR_API mr_status mr_row_partition(int32_t rid, int32_t cid, int32_t partitions, int32_t* out);
 /* ColumnPartitioner.getPartition (ColumnPartitioner.scala:32-38) */
@@ -186,7 +186,7 @@ MR_API mr_status mr_gen_block_cyclic(int64_t nrows, int64_t ncols, int32_t blkSi
 /* BlockCyclicPartitioner.getPartition / numPartitions (BlockCyclicPartitioner.scala:31-62) */
 MR_API mr_status mr_block_cyclic_partition(const int32_t params[4], int32_t rid, int32_t cid, int32_t* out);
 MR_API mr_status mr_block_cyclic_num_partitions(const int32_t params[4], int32_t* out);
-/* One entry point over the four schemes (Partitioner.getPartition of M/partitioner/*.scala): params[0] = partitions for
+/* One entry point over the four schemes (Partitioner.getPartition of the four M/partitioner classes): params[0] = partitions for
  * MR_PART_ROW / MR_PART_COLUMN / MR_PART_INDEX (INDEX keys on rid), params[0..3] = the mr_gen_block_cyclic tuple for
  * MR_PART_BLOCK_CYCLIC. */
 typedef enum mr_partition_scheme { MR_PART_ROW = 0, MR_PART_COLUMN = 1, MR_PART_INDEX = 2, MR_PART_BLOCK_CYCLIC = 3 } mr_partition_scheme;

@@ -142,3 +142,19 @@ def test_cpp_facade_compiles():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-"],
                        input=src, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_jni_shim_type_checks_against_the_abi():
+    """bindings/jni/matrel_jni.cpp cannot be built here (no JDK); with a stand-in <jni.h> that declares only what the shim uses
+    (tests/cpp/jni_stub) g++ still checks every call it makes into include/matrel.h, so the shim cannot drift from the ABI."""
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Wno-comment", "-Werror",
+                        "-I", os.path.join(ROOT, "tests", "cpp", "jni_stub"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "bindings", "jni", "matrel_jni.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_header_is_plain_c():
+    """include/matrel.h is consumable from C (the cgo / JNI / ctypes boundary): gcc -std=c99 parses it."""
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-x", "c", os.path.join(ROOT, "include", "matrel.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
