@@ -127,98 +127,135 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference ALGORITHM restated on host cores (oracle/)
+#
+# Both legs run in a SUBPROCESS (`bench.py --_cpu-worker ...`) whose environment pins every BLAS / OpenMP pool to one
+# thread BEFORE numpy loads, and whose parallelism is one forked worker PROCESS per host core.  (Round 1 ran 128 Python
+# threads into the numpy-bundled OpenBLAS, which is built for 64: "precompiled NUM_THREADS exceeded" -> heap corruption
+# -> rc 134 / 139 on the 128-thread GPU hosts, and a 4.5x swing of the reported baseline.)  The GPU process itself never
+# runs the CPU legs.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n: int, blk: int, budget_s: float = 20.0):
-    """matrixMultiplyGeneral restated on the host cores the way Spark local[*] runs it: one task per
-    output block (i, j), `cpu_count` tasks in flight, each task single-threaded -- for every k:
-    MLMatrixSerializer copy-in of A(i,k), B(k,j), a fresh C + dgemm per pair (MLMatrix.multiply,
-    OpenBLAS 0.3.30 = the best case a netlib-native install reaches), pairwise LocalMatrix.add,
-    serializer copy-out.  Bounded sample of the N x N workload (as many output blocks as fit the
-    time budget); GFLOP/s = sample flops / wall seconds.  Upper bound on the reference's speed: no
-    Spark scheduling, shuffle, Kryo or GC is modelled."""
+_W = {}
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _cpu_task(ij):
+    """One Spark task of matrixMultiplyGeneral = one output block (i, j): for every k the MLMatrixSerializer copy-in of
+    A(i,k) and B(k,j) (:50-69), a fresh C + dgemm per pair (MLMatrix.multiply :100-104 -> BLAS.gemm), the pairwise
+    LocalMatrix.add of reduceByKey (:255), and the serializer copy-out (:26-48)."""
+    O, nb, A, B = _W["O"], _W["nb"], _W["A"], _W["B"]
+    i, j = ij
+    acc = None
+    for k in range(nb):
+        a = O.deserialize(O.serialize(A[(i + k) % nb]))
+        b = O.deserialize(O.serialize(B[(k + j) % nb]))
+        p = O.matrixMultiplication(a, b)
+        acc = p if acc is None else O.add(acc, p)
+    return float(O.serialize(acc)[5][0])
+
+
+def _cpu_worker_main(mode: str, n: int, blk: int, steps: int, warmup: int, budget_s: float):
+    """Runs inside the subprocess; prints one JSON document."""
     import numpy as np
-    from concurrent.futures import ThreadPoolExecutor
-    from threadpoolctl import threadpool_limits
-    from oracle import matrel_oracle as O
     nb = n // blk
-    cores = os.cpu_count() or 1
-    rng = np.random.default_rng(42)
-    # timing inputs: U(0,1) like DenseMatrix.rand (values do not change dgemm's speed)
-    Arow = {}
-    Bcol = {}
-
-    def getA(i, k):
-        if (i, k) not in Arow:
-            Arow[(i, k)] = O.DenseMatrix(blk, blk, rng.random(blk * blk))
-        return Arow[(i, k)]
-
-    def getB(k, j):
-        if (k, j) not in Bcol:
-            Bcol[(k, j)] = O.DenseMatrix(blk, blk, rng.random(blk * blk))
-        return Bcol[(k, j)]
-
-    def task(ij):
-        i, j = ij
-        acc = None
-        for k in range(nb):
-            a = O.deserialize(O.serialize(Arow[(i, k)]))     # MLMatrixSerializer copy-in (:50-69)
-            b = O.deserialize(O.serialize(Bcol[(k, j)]))
-            p = O.matrixMultiplication(a, b)                 # fresh C + dgemm
-            acc = p if acc is None else O.add(acc, p)        # reduceByKey(LocalMatrix.add)
-        return float(O.serialize(acc)[5][0])                 # copy-out (:26-48)
-
-    task_flops = 2.0 * blk * blk * blk * nb
-    with threadpool_limits(limits=1, user_api="blas"):
-        for k in range(nb):
-            getA(0, k), getB(k, 0)
-        task((0, 0))                                         # warm-up (untimed)
+    cores = host_cores()
+    if mode == "f2j":
+        from oracle import c_port
+        if not c_port.available():
+            print(json.dumps({"error": "oracle/liboracle.so not built"}))
+            return
+        threads = c_port.max_threads()
+        ntasks = min(nb * nb, threads)
+        rng = np.random.default_rng(7)
+        uniq = [rng.random(blk * blk) for _ in range(2 * nb)]          # block values do not change dgemm's speed
+        A = [uniq[(i + k) % nb] for i in range(nb) for k in range(nb)]
+        B = [uniq[nb + (k + j) % nb] for k in range(nb) for j in range(nb)]
         t0 = time.perf_counter()
-        task((0, 0))
-        t1 = time.perf_counter() - t0                        # one single-threaded task
-        waves = max(1, int(budget_s / max(t1 * 1.5, 1e-3)))
-        ntasks = min(nb * nb, cores * waves)
-        todo = [(t // nb, t % nb) for t in range(ntasks)]
-        for (i, j) in todo:
-            for k in range(nb):
-                getA(i, k), getB(k, j)
-        with ThreadPoolExecutor(max_workers=min(cores, ntasks)) as pool:
+        c_port.block_multiply_f2j(A, B, nb, blk, 1, 1, 1)              # calibrate: one block pair, one thread
+        t_pair = time.perf_counter() - t0
+        nk = max(1, min(nb, int(budget_s / max(t_pair * 6.0, 1e-3))))   # all-core runs are ~3x slower per pair than one thread alone
+        t0 = time.perf_counter()
+        c_port.block_multiply_f2j(A, B, nb, blk, ntasks, threads, nk)
+        wall = time.perf_counter() - t0
+        fl = ntasks * 2.0 * blk ** 3 * nk
+        print(json.dumps({"value": fl / wall / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                          "sample": f"{ntasks} of {nb * nb} output blocks x first {nk} of {nb} k-blocks in {wall:.1f} s, reference-BLAS "
+                                    f"(F2J-equivalent) dgemm loop nest, {threads} OpenMP threads (oracle/oracle.c)"}))
+        return
+    import multiprocessing as mp
+    from oracle import matrel_oracle as O
+    rng = np.random.default_rng(42)
+    # timing inputs: U(0,1) like DenseMatrix.rand (values do not change dgemm's speed); 2 nb distinct blocks are shared
+    # copy-on-write by the forked workers and rotated so that every task touches nb different A and nb different B blocks
+    _W.update(O=O, nb=nb,
+              A=[O.DenseMatrix(blk, blk, rng.random(blk * blk)) for _ in range(nb)],
+              B=[O.DenseMatrix(blk, blk, rng.random(blk * blk)) for _ in range(nb)])
+    task_flops = 2.0 * blk * blk * blk * nb
+    _cpu_task((0, 0))                                          # warm-up (untimed)
+    t0 = time.perf_counter()
+    _cpu_task((0, 0))
+    t1 = time.perf_counter() - t0                              # one single-threaded task on an otherwise idle host
+    # under full load a task runs ~2-4x slower than alone (shared L3 / DRAM bandwidth): size the sample for that
+    waves = max(1, int(budget_s / max(t1 * 3.0, 1e-3)))
+    ntasks = min(nb * nb, cores * waves)
+    nproc = min(cores, ntasks)
+    todo = [(t // nb, t % nb) for t in range(ntasks)]
+    out = []
+    with mp.get_context("fork").Pool(nproc) as pool:
+        pool.map(_cpu_task, todo[:nproc])                      # every worker process has started and touched its pages
+        for s in range(warmup + steps):
             t0 = time.perf_counter()
-            res = list(pool.map(task, todo))
+            res = pool.map(_cpu_task, todo, chunksize=1)
             wall = time.perf_counter() - t0
-    return {"value": ntasks * task_flops / wall / 1e9, "unit": UNIT, "cores": int(min(cores, ntasks)), "kind": "port",
-            "sample": f"{ntasks} of {nb * nb} output blocks of the {n}x{n}/{blk} multiply in {wall:.1f} s: one "
-                      f"single-threaded task per output block, {min(cores, ntasks)} tasks in flight (host cpu_count={cores}); "
-                      "per pair: serializer copy-in, fresh C + OpenBLAS dgemm, LocalMatrix.add; single task = "
-                      f"{t1:.2f} s ({task_flops / t1 / 1e9:.1f} GFLOP/s/core)",
-            "seconds": wall, "flops": ntasks * task_flops, "checksum": res[0]}
+            if s >= warmup:
+                out.append({"seconds": wall, "flops": ntasks * task_flops, "checksum": res[0]})
+    tot_f = sum(r["flops"] for r in out)
+    tot_t = sum(r["seconds"] for r in out)
+    print(json.dumps({"value": tot_f / tot_t / 1e9, "unit": UNIT, "cores": int(nproc), "kind": "port",
+                      "sample": f"{ntasks} of {nb * nb} output blocks of the {n}x{n}/{blk} multiply per step, {len(out)} timed step(s) "
+                                f"of {tot_t / max(1, len(out)):.1f} s: one single-threaded task (process) per output block, {nproc} in flight "
+                                f"(host cores={cores}); per pair: serializer copy-in, fresh C + OpenBLAS dgemm (1 thread), LocalMatrix.add; "
+                                f"a single task on the idle host = {t1:.2f} s ({task_flops / t1 / 1e9:.1f} GFLOP/s/core)",
+                      "seconds": tot_t, "flops": tot_f, "steps": len(out), "checksum": out[0]["checksum"] if out else None}))
+
+
+def _run_cpu_worker(mode: str, n: int, blk: int, steps: int, warmup: int, budget_s: float, timeout_s: float = 1500.0):
+    env = dict(os.environ)
+    cores = host_cores()
+    one = "1" if mode != "f2j" else str(cores)
+    for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "VECLIB_MAXIMUM_THREADS"):
+        env[k] = one
+    if mode != "f2j":
+        env["OPENBLAS_NUM_THREADS"] = "1"
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):   # not a torchrun rank
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--_cpu-worker", mode, "--n", str(n), "--blk", str(blk),
+           "--steps", str(steps), "--warmup", str(warmup), "--cpu-budget", str(budget_s)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout_s, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError(f"cpu worker ({mode}) rc={r.returncode}: {(r.stderr or r.stdout)[-400:]}")
+    return json.loads(lines[-1])
+
+
+def cpu_reference_sample(n: int, blk: int, budget_s: float = 20.0, steps: int = 1, warmup: int = 0):
+    """matrixMultiplyGeneral restated on the host cores the way Spark local[*] runs it: one task per output block (i, j),
+    one single-threaded worker process per host core.  Bounded sample of the N x N workload (as many output blocks as fit
+    the time budget, the whole multiply on a 128-core host); GFLOP/s = sample flops / wall seconds.  Upper bound on the
+    reference's speed: no Spark scheduling, shuffle, Kryo or GC is modelled, and dgemm is OpenBLAS (the best case a
+    netlib-native install reaches)."""
+    return _run_cpu_worker("port", n, blk, steps, warmup, budget_s)
 
 
 def cpu_f2j_sample(n: int, blk: int, budget_s: float = 8.0):
-    """Same algorithm with the pure-loop reference-BLAS dgemm (what netlib-java's F2jBLAS runs when no
-    native BLAS is installed = stock Spark 2.1.0), oracle/oracle.c, OpenMP threads = host cores; one wave
-    of output blocks."""
-    import numpy as np
-    from oracle import c_port
-    if not c_port.available():
-        return None
-    nb = n // blk
-    threads = c_port.max_threads()
-    ntasks = min(nb * nb, threads)
-    rng = np.random.default_rng(7)
-    uniq = [rng.random(blk * blk) for _ in range(2 * nb)]          # block values do not change dgemm's speed
-    A = [uniq[(i + k) % nb] for i in range(nb) for k in range(nb)]
-    B = [uniq[nb + (k + j) % nb] for k in range(nb) for j in range(nb)]
-    t0 = time.perf_counter()
-    c_port.block_multiply_f2j(A, B, nb, blk, 1, 1, 1)              # calibrate: one block pair, one thread
-    t_pair = time.perf_counter() - t0
-    nk = max(1, min(nb, int(budget_s / max(t_pair * 6.0, 1e-3))))   # all-core runs are ~3x slower per pair than one thread alone
-    t0 = time.perf_counter()
-    c_port.block_multiply_f2j(A, B, nb, blk, ntasks, threads, nk)
-    wall = time.perf_counter() - t0
-    fl = ntasks * 2.0 * blk ** 3 * nk
-    return {"value": fl / wall / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{ntasks} of {nb * nb} output blocks x first {nk} of {nb} k-blocks in {wall:.1f} s, reference-BLAS "
-                      f"(F2J-equivalent) dgemm loop nest, {threads} OpenMP threads (oracle/oracle.c)"}
+    """Same algorithm with the pure-loop reference-BLAS dgemm (what netlib-java's F2jBLAS runs when no native BLAS is
+    installed = stock Spark 2.1.0), oracle/oracle.c, OpenMP threads = host cores; one wave of output blocks."""
+    return _run_cpu_worker("f2j", n, blk, 1, 0, budget_s)
 
 
 def run_reference(args):
@@ -226,22 +263,15 @@ def run_reference(args):
     if rank != 0:
         return
     n, blk = args.n, args.blk
-    vals = []
-    last = None
-    per_step_budget = max(2.0, 120.0 / max(1, args.steps + args.warmup))
-    for s in range(args.warmup + args.steps):
-        r = cpu_reference_sample(n, blk, budget_s=per_step_budget)
-        if s >= args.warmup:
-            vals.append(r)
-        last = r
-    tot_f = sum(r["flops"] for r in vals)
-    tot_t = sum(r["seconds"] for r in vals)
-    v = tot_f / tot_t / 1e9
+    # each step = a bounded sample of the workload; the whole --steps/--warmup run is sized to end within ~2.5 minutes
+    per_step_budget = max(2.0, 150.0 / max(1, args.steps + args.warmup))
+    r = cpu_reference_sample(n, blk, budget_s=per_step_budget, steps=args.steps, warmup=args.warmup)
+    v = r["value"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * (2.0 * n ** 3 / (v * 1e9)), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{n}x{n} fp64 dense multiply, {blk}-block (reference algorithm on host cores)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -425,8 +455,12 @@ def run_ours(args):
                 s.set_option("gemm_algo", 0)
         s.stop()
 
-    cpu = cpu_reference_sample(n, blk, budget_s=args.cpu_budget)
-    cpu.pop("seconds", None); cpu.pop("flops", None); cpu.pop("checksum", None)
+    try:
+        cpu = cpu_reference_sample(n, blk, budget_s=args.cpu_budget)
+        for k_ in ("seconds", "flops", "checksum", "steps"):
+            cpu.pop(k_, None)
+    except Exception as e:  # the CPU leg runs in its own process; whatever happens there, the GPU line is printed
+        cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": "cpu worker failed", "error": str(e)[-300:]}
     try:
         cpu["f2j"] = cpu_f2j_sample(n, blk)
     except Exception as e:  # the secondary baseline must never take the bench line down
@@ -467,7 +501,10 @@ def main():
     ap.add_argument("--ozaki-slices", type=int, default=7)
     ap.add_argument("--tc-algo", type=int, default=4, choices=(2, 4), help="tcgen05 fp64 emulation reported beside the headline")
     ap.add_argument("--crt-moduli", type=int, default=16)
+    ap.add_argument("--_cpu-worker", dest="cpu_worker", default=None, choices=("port", "f2j"), help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_worker:
+        return _cpu_worker_main(args.cpu_worker, args.n, args.blk, args.steps, args.warmup, args.cpu_budget)
     if args.impl == "reference":
         run_reference(args)
     else:
