@@ -28,13 +28,6 @@ METRIC = "fp64 block-matmul GFLOP/s at N=16384"
 UNIT = "GFLOP/s"
 
 
-def tc_algo_name(args):
-    if getattr(args, "tc_algo", 4) == 4:
-        return ("Ozaki-II, %d coprime moduli <= 256: int8 residue GEMMs on tcgen05.mma kind::i8 (exact s32 TMEM accumulators), "
-                "CRT reconstruction to fp64" % getattr(args, "crt_moduli", 16))
-    return "Ozaki-I, %d balanced int8 slices, tcgen05.mma kind::i8 (s32 TMEM accumulators), fp64 epilogue" % getattr(args, "ozaki_slices", 7)
-
-
 def fp64_peak_tflops():
     """Roofline denominator for the fp64 tensor pipe: MEASURED_PEAKS.json has no fp64 entry, so the
     measured DMMA peak of tools/fp64_peak.cu (profiles/fp64_peaks_r01.jsonl) is used."""
@@ -280,6 +273,43 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def tc_peaks():
+    """Measured tcgen05 peaks of tools/tc_peak.cu (profiles/tc_peaks_r02.jsonl): {bench: value}."""
+    out = {}
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "tc_peaks_r02.jsonl")):
+            if line.startswith("{"):
+                d = json.loads(line)
+                out[d["bench"]] = d["value"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return out
+
+
+def int8_peak_tops():
+    pk = tc_peaks()
+    if "tcgen05_i8_sustained" in pk:
+        return pk["tcgen05_i8_sustained"], ("profiles/tc_peaks_r02.jsonl tcgen05_i8_sustained (tools/tc_peak.cu: back-to-back 128x256x32 kind::i8 MMAs "
+                                            "on shared-memory operands, all SMs, ~3 s; MEASURED_PEAKS.json has no int8 entry)")
+    try:
+        bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+        return 2.0 * bf16, "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2 x bf16 dense on this part; no int8 microbenchmark file)"
+    except (OSError, ValueError, KeyError):
+        return 2.0 * 1400.0, "2 x the profiling guide's sustained bf16 fallback (1.4 PFLOP/s)"
+
+
+def time_multiply(torch, stream, A, B, n, blk, steps):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        e0.record(stream)
+        C = A.matrixMultiply(n, n, B, n, n, blk)
+        e1.record(stream)
+        del C
+    torch.cuda.synchronize()
+    ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    return sum(ms) / len(ms)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -297,16 +327,18 @@ def run_ours(args):
 
     if world > 1:
         from matrel_b200 import distributed as dist_mm
-        return dist_mm.bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample)
+        return dist_mm.bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample, int8_peak_tops)
 
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         s = mb.MatfastSession(device=local_rank, stream=stream.cuda_stream)
+        s.set_option("gemm_algo", args.algo)
+        s.set_option("crt_moduli", args.crt_moduli)
         A = s.rand(n, n, blk, 42)
         B = s.rand(n, n, blk, 43)
         s.sync()
 
-        # ---- device-resident: value + roofline (CUDA events on the launching stream)
+        # ---- device-resident: value (CUDA events on the launching stream around whole operator calls)
         sampler = ClockSampler(local_rank)
         sampler.start()
         for _ in range(args.warmup):
@@ -314,72 +346,89 @@ def run_ours(args):
             del C
         s.sync()
         s.reset_stats()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         torch.cuda.synchronize()
         sampler.mark()
         t_wall0 = time.perf_counter()
-        for e0, e1 in evs:
-            e0.record(stream)
-            C = A.matrixMultiply(n, n, B, n, n, blk)
-            e1.record(stream)
-            del C
-        torch.cuda.synchronize()
+        ms_per_step = time_multiply(torch, stream, A, B, n, blk, args.steps)
         t_wall = time.perf_counter() - t_wall0
         clocks = sampler.stop()
-        ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-        ms_per_step = sum(ms) / len(ms)
         st = s.stats()
         launches_per_step = st["kernel_launches"] / args.steps
-        gemm_launches_per_step = st["gemm_launches"] / args.steps
+        on_tc = st["tc_gemm_launches"] > 0
 
-        # GEMM kernel alone (events inside the library, around the launch)
+        # ---- the dominant kernel alone (events inside the library, around its launches)
         s.set_option("time_kernels", 1)
         s.reset_stats()
-        for _ in range(max(3, args.steps)):
+        reps = max(3, min(args.steps, 10))
+        for _ in range(reps):
             C = A.matrixMultiply(n, n, B, n, n, blk)
             del C
         st2 = s.stats()
         s.set_option("time_kernels", 0)
-        kern_ms = st2["gemm_ms_total"] / st2["gemm_launches"]
-        peak, peak_src = fp64_peak_tflops()
-        achieved = flops / (kern_ms * 1e-3) / 1e12
+        dpeak, dpeak_src = fp64_peak_tflops()
+        if on_tc:
+            kern_ms = st2["tc_gemm_ms_total"] / reps
+            ipeak, ipeak_src = int8_peak_tops()
+            ach = st2["tc_int8_ops"] / (kern_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": ipeak, "unit": "TFLOP/s", "frac": ach / ipeak, "traffic": None,
+                        "op": "int8 multiply-add x 2 (TOPS) on tcgen05.mma kind::i8, s32 accumulators in TMEM",
+                        "kernel": "ozaki_gemm_i8_kernel (persistent, TMA -> 4-stage smem ring -> UTCIMMA 128x256x32 -> TMEM -> residue epilogue)",
+                        "kernel_ms": kern_ms, "launches_per_step": 1.0,
+                        "algorithmic": f"{args.crt_moduli} moduli x 2*N^3 = {st2['tc_int8_ops']:.4g} int8 ops per launch (one launch = all moduli x all tiles)",
+                        "peak_source": ipeak_src,
+                        "fp64_equivalent": {"achieved": flops / (ms_per_step * 1e-3) / 1e12, "dmma_peak": dpeak, "x_dmma_roof": flops / (ms_per_step * 1e-3) / 1e12 / dpeak,
+                                            "note": "whole multiply (absmax + residues + int8 GEMM + CRT) as fp64 flop/s against the measured native-fp64 (DMMA) roof"}}
+        else:
+            kern_ms = st2["gemm_ms_total"] / max(1, st2["gemm_launches"])
+            ach = flops / (kern_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": dpeak, "unit": "TFLOP/s", "frac": ach / dpeak,
+                        "traffic": (dram_traffic_per_launch(n) or {}).get("bytes"), "traffic_detail": dram_traffic_per_launch(n),
+                        "kernel": "gemm_f64_dmma_kernel<128,128,2,4,5>", "kernel_ms": kern_ms, "launches_per_step": 1.0,
+                        "algorithmic": f"2*N^3 = {flops:.4g} flop per launch (whole block multiply, K reduction fused)", "peak_source": dpeak_src}
 
-        # ---- the same multiply on the 5th-gen tensor cores: Ozaki fp64 emulation on tcgen05 kind::i8 (gemm_algo = 4: CRT
-        #      residues, or 2: digit slices), reported beside the native-fp64 headline together with its measured deviation
-        #      from the DMMA result
-        ozaki = None
+        # ---- host-side check of the timed configuration: one output block against numpy fp64 on the host
+        check = None
         try:
-            Cref = A.matrixMultiply(n, n, B, n, n, blk)
-            s.set_option("gemm_algo", args.tc_algo)
-            s.set_option("ozaki_slices", args.ozaki_slices)
-            s.set_option("crt_moduli", args.crt_moduli)
-            for _ in range(2):
-                C2 = A.matrixMultiply(n, n, B, n, n, blk)
-                del C2
-            s.sync()
-            oz_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            for e0, e1 in oz_evs:
-                e0.record(stream)
-                C2 = A.matrixMultiply(n, n, B, n, n, blk)
-                e1.record(stream)
-                if e0 is not oz_evs[-1][0]:
-                    del C2
-            torch.cuda.synchronize()
-            oz_ms = sum(e0.elapsed_time(e1) for e0, e1 in oz_evs) / len(oz_evs)
-            worst = 0.0
-            for key in [(0, 0), (nb // 2, nb // 3), (nb - 1, nb - 1)]:
-                a_, b_ = Cref.get_block(*key).values, C2.get_block(*key).values
-                worst = max(worst, float(np.max(np.abs(a_ - b_)) / np.max(np.abs(a_))))
-            ngemm = args.crt_moduli if args.tc_algo == 4 else args.ozaki_slices * (args.ozaki_slices + 1) // 2
-            ozaki = {"algo": tc_algo_name(args),
-                     "value": flops / (oz_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": oz_ms,
-                     "int8_gemms_per_multiply": ngemm, "int8_tensor_TOPS": ngemm * flops / (oz_ms * 1e-3) / 1e12,
-                     "max_rel_dev_vs_dmma_fp64": worst, "x_dmma_roof": flops / (oz_ms * 1e-3) / 1e12 / fp64_peak_tflops()[0]}
-            del C2, Cref
-        except Exception as e:  # never take the headline down
-            ozaki = {"error": str(e)}
-        finally:
-            s.set_option("gemm_algo", 0)
+            from threadpoolctl import threadpool_limits
+            Ck = A.matrixMultiply(n, n, B, n, n, blk)
+            i_, j_ = nb // 2, nb // 3
+            with threadpool_limits(limits=16, user_api="blas"):
+                want = sum(A.get_block(i_, k).to_numpy() @ B.get_block(k, j_).to_numpy() for k in range(nb))
+            got = Ck.get_block(i_, j_).to_numpy()
+            check = {"block": [i_, j_], "max_rel_err_vs_host_fp64": float(np.max(np.abs(got - want)) / np.max(np.abs(want)))}
+            del Ck
+        except Exception as e:
+            check = {"error": str(e)[-200:]}
+
+        # ---- the exact native-fp64 kernel (gemm_algo 1, DMMA) beside the headline, with its own roofline fraction
+        dmma = None
+        if on_tc:
+            try:
+                s.set_option("gemm_algo", 1)
+                for _ in range(2):
+                    C = A.matrixMultiply(n, n, B, n, n, blk)
+                    del C
+                s.sync()
+                d_steps = max(3, min(args.steps, 5))
+                d_ms = time_multiply(torch, stream, A, B, n, blk, d_steps)
+                Cd = A.matrixMultiply(n, n, B, n, n, blk)
+                s.set_option("gemm_algo", args.algo)
+                Ct = A.matrixMultiply(n, n, B, n, n, blk)
+                worst = 0.0
+                for key in [(0, 0), (nb // 2, nb // 3), (nb - 1, nb - 1)]:
+                    a_, b_ = Cd.get_block(*key).values, Ct.get_block(*key).values
+                    worst = max(worst, float(np.max(np.abs(a_ - b_)) / np.max(np.abs(a_))))
+                del Cd, Ct
+                tr = dram_traffic_per_launch(n)
+                dmma = {"algo": "gemm_algo 1: gemm_f64_dmma_kernel (TMA -> 5-stage ring -> mma.sync m8n8k4 f64)", "value": flops / (d_ms * 1e-3) / 1e9,
+                        "unit": UNIT, "ms_per_step": d_ms, "steps": d_steps,
+                        "roofline": {"bound": "tensor", "achieved": flops / (d_ms * 1e-3) / 1e12, "peak": dpeak, "unit": "TFLOP/s",
+                                     "frac": flops / (d_ms * 1e-3) / 1e12 / dpeak, "traffic": (tr or {}).get("bytes"), "peak_source": dpeak_src},
+                        "max_rel_dev_tcgen05_vs_dmma": worst}
+            except Exception as e:
+                dmma = {"error": str(e)[-200:]}
+            finally:
+                s.set_option("gemm_algo", args.algo)
 
         # ---- end to end through the public API with pinned HOST buffers
         hostA = {k: A.get_block(*k) for k in A.block_ids()}
@@ -402,7 +451,8 @@ def run_ours(args):
         def e2e_step():
             # block row t of A and block column t of B are uploaded alternately; every put_block is an async copy on
             # the ingest stream tagged with an event, the multiply launches chunk after chunk as the operands each
-            # chunk needs have landed, and finished blocks of C stream back on the egress stream meanwhile
+            # chunk needs have landed (residues of a block row / column as soon as it is complete, then the int8 GEMM
+            # + CRT of the output blocks it unlocks), and finished blocks of C stream back on the egress stream meanwhile
             dbg = os.environ.get("MATREL_E2E_DEBUG")
             tq = [time.perf_counter()]
             dA, dB = s.emptyDataset(), s.emptyDataset()
@@ -425,34 +475,39 @@ def run_ours(args):
                     s.stats()["kernel_launches"]), file=sys.stderr, flush=True)
             return dC
 
-        e2e_warm = min(args.warmup, 2)
-        for _ in range(e2e_warm):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_steps = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-        checksum = float(outbuf[(0, 0)][0])
-        # the same end-to-end step with the tcgen05 Ozaki kernel (reported inside "tcgen05_ozaki")
-        if isinstance(ozaki, dict) and "error" not in ozaki:
-            try:
-                s.set_option("gemm_algo", args.tc_algo)
+        def e2e_time():
+            for _ in range(min(args.warmup, 2)):
                 e2e_step()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(e2e_steps):
-                    e2e_step()
-                torch.cuda.synchronize()
-                oz_e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-                ozaki["e2e"] = {"value": flops / (oz_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": oz_e2e_ms,
-                                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+            torch.cuda.synchronize()
+            k_ = max(1, min(args.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(k_):
+                e2e_step()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / k_ * 1e3, k_
+
+        e2e_ms, e2e_steps = e2e_time()
+        checksum = float(outbuf[(0, 0)][0])
+        e2e_blk = outbuf[(nb // 2, nb // 3)].copy()
+        if isinstance(check, dict) and "error" not in check:
+            try:   # the end-to-end result is the same product: compare the same block with the resident run's
+                Ck = A.matrixMultiply(n, n, B, n, n, blk)
+                ref_blk = Ck.get_block(nb // 2, nb // 3).values
+                check["e2e_block_equals_resident"] = bool(np.array_equal(ref_blk, e2e_blk))
+                check["e2e_block_max_rel_dev"] = float(np.max(np.abs(ref_blk - e2e_blk)) / np.max(np.abs(ref_blk)))
+                del Ck
             except Exception as e:
-                ozaki["e2e"] = {"error": str(e)}
+                check["e2e_error"] = str(e)[-200:]
+        if isinstance(dmma, dict) and "error" not in dmma:
+            try:
+                s.set_option("gemm_algo", 1)
+                d_e2e_ms, _ = e2e_time()
+                dmma["e2e"] = {"value": flops / (d_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": d_e2e_ms,
+                               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+            except Exception as e:
+                dmma["e2e"] = {"error": str(e)[-200:]}
             finally:
-                s.set_option("gemm_algo", 0)
+                s.set_option("gemm_algo", args.algo)
         s.stop()
 
     try:
@@ -464,7 +519,9 @@ def run_ours(args):
     try:
         cpu["f2j"] = cpu_f2j_sample(n, blk)
     except Exception as e:  # the secondary baseline must never take the bench line down
-        cpu["f2j"] = {"error": str(e)}
+        cpu["f2j"] = {"error": str(e)[-300:]}
+    algo_name = ("auto -> Ozaki-II on tcgen05 (int8 residue GEMMs modulo %d coprime moduli + CRT; device-side guard, DMMA fallback)" % args.crt_moduli
+                 if on_tc else "dmma_fp64")
     line = {
         "metric": METRIC, "value": flops / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -472,19 +529,16 @@ def run_ours(args):
         "config": {"workload": f"{n}x{n} fp64 dense multiply, {blk}-block, 1xB200 (BASELINE metric size)",
                    "inputs": "U(0,1) java.util.Random streams, every block present, column-major",
                    "l2": f"inputs 2 x {n * n * 8 / 2**30:.0f} GiB + output {n * n * 8 / 2**30:.0f} GiB >> 126 MB L2; no flush needed",
-                   "gemm_algo": "dmma_fp64", "wall_ms_per_step": t_wall / args.steps * 1e3, "c00": checksum},
+                   "gemm_algo": algo_name, "wall_ms_per_step": t_wall / args.steps * 1e3, "c00": checksum},
         "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "steps": e2e_steps},
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "gpu_launches_per_step": launches_per_step,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": (dram_traffic_per_launch(n) or {}).get("bytes"), "traffic_detail": dram_traffic_per_launch(n), "kernel": "gemm_f64_dmma_kernel<128,128,2,4,5>", "kernel_ms": kern_ms,
-                     "launches_per_step": gemm_launches_per_step,
-                     "algorithmic": f"2*N^3 = {flops:.4g} flop per launch (whole block multiply, K reduction fused)",
-                     "peak_source": peak_src},
+        "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
-        "tcgen05_ozaki": ozaki,
+        "check": check,
+        "dmma_fp64": dmma,
     }
     print(json.dumps(line), flush=True)
 
@@ -499,7 +553,8 @@ def main():
     ap.add_argument("--blk", type=int, default=BLK_DEFAULT)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ozaki-slices", type=int, default=7)
-    ap.add_argument("--tc-algo", type=int, default=4, choices=(2, 4), help="tcgen05 fp64 emulation reported beside the headline")
+    ap.add_argument("--algo", type=int, default=0, choices=(0, 1, 2, 4),
+                    help="gemm_algo of the headline: 0 = auto (tcgen05 Ozaki-II with the device-side guard), 1 = DMMA fp64")
     ap.add_argument("--crt-moduli", type=int, default=16)
     ap.add_argument("--_cpu-worker", dest="cpu_worker", default=None, choices=("port", "f2j"), help=argparse.SUPPRESS)
     args = ap.parse_args()

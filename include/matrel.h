@@ -60,9 +60,13 @@ typedef struct mr_block_desc {
 typedef struct mr_options {
   int32_t device;       /* CUDA device ordinal; -1 = current device */
   int32_t compat_bugs;  /* 1 = reproduce reference defects B3/B4; 0 = intended math */
-  int32_t gemm_algo;    /* 0 = auto (= 1), 1 = DMMA fp64 tensor-core kernel, 2 = Ozaki-I int8 tcgen05 kernel (digit slices),
-                           3 = 3xTF32 tcgen05 kernel (fp32 results), 4 = Ozaki-II int8 tcgen05 kernel (CRT residues;
-                           mr_set_option "crt_moduli" 6..16, default 16) */
+  int32_t gemm_algo;    /* 0 = auto: large regular dense products run on the tcgen05 tensor cores (Ozaki-II: int8 residue GEMMs +
+                           CRT, fp64-exact to 1e-14 on data of ordinary range), guarded on the device: Inf / NaN operands, a
+                           dynamic range of more than ~2^37 inside one row of A / column of B, K >= 2^17, irregular block grids
+                           and small products take the exact DMMA kernel instead;
+                           1 = DMMA fp64 tensor-core kernel (mma.sync m8n8k4 f64), always;
+                           2 = Ozaki-I int8 tcgen05 kernel (digit slices); 3 = 3xTF32 tcgen05 kernel (fp32 results);
+                           4 = Ozaki-II without the range guard (mr_set_option "crt_moduli" 6..16, default 16) */
   int32_t ozaki_slices; /* number of int8 slices for gemm_algo 2 (0 = default) */
   void* stream;         /* cudaStream_t to run on; NULL = a stream owned by the context */
 } mr_options;
@@ -71,7 +75,7 @@ typedef struct mr_options {
 MR_API mr_status mr_init(const mr_options* opts, mr_context** out);
 MR_API mr_status mr_shutdown(mr_context* ctx);
 MR_API mr_status mr_set_stream(mr_context* ctx, void* cuda_stream);
-/* keys: "compat_bugs", "gemm_algo", "ozaki_slices", "crt_moduli", "pipeline", "time_kernels", "gemm_variant" */
+/* keys: "compat_bugs", "gemm_algo", "ozaki_slices", "crt_moduli", "ozaki_scratch_mb", "pipeline", "time_kernels", "gemm_variant" */
 MR_API mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value);
 MR_API mr_status mr_sync(mr_context* ctx);
 MR_API const char* mr_last_error(void);
@@ -201,6 +205,9 @@ typedef struct mr_stats {
   double last_gemm_ms;      /* CUDA-event duration of the most recent GEMM kernel launch(es) */
   double gemm_ms_total;     /* sum of CUDA-event GEMM durations since reset (timing enabled only) */
   int64_t last_gemm_flops;
+  double tc_gemm_ms_total;  /* CUDA-event time of the tcgen05 int8 GEMM launches since reset (timing enabled only) */
+  int64_t tc_gemm_launches; /* multiplies that ran on the tcgen05 path since reset */
+  int64_t tc_int8_ops;      /* int8 multiply-add operations (x 2) of the most recent tcgen05 multiply */
 } mr_stats;
 MR_API mr_status mr_get_stats(mr_context* ctx, mr_stats* out);
 MR_API mr_status mr_reset_stats(mr_context* ctx);

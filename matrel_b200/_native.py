@@ -67,6 +67,9 @@ class mr_stats(C.Structure):
         ("last_gemm_ms", C.c_double),
         ("gemm_ms_total", C.c_double),
         ("last_gemm_flops", C.c_int64),
+        ("tc_gemm_ms_total", C.c_double),
+        ("tc_gemm_launches", C.c_int64),
+        ("tc_int8_ops", C.c_int64),
     ]
 
 

@@ -292,6 +292,8 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
     }
     CUDA_CHECK(cudaEventCreate(&ctx->ev0));
     CUDA_CHECK(cudaEventCreate(&ctx->ev1));
+    CUDA_CHECK(cudaEventCreate(&ctx->ev2));
+    CUDA_CHECK(cudaEventCreate(&ctx->ev3));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
@@ -341,6 +343,8 @@ mr_status mr_shutdown(mr_context* ctx) {
     if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
   });
@@ -371,6 +375,7 @@ mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
     else if (k == "gemm_algo") ctx->gemm_algo = static_cast<int>(value);
     else if (k == "ozaki_slices") ctx->ozaki_slices = static_cast<int>(value);
     else if (k == "crt_moduli") ctx->crt_moduli = static_cast<int>(value);
+    else if (k == "ozaki_scratch_mb") ctx->ozaki_scratch_mb = static_cast<int>(value);
     else if (k == "time_kernels") ctx->time_kernels = static_cast<int>(value);
     else if (k == "gemm_variant") ctx->force_variant = static_cast<int>(value);
     else if (k == "pipeline") ctx->pipeline = static_cast<int>(value);

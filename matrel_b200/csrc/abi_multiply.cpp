@@ -94,11 +94,10 @@ struct MultiplyPlanner {
 bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<double*>& cptr, int32_t blkSize, int64_t M,
                int64_t K, int64_t N, bool outer) {
   const bool tf32 = ctx->gemm_algo == 3;
-  const bool crt = ctx->gemm_algo == 4;
   const int S_eff = std::min(7, std::max(2, ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7));
   // s32 accumulator bound: up to S pairs x K terms of |digit product| <= 2^14 land in one accumulator
   if (M <= 0 || K <= 0 || N <= 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX / 2) return false;
-  if (crt ? K >= (1 << 17) : (!tf32 && K * S_eff >= (1 << 17))) return false;
+  if (!tf32 && K * S_eff >= (1 << 17)) return false;
   // Compact the block rows / columns that actually have output blocks (a rank of the process grid owns every pr-th
   // block row and pc-th block column: slicing and multiplying the absent ones would only produce zeros).
   std::map<int32_t, int32_t> crow, ccol;
@@ -138,12 +137,12 @@ bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<d
       if (!ia.count(g.a)) {
         ia[g.a] = 1;
         va.push_back(OzakiOperand{g.a->values.ptr<double>(), g.a->numRows, g.a->numCols, cr * blkSize, static_cast<int32_t>(k0),
-                                  static_cast<uint8_t>(g.a->isT)});
+                                  static_cast<uint8_t>(g.a->isT), {0}});
       }
       if (!ib.count(g.b)) {
         ib[g.b] = 1;
         vb.push_back(OzakiOperand{g.b->values.ptr<double>(), g.b->numRows, g.b->numCols, static_cast<int32_t>(k0), cc * blkSize,
-                                  static_cast<uint8_t>(g.b->isT)});
+                                  static_cast<uint8_t>(g.b->isT), {0}});
       }
     }
   }
@@ -153,10 +152,6 @@ bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<d
   if (tf32)
     CUDA_CHECK(tf32x3_gemm(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc, ctab.data(),
                            blkSize, static_cast<int>(nbr), static_cast<int>(nbc), &launches, ctx->stream));
-  else if (crt)
-    CUDA_CHECK(ozaki2_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc,
-                               ctx->crt_moduli > 0 ? ctx->crt_moduli : 16, ctab.data(), blkSize, static_cast<int>(nbr),
-                               static_cast<int>(nbc), &launches, &nonfinite, ctx->stream));
   else
     CUDA_CHECK(ozaki_gemm_f64(va.data(), static_cast<int>(va.size()), vb.data(), static_cast<int>(vb.size()), Mc, K, Nc,
                               ctx->ozaki_slices > 0 ? ctx->ozaki_slices : 7, ctab.data(), blkSize, static_cast<int>(nbr),
@@ -174,6 +169,277 @@ bool try_ozaki(mr_context* ctx, std::vector<OutPlan>& plans, const std::vector<d
   }
   return true;
 }
+
+// ------------------------------------------------------------------------------------------------
+// gemm_algo 0 (auto) / 4: the dense pairs through the Ozaki-II job engine (gemm_ozaki.cu), group by group.
+//
+// plan():    checks that the product fits the engine's regular-grid assumptions, assigns one residue slot per block row of A /
+//            block column of B that has output blocks, and turns every launch group (the chunks of a pipelined multiply, or the
+//            single group of a resident one) into jobs: which slots to prepare first, the tile list, the output-block table.
+//            Operands whose residues exceed the scratch budget are cut into (row panel x column panel) jobs that re-prepare.
+// upload_tables(): every table goes to the device up front (before the side streams fork).
+// run_group():     enqueues the jobs of one group on a stream.  No host synchronisation anywhere: see oz2_flag().
+// ------------------------------------------------------------------------------------------------
+struct Oz2Run {
+  struct Prep {
+    bool is_a = true;
+    int slot0 = 0, nslots = 0;
+    std::vector<OzakiOperand> blocks;
+    std::vector<int32_t> dims;
+    int max_rows = 1, max_cols = 1;
+    bool need_zero = true;
+    Buf d_blocks, d_dims;
+  };
+  struct Job {
+    int group = 0;
+    std::vector<Prep> preps;
+    std::vector<int2> tiles;
+    std::vector<double*> ctab;
+    Buf d_tiles, d_ctab;
+  };
+  mr_context* ctx = nullptr;
+  Oz2Engine* eng = nullptr;
+  std::vector<Job> jobs;
+  Buf d_maps;
+  int cap_r = 0, cap_c = 0;
+  int64_t int8_ops = 0;
+
+  Oz2Run() = default;
+  Oz2Run(const Oz2Run&) = delete;
+  Oz2Run& operator=(const Oz2Run&) = delete;
+  ~Oz2Run() {
+    if (eng) oz2_destroy(eng, ctx->stream);
+  }
+  const int* flag() const { return eng ? oz2_flag(eng) : nullptr; }
+
+  // Returns false when the multiply must stay on the exact kernel.  `group_of` may be rewritten to a single group (operands too
+  // large to keep every residue resident cannot be pipelined chunk by chunk).
+  bool plan(mr_context* c, const std::vector<OutPlan>& plans, const std::vector<size_t>& out_plan, const std::vector<double*>& cptr,
+            std::vector<int>& group_of, int& ngroups, int32_t blk, int64_t M, int64_t K, int64_t N, bool outer, bool guard) {
+    ctx = c;
+    if (M <= 0 || K <= 0 || N <= 0 || K >= (1 << 17) || out_plan.empty()) return false;
+    const int T = ctx->crt_moduli > 0 ? ctx->crt_moduli : 16;
+    const int ss = (blk + kOz2TileM - 1) / kOz2TileM * kOz2TileM;
+    std::map<int32_t, int> crow, ccol;
+    for (size_t oi : out_plan) {
+      crow.emplace(plans[oi].rid, 0);
+      ccol.emplace(plans[oi].cid, 0);
+    }
+    int i = 0;
+    for (auto& kv : crow) kv.second = i++;
+    i = 0;
+    for (auto& kv : ccol) kv.second = i++;
+    const int nr = static_cast<int>(crow.size()), nc = static_cast<int>(ccol.size());
+    if (static_cast<int64_t>(nr) * ss > INT32_MAX / 2 || static_cast<int64_t>(nc) * ss > INT32_MAX / 2) return false;
+    std::vector<int32_t> rdim(nr, -1), cdim(nc, -1);
+    std::vector<std::vector<const GemmSrc*>> asrc(nr), bsrc(nc);  // unique blocks per block row / column
+    std::map<const Block*, int> seen_a, seen_b;
+    for (size_t oi : out_plan) {
+      const OutPlan& o = plans[oi];
+      if (!o.spmm.empty() || !o.spsp.empty() || o.m <= 0 || o.n <= 0 || o.m > blk || o.n > blk) return false;
+      const int cr = crow[o.rid], cc = ccol[o.cid];
+      if (rdim[cr] < 0) rdim[cr] = o.m;
+      if (cdim[cc] < 0) cdim[cc] = o.n;
+      if (rdim[cr] != o.m || cdim[cc] != o.n) return false;
+      for (const GemmSrc& g : o.src) {
+        const int64_t k0 = outer ? 0 : static_cast<int64_t>(g.k) * blk;
+        if (g.a->numCols != g.b->numRows || g.a->numCols > blk || k0 + g.a->numCols > K) return false;
+        if (g.a->numRows != o.m || g.b->numCols != o.n) return false;
+        auto ia = seen_a.find(g.a);
+        if (ia == seen_a.end()) {
+          seen_a[g.a] = cr;
+          asrc[cr].push_back(&g);
+        } else if (ia->second != cr) {
+          return false;  // one block feeding two block rows: not a regular grid
+        }
+        auto ib = seen_b.find(g.b);
+        if (ib == seen_b.end()) {
+          seen_b[g.b] = cc;
+          bsrc[cc].push_back(&g);
+        } else if (ib->second != cc) {
+          return false;
+        }
+      }
+    }
+    // ---- capacity: everything resident, or (row panel x column panel) jobs within the scratch budget
+    auto panel_tiles = [&](int ncr, int ncc) {  // upper bound of a panel's tile count
+      const int64_t tm = static_cast<int64_t>(ncr) * (ss / kOz2TileM);
+      const int64_t tn = (static_cast<int64_t>(ncc) * ss + kOz2TileN - 1) / kOz2TileN;
+      return tm * tn;
+    };
+    const int64_t plane_cap_tiles = std::max<int64_t>(64, (2ll << 30) / (static_cast<int64_t>(T) * kOz2TileM * kOz2TileN));
+    const size_t budget = static_cast<size_t>(ctx->ozaki_scratch_mb > 0 ? ctx->ozaki_scratch_mb : 16384) << 20;
+    cap_r = nr;
+    cap_c = nc;
+    auto max_tiles_for = [&](int r, int cc_) { return static_cast<int>(std::min<int64_t>(plane_cap_tiles, panel_tiles(r, cc_))); };
+    while (oz2_scratch_bytes(blk, K, T, cap_r, cap_c, max_tiles_for(cap_r, cap_c)) > budget) {
+      if (cap_r == 1 && cap_c == 1) return false;
+      if (cap_r >= cap_c) cap_r = (cap_r + 1) / 2;
+      else cap_c = (cap_c + 1) / 2;
+    }
+    const bool resident = cap_r == nr && cap_c == nc;
+    if (!resident) {  // panels re-prepare their slots: one group, after every operand has landed
+      std::fill(group_of.begin(), group_of.end(), 0);
+      ngroups = 1;
+    }
+    const int64_t Kpad = (K + 127) / 128 * 128;
+    auto make_prep = [&](bool is_a, const std::vector<int>& ids /* compact ids, ascending */, int slot0) {
+      Prep p;
+      p.is_a = is_a;
+      p.slot0 = slot0;
+      p.nslots = static_cast<int>(ids.size());
+      int64_t area = 0, want = 0;
+      for (size_t s_ = 0; s_ < ids.size(); ++s_) {
+        const int id = ids[s_];
+        const int32_t base = static_cast<int32_t>((slot0 + static_cast<int>(s_)) * ss);
+        p.dims.push_back(is_a ? rdim[id] : cdim[id]);
+        want += static_cast<int64_t>(is_a ? rdim[id] : cdim[id]) * K;
+        for (const GemmSrc* g : (is_a ? asrc[id] : bsrc[id])) {
+          const Block* b = is_a ? g->a : g->b;
+          const int32_t k0 = outer ? 0 : g->k * blk;
+          p.blocks.push_back(OzakiOperand{b->values.ptr<double>(), b->numRows, b->numCols, is_a ? base : k0, is_a ? k0 : base,
+                                          static_cast<uint8_t>(b->isT), {0}});
+          p.max_rows = std::max(p.max_rows, b->numRows);
+          p.max_cols = std::max(p.max_cols, b->numCols);
+          area += static_cast<int64_t>(b->numRows) * b->numCols;
+        }
+      }
+      p.need_zero = !(area == want && K == Kpad);
+      return p;
+    };
+    auto runs_of = [](std::vector<int> ids) {  // ids -> maximal runs of consecutive values
+      std::sort(ids.begin(), ids.end());
+      std::vector<std::vector<int>> runs;
+      for (int id : ids) {
+        if (runs.empty() || runs.back().back() + 1 != id) runs.emplace_back();
+        runs.back().push_back(id);
+      }
+      return runs;
+    };
+    auto add_tiles = [&](Job& j, int rslot, int cslot, int m, int n) {
+      const int tm0 = rslot * ss / kOz2TileM, tm1 = (rslot * ss + m + kOz2TileM - 1) / kOz2TileM;
+      const int tn0 = cslot * ss / kOz2TileN, tn1 = (cslot * ss + n + kOz2TileN - 1) / kOz2TileN;
+      for (int a = tm0; a < tm1; ++a)
+        for (int b = tn0; b < tn1; ++b) j.tiles.push_back(make_int2(a, b));
+    };
+    auto finish_tiles = [&](Job& j) {
+      std::sort(j.tiles.begin(), j.tiles.end(), [](const int2& x, const int2& y) {
+        const int bx = x.y / 8, by = y.y / 8;  // bands of 8 n-tiles: the resident CTAs share A row- and B column-panels in L2
+        if (bx != by) return bx < by;
+        if (x.x != y.x) return x.x < y.x;
+        return x.y < y.y;
+      });
+      j.tiles.erase(std::unique(j.tiles.begin(), j.tiles.end(), [](const int2& x, const int2& y) { return x.x == y.x && x.y == y.y; }),
+                    j.tiles.end());
+      int8_ops += static_cast<int64_t>(j.tiles.size()) * T * 2ll * kOz2TileM * kOz2TileN * Kpad;
+    };
+    int max_tiles = 1;
+    if (resident) {
+      std::vector<char> rprep(nr, 0), cprep(nc, 0);
+      for (int gi = 0; gi < ngroups; ++gi) {
+        Job j;
+        j.group = gi;
+        j.ctab.assign(static_cast<size_t>(cap_r) * cap_c, nullptr);
+        std::vector<int> newr, newc;
+        for (size_t t = 0; t < out_plan.size(); ++t) {
+          if (group_of[t] != gi) continue;
+          const OutPlan& o = plans[out_plan[t]];
+          const int cr = crow[o.rid], cc = ccol[o.cid];
+          if (!rprep[cr]) {
+            rprep[cr] = 1;
+            newr.push_back(cr);
+          }
+          if (!cprep[cc]) {
+            cprep[cc] = 1;
+            newc.push_back(cc);
+          }
+          j.ctab[static_cast<size_t>(cr) * cap_c + cc] = cptr[out_plan[t]];
+          add_tiles(j, cr, cc, o.m, o.n);
+        }
+        if (j.tiles.empty()) continue;
+        for (auto& run : runs_of(newr)) j.preps.push_back(make_prep(true, run, run.front()));
+        for (auto& run : runs_of(newc)) j.preps.push_back(make_prep(false, run, run.front()));
+        finish_tiles(j);
+        max_tiles = std::max<int>(max_tiles, static_cast<int>(j.tiles.size()));
+        jobs.push_back(std::move(j));
+      }
+    } else {
+      std::map<std::pair<int, int>, size_t> at;  // (cr, cc) -> index into out_plan
+      for (size_t t = 0; t < out_plan.size(); ++t) at[{crow[plans[out_plan[t]].rid], ccol[plans[out_plan[t]].cid]}] = t;
+      for (int r0 = 0; r0 < nr; r0 += cap_r) {
+        const int r1 = std::min(nr, r0 + cap_r);
+        bool row_prepared = false;
+        for (int c0 = 0; c0 < nc; c0 += cap_c) {
+          const int c1 = std::min(nc, c0 + cap_c);
+          Job j;
+          j.group = 0;
+          j.ctab.assign(static_cast<size_t>(cap_r) * cap_c, nullptr);
+          for (int cr = r0; cr < r1; ++cr)
+            for (int cc = c0; cc < c1; ++cc) {
+              auto it = at.find({cr, cc});
+              if (it == at.end()) continue;
+              const OutPlan& o = plans[out_plan[it->second]];
+              j.ctab[static_cast<size_t>(cr - r0) * cap_c + (cc - c0)] = cptr[out_plan[it->second]];
+              add_tiles(j, cr - r0, cc - c0, o.m, o.n);
+            }
+          if (j.tiles.empty()) continue;
+          if (!row_prepared) {
+            std::vector<int> ids;
+            for (int cr = r0; cr < r1; ++cr) ids.push_back(cr);
+            j.preps.push_back(make_prep(true, ids, 0));
+            row_prepared = true;
+          }
+          std::vector<int> ids;
+          for (int cc = c0; cc < c1; ++cc) ids.push_back(cc);
+          j.preps.push_back(make_prep(false, ids, 0));
+          finish_tiles(j);
+          max_tiles = std::max<int>(max_tiles, static_cast<int>(j.tiles.size()));
+          jobs.push_back(std::move(j));
+        }
+      }
+    }
+    if (jobs.empty()) return false;
+    max_tiles = static_cast<int>(std::min<int64_t>(max_tiles, plane_cap_tiles));
+    cudaError_t e = oz2_create(&eng, blk, K, T, cap_r, cap_c, max_tiles, guard ? 1 : 0, ctx->stream);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      eng = nullptr;
+      jobs.clear();
+      return false;  // e.g. out of memory for the scratch: the exact kernel needs none
+    }
+    return true;
+  }
+
+  void upload_tables() {
+    size_t bytes = 0;
+    const void* hm = oz2_host_maps(eng, &bytes);
+    d_maps = upload_bytes(ctx, hm, bytes);
+    oz2_set_device_maps(eng, d_maps->p);
+    for (Job& j : jobs) {
+      for (Prep& p : j.preps) {
+        p.d_blocks = upload(ctx, p.blocks);
+        p.d_dims = upload(ctx, p.dims);
+      }
+      j.d_tiles = upload(ctx, j.tiles);
+      j.d_ctab = upload(ctx, j.ctab);
+    }
+  }
+
+  void run_group(int gi, cudaStream_t cs) {
+    const bool timed = ctx->time_kernels != 0;
+    double ms = 0.0;
+    for (Job& j : jobs) {
+      if (j.group != gi) continue;
+      for (Prep& p : j.preps)
+        CUDA_CHECK(oz2_prepare(eng, p.is_a, static_cast<const OzakiOperand*>(p.d_blocks->p), static_cast<int>(p.blocks.size()),
+                               p.max_rows, p.max_cols, p.slot0, p.nslots, static_cast<const int32_t*>(p.d_dims->p), p.need_zero, cs));
+      CUDA_CHECK(oz2_multiply(eng, static_cast<const int2*>(j.d_tiles->p), static_cast<int>(j.tiles.size()),
+                              static_cast<double* const*>(j.d_ctab->p), cs, timed ? &ms : nullptr, ctx->ev2, ctx->ev3));
+    }
+    note_launch(ctx, oz2_launches(eng));
+    if (timed) ctx->stats.tc_gemm_ms_total += ms;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Output blocks whose partial products are ALL low-density sparse x sparse (LocalMatrix.multiplySparseSparse,
@@ -372,8 +638,11 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
         wait_ready(ctx, *g.b);
       }
   };
+  // gemm_algo: 0 = auto (Ozaki-II on tcgen05 with the range guard when the product is large and regular, else DMMA), 1 = DMMA,
+  // 2 = Ozaki-I, 3 = 3xTF32, 4 = Ozaki-II without the range guard
+  const int algo = ctx->gemm_algo;
   bool ozaki_done = false;
-  if (!outs.empty() && (ctx->gemm_algo >= 2 && ctx->gemm_algo <= 4)) {
+  if (!outs.empty() && (algo == 2 || algo == 3)) {
     wait_all_sources();
     ozaki_done = try_ozaki(ctx, plans, cptr, blkSize, M, K, N, outer);
     if (ozaki_done) ctx->stats.last_gemm_flops = flops;
@@ -438,6 +707,12 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       }
       ngroups_dyn = gcur + 1;
     }
+    // The tcgen05 path (Ozaki-II residues + CRT) runs group by group in front of the DMMA launches, which then only execute
+    // when the engine's device flag reports operands it cannot represent.  Small products stay on the exact kernel in auto mode.
+    Oz2Run oz2;
+    bool use_oz2 = false;
+    if (algo == 4 || (algo == 0 && flops >= (1ll << 33)))
+      use_oz2 = oz2.plan(ctx, plans, out_plan, cptr, group_of, ngroups_dyn, blkSize, M, K, N, outer, algo == 0);
     auto grp = [&](const Keyed& k) { return group_of[k.t.out]; };
     std::sort(keyed.begin(), keyed.end(), [&](const Keyed& x, const Keyed& y) {
       const int gx = grp(x), gy = grp(y);
@@ -472,6 +747,11 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
         if (!pr.bT) pr.tmB = tmap_of(pr.B, pr.kdim, go.n, pr.ldb, BN);
       }
     Buf d_outs = upload(ctx, outs), d_pairs = upload(ctx, pairs), d_tiles = upload(ctx, tiles), d_tmaps = upload(ctx, tmaps);
+    if (use_oz2) {
+      oz2.upload_tables();
+      ctx->stats.tc_int8_ops = oz2.int8_ops;
+      ctx->stats.tc_gemm_launches += 1;
+    }
     if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
     const int ngroups = ngroups_dyn;
     const bool side = chunked && ngroups > 1;
@@ -495,9 +775,10 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
           wait_ready_on(cs, *g.b);
         }
       }
+      if (use_oz2) oz2.run_group(gi, cs);
       CUDA_CHECK(launch_gemm_f64(static_cast<const GemmOut*>(d_outs->p), static_cast<const GemmPair*>(d_pairs->p),
                                  static_cast<const GemmTile*>(d_tiles->p) + t0, static_cast<int>(t1 - t0), d_tmaps->p, variant,
-                                 cs));
+                                 cs, use_oz2 ? oz2.flag() : nullptr));
       note_launch(ctx);
       if (chunked) {  // consumers on the egress stream wait for this chunk only
         ReadyPtr r = std::make_shared<Ready>();

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -109,6 +110,11 @@ struct OzakiGemmParams {
   size_t plane_stride;
   int32_t mod_p[16];
   double mod_inv[16];          // 1 / p_t
+  // job mode (Ozaki-II engine): the tiles of this launch come from a list (any subset of the buffer's tile grid), the residue
+  // planes are compact ([modulus][list index][128 x 256] bytes), and the whole launch is skipped when *gate != 0
+  const int2* tile_list;       // (tm, tn) per tile, nullptr = the full tiles_m x tiles_n grid
+  int32_t ntiles_list;
+  const int* gate;
 };
 
 constexpr int EPI_WARPS = 8;                       // 2 per TMEM lane quarter (each takes 128 of the 256 columns)
@@ -134,9 +140,10 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.gate != nullptr && *p.gate != 0) return;  // uniform: non-finite / out-of-range operands take the exact DMMA kernel
   const int nk = p.nkc;
   const int per_tile = p.npairs * nk;
-  const int ntiles = p.tiles_m * p.tiles_n;
+  const int ntiles = p.tile_list ? p.ntiles_list : p.tiles_m * p.tiles_n;
   const int nitems = ntiles * (p.nmod ? p.nmod : 1);
 
   if (threadIdx.x == 0) {
@@ -166,7 +173,13 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
       for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
         const int mi = w / ntiles, t = w - mi * ntiles;
         int tm, tn;
-        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        if (p.tile_list) {
+          const int2 tl = p.tile_list[t];
+          tm = tl.x;
+          tn = tl.y;
+        } else {
+          tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        }
         const int m0 = tm * BM, n0 = tn * BN;
         for (int s = 0; s < p.npairs; ++s) {
           const void* tmA = p.tmaps + static_cast<size_t>(p.nmod ? mi : p.pair_a[s]) * 128;
@@ -220,7 +233,13 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
     for (int w = blockIdx.x; w < nitems; w += gridDim.x, ++lt) {
       const int mi = w / ntiles, t = w - mi * ntiles;
       int tm, tn;
-      tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+      if (p.tile_list) {
+        const int2 tl = p.tile_list[t];
+        tm = tl.x;
+        tn = tl.y;
+      } else {
+        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+      }
       const int m0 = tm * BM, n0 = tn * BN;
       const int buf = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
@@ -263,8 +282,10 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
             }
             packed[g] = wv;
           }
-          int8_t* dst = p.planes + static_cast<size_t>(mi) * p.plane_stride + static_cast<size_t>(row) * p.npad + col0;
-          *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);  // padded planes: no guards
+          // compact planes: [modulus][tile of this launch][128 rows][256 columns], always whole tiles (no guards)
+          int8_t* dst = p.planes + static_cast<size_t>(mi) * p.plane_stride + static_cast<size_t>(t) * (BM * BN) +
+                        static_cast<size_t>(q * 32 + lane) * BN + half * 128 + c;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         } else if (row_ok && col0 < p.N) {
           const int cid0 = col0 / p.blk;
           const bool one_block = (col0 + 15 < p.N) && ((col0 + 15) / p.blk == cid0);
@@ -326,57 +347,84 @@ __device__ __forceinline__ double blk_at(const OzBlock& b, int r, int c) {
 
 // by_row = true: out[row0 + r] = max_c |b(r,c)|; false: out[col0 + c] = max_r |b(r,c)|.  32x32 tiles, 256 threads;
 // tx runs along the block's contiguous dimension (rows for column-major, columns for row-major blocks).
+// minout (optional): the smallest NON-ZERO magnitude of the same line (initialised to all-ones by the caller); the Ozaki-II
+// auto-selection uses it to bound the dynamic range inside a row / column.
 __global__ void __launch_bounds__(256) absmax_kernel(const OzBlock* __restrict__ blocks, unsigned long long* __restrict__ out,
-                                                     int by_row, int tiles_c_max) {
+                                                     unsigned long long* __restrict__ minout, int by_row, int tiles_c_max) {
   __shared__ unsigned long long sm[8][32];
+  __shared__ unsigned long long sn[8][32];
   const OzBlock b = blocks[blockIdx.y];
   const int tr = blockIdx.x / tiles_c_max, tc = blockIdx.x % tiles_c_max;
   const int r0 = tr * 32, c0 = tc * 32;
   if (r0 >= b.rows || c0 >= b.cols) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const bool kept_is_fast = (by_row != 0) == (b.isT == 0);  // kept index == the one tx runs along
-  unsigned long long best = 0;
+  unsigned long long best = 0, least = ~0ull;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int r = b.isT ? r0 + ty + 8 * j : r0 + tx;
     const int c = b.isT ? c0 + tx : c0 + ty + 8 * j;
     unsigned long long bits = 0;
     if (r < b.rows && c < b.cols) bits = static_cast<unsigned long long>(__double_as_longlong(fabs(blk_at(b, r, c))));
+    unsigned long long nz = bits ? bits : ~0ull;
     if (kept_is_fast) {
       best = max(best, bits);  // reduce over the slow index: per-thread, then across ty below
+      least = min(least, nz);
     } else {
       // reduce over the fast index (the 32 lanes of this warp share one slow index)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+      for (int o = 16; o > 0; o >>= 1) {
+        bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+        nz = min(nz, __shfl_xor_sync(0xffffffffu, nz, o));
+      }
       const int slow = by_row ? r : c;
       const int lim = by_row ? b.rows : b.cols;
-      if (tx == 0 && slow < lim) atomicMax(&out[(by_row ? b.row0 : b.col0) + slow], bits);
+      if (tx == 0 && slow < lim) {
+        atomicMax(&out[(by_row ? b.row0 : b.col0) + slow], bits);
+        if (minout != nullptr && nz != ~0ull) atomicMin(&minout[(by_row ? b.row0 : b.col0) + slow], nz);
+      }
     }
   }
   if (kept_is_fast) {
     sm[ty][tx] = best;
+    sn[ty][tx] = least;
     __syncthreads();
     if (ty == 0) {
 #pragma unroll
-      for (int k = 1; k < 8; ++k) best = max(best, sm[k][tx]);
+      for (int k = 1; k < 8; ++k) {
+        best = max(best, sm[k][tx]);
+        least = min(least, sn[k][tx]);
+      }
       const int kept = (by_row ? r0 : c0) + tx;
       const int lim = by_row ? b.rows : b.cols;
-      if (kept < lim) atomicMax(&out[(by_row ? b.row0 : b.col0) + kept], best);
+      if (kept < lim) {
+        atomicMax(&out[(by_row ? b.row0 : b.col0) + kept], best);
+        if (minout != nullptr && least != ~0ull) atomicMin(&minout[(by_row ? b.row0 : b.col0) + kept], least);
+      }
     }
   }
 }
 
-// exponent table: e = ilogb(max) + 1 (so |x| * 2^-e < 1), 0 for all-zero lines; flags non-finite input
-__global__ void exp_kernel(const unsigned long long* __restrict__ maxbits, int32_t* __restrict__ e, double* __restrict__ scale, int n,
-                           int* __restrict__ bad) {
+// exponent table: e = ilogb(max) + 1 (so |x| * 2^-e < 1), 0 for all-zero lines; flags non-finite input.
+// range_bits > 0 (Ozaki-II auto-selection): also flags a line whose smallest non-zero magnitude lies more than range_bits
+// binary orders below its maximum -- such an element would keep too few of its significand bits after the per-line scaling.
+__global__ void exp_kernel(const unsigned long long* __restrict__ maxbits, const unsigned long long* __restrict__ minbits,
+                           int32_t* __restrict__ e, double* __restrict__ scale, int n, int range_bits, int* __restrict__ bad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double m = __longlong_as_double(static_cast<long long>(maxbits[i]));
   int ex = 0;
-  if (!isfinite(m)) *bad = 1;
-  else if (m != 0.0) ex = ilogb(m) + 1;
+  if (!isfinite(m)) {
+    *bad = 1;
+  } else if (m != 0.0) {
+    ex = ilogb(m) + 1;
+    if (range_bits > 0 && minbits != nullptr && minbits[i] != ~0ull) {
+      const double lo = __longlong_as_double(static_cast<long long>(minbits[i]));
+      if (ex - 1 - ilogb(lo) > range_bits) *bad = 1;
+    }
+  }
   e[i] = ex;
-  scale[i] = scalbn(1.0, ex);
+  if (scale != nullptr) scale[i] = scalbn(1.0, ex);
 }
 
 // ---- pass 2: balanced base-256 digits.  out_s[line * Kpad + k], line = row of A (transpose_out = 0) or column of B --
@@ -469,8 +517,9 @@ __constant__ CrtConst c_crt[CRT_MAX_T + 1];  // indexed by T, filled once on fir
 // out_t[line * Kpad + k] = symmetric residue of a'(line, k) mod p_t, same tiling / staging as slice_kernel
 __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict__ blocks, const int32_t* __restrict__ line_exp,
                                                       int8_t* __restrict__ out, size_t slice_stride, int Kpad, int T, int alpha,
-                                                      int lines_are_rows, int tiles_k_max) {
+                                                      int lines_are_rows, int tiles_k_max, const int* __restrict__ gate) {
   __shared__ double sm[32][129];
+  if (gate != nullptr && *gate != 0) return;
   const OzBlock b = blocks[blockIdx.y];
   const int tl = blockIdx.x / tiles_k_max, tk = blockIdx.x % tiles_k_max;
   const int nlines = lines_are_rows ? b.rows : b.cols;
@@ -531,18 +580,26 @@ __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict_
   }
 }
 
-// CRT reconstruction: one CTA = 32 rows x 128 columns of C.  Thread (row, 4 columns) reads its T residue quads (coalesced along
-// the plane rows), accumulates sum_t r_t w_t in 32-bit limbs (IMAD.WIDE into 64-bit lanes), reduces modulo P to the symmetric
-// range, converts to fp64 and scales by 2^(e_i + f_j - 2 alpha); the tile is transposed through shared memory so the stores
-// follow the column-major output blocks.
-__global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ planes, size_t plane_stride, int npad, int T,
-                                                  const int32_t* __restrict__ row_exp, const int32_t* __restrict__ col_exp,
-                                                  int two_alpha, double* const* __restrict__ ctab, int M, int N, int blk, int nbc) {
+// CRT reconstruction: one CTA = 32 rows x 128 columns of one 128 x 256 tile of the job (8 CTAs per tile).  Thread (row, 4 columns)
+// reads its T residue quads (coalesced along the compact plane rows), accumulates sum_t r_t w_t in 32-bit limbs (IMAD.WIDE into
+// 64-bit lanes), reduces modulo P to the symmetric range, converts to fp64 and scales by 2^(e_i + f_j - 2 alpha); the tile is
+// transposed through shared memory so the stores follow the column-major output blocks.  Buffer rows / columns are organised
+// in slots of `sstride` lines (one block row / block column each); ctab[rslot * ncslots + cslot] is the output block or nullptr.
+__global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ planes, size_t plane_stride, int T,
+                                                  const int2* __restrict__ tiles, const int32_t* __restrict__ row_exp,
+                                                  const int32_t* __restrict__ col_exp, int two_alpha, double* const* __restrict__ ctab,
+                                                  const int32_t* __restrict__ rdims, const int32_t* __restrict__ cdims, int sstride,
+                                                  int ncslots, const int* __restrict__ gate) {
   __shared__ double tile[128][33];
+  if (gate != nullptr && *gate != 0) return;
   const CrtConst& cc = c_crt[T];
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 128;  // row tiles on x (no 65535 limit)
+  const int t_idx = blockIdx.x >> 3, sub = blockIdx.x & 7;
+  const int2 tl = tiles[t_idx];
+  const int r0t = (sub >> 1) * 32, c0t = (sub & 1) * 128;  // inside the tile
+  const int r0 = tl.x * BM + r0t, c0 = tl.y * BN + c0t;     // buffer coordinates
   const int tid = threadIdx.x;
   const int lr = tid >> 5, lc = (tid & 31) * 4;  // 8 rows per pass, 4 passes
+  const int8_t* tbase = planes + static_cast<size_t>(t_idx) * (BM * BN);
   for (int pass = 0; pass < 4; ++pass) {
     const int row = r0 + pass * 8 + lr;
     unsigned long long acc[4][4];
@@ -550,7 +607,7 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][i] = 0ull;
-    const int8_t* src = planes + static_cast<size_t>(row) * npad + c0 + lc;
+    const int8_t* src = tbase + static_cast<size_t>(r0t + pass * 8 + lr) * BN + c0t + lc;
     for (int t = 0; t < T; ++t) {
       const uint32_t quad = *reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(t) * plane_stride);
       const uint32_t w0 = cc.w[t][0], w1 = cc.w[t][1], w2 = cc.w[t][2], w3 = cc.w[t][3];
@@ -563,7 +620,7 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
         acc[j][3] += static_cast<unsigned long long>(ru) * w3;
       }
     }
-    const int er = row < M ? row_exp[row] : 0;
+    const int er = row_exp[row];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       // carry-normalise to five 32-bit limbs (value < T * 256 * P < 2^140)
@@ -636,8 +693,7 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
       }
       const double mag = static_cast<double>((static_cast<unsigned long long>(l[3]) << 32) | l[2]) * 18446744073709551616.0 +
                          static_cast<double>((static_cast<unsigned long long>(l[1]) << 32) | l[0]);
-      const int col = c0 + lc + j;
-      const int ec = col < N ? col_exp[col] : 0;
+      const int ec = col_exp[c0 + lc + j];
       tile[lc + j][pass * 8 + lr] = scalbn(gt ? -mag : mag, er + ec - two_alpha);
     }
   }
@@ -645,16 +701,18 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
   // store: warp w writes columns w, w + 8, ...; lanes run along the 32 rows (contiguous in the column-major block)
   const int warp = tid >> 5, lane = tid & 31;
   const int row = r0 + lane;
-  if (row >= M) return;
-  const int rid = row / blk;
-  const int brows = min(blk, M - rid * blk);
-  const int lrow = row - rid * blk;
+  const int rslot = row / sstride;
+  const int lrow = row - rslot * sstride;
+  const int brows = rdims[rslot];
+  if (lrow >= brows) return;
   for (int cidx = warp; cidx < 128; cidx += 8) {
     const int col = c0 + cidx;
-    if (col >= N) break;
-    const int cid = col / blk;
-    double* blkp = ctab[rid * nbc + cid];
-    if (blkp != nullptr) blkp[lrow + static_cast<size_t>(brows) * (col - cid * blk)] = tile[cidx][lane];
+    const int cslot = col / sstride;
+    if (cslot >= ncslots) break;
+    const int lcol = col - cslot * sstride;
+    if (lcol >= cdims[cslot]) continue;
+    double* blkp = ctab[static_cast<size_t>(rslot) * ncslots + cslot];
+    if (blkp != nullptr) blkp[lrow + static_cast<size_t>(brows) * lcol] = tile[cidx][lane];
   }
 }
 
@@ -828,14 +886,14 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   {
     const int tc = (max_ac + 31) / 32, tr = (max_ar + 31) / 32;
     OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
-      absmax_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, rowmax, 1, tc);
+      absmax_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, rowmax, nullptr, 1, tc);
     }));
     const int tcb = (max_bc + 31) / 32, trb = (max_br + 31) / 32;
     OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
-      absmax_kernel<<<dim3(trb * tcb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, colmax, 0, tcb);
+      absmax_kernel<<<dim3(trb * tcb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, colmax, nullptr, 0, tcb);
     }));
-    exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, row_exp, static_cast<double*>(d_scale.p),
-                                                                                      static_cast<int>(Mpad + Npad), static_cast<int*>(d_bad.p));
+    exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, nullptr, row_exp, static_cast<double*>(d_scale.p),
+                                                                                      static_cast<int>(Mpad + Npad), 0, static_cast<int*>(d_bad.p));
     *launches += 3;
   }
   int h_bad = 0;
@@ -970,14 +1028,49 @@ cudaError_t crt_constants(int* log2P) {
 }
 }  // namespace
 
-// gemm_algo 4: Ozaki scheme II.  Same contract as ozaki_gemm_f64 (C = A B into the fp64 output blocks; non-finite input is
-// reported through *nonfinite and nothing is written).  moduli in [6, 16] sets the operand precision alpha =
-// floor((floor(log2 P) - 1 - ceil(log2 K)) / 2) bits relative to the row / column maximum (16 moduli, K = 16384: 55 bits).
-cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K,
-                            int64_t N, int moduli, double* const* h_ctab, int blk, int nbr, int nbc, int* launches, int* nonfinite,
-                            cudaStream_t stream) {
-  *nonfinite = 0;
-  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+// ------------------------------------------------------------------------------------------------
+// gemm_algo 4 / auto: Ozaki scheme II as a job engine.
+//
+// The scaled-integer residue matrices A' mod p_t [T][Mpad][Kpad] and B' mod p_t [T][Npad][Kpad] live in slot-organised buffers:
+// slot s of A' holds one block row of A (rows [s * sstride, s * sstride + rows)), slot s of B' one block column of B.  A block
+// row / column is PREPARED (absmax -> exponents -> residues) as soon as all of its blocks have landed, independently of the
+// others, and a JOB multiplies any set of output blocks whose row and column slots are prepared: one persistent tcgen05 launch
+// over (modulus x tile list) work items writing compact residue planes, then the CRT kernel over the same tile list.  That is
+// what lets the multiply run chunk by chunk behind the host->device ingest, and what panels the scratch for operands whose
+// residues do not fit the budget.  Nothing here synchronises with the host: non-finite input (and, in auto mode, a dynamic range
+// inside a line that the per-line scaling cannot carry) raises a device flag that turns the remaining engine kernels into no-ops
+// and un-gates the exact DMMA launch the caller enqueues behind every job.
+// ------------------------------------------------------------------------------------------------
+struct Oz2Engine {
+  int T = 0, alpha = 0, blk = 0, sstride = 0, cap_r = 0, cap_c = 0, max_tiles = 0, range_bits = 0;
+  int64_t K = 0, Kpad = 0, Mpad = 0, Npad = 0;
+  size_t a_stride = 0, b_stride = 0, plane_stride = 0, smem_bytes = 0;
+  int8_t *As = nullptr, *Bs = nullptr, *planes = nullptr;
+  unsigned long long *maxb = nullptr, *minb = nullptr;
+  int32_t *exps = nullptr, *dims = nullptr;   // exps: [Mpad + Npad]; dims: rows per row slot [cap_r] then columns per column slot [cap_c]
+  int* bad = nullptr;
+  const unsigned char* d_maps = nullptr;      // uploaded by the caller (oz2_host_maps)
+  std::vector<unsigned char> h_maps;
+  int sms = 148;
+  int launches = 0;
+};
+
+size_t oz2_scratch_bytes(int blk, int64_t K, int T, int cap_r, int cap_c, int max_tiles) {
+  const int64_t sstride = (blk + BM - 1) / BM * BM;
+  const int64_t Kpad = (K + BKB - 1) / BKB * BKB;
+  const int64_t Mpad = sstride * cap_r, Npad = (sstride * cap_c + BN - 1) / BN * BN;
+  return static_cast<size_t>(T) * (Mpad + Npad) * Kpad + static_cast<size_t>(T) * max_tiles * (BM * BN);
+}
+
+int oz2_tiles_per_block(int blk) {
+  const int s = (blk + BM - 1) / BM * BM;
+  return (s / BM) * ((s + BN - 1) / BN);
+}
+
+// Creates the engine and its scratch (stream-ordered allocations).  cap_r / cap_c = row / column slots held at once.
+cudaError_t oz2_create(Oz2Engine** out, int blk, int64_t K, int moduli, int cap_r, int cap_c, int max_tiles, int guard_range,
+                       cudaStream_t stream) {
+  *out = nullptr;
   const int T = moduli < CRT_MIN_T ? CRT_MIN_T : (moduli > CRT_MAX_T ? CRT_MAX_T : moduli);
   int log2P[CRT_MAX_T + 1];
   OZ_CHECK(crt_constants(log2P));
@@ -985,123 +1078,182 @@ cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOpe
   while ((1ll << lgK) < K) ++lgK;
   int alpha = (log2P[T] - 1 - lgK) / 2;  // K * (2^alpha)^2 <= 2^(floor(log2 P) - 1) < P / 2
   if (alpha > 62) alpha = 62;
-  if (alpha < 8) return cudaErrorInvalidValue;
-  const int64_t Mpad = (M + BM - 1) / BM * BM, Npad = (N + BN - 1) / BN * BN, Kpad = (K + BKB - 1) / BKB * BKB;
-  const size_t smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
-  OZ_CHECK(configure_gemm_kernel(smem_bytes));
-  std::vector<OzBlock> ha(na), hb(nb);
-  int max_ar = 1, max_ac = 1, max_br = 1, max_bc = 1;
-  for (int i = 0; i < na; ++i) {
-    ha[i] = OzBlock{a_blocks[i].v, a_blocks[i].rows, a_blocks[i].cols, a_blocks[i].row0, a_blocks[i].col0, a_blocks[i].isT, {0}};
-    max_ar = std::max(max_ar, a_blocks[i].rows);
-    max_ac = std::max(max_ac, a_blocks[i].cols);
+  if (alpha < 8 || K >= (1 << 17) || cap_r <= 0 || cap_c <= 0 || max_tiles <= 0) return cudaErrorInvalidValue;
+  std::unique_ptr<Oz2Engine> e(new Oz2Engine);
+  e->T = T;
+  e->alpha = alpha;
+  e->blk = blk;
+  e->sstride = (blk + BM - 1) / BM * BM;
+  e->cap_r = cap_r;
+  e->cap_c = cap_c;
+  e->max_tiles = max_tiles;
+  // auto mode: every non-zero element must keep >= 18 bits after the per-line scaling, which bounds the error of every product
+  // term by 2^-17 of the term itself, i.e. the result by 2^-17 |A||B| element-wise (north-star tolerance 1e-5) in the worst
+  // case; data of ordinary dynamic range sees the full alpha bits (1e-14 .. 1e-16)
+  e->range_bits = guard_range ? std::max(1, alpha - 18) : 0;
+  e->K = K;
+  e->Kpad = (K + BKB - 1) / BKB * BKB;
+  e->Mpad = static_cast<int64_t>(e->sstride) * cap_r;
+  e->Npad = (static_cast<int64_t>(e->sstride) * cap_c + BN - 1) / BN * BN;
+  e->a_stride = static_cast<size_t>(e->Mpad) * e->Kpad;
+  e->b_stride = static_cast<size_t>(e->Npad) * e->Kpad;
+  e->plane_stride = static_cast<size_t>(max_tiles) * (BM * BN);
+  e->smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+  OZ_CHECK(configure_gemm_kernel(e->smem_bytes));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, dev);
+  auto alloc = [&](void** p, size_t n) { return cudaMallocAsync(p, n ? n : 16, stream); };
+  cudaError_t err = cudaSuccess;
+  const size_t lines = static_cast<size_t>(e->Mpad + e->Npad);
+  if ((err = alloc(reinterpret_cast<void**>(&e->As), e->a_stride * T)) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->Bs), e->b_stride * T)) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->planes), e->plane_stride * T)) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->maxb), lines * 8)) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->minb), lines * 8)) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->exps), lines * 4)) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->dims), static_cast<size_t>(cap_r + cap_c) * 4)) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->bad), sizeof(int))) != cudaSuccess) {
+    Oz2Engine* raw = e.release();
+    oz2_destroy(raw, stream);
+    return err;
   }
-  for (int i = 0; i < nb; ++i) {
-    hb[i] = OzBlock{b_blocks[i].v, b_blocks[i].rows, b_blocks[i].cols, b_blocks[i].row0, b_blocks[i].col0, b_blocks[i].isT, {0}};
-    max_br = std::max(max_br, b_blocks[i].rows);
-    max_bc = std::max(max_bc, b_blocks[i].cols);
-  }
-  AsyncBuf d_ab(stream), d_bb(stream), d_max(stream), d_exp(stream), d_scale(stream), d_bad(stream), d_As(stream), d_Bs(stream),
-      d_maps(stream), d_ctab(stream), d_planes(stream);
-  OZ_CHECK(d_ab.alloc(sizeof(OzBlock) * na));
-  OZ_CHECK(d_bb.alloc(sizeof(OzBlock) * nb));
-  OZ_CHECK(cudaMemcpyAsync(d_ab.p, ha.data(), sizeof(OzBlock) * na, cudaMemcpyHostToDevice, stream));
-  OZ_CHECK(cudaMemcpyAsync(d_bb.p, hb.data(), sizeof(OzBlock) * nb, cudaMemcpyHostToDevice, stream));
-  OZ_CHECK(d_max.alloc(sizeof(unsigned long long) * (Mpad + Npad)));
-  OZ_CHECK(d_exp.alloc(sizeof(int32_t) * (Mpad + Npad)));
-  OZ_CHECK(d_scale.alloc(sizeof(double) * (Mpad + Npad)));
-  OZ_CHECK(d_bad.alloc(sizeof(int)));
-  OZ_CHECK(cudaMemsetAsync(d_max.p, 0, sizeof(unsigned long long) * (Mpad + Npad), stream));
-  OZ_CHECK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), stream));
-  unsigned long long* rowmax = static_cast<unsigned long long*>(d_max.p);
-  unsigned long long* colmax = rowmax + Mpad;
-  int32_t* row_exp = static_cast<int32_t*>(d_exp.p);
-  int32_t* col_exp = row_exp + Mpad;
-  {
-    const int tc = (max_ac + 31) / 32, tr = (max_ar + 31) / 32;
-    OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
-      absmax_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, rowmax, 1, tc);
-    }));
-    const int tcb = (max_bc + 31) / 32, trb = (max_br + 31) / 32;
-    OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
-      absmax_kernel<<<dim3(trb * tcb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, colmax, 0, tcb);
-    }));
-    exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, row_exp, static_cast<double*>(d_scale.p),
-                                                                                      static_cast<int>(Mpad + Npad), static_cast<int*>(d_bad.p));
-    *launches += 3;
-  }
-  int h_bad = 0;
-  OZ_CHECK(cudaMemcpyAsync(&h_bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  OZ_CHECK(cudaStreamSynchronize(stream));
-  if (h_bad) {
-    *nonfinite = 1;
-    return cudaSuccess;
-  }
-  const size_t a_stride = static_cast<size_t>(Mpad) * Kpad, b_stride = static_cast<size_t>(Npad) * Kpad;
-  const size_t plane_stride = static_cast<size_t>(Mpad) * Npad;
-  OZ_CHECK(d_As.alloc(a_stride * T));
-  OZ_CHECK(d_Bs.alloc(b_stride * T));
-  OZ_CHECK(d_planes.alloc(plane_stride * T));
-  if (!covers_operand(a_blocks, na, M, K, Kpad)) OZ_CHECK(cudaMemsetAsync(d_As.p, 0, a_stride * T, stream));
-  if (!covers_operand(b_blocks, nb, N, K, Kpad)) OZ_CHECK(cudaMemsetAsync(d_Bs.p, 0, b_stride * T, stream));
-  {
-    const int tk = (max_ac + 127) / 128, tl = (max_ar + 31) / 32;
-    OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
-      residue_kernel<<<dim3(tl * tk, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, row_exp,
-                                                             static_cast<int8_t*>(d_As.p), a_stride, static_cast<int>(Kpad), T, alpha, 1, tk);
-    }));
-    const int tkb = (max_br + 127) / 128, tlb = (max_bc + 31) / 32;
-    OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
-      residue_kernel<<<dim3(tlb * tkb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, col_exp,
-                                                               static_cast<int8_t*>(d_Bs.p), b_stride, static_cast<int>(Kpad), T, alpha, 0, tkb);
-    }));
-    *launches += 2;
-  }
-  std::vector<unsigned char> hmaps(static_cast<size_t>(2 * T) * 128);
+  OZ_CHECK(cudaMemsetAsync(e->bad, 0, sizeof(int), stream));
+  // B' rows beyond the last column slot (Npad rounding to the 256-wide tile) are read by the last tile: keep them defined
+  if (e->Npad > static_cast<int64_t>(e->sstride) * cap_c)
+    for (int t = 0; t < T; ++t)
+      OZ_CHECK(cudaMemsetAsync(e->Bs + e->b_stride * t + static_cast<size_t>(e->sstride) * cap_c * e->Kpad, 0,
+                               static_cast<size_t>(e->Npad - static_cast<int64_t>(e->sstride) * cap_c) * e->Kpad, stream));
+  e->h_maps.resize(static_cast<size_t>(2 * T) * 128);
   for (int t = 0; t < T; ++t) {
-    if (!make_i8_map(&hmaps[static_cast<size_t>(t) * 128], static_cast<int8_t*>(d_As.p) + a_stride * t, Kpad, Mpad, BM) ||
-        !make_i8_map(&hmaps[static_cast<size_t>(T + t) * 128], static_cast<int8_t*>(d_Bs.p) + b_stride * t, Kpad, Npad, BN))
+    if (!make_i8_map(&e->h_maps[static_cast<size_t>(t) * 128], e->As + e->a_stride * t, e->Kpad, e->Mpad, BM) ||
+        !make_i8_map(&e->h_maps[static_cast<size_t>(T + t) * 128], e->Bs + e->b_stride * t, e->Kpad, e->Npad, BN)) {
+      Oz2Engine* raw = e.release();
+      oz2_destroy(raw, stream);
       return cudaErrorInvalidValue;
+    }
   }
-  OZ_CHECK(d_maps.alloc(hmaps.size()));
-  OZ_CHECK(cudaMemcpyAsync(d_maps.p, hmaps.data(), hmaps.size(), cudaMemcpyHostToDevice, stream));
-  OZ_CHECK(d_ctab.alloc(sizeof(double*) * nbr * nbc));
-  OZ_CHECK(cudaMemcpyAsync(d_ctab.p, h_ctab, sizeof(double*) * nbr * nbc, cudaMemcpyHostToDevice, stream));
+  *out = e.release();
+  return cudaSuccess;
+}
+
+void oz2_destroy(Oz2Engine* e, cudaStream_t stream) {
+  if (!e) return;
+  void* ptrs[] = {e->As, e->Bs, e->planes, e->maxb, e->minb, e->exps, e->dims, e->bad};
+  for (void* p : ptrs)
+    if (p) cudaFreeAsync(p, stream);
+  delete e;
+}
+
+const void* oz2_host_maps(const Oz2Engine* e, size_t* bytes) {
+  *bytes = e->h_maps.size();
+  return e->h_maps.data();
+}
+void oz2_set_device_maps(Oz2Engine* e, const void* d_maps) { e->d_maps = static_cast<const unsigned char*>(d_maps); }
+const int* oz2_flag(const Oz2Engine* e) { return e->bad; }
+int oz2_alpha(const Oz2Engine* e) { return e->alpha; }
+int oz2_slot_stride(const Oz2Engine* e) { return e->sstride; }
+int oz2_launches(Oz2Engine* e) {
+  const int n = e->launches;
+  e->launches = 0;
+  return n;
+}
+
+// Prepares slots [slot0, slot0 + nslots) of the A side (is_a) or B side from `nblocks` device-resident block descriptors whose
+// row0 (A) / col0 (B) already point into those slots.  d_dims = the slots' line counts (device, nslots ints).  need_zero: the
+// blocks do not cover every (line, k) of the slots (absent k-blocks, K padding): the residue rows are cleared first.
+cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, int nblocks, int max_rows, int max_cols, int slot0,
+                        int nslots, const int32_t* d_dims, bool need_zero, cudaStream_t stream) {
+  if (nslots <= 0) return cudaSuccess;
+  if (slot0 < 0 || slot0 + nslots > (is_a ? e->cap_r : e->cap_c)) return cudaErrorInvalidValue;
+  static_assert(sizeof(OzakiOperand) == sizeof(OzBlock), "OzakiOperand is the device block descriptor");
+  const OzBlock* blocks = reinterpret_cast<const OzBlock*>(d_blocks);
+  const size_t line0 = (is_a ? 0 : static_cast<size_t>(e->Mpad)) + static_cast<size_t>(slot0) * e->sstride;
+  const size_t nlines = static_cast<size_t>(nslots) * e->sstride;
+  // the tables are indexed by buffer line: A lines first, then B lines
+  unsigned long long* maxb = e->maxb + (is_a ? 0 : e->Mpad);
+  unsigned long long* minb = e->minb + (is_a ? 0 : e->Mpad);
+  int32_t* exps = e->exps + (is_a ? 0 : e->Mpad);
+  OZ_CHECK(cudaMemsetAsync(e->maxb + line0, 0, nlines * 8, stream));
+  OZ_CHECK(cudaMemsetAsync(e->minb + line0, 0xff, nlines * 8, stream));
+  OZ_CHECK(cudaMemcpyAsync(e->dims + (is_a ? 0 : e->cap_r) + slot0, d_dims, static_cast<size_t>(nslots) * 4, cudaMemcpyDeviceToDevice, stream));
+  int8_t* res = is_a ? e->As : e->Bs;
+  const size_t stride = is_a ? e->a_stride : e->b_stride;
+  if (need_zero)
+    for (int t = 0; t < e->T; ++t)
+      OZ_CHECK(cudaMemsetAsync(res + stride * t + static_cast<size_t>(slot0) * e->sstride * e->Kpad, 0, nlines * e->Kpad, stream));
+  if (nblocks > 0) {
+    const int tc = (max_cols + 31) / 32, tr = (max_rows + 31) / 32;
+    OZ_CHECK(for_block_chunks(nblocks, [&](int off, int cnt) {
+      absmax_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(blocks + off, maxb, e->range_bits ? minb : nullptr, is_a ? 1 : 0, tc);
+    }));
+    e->launches += 1;
+  }
+  exp_kernel<<<static_cast<unsigned>((nlines + 255) / 256), 256, 0, stream>>>(e->maxb + line0, e->range_bits ? e->minb + line0 : nullptr,
+                                                                               e->exps + line0, nullptr, static_cast<int>(nlines),
+                                                                               e->range_bits, e->bad);
+  OZ_CHECK(cudaGetLastError());
+  e->launches += 1;
+  if (nblocks > 0) {
+    // "line" = row of A / column of B, "k" = the other index
+    const int max_l = is_a ? max_rows : max_cols, max_k = is_a ? max_cols : max_rows;
+    const int tk = (max_k + 127) / 128, tl = (max_l + 31) / 32;
+    OZ_CHECK(for_block_chunks(nblocks, [&](int off, int cnt) {
+      residue_kernel<<<dim3(tl * tk, cnt), 256, 0, stream>>>(blocks + off, exps, res, stride, static_cast<int>(e->Kpad), e->T, e->alpha,
+                                                             is_a ? 1 : 0, tk, e->bad);
+    }));
+    e->launches += 1;
+  }
+  return cudaSuccess;
+}
+
+// One job: C blocks (+)= A' B' over the tiles of d_tiles (buffer tile coordinates (tm, tn), device array; the order is the
+// execution order, so the caller bands it for L2 reuse), written through d_ctab[rslot * cap_c + cslot] (nullptr = not part of
+// this job).  Lists longer than the plane capacity are processed in consecutive pieces.  ms_gemm (optional) accumulates the
+// tcgen05 launch time (events, synchronises): used for the roofline figure only.
+cudaError_t oz2_multiply(Oz2Engine* e, const int2* d_tiles, int ntiles, double* const* d_ctab, cudaStream_t stream, double* ms_gemm,
+                         cudaEvent_t ev0, cudaEvent_t ev1) {
+  if (ntiles <= 0) return cudaSuccess;
+  if (e->d_maps == nullptr) return cudaErrorInvalidValue;
   OzakiGemmParams p{};
-  p.tmaps = static_cast<const unsigned char*>(d_maps.p);
-  p.M = static_cast<int32_t>(M);
-  p.N = static_cast<int32_t>(N);
-  p.Kpad = static_cast<int32_t>(Kpad);
-  p.blk = blk;
-  p.nbr = nbr;
-  p.nbc = nbc;
+  p.tmaps = e->d_maps;
+  p.Kpad = static_cast<int32_t>(e->Kpad);
   p.kstep = BKB;
   p.kc0 = 0;
-  p.nkc = static_cast<int32_t>(Kpad / BKB);
+  p.nkc = static_cast<int32_t>(e->Kpad / BKB);
   p.npairs = 1;
   p.idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
-  p.tiles_m = static_cast<int32_t>(Mpad / BM);
-  p.tiles_n = static_cast<int32_t>(Npad / BN);
-  p.nmod = T;
-  p.npad = static_cast<int32_t>(Npad);
-  p.planes = static_cast<int8_t*>(d_planes.p);
-  p.plane_stride = plane_stride;
-  for (int t = 0; t < T; ++t) {
+  p.tiles_m = static_cast<int32_t>(e->Mpad / BM);
+  p.tiles_n = static_cast<int32_t>(e->Npad / BN);
+  p.nmod = e->T;
+  p.planes = e->planes;
+  p.plane_stride = e->plane_stride;
+  p.gate = e->bad;
+  for (int t = 0; t < e->T; ++t) {
     p.mod_p[t] = kCrtModuli[t];
     p.mod_inv[t] = 1.0 / kCrtModuli[t];
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t nitems = static_cast<int64_t>(p.tiles_m) * p.tiles_n * T;
-  if (nitems > INT32_MAX) return cudaErrorInvalidValue;
-  ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(nitems, sms)), GEMM_THREADS_P, smem_bytes, stream>>>(p);
-  OZ_CHECK(cudaGetLastError());
-  crt_kernel<<<dim3(static_cast<unsigned>((M + 31) / 32), static_cast<unsigned>((N + 127) / 128)), 256, 0, stream>>>(
-      static_cast<const int8_t*>(d_planes.p), plane_stride, static_cast<int>(Npad), T, row_exp, col_exp, 2 * alpha,
-      static_cast<double* const*>(d_ctab.p), static_cast<int>(M), static_cast<int>(N), blk, nbc);
-  OZ_CHECK(cudaGetLastError());
-  *launches += 2;
+  for (int off = 0; off < ntiles; off += e->max_tiles) {
+    const int cnt = std::min(e->max_tiles, ntiles - off);
+    p.tile_list = d_tiles + off;
+    p.ntiles_list = cnt;
+    const int64_t nitems = static_cast<int64_t>(cnt) * e->T;
+    if (ms_gemm) OZ_CHECK(cudaEventRecord(ev0, stream));
+    ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(nitems, e->sms)), GEMM_THREADS_P, e->smem_bytes, stream>>>(p);
+    OZ_CHECK(cudaGetLastError());
+    if (ms_gemm) {
+      OZ_CHECK(cudaEventRecord(ev1, stream));
+      OZ_CHECK(cudaEventSynchronize(ev1));
+      float ms = 0.f;
+      OZ_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+      *ms_gemm += ms;
+    }
+    crt_kernel<<<static_cast<unsigned>(cnt) * 8u, 256, 0, stream>>>(e->planes, e->plane_stride, e->T, d_tiles + off, e->exps,
+                                                                      e->exps + e->Mpad, 2 * e->alpha, d_ctab, e->dims,
+                                                                      e->dims + e->cap_r, e->sstride, e->cap_c, e->bad);
+    OZ_CHECK(cudaGetLastError());
+    e->launches += 2;
+  }
   return cudaSuccess;
 }
 

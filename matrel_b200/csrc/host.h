@@ -86,9 +86,10 @@ struct mr_context {
   int gemm_algo = 0;
   int ozaki_slices = 0;
   int crt_moduli = 0;
+  int ozaki_scratch_mb = 0;  // budget of the Ozaki-II residue scratch (0 = 16 GiB)
   int time_kernels = 0;
   int force_variant = -1;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_alloc = nullptr, ev_order = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_alloc = nullptr, ev_order = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // ingest / egress overlap with compute on `stream`
   // The chunks of a pipelined multiply are independent launches: issued round-robin on these side streams, the last
   // (partial) wave of one chunk overlaps the first waves of the next instead of leaving SMs idle between launches.

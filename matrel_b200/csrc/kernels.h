@@ -66,8 +66,9 @@ int gemm_tile_n(int variant);
 // box {16, tile_rows}, SWIZZLE_128B).  Returns false when TMA cannot address it (odd ld / unaligned base).
 bool encode_kcontig_tmap(void* out128, const double* base, int64_t kdim, int64_t rows, int64_t ld, int tile_rows);
 
+// run_if (optional, device): the launch is a no-op unless *run_if != 0 (the fallback behind an Ozaki-II job)
 cudaError_t launch_gemm_f64(const GemmOut* d_outs, const GemmPair* d_pairs, const GemmTile* d_tiles,
-                            int ntiles, const void* d_tmaps, int variant, cudaStream_t stream);
+                            int ntiles, const void* d_tmaps, int variant, cudaStream_t stream, const int* run_if = nullptr);
 
 // ---- fp64 block GEMM on tcgen05 (kind::i8) through Ozaki splitting (gemm_ozaki.cu) --------------------------------
 struct OzakiOperand {
@@ -75,6 +76,7 @@ struct OzakiOperand {
   int32_t rows, cols;  // logical block dims
   int32_t row0, col0;  // global offset of the block inside its operand matrix
   uint8_t isT;
+  uint8_t pad[7];
 };
 // C(blocks in h_ctab, nbr x nbc grid of blk-sized column-major blocks) (+)= A(M x K) * B(K x N); absent blocks are zeros.
 // *nonfinite = 1 (and nothing written) when an operand holds Inf/NaN: the caller must use the exact kernel instead.
@@ -82,10 +84,28 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
                            int64_t N, int slices, double* const* h_ctab, int blk, int nbr, int nbc, bool accumulate,
                            int* launches, int* nonfinite, cudaStream_t stream);
 
-// Ozaki scheme II (gemm_algo 4): `moduli` int8 GEMMs of residue matrices + Chinese-remainder reconstruction (gemm_ozaki.cu)
-cudaError_t ozaki2_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K,
-                            int64_t N, int moduli, double* const* h_ctab, int blk, int nbr, int nbc, int* launches, int* nonfinite,
-                            cudaStream_t stream);
+// Ozaki scheme II (gemm_algo 4 and the auto selection): residues modulo `moduli` pairwise-coprime p_t <= 256, one int8 tensor-core
+// GEMM per modulus, Chinese-remainder reconstruction -- as a job engine over slot-organised residue buffers (gemm_ozaki.cu).
+// All table arguments are DEVICE pointers (the caller uploads them through its own staging path); nothing synchronises with the
+// host.  *oz2_flag() != 0 on the device means "operands not representable (Inf / NaN, or too wide a range in auto mode)": the
+// engine's remaining kernels are no-ops then and the caller's gated DMMA launch produces the blocks instead.
+struct Oz2Engine;
+size_t oz2_scratch_bytes(int blk, int64_t K, int moduli, int cap_r, int cap_c, int max_tiles);
+int oz2_tiles_per_block(int blk);
+cudaError_t oz2_create(Oz2Engine** out, int blk, int64_t K, int moduli, int cap_r, int cap_c, int max_tiles, int guard_range,
+                       cudaStream_t stream);
+void oz2_destroy(Oz2Engine* e, cudaStream_t stream);
+const void* oz2_host_maps(const Oz2Engine* e, size_t* bytes);   // 2 * moduli CUtensorMaps to be uploaded by the caller ...
+void oz2_set_device_maps(Oz2Engine* e, const void* d_maps);     // ... and handed back as a device pointer
+const int* oz2_flag(const Oz2Engine* e);
+int oz2_alpha(const Oz2Engine* e);
+int oz2_slot_stride(const Oz2Engine* e);
+int oz2_launches(Oz2Engine* e);                                  // kernels launched since the last call
+cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, int nblocks, int max_rows, int max_cols, int slot0,
+                        int nslots, const int32_t* d_dims, bool need_zero, cudaStream_t stream);
+cudaError_t oz2_multiply(Oz2Engine* e, const int2* d_tiles, int ntiles, double* const* d_ctab, cudaStream_t stream, double* ms_gemm,
+                         cudaEvent_t ev0, cudaEvent_t ev1);
+constexpr int kOz2TileM = 128, kOz2TileN = 256;
 // fp32 multiply on tcgen05 kind::tf32 (3xTF32 split, fp32 TMEM accumulation); same operand / output conventions.
 cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand* b_blocks, int nb, int64_t M, int64_t K, int64_t N,
                         double* const* h_ctab, int blk, int nbr, int nbc, int* launches, cudaStream_t stream);

@@ -343,7 +343,7 @@ def sharded_aggregate(kind: str, groups: GridGroups, A: ShardedMatrix):
     raise ValueError(kind)
 
 
-def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample):
+def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample, int8_peak_tops=None):
     import json
     import time
     import numpy as np

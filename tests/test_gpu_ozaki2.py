@@ -126,3 +126,109 @@ def test_crt_matches_dmma_at_4096(oz2, session):
         a, b = C1.get_block(*key).values, C2.get_block(*key).values
         worst = max(worst, float(np.max(np.abs(a - b)) / np.max(np.abs(a))))
     assert worst <= 2e-14, worst      # the deviation is the DMMA kernel's own accumulated rounding (K = 4096)
+
+
+# ---------------------------------------------------------------------------------- job engine (round 2)
+def _pinned_blocks(ds):
+    import torch
+    pin = lambda m: mb.DenseMatrix(m.numRows, m.numCols, torch.from_numpy(m.values).pin_memory().numpy(), m.isTransposed)  # noqa: E731
+    return [mb.MatrixBlock(i, j, pin(m)) for (i, j), m in ds.items()]
+
+
+def test_crt_pipelined_behind_ingest_is_bit_identical(oz2):
+    """The tcgen05 path runs chunk by chunk behind the host->device ingest (residues of a block row / column as soon as it is
+    complete, int8 GEMM + CRT of the output blocks it unlocks).  Row / column exponents do not depend on the chunking and the
+    integer product is exact, so the blocks must equal the resident run's bit for bit -- whatever order the blocks arrive in."""
+    n, blk = 2048, 256
+    nb = n // blk
+    A = O.rand_dense_dataset(n, n, blk, 42, transposed_mask=lambda i, j: (i * 3 + j) % 4 == 0)
+    B = O.rand_dense_dataset(n, n, blk, 43)
+    ref = from_dataset(to_dataset(oz2, A).matrixMultiply(n, n, to_dataset(oz2, B), n, n, blk))
+    want = O.matrix_multiply(A, n, n, B, n, n, blk)
+    assert_same_dataset(ref, want, tol=1e-13)
+    pA, pB = _pinned_blocks(A), _pinned_blocks(B)
+    rowsA = {t: [b for b in pA if b.rid == t] for t in range(nb)}
+    colsB = {t: [b for b in pB if b.cid == t] for t in range(nb)}
+    for order in ("alternate", "b_first", "a_first"):
+        oz2.reset_stats()
+        dA, dB = oz2.emptyDataset(), oz2.emptyDataset()
+        if order == "alternate":
+            for t in range(nb):
+                dA.put_blocks(rowsA[t])
+                dB.put_blocks(colsB[t])
+        elif order == "b_first":
+            dB.put_blocks(pB)
+            dA.put_blocks(pA)
+        else:
+            dA.put_blocks(pA)
+            dB.put_blocks(pB)
+        got = from_dataset(dA.matrixMultiply(n, n, dB, n, n, blk))
+        assert oz2.stats()["tc_gemm_launches"] == 1, order
+        assert_same_dataset(got, {k: O.DenseMatrix(v.numRows, v.numCols, v.values) for k, v in ref.items()}, exact_storage=True)
+
+
+def test_crt_panelled_scratch_is_bit_identical():
+    """Operands whose residues exceed the scratch budget are multiplied as (row panel x column panel) jobs that re-prepare their
+    slots; same bits as the resident run.  (Budgets of 6 / 12 / 24 MiB at n ~ 1024, blk = 128 give 1 x 1 up to 4 x 4-slot panels; everything resident needs 40 MiB.)"""
+    rng = np.random.default_rng(99)
+    n, k, m, blk = 1024 - 40, 768, 1024 - 100, 128
+    A = random_block_dataset(rng, n, k, blk, p_transposed=0.4)
+    B = random_block_dataset(rng, k, m, blk, p_transposed=0.4)
+    with mb.MatfastSession(device=0, gemm_algo=4) as s:
+        ref = from_dataset(to_dataset(s, A).matrixMultiply(n, k, to_dataset(s, B), k, m, blk))
+        for mbytes in (6, 12, 24):
+            s.set_option("ozaki_scratch_mb", mbytes)
+            s.reset_stats()
+            got = from_dataset(to_dataset(s, A).matrixMultiply(n, k, to_dataset(s, B), k, m, blk))
+            assert s.stats()["tc_gemm_launches"] == 1
+            assert_same_dataset(got, {kk: O.DenseMatrix(v.numRows, v.numCols, v.values) for kk, v in ref.items()}, exact_storage=True)
+    assert_same_dataset(ref, O.matrix_multiply(A, n, k, B, k, m, blk), tol=1e-13)
+
+
+def _adversarial(rng, n, tiny):
+    """Row i of A = (1, tiny, tiny, ...), column j of B = (0, 1, 1, ...): |A||B|_ij = (n - 1) * tiny, carried ONLY by elements
+    2^-60 below their row maximum -- the per-row scaling of the residue scheme rounds them away."""
+    Af = np.full((n, n), tiny) * rng.uniform(1.0, 2.0, (n, n))
+    Af[:, 0] = 1.0
+    Bf = rng.uniform(1.0, 2.0, (n, n))
+    Bf[0, :] = 0.0
+    return Af, Bf
+
+
+def test_auto_selection_guards_in_row_dynamic_range():
+    """gemm_algo 0 (auto): the tcgen05 path is taken for data of ordinary range (element-wise error <= 1e-13 |A||B|) and
+    refused ON THE DEVICE when a non-zero element lies too far below its row / column maximum -- the exact DMMA kernel then
+    runs instead and the element-wise bound against |A||B| holds.  gemm_algo 4 (unguarded) shows why the guard exists."""
+    rng = np.random.default_rng(7)
+    n, blk = 2048, 256
+    with mb.MatfastSession(device=0, gemm_algo=0) as s:
+        # ordinary data: in-row range of U(-1,1) over 2048 elements is ~2^-12..2^-25
+        Af, Bf = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+        s.reset_stats()
+        got = full(from_dataset(to_dataset(s, blocks_of(Af, blk)).matrixMultiply(n, n, to_dataset(s, blocks_of(Bf, blk)), n, n, blk)), n, n, blk)
+        assert s.stats()["tc_gemm_launches"] == 1            # large regular product: the tcgen05 path was planned
+        assert np.max(np.abs(got - Af @ Bf) / (np.abs(Af) @ np.abs(Bf))) <= 1e-13
+        # adversarial rows: guard trips, DMMA result
+        Af, Bf = _adversarial(rng, n, 2.0 ** -60)
+        want, scale = Af @ Bf, np.abs(Af) @ np.abs(Bf)
+        got = full(from_dataset(to_dataset(s, blocks_of(Af, blk)).matrixMultiply(n, n, to_dataset(s, blocks_of(Bf, blk)), n, n, blk)), n, n, blk)
+        assert np.max(np.abs(got - want) / scale) <= 1e-12
+        # a range the guard accepts (2^-30 below the maximum keeps 25+ bits): still within the north-star tolerance of |A||B|
+        Af, Bf = _adversarial(rng, n, 2.0 ** -30)
+        want, scale = Af @ Bf, np.abs(Af) @ np.abs(Bf)
+        got = full(from_dataset(to_dataset(s, blocks_of(Af, blk)).matrixMultiply(n, n, to_dataset(s, blocks_of(Bf, blk)), n, n, blk)), n, n, blk)
+        assert np.max(np.abs(got - want) / scale) <= 1e-5
+    with mb.MatfastSession(device=0, gemm_algo=4) as s:          # unguarded: the tiny elements vanish
+        Af, Bf = _adversarial(rng, n, 2.0 ** -60)
+        want, scale = Af @ Bf, np.abs(Af) @ np.abs(Bf)
+        got = full(from_dataset(to_dataset(s, blocks_of(Af, blk)).matrixMultiply(n, n, to_dataset(s, blocks_of(Bf, blk)), n, n, blk)), n, n, blk)
+        assert np.max(np.abs(got - want) / scale) > 1e-2
+
+
+def test_auto_selection_small_products_stay_on_dmma(session):
+    n, blk = 512, 128
+    A, B = session.rand(n, n, blk, 1), session.rand(n, n, blk, 2)
+    session.reset_stats()
+    A.matrixMultiply(n, n, B, n, n, blk)
+    st = session.stats()
+    assert st["tc_gemm_launches"] == 0 and st["kernel_launches"] == 1
