@@ -131,10 +131,28 @@ _W = {}
 
 
 def host_cores() -> int:
+    """Cores this process may actually use: the affinity mask, capped by the cgroup CPU quota (a 1-GPU lease of the 128-thread
+    GPU host gets a fraction of its CPUs: round 1 read 353 GFLOP/s there and 1600 on the 8-GPU lease of the same host class)."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]           # cgroup v2
+        if q != "max":
+            quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())   # cgroup v1
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
 
 
 def _cpu_task(ij):
@@ -327,7 +345,12 @@ def run_ours(args):
 
     if world > 1:
         from matrel_b200 import distributed as dist_mm
-        return dist_mm.bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample, int8_peak_tops)
+        line = dist_mm.bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample, int8_peak_tops)
+        if line is not None:   # rank 0
+            # the per-rank sampled blocks are checked against numpy fp64 on the host (= the oracle's dgemm), MAX over ranks
+            line["max_rel_err_vs_oracle"] = line["check"]["max_rel_err_vs_host_fp64"]
+            print(json.dumps(line), flush=True)
+        return
 
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
@@ -556,6 +579,7 @@ def main():
     ap.add_argument("--algo", type=int, default=0, choices=(0, 1, 2, 4),
                     help="gemm_algo of the headline: 0 = auto (tcgen05 Ozaki-II with the device-side guard), 1 = DMMA fp64")
     ap.add_argument("--crt-moduli", type=int, default=16)
+    ap.add_argument("--pull-chunks", type=int, default=4, help="N > 1: pieces the peer pull of A is cut into")
     ap.add_argument("--_cpu-worker", dest="cpu_worker", default=None, choices=("port", "f2j"), help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_worker:

@@ -36,11 +36,14 @@ enum {
   MR_ENOMEM = 3,
   MR_ECUDA = 4,
   MR_ENOTSUP = 5, /* SparkException("Unsupported matrix type ...") / out-of-scope dispatch row */
-  MR_ENOTFOUND = 6
+  MR_ENOTFOUND = 6,
+  MR_ENCCL = 7    /* a collective of the multi-GPU layer failed, or NCCL could not be loaded */
 };
 
 typedef struct mr_context mr_context; /* one per process per GPU (replaces MatfastSession) */
 typedef struct mr_matrix mr_matrix;   /* a Dataset of MatrixBlock rows, device resident */
+typedef struct mr_grid mr_grid;       /* one process driving several GPUs: a pr x pc grid of contexts (mr_init_grid) */
+typedef struct mr_dmatrix mr_dmatrix; /* a Dataset sharded over the GPUs of an mr_grid */
 
 /* The 7-field block struct of MatrixUDT / MLMatrixSerializer
  * (M/matrix/MLMatrix.scala:176-184, M/util/MLMatrixSerializer.scala:26-48). */
@@ -78,6 +81,8 @@ MR_API mr_status mr_set_stream(mr_context* ctx, void* cuda_stream);
 /* keys: "compat_bugs", "gemm_algo", "ozaki_slices", "crt_moduli", "ozaki_scratch_mb", "pipeline", "time_kernels", "gemm_variant" */
 MR_API mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value);
 MR_API mr_status mr_sync(mr_context* ctx);
+/* Orders the context stream (device side, no host wait) after every host->device block copy submitted so far. */
+MR_API mr_status mr_wait_ingest(mr_context* ctx);
 MR_API const char* mr_last_error(void);
 MR_API const char* mr_version(void);
 
@@ -196,6 +201,80 @@ MR_API mr_status mr_block_cyclic_num_partitions(const int32_t params[4], int32_t
 typedef enum mr_partition_scheme { MR_PART_ROW = 0, MR_PART_COLUMN = 1, MR_PART_INDEX = 2, MR_PART_BLOCK_CYCLIC = 3 } mr_partition_scheme;
 MR_API mr_status mr_partition_id(int32_t scheme, const int32_t params[4], int32_t rid, int32_t cid, int32_t* out);
 
+
+/* ======================================================================================================================
+ * Multi-GPU: block partitions sharded across the GPUs of one box.
+ *
+ * Placement is the reference's RowPartitioner x ColumnPartitioner arithmetic on a pr x pc process grid
+ * (M/partitioner/RowPartitioner.scala:34, ColumnPartitioner.scala:34): rank (r, c) owns the blocks with rid % pr == r and
+ * cid % pc == c.  A SHARDED dataset keeps the blocks a rank owns in ONE device slab: block (rid, cid) is the blkSize^2-double slot
+ * (rid / pr) * ceil(nbc / pc) + cid / pc, column-major, leading dimension = the block's own row count.  A sharded dataset is
+ * dense over its block grid (slots never written read as zeros) and all of its blocks share one isTransposed flag.
+ *
+ * Two ways to drive the GPUs:
+ *   (1) one process per GPU (torch.distributed / MPI launch): each process creates its shard with mr_matrix_create_sharded,
+ *       exports the slab with mr_ipc_export, opens its peers' slabs with mr_ipc_open and calls mr_grid_multiply;
+ *   (2) one process for all GPUs: mr_init_grid + the mr_dmatrix_* entry points below (no Spark executors, no MPI).
+ * Either way the groupByKey + join shuffles of matrixMultiplyGeneral (M/execution/MatfastExecutionHelper.scala:236-249) become
+ * copy-engine pulls of the peers' slabs over NVLink, chunked so that the multiply overlaps them; reduceByKey (:255) disappears
+ * (C-stationary); reductions and re-partitioning go through NCCL (ncclCommInitAll; failures are reported as MR_ENCCL).
+ * ====================================================================================================================== */
+typedef struct mr_grid_layout {
+  int64_t nrows, ncols;   /* matrix dimensions */
+  int32_t blkSize;
+  int32_t pr, pc;         /* process grid */
+  int32_t r, c;           /* this rank's coordinates */
+} mr_grid_layout;
+
+/* A zero-filled sharded dataset of this rank (cudaMalloc-backed, exportable through CUDA IPC). */
+MR_API mr_status mr_matrix_create_sharded(mr_context* ctx, const mr_grid_layout* layout, mr_matrix** out);
+/* The same over a caller-owned device slab (e.g. a torch tensor); not freed by the library. */
+MR_API mr_status mr_matrix_adopt_sharded(mr_context* ctx, const mr_grid_layout* layout, double* dslab, uint8_t isTransposed,
+                                         mr_matrix** out);
+MR_API mr_status mr_matrix_layout(const mr_matrix* m, mr_grid_layout* out);
+MR_API mr_status mr_matrix_slab(mr_matrix* m, double** dslab, int64_t* bytes);
+/* CUDA IPC plumbing for (1): handle64 = the 64-byte cudaIpcMemHandle_t of the allocation containing dptr, *offset = dptr's
+ * offset inside it.  mr_ipc_open maps a peer's allocation (once per handle) and returns the pointer at that offset. */
+MR_API mr_status mr_ipc_export(const void* dptr, void* handle64, int64_t* offset);
+MR_API mr_status mr_ipc_open(mr_context* ctx, const void* handle64, int64_t offset, void** dptr);
+MR_API mr_status mr_ipc_close_all(mr_context* ctx);
+/* Synchronous read of device memory valid in this process (own, peer-mapped or mr_ipc_open'ed) into a host buffer. */
+MR_API mr_status mr_memcpy_d2h(mr_context* ctx, const void* dptr, void* host, int64_t bytes);
+/* This rank's share of C = A B (Dataset.matrixMultiply, M/Dataset.scala:134-142, on the grid).  A, B: this rank's sharded operands;
+ * slabsA_row[c'] (c' = 0 .. pc-1) / slabsB_col[r'] (r' = 0 .. pr-1): slab base pointers of the ranks of this rank's grid row / grid
+ * column, valid in this process (own slab, peer-mapped, or mr_ipc_open'ed).  The caller makes sure the peers' slabs are complete
+ * before the call and stay untouched until every rank's call has run on the device (a stream barrier before and after; mr_dmatrix
+ * does it with events).  nchunks >= 1: pieces the pull of A is cut into (the multiply starts on the first).  *out is sharded. */
+MR_API mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
+                                  int32_t nchunks, mr_matrix** out);
+
+/* ---- (2) one process, all GPUs.  Replaces MatfastSession + the executors (M/MatfastSession.scala:177-234). */
+MR_API mr_status mr_init_grid(const mr_options* opts, int32_t ngpus, mr_grid** out);  /* devices 0 .. ngpus-1, grid 1x1 / 1x2 / 2x2 / 2x4 */
+MR_API mr_status mr_grid_shutdown(mr_grid* g);
+MR_API mr_status mr_grid_info(const mr_grid* g, int32_t* ngpus, int32_t* pr, int32_t* pc, int32_t* has_nccl);
+MR_API mr_status mr_grid_context(mr_grid* g, int32_t rank, mr_context** ctx);          /* rank = r * pc + c, on device `rank` */
+MR_API mr_status mr_grid_sync(mr_grid* g);
+/* mr_matrix_create(nrows, ncols, blk, ...) of SURVEY.md 8b: the dimensions live in the handle. */
+MR_API mr_status mr_dmatrix_create(mr_grid* g, int64_t nrows, int64_t ncols, int32_t blkSize, mr_dmatrix** out);
+MR_API mr_status mr_dmatrix_rand(mr_grid* g, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t seed0, mr_dmatrix** out);
+MR_API mr_status mr_dmatrix_free(mr_dmatrix* m);
+MR_API mr_status mr_dmatrix_dims(const mr_dmatrix* m, int64_t* nrows, int64_t* ncols, int32_t* blkSize);
+MR_API mr_status mr_dmatrix_owner(const mr_dmatrix* m, int32_t rid, int32_t cid, int32_t* rank);
+MR_API mr_status mr_dmatrix_part(mr_dmatrix* m, int32_t rank, mr_matrix** out);         /* borrowed: the blocks that rank owns */
+MR_API mr_status mr_dmatrix_put_block(mr_dmatrix* m, int32_t rid, int32_t cid, const mr_block_desc* blk);  /* routed to the owner */
+MR_API mr_status mr_dmatrix_get_block(mr_dmatrix* m, int32_t rid, int32_t cid, mr_block_desc* inout);
+MR_API mr_status mr_dmatrix_has_block(const mr_dmatrix* m, int32_t rid, int32_t cid, int32_t* out);
+MR_API mr_status mr_dmatrix_num_blocks(const mr_dmatrix* m, int64_t* out);
+/* Dataset.matrixMultiply :134-142 */
+MR_API mr_status mr_dmatrix_multiply(mr_dmatrix* A, mr_dmatrix* B, mr_dmatrix** out);
+/* Dataset.addElement / multiplyElement / divideElement :105-132 on co-partitioned operands (op 0 / 1 / 2): no block moves */
+MR_API mr_status mr_dmatrix_elementwise(int32_t op, mr_dmatrix* A, mr_dmatrix* B, mr_dmatrix** out);
+/* Dataset.sum / trace :73-82 (what = 0 / 1): local reduction kernels + one ncclAllReduce */
+MR_API mr_status mr_dmatrix_reduce_scalar(mr_dmatrix* A, int32_t what, double* value);
+/* repartitionWithTargetPartitioner (MatfastExecutionHelper.scala:34-44): the blocks move to their owners under a new_pr x new_pc
+ * grid of the same GPUs ((P, 1) = RowPartitioner, (1, P) = ColumnPartitioner) as grouped ncclSend / ncclRecv between the slabs. */
+MR_API mr_status mr_dmatrix_repartition(mr_dmatrix* A, int32_t new_pr, int32_t new_pc, mr_dmatrix** out);
+
 /* ---- introspection used by bench/tests (not part of the reference surface) */
 typedef struct mr_stats {
   int64_t kernel_launches;  /* CUDA kernels launched by this library since mr_init / reset */
@@ -208,6 +287,7 @@ typedef struct mr_stats {
   double tc_gemm_ms_total;  /* CUDA-event time of the tcgen05 int8 GEMM launches since reset (timing enabled only) */
   int64_t tc_gemm_launches; /* multiplies that ran on the tcgen05 path since reset */
   int64_t tc_int8_ops;      /* int8 multiply-add operations (x 2) of the most recent tcgen05 multiply */
+  int64_t p2p_bytes;        /* bytes pulled from peer GPUs over NVLink by this context (grid multiply) */
 } mr_stats;
 MR_API mr_status mr_get_stats(mr_context* ctx, mr_stats* out);
 MR_API mr_status mr_reset_stats(mr_context* ctx);

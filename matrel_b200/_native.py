@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmatrel_b200.so")
 
-MR_OK, MR_EINVAL, MR_EDIM, MR_ENOMEM, MR_ECUDA, MR_ENOTSUP, MR_ENOTFOUND = range(7)
+MR_OK, MR_EINVAL, MR_EDIM, MR_ENOMEM, MR_ECUDA, MR_ENOTSUP, MR_ENOTFOUND, MR_ENCCL = range(8)
 
 
 class MatrelError(RuntimeError):
@@ -70,6 +70,19 @@ class mr_stats(C.Structure):
         ("tc_gemm_ms_total", C.c_double),
         ("tc_gemm_launches", C.c_int64),
         ("tc_int8_ops", C.c_int64),
+        ("p2p_bytes", C.c_int64),
+    ]
+
+
+class mr_grid_layout(C.Structure):
+    _fields_ = [
+        ("nrows", C.c_int64),
+        ("ncols", C.c_int64),
+        ("blkSize", C.c_int32),
+        ("pr", C.c_int32),
+        ("pc", C.c_int32),
+        ("r", C.c_int32),
+        ("c", C.c_int32),
     ]
 
 
@@ -85,6 +98,7 @@ SIGNATURES = {
     "mr_set_stream": [_P, _P],
     "mr_set_option": [_P, C.c_char_p, _i64],
     "mr_sync": [_P],
+    "mr_wait_ingest": [_P],
     "mr_matrix_create": [_P, _PP],
     "mr_matrix_free": [_P],
     "mr_matrix_put_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
@@ -123,6 +137,34 @@ SIGNATURES = {
     "mr_block_cyclic_partition": [C.POINTER(_i32), _i32, _i32, C.POINTER(_i32)],
     "mr_block_cyclic_num_partitions": [C.POINTER(_i32), C.POINTER(_i32)],
     "mr_partition_id": [_i32, C.POINTER(_i32), _i32, _i32, C.POINTER(_i32)],
+    "mr_matrix_create_sharded": [_P, C.POINTER(mr_grid_layout), _PP],
+    "mr_matrix_adopt_sharded": [_P, C.POINTER(mr_grid_layout), _P, C.c_uint8, _PP],
+    "mr_matrix_layout": [_P, C.POINTER(mr_grid_layout)],
+    "mr_matrix_slab": [_P, _PP, C.POINTER(_i64)],
+    "mr_ipc_export": [_P, _P, C.POINTER(_i64)],
+    "mr_ipc_open": [_P, _P, _i64, _PP],
+    "mr_ipc_close_all": [_P],
+    "mr_memcpy_d2h": [_P, _P, _P, _i64],
+    "mr_grid_multiply": [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32, _PP],
+    "mr_init_grid": [C.POINTER(mr_options), _i32, _PP],
+    "mr_grid_shutdown": [_P],
+    "mr_grid_info": [_P, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)],
+    "mr_grid_context": [_P, _i32, _PP],
+    "mr_grid_sync": [_P],
+    "mr_dmatrix_create": [_P, _i64, _i64, _i32, _PP],
+    "mr_dmatrix_rand": [_P, _i64, _i64, _i32, _i64, _PP],
+    "mr_dmatrix_free": [_P],
+    "mr_dmatrix_dims": [_P, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)],
+    "mr_dmatrix_owner": [_P, _i32, _i32, C.POINTER(_i32)],
+    "mr_dmatrix_part": [_P, _i32, _PP],
+    "mr_dmatrix_put_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
+    "mr_dmatrix_get_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
+    "mr_dmatrix_has_block": [_P, _i32, _i32, C.POINTER(_i32)],
+    "mr_dmatrix_num_blocks": [_P, C.POINTER(_i64)],
+    "mr_dmatrix_multiply": [_P, _P, _PP],
+    "mr_dmatrix_elementwise": [_i32, _P, _P, _PP],
+    "mr_dmatrix_reduce_scalar": [_P, _i32, C.POINTER(_f64)],
+    "mr_dmatrix_repartition": [_P, _i32, _i32, _PP],
     "mr_get_stats": [_P, C.POINTER(mr_stats)],
     "mr_reset_stats": [_P],
 }

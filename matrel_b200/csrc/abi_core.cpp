@@ -298,6 +298,7 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->p2p_stream, cudaStreamNonBlocking));
     for (int i = 0; i < mr_context::kChunkStreams; ++i) {
       CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->chunk_stream[i], cudaStreamNonBlocking));
       CUDA_CHECK(cudaEventCreateWithFlags(&ctx->chunk_join[i], cudaEventDisableTiming));
@@ -329,11 +330,15 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
 mr_status mr_shutdown(mr_context* ctx) {
   return guarded([&] {
     if (!ctx) return;
+    DeviceScope dev(ctx);
     cudaStreamSynchronize(ctx->h2d_stream);
+    cudaStreamSynchronize(ctx->p2p_stream);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->d2h_stream);
+    for (auto& kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
     cudaStreamDestroy(ctx->h2d_stream);
     cudaStreamDestroy(ctx->d2h_stream);
+    cudaStreamDestroy(ctx->p2p_stream);
     for (int i = 0; i < mr_context::kChunkStreams; ++i) {
       if (ctx->chunk_stream[i]) cudaStreamDestroy(ctx->chunk_stream[i]);
       if (ctx->chunk_join[i]) cudaEventDestroy(ctx->chunk_join[i]);
@@ -386,9 +391,23 @@ mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
 mr_status mr_sync(mr_context* ctx) {
   return guarded([&] {
     MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    DeviceScope dev(ctx);
     CUDA_CHECK(cudaStreamSynchronize(ctx->h2d_stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->p2p_stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->d2h_stream));
+  });
+}
+
+// Orders the context stream after every host->device block copy submitted so far (they run on a private ingest stream):
+// what a caller needs before a cross-process barrier that tells peers "my blocks are in place".
+mr_status mr_wait_ingest(mr_context* ctx) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    DeviceScope dev(ctx);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_CHECK(cudaEventRecord(ctx->ev_alloc, ctx->h2d_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_alloc, 0));
   });
 }
 
@@ -417,7 +436,11 @@ mr_status mr_matrix_create(mr_context* ctx, mr_matrix** out) {
 }
 
 mr_status mr_matrix_free(mr_matrix* m) {
-  return guarded([&] { delete m; });
+  return guarded([&] {
+    if (!m) return;
+    DeviceScope dev(m->ctx);
+    delete m;
+  });
 }
 
 mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_block_desc* d) {
@@ -425,6 +448,42 @@ mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_b
     MR_REQUIRE(m != nullptr, MR_EINVAL, "matrix is null");
     validate_desc(d);
     mr_context* ctx = m->ctx;
+    DeviceScope dev(ctx);
+    if (m->shard) {
+      // a sharded dataset is dense over its block grid: the block is copied into its slot of the slab
+      const ShardLayout& L = m->shard->L;
+      MR_REQUIRE(d->type == 1, MR_ENOTSUP, "sharded datasets hold dense blocks; got a SparseMatrix for block (%d, %d)", rid, cid);
+      MR_REQUIRE(rid >= 0 && cid >= 0 && rid < L.nbr && cid < L.nbc, MR_EINVAL, "block (%d, %d) outside the %lld x %lld block grid", rid,
+                 cid, (long long)L.nbr, (long long)L.nbc);
+      MR_REQUIRE(rid % L.pr == L.r && cid % L.pc == L.c, MR_EINVAL, "block (%d, %d) belongs to rank (%d, %d) of the %d x %d grid, not (%d, %d)",
+                 rid, cid, rid % L.pr, cid % L.pc, L.pr, L.pc, L.r, L.c);
+      auto it = m->blocks.find({rid, cid});
+      MR_REQUIRE(it != m->blocks.end(), MR_EINVAL, "block (%d, %d) is not registered", rid, cid);
+      Block& tgt = it->second;
+      MR_REQUIRE(d->numRows == tgt.numRows && d->numCols == tgt.numCols, MR_EDIM, "block (%d, %d) is %d x %d, the layout expects %d x %d",
+                 rid, cid, d->numRows, d->numCols, tgt.numRows, tgt.numCols);
+      MR_REQUIRE((d->isTransposed != 0) == m->shard->isT, MR_ENOTSUP,
+                 "block (%d, %d): isTransposed differs from the dataset's (all blocks of a sharded dataset share one layout flag)", rid, cid);
+      cudaStream_t cs = ctx->pipeline ? ctx->h2d_stream : ctx->stream;
+      if (ctx->pipeline) {  // the slab (and whatever produced its previous content) is ordered on the context stream
+        CUDA_CHECK(cudaEventRecord(ctx->ev_alloc, ctx->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_alloc, 0));
+      }
+      const size_t bytes = static_cast<size_t>(d->valuesLen) * sizeof(double);
+      if (bytes) {
+        CUDA_CHECK(cudaMemcpyAsync(tgt.values.ptr<double>(), d->values, bytes, cudaMemcpyHostToDevice, cs));
+        ctx->stats.h2d_bytes += static_cast<int64_t>(bytes);
+      }
+      if (ctx->pipeline) {
+        ReadyPtr r = std::make_shared<Ready>();
+        CUDA_CHECK(cudaEventRecord(r->ev, cs));
+        tgt.ready = r;
+        tgt.settled = false;
+        tgt.seq = ++ctx->ingest_seq;
+        m->shard->slab->ready = r;
+      }
+      return;
+    }
     Block b;
     b.type = d->type;
     b.numRows = d->numRows;
@@ -554,6 +613,7 @@ mr_status mr_matrix_get_block(mr_matrix* m, int32_t rid, int32_t cid, mr_block_d
     if (it == m->blocks.end()) fail(MR_ENOTFOUND, "no block (%d, %d) in this dataset", rid, cid);
     const Block& b = it->second;
     mr_context* ctx = m->ctx;
+    DeviceScope dev(ctx);
     ReadyPtr ready;
     bool settled;
     {

@@ -575,6 +575,7 @@ void run_sparse_chains(mr_context* ctx, std::vector<OutPlan>& plans, const std::
 
 void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner& planner, int32_t blkSize,
                   mr_matrix* result, int64_t M, int64_t K, int64_t N, bool outer) {
+  const ShardInfo* out_shard = result->shard.get();
   // Low-density sparse x sparse pairs: next to any dense partial the block sum is dense whatever the partial's own format
   // (LocalMatrix.add), so there they are ordinary sparse x dense products of the densified right operand; an output block
   // made of such pairs ONLY replays the reference's format rules (run_sparse_chains).
@@ -589,16 +590,31 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       o.spsp.clear();
     }
   }
-  // allocate all output blocks from one slab
-  size_t total = 0;
-  for (auto& o : plans) total += align_up(static_cast<size_t>(o.m) * o.n * sizeof(double));
-  Slab slab(ctx, total);
+  // allocate all output blocks from one slab (packed in plan order, or at their slots when the result is a sharded dataset)
   std::vector<double*> cptr(plans.size());
-  for (size_t i = 0; i < plans.size(); ++i) {
-    auto& o = plans[i];
-    Span s = slab.take(static_cast<size_t>(o.m) * o.n * sizeof(double));
-    cptr[i] = s.ptr<double>();
-    result->blocks[{o.rid, o.cid}] = dense_block(o.m, o.n, s, false);  // product is never transposed (MLMatrix.scala:101)
+  if (out_shard) {
+    const ShardLayout& L = out_shard->L;
+    // absent output blocks must read as zeros for whoever pulls this slab later (a sharded dataset is dense over its grid)
+    if (static_cast<int64_t>(plans.size()) < L.slots_r_of(L.r) * ((L.nbc > L.c ? (L.nbc - L.c + L.pc - 1) / L.pc : 0)))
+      CUDA_CHECK(cudaMemsetAsync(out_shard->slab->p, 0, out_shard->slab->bytes, ctx->stream));
+    for (size_t i = 0; i < plans.size(); ++i) {
+      auto& o = plans[i];
+      MR_REQUIRE(o.rid % L.pr == L.r && o.cid % L.pc == L.c && o.rid < L.nbr && o.cid < L.nbc, MR_EINVAL,
+                 "output block (%d, %d) does not belong to rank (%d, %d)", o.rid, o.cid, L.r, L.c);
+      Span s{out_shard->slab, static_cast<size_t>(L.slot(o.rid, o.cid)) * L.slot_elems * sizeof(double)};
+      cptr[i] = s.ptr<double>();
+      result->blocks[{o.rid, o.cid}] = dense_block(o.m, o.n, s, false);
+    }
+  } else {
+    size_t total = 0;
+    for (auto& o : plans) total += align_up(static_cast<size_t>(o.m) * o.n * sizeof(double));
+    Slab slab(ctx, total);
+    for (size_t i = 0; i < plans.size(); ++i) {
+      auto& o = plans[i];
+      Span s = slab.take(static_cast<size_t>(o.m) * o.n * sizeof(double));
+      cptr[i] = s.ptr<double>();
+      result->blocks[{o.rid, o.cid}] = dense_block(o.m, o.n, s, false);  // product is never transposed (MLMatrix.scala:101)
+    }
   }
 
   // ---- fused GEMM launch over every output block that has dense pairs
@@ -763,7 +779,9 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     for (int gi = 0; gi < ngroups; ++gi) {
       size_t t1 = t0;
       while (t1 < keyed.size() && grp(keyed[t1]) == gi) ++t1;
-      cudaStream_t cs = side ? ctx->chunk_stream[gi % mr_context::kChunkStreams] : ctx->stream;
+      // DMMA chunks are independent launches: round-robin over the side streams so that tails overlap.  The tcgen05 engine's
+      // jobs share its residue planes and each fills the machine by itself (persistent kernel): one side stream, in order.
+      cudaStream_t cs = side ? ctx->chunk_stream[use_oz2 ? 0 : gi % mr_context::kChunkStreams] : ctx->stream;
       // wait for exactly the operand blocks this chunk reads
       std::vector<char> seen(outs.size(), 0);
       for (size_t t = t0; t < t1; ++t) {
@@ -881,6 +899,70 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
 
 }  // namespace
 
+namespace mrhost {
+
+mr_matrix* multiply_impl(mr_context* ctx, mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right, int64_t rightRowNum,
+                         int64_t rightColNum, int32_t blkSize, const ShardLayout* out_layout) {
+  for (auto& kv : left->blocks)
+    if (!kv.second.dense()) wait_ready(ctx, kv.second);
+  for (auto& kv : right->blocks)
+    if (!kv.second.dense()) wait_ready(ctx, kv.second);
+  MultiplyPlanner planner{ctx};
+  std::vector<OutPlan> plans;
+  const int64_t leftColBlkNum = ceil_div(leftColNum, blkSize);    // MatfastExecution.scala:712
+  const int64_t rightRowBlkNum = ceil_div(rightRowNum, blkSize);  // :713
+  if (leftColBlkNum == 1 && rightRowBlkNum == 1) {
+    // outer-product paths (:714-721 -> helper :175-221): every left block x every right block, no
+    // reduce.  Reference defect B1 (DuplicateLeft throws) is not reproduced; both branches return
+    // what DuplicateRight returns.
+    std::map<std::pair<int32_t, int32_t>, size_t> seen;
+    for (auto& l : left->blocks)
+      for (auto& r : right->blocks) {
+        OutPlan o;
+        o.rid = l.first.first;
+        o.cid = r.first.second;
+        planner.add_pair(o, l.second, r.second, 0);
+        auto key = std::make_pair(o.rid, o.cid);
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+          seen[key] = plans.size();
+          plans.push_back(std::move(o));
+        } else {
+          plans[it->second] = std::move(o);  // duplicate keys: the last row wins when collected into a map
+        }
+      }
+  } else {
+    // matrixMultiplyGeneral (helper :235-263): join on k, then reduce by (i, j) in ascending k.
+    std::map<int32_t, std::vector<std::pair<int32_t, const Block*>>> rights;  // k -> (j, B(k,j))
+    for (auto& r : right->blocks) rights[r.first.first].push_back({r.first.second, &r.second});
+    std::map<std::pair<int32_t, int32_t>, size_t> index;
+    // left->blocks is ordered by (i, k): iterating it visits k ascending within each i
+    for (auto& l : left->blocks) {
+      const int32_t i = l.first.first, k = l.first.second;
+      auto rit = rights.find(k);
+      if (rit == rights.end()) continue;
+      for (auto& jb : rit->second) {
+        auto key = std::make_pair(i, jb.first);
+        auto it = index.find(key);
+        if (it == index.end()) {
+          OutPlan o;
+          o.rid = i;
+          o.cid = jb.first;
+          it = index.emplace(key, plans.size()).first;
+          plans.push_back(std::move(o));
+        }
+        planner.add_pair(plans[it->second], l.second, *jb.second, k);
+      }
+    }
+  }
+  std::unique_ptr<mr_matrix> result(out_layout ? new_sharded(ctx, *out_layout, false, false) : new_matrix(ctx));
+  if (out_layout) result->blocks.clear();  // only the blocks the product has are present (join semantics); absent ones stay absent
+  run_multiply(ctx, plans, planner, blkSize, result.get(), leftRowNum, leftColNum, rightColNum, leftColBlkNum == 1 && rightRowBlkNum == 1);
+  return result.release();
+}
+
+}  // namespace mrhost
+
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------
@@ -895,66 +977,10 @@ mr_status mr_matrix_multiply(mr_matrix* left, int64_t leftRowNum, int64_t leftCo
     // MatfastExecution.scala:702-703
     MR_REQUIRE(leftColNum == rightRowNum, MR_EDIM, "Matrix dimension not match, leftColNum = %lld, rightRowNum = %lld",
                (long long)leftColNum, (long long)rightRowNum);
-    (void)leftRowNum;
-    (void)rightColNum;
     mr_context* ctx = left->ctx;
+    DeviceScope dev(ctx);
     std::lock_guard<std::mutex> lock(ctx->mu);
-    for (auto& kv : left->blocks)
-      if (!kv.second.dense()) wait_ready(ctx, kv.second);
-    for (auto& kv : right->blocks)
-      if (!kv.second.dense()) wait_ready(ctx, kv.second);
-    MultiplyPlanner planner{ctx};
-    std::vector<OutPlan> plans;
-    const int64_t leftColBlkNum = ceil_div(leftColNum, blkSize);    // :712
-    const int64_t rightRowBlkNum = ceil_div(rightRowNum, blkSize);  // :713
-    if (leftColBlkNum == 1 && rightRowBlkNum == 1) {
-      // outer-product paths (:714-721 -> helper :175-221): every left block x every right block, no
-      // reduce.  Reference defect B1 (DuplicateLeft throws) is not reproduced; both branches return
-      // what DuplicateRight returns.
-      std::map<std::pair<int32_t, int32_t>, size_t> seen;
-      for (auto& l : left->blocks)
-        for (auto& r : right->blocks) {
-          OutPlan o;
-          o.rid = l.first.first;
-          o.cid = r.first.second;
-          planner.add_pair(o, l.second, r.second, 0);
-          auto key = std::make_pair(o.rid, o.cid);
-          auto it = seen.find(key);
-          if (it == seen.end()) {
-            seen[key] = plans.size();
-            plans.push_back(std::move(o));
-          } else {
-            plans[it->second] = std::move(o);  // duplicate keys: the last row wins when collected into a map
-          }
-        }
-    } else {
-      // matrixMultiplyGeneral (helper :235-263): join on k, then reduce by (i, j) in ascending k.
-      std::map<int32_t, std::vector<std::pair<int32_t, const Block*>>> rights;  // k -> (j, B(k,j))
-      for (auto& r : right->blocks) rights[r.first.first].push_back({r.first.second, &r.second});
-      std::map<std::pair<int32_t, int32_t>, size_t> index;
-      // left->blocks is ordered by (i, k): iterating it visits k ascending within each i
-      for (auto& l : left->blocks) {
-        const int32_t i = l.first.first, k = l.first.second;
-        auto rit = rights.find(k);
-        if (rit == rights.end()) continue;
-        for (auto& jb : rit->second) {
-          auto key = std::make_pair(i, jb.first);
-          auto it = index.find(key);
-          if (it == index.end()) {
-            OutPlan o;
-            o.rid = i;
-            o.cid = jb.first;
-            it = index.emplace(key, plans.size()).first;
-            plans.push_back(std::move(o));
-          }
-          planner.add_pair(plans[it->second], l.second, *jb.second, k);
-        }
-      }
-    }
-    std::unique_ptr<mr_matrix> result(new_matrix(ctx));
-    run_multiply(ctx, plans, planner, blkSize, result.get(), leftRowNum, leftColNum, rightColNum,
-                 leftColBlkNum == 1 && rightRowBlkNum == 1);
-    *out = result.release();
+    *out = multiply_impl(ctx, left, leftRowNum, leftColNum, right, rightRowNum, rightColNum, blkSize, nullptr);
   });
 }
 

@@ -102,6 +102,8 @@ struct mr_context {
   char* stage_dev = nullptr;
   size_t stage_cap = 0, stage_off = 0;
   int pipeline = 1;
+  cudaStream_t p2p_stream = nullptr;             // pulls of peers' blocks over NVLink (copy engines), see abi_grid.cpp
+  std::map<std::string, void*> ipc_open;         // CUDA IPC handles opened by this context (handle bytes -> mapped base)
   mr_stats stats{};
   std::mutex mu;
 };
@@ -127,6 +129,15 @@ struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   bool owned = true;
+  bool sync_alloc = false;  // cudaMalloc / cudaFree (exportable through CUDA IPC) instead of the stream-ordered pool
+  struct SyncAlloc {};
+  DevBuf(mr_context* c, size_t n, SyncAlloc) : ctx(c), bytes(n), sync_alloc(true) {
+    cudaError_t e = cudaMalloc(&p, n ? n : 16);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      fail(e == cudaErrorMemoryAllocation ? MR_ENOMEM : MR_ECUDA, "cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+    }
+  }
   DevBuf(mr_context* c, size_t n) : ctx(c), bytes(n) {
     if (n == 0) return;
     cudaError_t e = cudaMallocAsync(&p, n, ctx->stream);
@@ -139,8 +150,12 @@ struct DevBuf {
   DevBuf(mr_context* c, void* borrowed, size_t n) : ctx(c), p(borrowed), bytes(n), owned(false) {}
   ~DevBuf() {
     if (owned && p) {
-      if (ready) cudaStreamWaitEvent(ctx->stream, ready->ev, 0);
-      cudaFreeAsync(p, ctx->stream);
+      if (sync_alloc) {
+        cudaFree(p);  // synchronises the device: nothing can still be using it
+      } else {
+        if (ready) cudaStreamWaitEvent(ctx->stream, ready->ev, 0);
+        cudaFreeAsync(p, ctx->stream);
+      }
     }
   }
   DevBuf(const DevBuf&) = delete;
@@ -177,10 +192,57 @@ inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 }  // namespace mrhost
 
+namespace mrhost {
+// Placement of a dataset sharded over a pr x pc process grid: rank (r, c) owns the blocks with rid % pr == r (RowPartitioner.scala:34)
+// and cid % pc == c (ColumnPartitioner.scala:34); block (rid, cid) is slot (rid / pr) * slots_c + cid / pc of its owner's slab.
+struct ShardLayout {
+  int64_t nrows = 0, ncols = 0;
+  int32_t blk = 0, pr = 1, pc = 1, r = 0, c = 0;
+  int64_t nbr = 0, nbc = 0, slots_r = 0, slots_c = 0, slot_elems = 0;
+  int64_t slot(int64_t rid, int64_t cid) const { return (rid / pr) * slots_c + cid / pc; }
+  int64_t local_slots() const { return slots_r * slots_c; }
+  int64_t slots_r_of(int rr) const { return nbr > rr ? (nbr - rr + pr - 1) / pr : 0; }  // block rows owned by grid row rr
+  bool same_as(const ShardLayout& o) const {
+    return nrows == o.nrows && ncols == o.ncols && blk == o.blk && pr == o.pr && pc == o.pc && r == o.r && c == o.c;
+  }
+};
+struct ShardInfo {
+  ShardLayout L;
+  Buf slab;             // local_slots x blk^2 doubles; every owned block is a window of it
+  bool ipc_capable = false;
+  bool isT = false;     // the isTransposed flag shared by all blocks of the dataset
+};
+}  // namespace mrhost
+
 struct mr_matrix {
   mr_context* ctx;
   std::map<std::pair<int32_t, int32_t>, mrhost::Block> blocks;
+  std::shared_ptr<mrhost::ShardInfo> shard;   // set for datasets laid out on a process grid (abi_grid.cpp)
+  std::vector<mrhost::Buf> temps;             // scratch that must outlive work enqueued on behalf of this dataset
 };
+
+namespace mrhost {
+// One process may drive several GPUs (mr_init_grid): every entry point that launches or allocates runs on its context's device.
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(const mr_context* ctx) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != ctx->device) cudaSetDevice(ctx->device);
+    else prev = -1;
+  }
+  ~DeviceScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+ShardLayout make_layout(int64_t nrows, int64_t ncols, int32_t blk, int32_t pr, int32_t pc, int32_t r, int32_t c);
+mr_matrix* new_sharded(mr_context* ctx, const ShardLayout& L, bool ipc_capable, bool zero);
+// The body of mr_matrix_multiply (abi_multiply.cpp).  out_layout != nullptr: the result is a sharded dataset in that layout
+// (its blocks are windows of one slab at their slots) instead of a packed one.  The caller holds ctx->mu.
+mr_matrix* multiply_impl(mr_context* ctx, mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right, int64_t rightRowNum,
+                         int64_t rightColNum, int32_t blkSize, const ShardLayout* out_layout);
+}  // namespace mrhost
 
 namespace mrhost {
 

@@ -62,6 +62,10 @@ class MatfastSession:
     def sync(self) -> None:
         N.check(N.lib.mr_sync(self._ctx))
 
+    def wait_ingest(self) -> None:
+        """Device-side: the session stream waits for every host->device block copy submitted so far."""
+        N.check(N.lib.mr_wait_ingest(self._ctx))
+
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         N.check(N.lib.mr_set_stream(self._ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
 
@@ -102,6 +106,56 @@ def rand_partition(session: "MatfastSession", nrows: int, ncols: int, blkSize: i
     h = C.c_void_p()
     N.check(N.lib.mr_matrix_rand_partition(session._ctx, nrows, ncols, blkSize, seed0, pr, pc, r, c,
                                            C.c_void_p(slab_ptr), slot_elems, C.byref(h)))
+    return Dataset(session, h)
+
+
+def _layout(nrows, ncols, blkSize, pr, pc, r, c):
+    return N.mr_grid_layout(int(nrows), int(ncols), int(blkSize), int(pr), int(pc), int(r), int(c))
+
+
+def create_sharded(session: "MatfastSession", nrows: int, ncols: int, blkSize: int, pr: int, pc: int, r: int, c: int) -> "Dataset":
+    """A zero-filled dataset sharded over a pr x pc process grid: this rank's blocks in one IPC-exportable slab."""
+    h = C.c_void_p()
+    lay = _layout(nrows, ncols, blkSize, pr, pc, r, c)
+    N.check(N.lib.mr_matrix_create_sharded(session._ctx, C.byref(lay), C.byref(h)))
+    return Dataset(session, h)
+
+
+def adopt_sharded(session: "MatfastSession", nrows: int, ncols: int, blkSize: int, pr: int, pc: int, r: int, c: int,
+                  slab_ptr: int, isTransposed: bool = False) -> "Dataset":
+    """The same over a caller-owned device slab (e.g. a torch tensor)."""
+    h = C.c_void_p()
+    lay = _layout(nrows, ncols, blkSize, pr, pc, r, c)
+    N.check(N.lib.mr_matrix_adopt_sharded(session._ctx, C.byref(lay), C.c_void_p(slab_ptr), 1 if isTransposed else 0, C.byref(h)))
+    return Dataset(session, h)
+
+
+def ipc_export(device_ptr: int):
+    """(64-byte CUDA IPC handle, offset) of the allocation that contains device_ptr."""
+    buf = C.create_string_buffer(64)
+    off = C.c_int64()
+    N.check(N.lib.mr_ipc_export(C.c_void_p(device_ptr), buf, C.byref(off)))
+    return bytes(buf.raw), int(off.value)
+
+
+def ipc_open(session: "MatfastSession", handle: bytes, offset: int) -> int:
+    p = C.c_void_p()
+    N.check(N.lib.mr_ipc_open(session._ctx, C.create_string_buffer(handle, 64), int(offset), C.byref(p)))
+    return p.value or 0
+
+
+def memcpy_d2h(session: "MatfastSession", device_ptr: int, out: np.ndarray) -> np.ndarray:
+    N.check(N.lib.mr_memcpy_d2h(session._ctx, C.c_void_p(device_ptr), out.ctypes.data_as(C.c_void_p), out.nbytes))
+    return out
+
+
+def grid_multiply(session: "MatfastSession", A: "Dataset", B: "Dataset", slabsA_row: Sequence[int], slabsB_col: Sequence[int],
+                  nchunks: int = 4) -> "Dataset":
+    """``mr_grid_multiply``: this rank's share of C = A B; the slab pointers are valid in this process (IPC-opened peers)."""
+    pa = (C.c_void_p * len(slabsA_row))(*[int(x) for x in slabsA_row])
+    pb = (C.c_void_p * len(slabsB_col))(*[int(x) for x in slabsB_col])
+    h = C.c_void_p()
+    N.check(N.lib.mr_grid_multiply(A._h, B._h, pa, pb, int(nchunks), C.byref(h)))
     return Dataset(session, h)
 
 

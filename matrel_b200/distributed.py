@@ -1,10 +1,13 @@
 """Grid-partitioned block multiply across the GPUs of one box: one process per GPU,
-``torch.distributed`` (NCCL over NVLink 5 / NVSwitch) for the exchange, the engine's own sm_100a
-kernels for the arithmetic.
+``torch.distributed`` for the plumbing (rendezvous, barriers, IPC handle exchange, small reductions), the
+engine's own C ABI for the data path: every rank PULLS the operand blocks it needs straight out of its
+peers' device slabs over NVLink 5 / NVSwitch with the copy engines (CUDA IPC mappings, ``mr_grid_multiply``),
+block row by block row, while its own sm_100a kernels already multiply what has arrived.
 
 What it replaces in the reference (M/ = /root/reference/src/main/scala/org/apache/spark/sql/matfast/):
   * the 2 x groupByKey + join that co-locate A(:, k) with B(k, :) (M/execution/MatfastExecutionHelper.scala:236-249)
-    -> ONE all-gather of A along the grid row and ONE all-gather of B along the grid column;
+    -> chunked peer pulls of A along the grid row and of B along the grid column, overlapped with the multiply
+    (``sharded_multiply``; the NCCL all-gather form is kept as ``sharded_multiply_allgather``);
   * reduceByKey(LocalMatrix.add) (:255) -> nothing: the layout is C-stationary, every rank owns whole
     output blocks and keeps the full K reduction inside the GEMM kernel's accumulators;
   * RowPartitioner / ColumnPartitioner placement (M/partitioner/RowPartitioner.scala:34,
@@ -132,10 +135,17 @@ def panel_blocks_B(plan: GridPlan, rank: int):
 
 
 class ShardedMatrix:
-    """The blocks of one matrix that this rank owns, in one contiguous device slab (torch tensor)."""
+    """The blocks of one matrix that this rank owns, in one contiguous device slab (torch tensor).
 
-    def __init__(self, plan: GridPlan, rank: int, slab, dataset=None):
+    ``dataset`` registers the owned blocks as an ordinary Dataset (borrowed windows of the slab); ``sharded`` is the same slab
+    adopted as a sharded dataset of the C ABI (``mr_matrix_adopt_sharded``), the operand type of ``mr_grid_multiply``."""
+
+    def __init__(self, plan: GridPlan, rank: int, slab, dataset=None, session=None, transposed: bool = False):
         self.plan, self.rank, self.slab, self.dataset = plan, rank, slab, dataset
+        self.session = session if session is not None else (dataset.matfastSession if dataset is not None else None)
+        self.transposed = transposed
+        self._sharded = None
+        self._peers = None
 
     @staticmethod
     def rand(session, plan: GridPlan, rank: int, seed0: int, device) -> "ShardedMatrix":
@@ -145,11 +155,64 @@ class ShardedMatrix:
         r, c = plan.coords(rank)
         ds = rand_partition(session, plan.nrows, plan.ncols, plan.blk, seed0, plan.pr, plan.pc, r, c,
                             slab.data_ptr(), plan.slot_elems)
-        return ShardedMatrix(plan, rank, slab, ds)
+        return ShardedMatrix(plan, rank, slab, ds, session)
+
+    @property
+    def sharded(self):
+        if self._sharded is None:
+            from .dataset import adopt_sharded
+            r, c = self.plan.coords(self.rank)
+            self._sharded = adopt_sharded(self.session, self.plan.nrows, self.plan.ncols, self.plan.blk, self.plan.pr, self.plan.pc,
+                                          r, c, self.slab.data_ptr(), self.transposed)
+        return self._sharded
+
+    def peer_slabs(self) -> List[int]:
+        """Device pointers, valid in THIS process, of every rank's slab of this matrix (collective: every rank must call it).
+        The peers' allocations are mapped through CUDA IPC once and cached."""
+        if self._peers is None:
+            import torch.distributed as dist
+            from .dataset import ipc_export, ipc_open
+            mine = ipc_export(self.slab.data_ptr())
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                everyone = [None] * dist.get_world_size()
+                dist.all_gather_object(everyone, mine)
+            else:
+                everyone = [mine]
+            self._peers = [self.slab.data_ptr() if q == self.rank else ipc_open(self.session, h, off)
+                           for q, (h, off) in enumerate(everyone)]
+        return self._peers
 
 
-def sharded_multiply(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMatrix, planA: GridPlan, planB: GridPlan):
-    """C = A * B, C-stationary on the process grid.  Returns (local C Dataset, keep-alive tensors).
+def sharded_multiply(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMatrix, planA: GridPlan, planB: GridPlan,
+                     nchunks: int = 4):
+    """C = A * B, C-stationary on the process grid, through ``mr_grid_multiply``: this rank pulls A(i, :) of its block rows from
+    the ranks of its grid row and B(:, j) of its block columns from its grid column out of their slabs (copy engines over
+    NVLink, ``nchunks`` pieces along the block rows) while the multiply already runs on the pieces that have landed.
+    The peers' slabs must be complete when the pulls run and stay untouched until every rank's multiply has consumed them:
+    callers that rewrite slabs between steps put a stream barrier around the call (``stream_barrier``).
+    Returns (local C Dataset -- a sharded dataset --, keep-alive objects)."""
+    from .dataset import grid_multiply
+    rank = groups.rank
+    r, c = planA.coords(rank)
+    pa, pb = A.peer_slabs(), B.peer_slabs()
+    rowA = [pa[planA.rank_of(r, cc)] for cc in range(planA.pc)]
+    colB = [pb[planB.rank_of(rr, c)] for rr in range(planB.pr)]
+    dC = grid_multiply(session, A.sharded, B.sharded, rowA, colB, nchunks)
+    return dC, (A, B)
+
+
+def stream_barrier(device):
+    """All ranks have reached this point of their CURRENT CUDA streams (a one-element NCCL all-reduce; no host sync)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.zeros(1, device=device)
+        dist.all_reduce(t)
+
+
+def sharded_multiply_allgather(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMatrix, planA: GridPlan, planB: GridPlan):
+    """C = A * B, C-stationary on the process grid, with NCCL all-gathers of the operand slabs (the form round 1 benchmarked;
+    kept for comparison and for ranks that cannot map their peers' memory).  Returns (local C Dataset, keep-alive tensors).
 
     planA describes A (n x k), planB describes B (k x m); both share blk and the grid."""
     from .dataset import Dataset
@@ -305,7 +368,7 @@ def sharded_transpose(session, A: ShardedMatrix) -> ShardedMatrix:
     shapes = [pt.block_shape(i, j) for i, j in blocks]
     ds.put_blocks_device([b[0] for b in blocks], [b[1] for b in blocks], [sh[0] for sh in shapes], [sh[1] for sh in shapes],
                          [slab.data_ptr() + pt.slot(i, j) * pt.slot_elems * esz for i, j in blocks], [1] * len(blocks))
-    return ShardedMatrix(pt, A.rank, slab, ds)
+    return ShardedMatrix(pt, A.rank, slab, ds, A.session, transposed=True)
 
 
 def sharded_aggregate(kind: str, groups: GridGroups, A: ShardedMatrix):
@@ -344,12 +407,13 @@ def sharded_aggregate(kind: str, groups: GridGroups, A: ShardedMatrix):
 
 
 def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference_sample, int8_peak_tops=None):
+    """bench.py's N > 1 arm: one rank per GPU, C-stationary grid, peer pulls overlapped with the multiply."""
     import json
     import time
     import numpy as np
     import torch
     import torch.distributed as dist
-    from .dataset import MatfastSession
+    from .dataset import MatfastSession, memcpy_d2h
     from .matrix import DenseMatrix, MatrixBlock
 
     world = int(os.environ["WORLD_SIZE"])
@@ -358,22 +422,50 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
     device = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=device)
     n, blk = args.n, args.blk
+    nb = n // blk
     plan = GridPlan(world, n, n, blk)
     groups = GridGroups(plan, rank)
     flops = 2.0 * n ** 3
+    algo = getattr(args, "algo", 0)
+
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     stream = torch.cuda.Stream(device=device)
     with torch.cuda.stream(stream):
         s = MatfastSession(device=local_rank, stream=stream.cuda_stream)
+        s.set_option("gemm_algo", algo)
+        s.set_option("crt_moduli", getattr(args, "crt_moduli", 16))
         A = ShardedMatrix.rand(s, plan, rank, 42, device)
         B = ShardedMatrix.rand(s, plan, rank, 43, device)
         s.sync()
+        A.peer_slabs()
+        B.peer_slabs()            # collective: CUDA IPC handles exchanged and mapped once
+        torch.cuda.synchronize()
+        dist.barrier()
 
         def step():
-            # one exchange + one GEMM launch per rank.  (sharded_multiply_overlapped pipelines the A exchange against the
-            # GEMM in chunks; measured at 8 GPUs it LOSES -- 36.9 vs 33.4 ms -- because 2048 tiles per rank split into 4
-            # launches quantise to 4 x 4 waves instead of 13.8, which costs more than the ~2 ms of exposed all-gather.)
-            return sharded_multiply(s, groups, A, B, plan, plan)
+            return sharded_multiply(s, groups, A, B, plan, plan, nchunks=getattr(args, "pull_chunks", 4))
+
+        def timed(steps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                out = step()
+                del out
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            return allmax(e0.elapsed_time(e1) / steps)
 
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -383,25 +475,15 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
         torch.cuda.synchronize()
         dist.barrier()
         s.reset_stats()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        dist.barrier()
         sampler.mark()
-        e0.record(stream)
-        for _ in range(args.steps):
-            out = step()
-            del out
-        e1.record(stream)
-        torch.cuda.synchronize()
-        dist.barrier()
+        ms_max = timed(args.steps)
         clocks = sampler.stop()
-        ms = e0.elapsed_time(e1) / args.steps
         st = s.stats()
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
+        on_tc = st["tc_gemm_launches"] > 0
+        launches = allsum(st["kernel_launches"])
+        p2p = allsum(st["p2p_bytes"]) / args.steps
 
-        # GEMM kernel alone on this rank (library-side CUDA events)
+        # the dominant kernel alone on this rank (library-side CUDA events), max over ranks
         s.set_option("time_kernels", 1)
         s.reset_stats()
         for _ in range(3):
@@ -409,62 +491,104 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
             del out
         st2 = s.stats()
         s.set_option("time_kernels", 0)
-        kern_ms = st2["gemm_ms_total"] / 3.0          # all GEMM launches of one step
-        kt = torch.tensor([kern_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
-        kern_ms = float(kt.item())
+        dpeak, dpeak_src = fp64_peak_tflops()
+        if on_tc:
+            kern_ms = allmax(st2["tc_gemm_ms_total"] / 3.0)
+            ipeak, ipeak_src = int8_peak_tops() if int8_peak_tops else (2.0 * 1364.4, "2 x bf16 sustained")
+            ach = st2["tc_int8_ops"] / (kern_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": ipeak, "unit": "TFLOP/s", "frac": ach / ipeak, "traffic": None,
+                        "op": "int8 multiply-add x 2 (TOPS) on tcgen05.mma kind::i8, per rank",
+                        "kernel": "ozaki_gemm_i8_kernel", "kernel_ms": kern_ms,
+                        "algorithmic": f"{st2['tc_int8_ops']:.4g} int8 ops per rank per step (moduli x 2 M_loc N_loc K; max-over-ranks kernel time)",
+                        "peak_source": ipeak_src,
+                        "fp64_equivalent": {"achieved": flops / (ms_max * 1e-3) / 1e12, "dmma_peak": world * dpeak,
+                                            "x_dmma_roof": flops / (ms_max * 1e-3) / 1e12 / (world * dpeak)}}
+        else:
+            kern_ms = allmax(st2["gemm_ms_total"] / 3.0)
+            ach = (flops / world) / (kern_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": dpeak, "unit": "TFLOP/s", "frac": ach / dpeak, "traffic": None,
+                        "kernel": "gemm_f64_dmma_kernel<128,128,2,4,5>", "kernel_ms": kern_ms,
+                        "algorithmic": f"2*N^3/{world} = {flops / world:.4g} flop per launch per rank (max-over-ranks kernel time)",
+                        "peak_source": dpeak_src}
 
-        # ---- the same sharded multiply with the tcgen05 Ozaki kernel on every rank (reported beside the headline)
-        ozaki = None
-        try:
-            s.set_option("gemm_algo", getattr(args, "tc_algo", 4))
-            s.set_option("ozaki_slices", getattr(args, "ozaki_slices", 7))
-            s.set_option("crt_moduli", getattr(args, "crt_moduli", 16))
-            for _ in range(2):
-                out = step()
-                del out
-            torch.cuda.synchronize()
-            dist.barrier()
-            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            o0.record(stream)
-            for _ in range(args.steps):
-                out = step()
-                del out
-            o1.record(stream)
-            torch.cuda.synchronize()
-            ot = torch.tensor([o0.elapsed_time(o1) / args.steps], dtype=torch.float64, device=device)
-            dist.all_reduce(ot, op=dist.ReduceOp.MAX)
-            oz_ms = float(ot.item())
-            ozaki = {"algo": ("Ozaki-II, %d moduli" % getattr(args, "crt_moduli", 16) if getattr(args, "tc_algo", 4) == 4 else
-                              "Ozaki-I, %d int8 slices" % getattr(args, "ozaki_slices", 7)) + ", tcgen05 kind::i8 on every rank",
-                     "value": flops / (oz_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": oz_ms}
-        except Exception as e:
-            ozaki = {"error": str(e)}
-        finally:
-            s.set_option("gemm_algo", 0)
+        # ---- correctness of the timed configuration: one output block per rank against numpy fp64 on the host, from the operand
+        #      blocks as they sit in the owners' slabs (read through the IPC mappings); MAX over ranks
+        def host_reference(i, j):
+            from threadpoolctl import threadpool_limits
+            pa, pb = A.peer_slabs(), B.peer_slabs()
+            want = np.zeros((blk, blk))
+            bufa, bufb = np.empty(blk * blk), np.empty(blk * blk)
+            with threadpool_limits(limits=8, user_api="blas"):
+                for k in range(nb):
+                    memcpy_d2h(s, pa[plan.owner(i, k)] + plan.slot(i, k) * plan.slot_elems * 8, bufa)
+                    memcpy_d2h(s, pb[plan.owner(k, j)] + plan.slot(k, j) * plan.slot_elems * 8, bufb)
+                    want += bufa.reshape(blk, blk).T @ bufb.reshape(blk, blk).T      # blocks are column-major
+            return want
+
+        def check_block(dC):
+            mine = plan.owned(rank)
+            i, j = mine[(len(mine) * 2) // 3]
+            got = dC.get_block(i, j).to_numpy()
+            want = host_reference(i, j)
+            return float(np.max(np.abs(got - want)) / np.max(np.abs(want))), [int(i), int(j)]
+
+        dC, keep = step()
+        err, blk_id = check_block(dC)
+        nblocks = allsum(len(dC.block_ids()))
+        del dC, keep
+        check = {"max_rel_err_vs_host_fp64": allmax(err), "blocks_checked": world, "rank0_block": blk_id,
+                 "output_blocks_total": int(nblocks), "expected_blocks": nb * nb}
+
+        # ---- the exact native-fp64 kernel (DMMA) on every rank, beside the headline
+        dmma = None
+        if on_tc:
+            try:
+                s.set_option("gemm_algo", 1)
+                for _ in range(2):
+                    out = step()
+                    del out
+                d_ms = timed(max(3, min(args.steps, 5)))
+                dC, keep = step()
+                derr, _ = check_block(dC)
+                del dC, keep
+                dmma = {"algo": "gemm_algo 1: gemm_f64_dmma_kernel on every rank", "value": flops / (d_ms * 1e-3) / 1e9, "unit": UNIT,
+                        "ms_per_step": d_ms, "frac_of_dmma_roof": flops / (d_ms * 1e-3) / 1e12 / (world * dpeak),
+                        "max_rel_err_vs_host_fp64": allmax(derr)}
+            except Exception as e:
+                dmma = {"error": str(e)[-200:]}
+            finally:
+                s.set_option("gemm_algo", algo)
         dist.barrier()
 
-        # ---- end to end: each rank feeds its own A/B blocks from pinned host memory and reads its C blocks back
+        # ---- end to end: every rank feeds its own A / B blocks from pinned host memory into its slabs, pulls what it needs from
+        #      its peers, multiplies, and reads its C blocks back
         hostA = [(k, A.dataset.get_block(*k)) for k in A.dataset.block_ids()]
         hostB = [(k, B.dataset.get_block(*k)) for k in B.dataset.block_ids()]
-        pin = lambda v: torch.from_numpy(v).pin_memory()  # noqa: E731
-        pA = [(k, pin(m.values)) for k, m in hostA]
-        pB = [(k, pin(m.values)) for k, m in hostB]
+        pin = lambda v: torch.from_numpy(v).pin_memory().numpy()  # noqa: E731
+        pA = [MatrixBlock(i, j, DenseMatrix(m.numRows, m.numCols, pin(m.values), m.isTransposed)) for (i, j), m in hostA]
+        pB = [MatrixBlock(i, j, DenseMatrix(m.numRows, m.numCols, pin(m.values), m.isTransposed)) for (i, j), m in hostB]
+        ref00 = hostA[0][1].values[:4].copy()
+        del hostA, hostB
         outbuf = {k: torch.empty(blk * blk, dtype=torch.float64).pin_memory().numpy() for k in plan.owned(rank)}
-        h2d = sum(v.numel() * 8 for _, v in pA) + sum(v.numel() * 8 for _, v in pB)
+        h2d = sum(b.matrix.values.nbytes for b in pA) + sum(b.matrix.values.nbytes for b in pB)
         d2h = sum(v.nbytes for v in outbuf.values())
-        slabA = torch.zeros_like(A.slab)
-        slabB = torch.zeros_like(B.slab)
+        eA = ShardedMatrix(plan, rank, torch.zeros_like(A.slab), None, s)
+        eB = ShardedMatrix(plan, rank, torch.zeros_like(B.slab), None, s)
+        eA.peer_slabs()
+        eB.peer_slabs()
+        torch.cuda.synchronize()
+        dist.barrier()
 
         def e2e_step():
-            for (i, j), v in pA:
-                slabA[plan.slot(i, j), :v.numel()].copy_(v, non_blocking=True)
-            for (i, j), v in pB:
-                slabB[plan.slot(i, j), :v.numel()].copy_(v, non_blocking=True)
-            dC, keep = sharded_multiply(s, groups, ShardedMatrix(plan, rank, slabA), ShardedMatrix(plan, rank, slabB), plan, plan)
-            for k in dC.block_ids():
+            eB.sharded.put_blocks(pB)          # async copies on the ingest stream, one event per block
+            eA.sharded.put_blocks(pA)
+            s.wait_ingest()                    # device-side: the session stream follows the ingest ...
+            stream_barrier(device)             # ... so this barrier tells every peer "my slabs are in place"
+            dC, keep = sharded_multiply(s, groups, eA, eB, plan, plan, nchunks=getattr(args, "pull_chunks", 4))
+            for k in sorted(dC.block_ids()):   # block rows complete in order; egress overlaps the later chunks
                 dC.get_block(*k, out=outbuf[k])
-            return dC, keep
+            stream_barrier(device)             # nobody rewrites a slab while a peer may still be pulling from it
+            return dC
 
         for _ in range(min(2, args.warmup)):
             e2e_step()
@@ -476,38 +600,40 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
             e2e_step()
         torch.cuda.synchronize()
         dist.barrier()
-        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-        et = torch.tensor([e2e_ms, float(h2d), float(d2h)], dtype=torch.float64, device=device)
-        emax = et.clone()
-        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(et, op=dist.ReduceOp.SUM)
-        e2e_ms = float(emax[0].item())
-        h2d_total, d2h_total = int(et[1].item()), int(et[2].item())
-        launches = torch.tensor([float(st["kernel_launches"])], dtype=torch.float64, device=device)
-        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        e2e_ms = allmax((time.perf_counter() - t0) / e2e_steps * 1e3)
+        dC = e2e_step()
+        mine = plan.owned(rank)
+        i, j = mine[(len(mine) * 2) // 3]
+        e2e_err = float(np.max(np.abs(outbuf[(i, j)].reshape(blk, blk).T - host_reference(i, j))) / np.max(np.abs(outbuf[(i, j)])))
+        check["e2e_max_rel_err_vs_host_fp64"] = allmax(e2e_err)
+        del dC
+        h2d_total, d2h_total = int(allsum(h2d)), int(allsum(d2h))
+        torch.cuda.synchronize()
+        dist.barrier()
         s.stop()
 
     if rank == 0:
-        peak, peak_src = fp64_peak_tflops()
-        achieved = (flops / world) / (kern_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": flops / (ms_max * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{n}x{n} fp64 dense multiply, {blk}-block, grid-partitioned {plan.pr}x{plan.pc} over {world}xB200",
-                       "parallelism": f"C-stationary {plan.pr}x{plan.pc} block-cyclic grid; all-gather A along grid rows, B along grid columns (NCCL), no reduction",
+                       "parallelism": (f"C-stationary {plan.pr}x{plan.pc} block-cyclic grid; every rank pulls A along its grid row and B along its grid "
+                                       "column out of its peers' slabs (CUDA IPC, copy engines over NVLink), chunked and overlapped with the multiply; no reduction"),
                        "inputs": "U(0,1) java.util.Random streams, every block present, column-major",
-                       "l2": "per-rank operands after all-gather >> 126 MB L2; no flush needed", "gemm_algo": "dmma_fp64"},
+                       "l2": "per-rank operands after the pulls >> 126 MB L2; no flush needed",
+                       "gemm_algo": "auto -> Ozaki-II on tcgen05 on every rank" if on_tc else "dmma_fp64",
+                       "p2p_bytes_per_step": p2p},
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
                     "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms, "steps": e2e_steps},
-            "gpu_launches": int(launches.item()), "gpu_launches_per_step_per_rank": st["kernel_launches"] / args.steps,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gemm_f64_dmma_kernel<128,128,2,4,5>", "kernel_ms": kern_ms,
-                         "algorithmic": f"2*N^3/{world} = {flops / world:.4g} flop per launch per rank (max-over-ranks kernel time)",
-                         "peak_source": peak_src},
+            "gpu_launches": int(launches), "gpu_launches_per_step_per_rank": st["kernel_launches"] / args.steps,
+            "roofline": roofline,
             "clocks": clocks,
-            "tcgen05_ozaki": ozaki,
+            "check": check,
+            "dmma_fp64": dmma,
         }
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
     dist.barrier()
     dist.destroy_process_group()
+    return line

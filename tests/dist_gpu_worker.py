@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import matrel_b200 as mb  # noqa: E402
 from matrel_b200.distributed import (GridGroups, GridPlan, ShardedMatrix, sharded_aggregate,  # noqa: E402
-                                     sharded_elementwise, sharded_multiply, sharded_multiply_overlapped, sharded_transpose)
+                                     sharded_elementwise, sharded_multiply, sharded_multiply_allgather, sharded_multiply_overlapped,
+                                     sharded_transpose, stream_barrier)
 from oracle import matrel_oracle as O  # noqa: E402
 
 
@@ -59,16 +60,44 @@ def main():
             s = mb.MatfastSession(device=local_rank, stream=stream.cuda_stream, gemm_algo=algo)
             A = ShardedMatrix.rand(s, planA, rank, 42, device)
             B = ShardedMatrix.rand(s, planB, rank, 43, device)
-            dC, keep = sharded_multiply(s, groups, A, B, planA, planB)
+            # the product path: peer pulls over CUDA IPC (copy engines), chunked and overlapped with the multiply
+            s.sync()
+            dist.barrier()
+            dC, keep = sharded_multiply(s, groups, A, B, planA, planB, nchunks=3)
             got = {(b.rid, b.cid): b.matrix for b in dC.collect()}
             s_launches = s.stats()["kernel_launches"]
+            assert world == 1 or s.stats()["p2p_bytes"] > 0
+            # the NCCL all-gather form must give the same blocks (bit for bit: same kernels, same summation order)
+            dG, keepG = sharded_multiply_allgather(s, groups, A, B, planA, planB)
+            gotG = {(b.rid, b.cid): b.matrix for b in dG.collect()}
+            assert sorted(gotG) == sorted(got)
+            for key in got:
+                assert np.array_equal(gotG[key].values, got[key].values), key
+            # operands that arrive from the HOST into sharded datasets (put_block on the ingest stream), barrier, pull, multiply
+            from matrel_b200.dataset import create_sharded
+            Ah = O.rand_dense_dataset(n, k, blk, 42)
+            Bh = O.rand_dense_dataset(k, m, blk, 43)
+            eA = ShardedMatrix(planA, rank, torch.zeros_like(A.slab), None, s)
+            eB = ShardedMatrix(planB, rank, torch.zeros_like(B.slab), None, s)
+            eA.peer_slabs(); eB.peer_slabs()
+            for rep in range(2):
+                eA.sharded.put_blocks(mb.MatrixBlock(i, j, mb.DenseMatrix(Ah[(i, j)].numRows, Ah[(i, j)].numCols, Ah[(i, j)].values)) for (i, j) in planA.owned(rank))
+                eB.sharded.put_blocks(mb.MatrixBlock(i, j, mb.DenseMatrix(Bh[(i, j)].numRows, Bh[(i, j)].numCols, Bh[(i, j)].values)) for (i, j) in planB.owned(rank))
+                s.wait_ingest()
+                stream_barrier(device)
+                dE, keepE = sharded_multiply(s, groups, eA, eB, planA, planB, nchunks=2)
+                gotE = {(b.rid, b.cid): b.matrix for b in dE.collect()}
+                stream_barrier(device)
+                assert sorted(gotE) == sorted(got)
+                for key in got:
+                    assert np.array_equal(gotE[key].values, got[key].values), (rep, key)
             # the overlapped exchange (A gathered in chunks on a side stream) must give the same blocks
             outs, keep2 = sharded_multiply_overlapped(s, groups, A, B, planA, planB, torch.cuda.Stream(device=device), nchunks=3)
             got2 = {(b.rid, b.cid): b.matrix for d in outs for b in d.collect()}
             assert sorted(got2) == sorted(got)
             for key in got:
                 assert np.array_equal(got2[key].values, got[key].values), key
-            if algo == 0:
+            if algo in (0, 1):
                 siblings(s, groups, A, planA, rank, device, n, k, blk)
             s.stop()
         want = O.matrix_multiply(O.rand_dense_dataset(n, k, blk, 42), n, k, O.rand_dense_dataset(k, m, blk, 43), k, m, blk)
@@ -77,7 +106,7 @@ def main():
             w = want[key]
             assert (g.numRows, g.numCols, g.isTransposed) == (w.numRows, w.numCols, False)
             err = float(np.max(np.abs(g.values - w.values)) / np.max(np.abs(w.values)))
-            assert err <= 1e-12, (key, err)
+            assert err <= (5e-5 if algo == 3 else 1e-12), (key, err)      # algo 3 = fp32 results (3xTF32)
         if algo == 2:
             assert s_launches >= 8, s_launches     # absmax/slice passes + one GEMM per diagonal: the tcgen05 path really ran
         if algo == 4:

@@ -14,7 +14,7 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("algo", [0, 2, 4])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_multiply_nccl(world, algo):
     if _ngpus() < world:
