@@ -417,6 +417,8 @@ struct mr_dmatrix {
   mr_grid* g = nullptr;
   int64_t nrows = 0, ncols = 0;
   int32_t blk = 0;
+  int32_t pr = 1, pc = 1;             // the placement grid of THIS dataset (the grid's own shape unless re-partitioned)
+  int owner(int32_t rid, int32_t cid) const { return (rid % pr) * pc + (cid % pc); }
   std::vector<mr_matrix*> part;       // rank -> the blocks that rank owns (sharded dataset)
   ~mr_dmatrix() {
     for (size_t i = 0; i < part.size(); ++i)
@@ -429,17 +431,38 @@ struct mr_dmatrix {
 
 namespace {
 
-ShardLayout layout_of(const mr_dmatrix* m, int rank) { return make_layout(m->nrows, m->ncols, m->blk, m->g->pr, m->g->pc, rank / m->g->pc, rank % m->g->pc); }
+ShardLayout layout_of(const mr_dmatrix* m, int rank) { return make_layout(m->nrows, m->ncols, m->blk, m->pr, m->pc, rank / m->pc, rank % m->pc); }
 
-std::unique_ptr<mr_dmatrix> new_dmatrix(mr_grid* g, int64_t nrows, int64_t ncols, int32_t blk) {
+std::unique_ptr<mr_dmatrix> new_dmatrix(mr_grid* g, int64_t nrows, int64_t ncols, int32_t blk, int pr = 0, int pc = 0) {
   std::unique_ptr<mr_dmatrix> m(new mr_dmatrix);
   m->g = g;
   m->nrows = nrows;
   m->ncols = ncols;
   m->blk = blk;
+  m->pr = pr > 0 ? pr : g->pr;
+  m->pc = pc > 0 ? pc : g->pc;
   m->part.assign(g->n, nullptr);
   return m;
 }
+
+// An operand that lives on another placement grid is first moved to (pr, pc): repartitionWithTargetPartitioner
+// (MatfastExecutionHelper.scala:34-44) -- what the reference does before every co-partitioned operator.
+struct OnGrid {
+  mr_dmatrix* m;
+  mr_dmatrix* owned = nullptr;
+  OnGrid(mr_dmatrix* a, int pr, int pc) : m(a) {
+    if (a->pr != pr || a->pc != pc) {
+      const mr_status st = mr_dmatrix_repartition(a, pr, pc, &owned);
+      if (st != MR_OK) throw MrError{st, g_last_error};
+      m = owned;
+    }
+  }
+  ~OnGrid() {
+    if (owned) mr_dmatrix_free(owned);
+  }
+  OnGrid(const OnGrid&) = delete;
+  OnGrid& operator=(const OnGrid&) = delete;
+};
 
 // A part that is not backed by a slab in this layout (e.g. the result of an element-wise operator) is copied into one.
 mr_matrix* ensure_sharded(mr_matrix* part, const ShardLayout& L, std::unique_ptr<mr_matrix>& keep) {
@@ -626,7 +649,7 @@ mr_status mr_dmatrix_dims(const mr_dmatrix* m, int64_t* nrows, int64_t* ncols, i
 mr_status mr_dmatrix_owner(const mr_dmatrix* m, int32_t rid, int32_t cid, int32_t* rank) {
   return guarded([&] {
     MR_REQUIRE(m != nullptr && rank != nullptr && rid >= 0 && cid >= 0, MR_EINVAL, "bad argument");
-    *rank = (rid % m->g->pr) * m->g->pc + (cid % m->g->pc);
+    *rank = m->owner(rid, cid);
   });
 }
 
@@ -635,8 +658,7 @@ mr_status mr_dmatrix_put_block(mr_dmatrix* m, int32_t rid, int32_t cid, const mr
     g_last_error = "requirement failed: bad argument";
     return MR_EINVAL;
   }
-  mr_matrix* part = m->part[(rid % m->g->pr) * m->g->pc + (cid % m->g->pc)];
-  return mr_matrix_put_block(part, rid, cid, blk);
+  return mr_matrix_put_block(m->part[m->owner(rid, cid)], rid, cid, blk);
 }
 
 mr_status mr_dmatrix_has_block(const mr_dmatrix* m, int32_t rid, int32_t cid, int32_t* out) {
@@ -644,7 +666,7 @@ mr_status mr_dmatrix_has_block(const mr_dmatrix* m, int32_t rid, int32_t cid, in
     g_last_error = "requirement failed: bad argument";
     return MR_EINVAL;
   }
-  return mr_matrix_has_block(m->part[(rid % m->g->pr) * m->g->pc + (cid % m->g->pc)], rid, cid, out);
+  return mr_matrix_has_block(m->part[m->owner(rid, cid)], rid, cid, out);
 }
 
 mr_status mr_dmatrix_get_block(mr_dmatrix* m, int32_t rid, int32_t cid, mr_block_desc* inout) {
@@ -652,7 +674,7 @@ mr_status mr_dmatrix_get_block(mr_dmatrix* m, int32_t rid, int32_t cid, mr_block
     g_last_error = "requirement failed: bad argument";
     return MR_EINVAL;
   }
-  return mr_matrix_get_block(m->part[(rid % m->g->pr) * m->g->pc + (cid % m->g->pc)], rid, cid, inout);
+  return mr_matrix_get_block(m->part[m->owner(rid, cid)], rid, cid, inout);
 }
 
 mr_status mr_dmatrix_num_blocks(const mr_dmatrix* m, int64_t* out) {
@@ -694,14 +716,16 @@ mr_status mr_dmatrix_rand(mr_grid* g, int64_t nrows, int64_t ncols, int32_t blkS
 }
 
 // Dataset.matrixMultiply (M/Dataset.scala:134-142) on the grid: dimensions and block size come from the handles.
-mr_status mr_dmatrix_multiply(mr_dmatrix* A, mr_dmatrix* B, mr_dmatrix** out) {
+mr_status mr_dmatrix_multiply(mr_dmatrix* A_in, mr_dmatrix* B_in, mr_dmatrix** out) {
   return guarded([&] {
-    MR_REQUIRE(A && B && out, MR_EINVAL, "null argument");
-    MR_REQUIRE(A->g == B->g, MR_EINVAL, "operands live on different grids");
-    MR_REQUIRE(A->blk == B->blk, MR_EINVAL, "operands have different block sizes (%d, %d)", A->blk, B->blk);
-    MR_REQUIRE(A->ncols == B->nrows, MR_EDIM, "Matrix dimension not match, leftColNum = %lld, rightRowNum = %lld", (long long)A->ncols,
-               (long long)B->nrows);
-    mr_grid* g = A->g;
+    MR_REQUIRE(A_in && B_in && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(A_in->g == B_in->g, MR_EINVAL, "operands live on different grids");
+    MR_REQUIRE(A_in->blk == B_in->blk, MR_EINVAL, "operands have different block sizes (%d, %d)", A_in->blk, B_in->blk);
+    MR_REQUIRE(A_in->ncols == B_in->nrows, MR_EDIM, "Matrix dimension not match, leftColNum = %lld, rightRowNum = %lld",
+               (long long)A_in->ncols, (long long)B_in->nrows);
+    mr_grid* g = A_in->g;
+    OnGrid ga(A_in, g->pr, g->pc), gb(B_in, g->pr, g->pc);   // the multiply runs on the grid's own (C-stationary) placement
+    mr_dmatrix *A = ga.m, *B = gb.m;
     const int n = g->n, pr = g->pr, pc = g->pc;
     // operands in slab form on every rank
     std::vector<std::unique_ptr<mr_matrix>> keepA(n), keepB(n);
@@ -756,12 +780,15 @@ mr_status mr_dmatrix_multiply(mr_dmatrix* A, mr_dmatrix* B, mr_dmatrix** out) {
 // Co-partitioned element-wise operators (MatrixElement{Add,Multiply,Divide}Execution, the zipPartitions fast path of
 // MatfastExecutionHelper.scala:64-173): op 0 = add, 1 = multiply, 2 = divide.  Both operands live on the same grid with the same
 // placement function, so no block moves.
-mr_status mr_dmatrix_elementwise(int32_t op, mr_dmatrix* A, mr_dmatrix* B, mr_dmatrix** out) {
+mr_status mr_dmatrix_elementwise(int32_t op, mr_dmatrix* A, mr_dmatrix* B_in, mr_dmatrix** out) {
   return guarded([&] {
-    MR_REQUIRE(A && B && out, MR_EINVAL, "null argument");
-    MR_REQUIRE(A->g == B->g, MR_EINVAL, "operands live on different grids");
+    MR_REQUIRE(A && B_in && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(A->g == B_in->g, MR_EINVAL, "operands live on different grids");
     MR_REQUIRE(op >= 0 && op <= 2, MR_EINVAL, "unknown element-wise op %d", op);
-    auto res = new_dmatrix(A->g, A->nrows, A->ncols, A->blk);
+    // MatrixElementAddExecution picks the left operand's partitioner (MatfastExecution.scala:590-606) and re-partitions the right
+    OnGrid gb(B_in, A->pr, A->pc);
+    mr_dmatrix* B = gb.m;
+    auto res = new_dmatrix(A->g, A->nrows, A->ncols, A->blk, A->pr, A->pc);
     for (int i = 0; i < A->g->n; ++i) {
       DeviceScope dev(A->g->ctx[i]);
       mr_matrix* o = nullptr;
@@ -827,12 +854,7 @@ mr_status mr_dmatrix_repartition(mr_dmatrix* A, int32_t new_pr, int32_t new_pc, 
       src[i] = ensure_sharded(A->part[i], A->part[i]->shard ? A->part[i]->shard->L : layout_of(A, i), keep[i]);
       wait_ready_all(g->ctx[i], src[i]);
     }
-    std::unique_ptr<mr_dmatrix> res(new mr_dmatrix);
-    res->g = g;
-    res->nrows = A->nrows;
-    res->ncols = A->ncols;
-    res->blk = A->blk;
-    res->part.assign(n, nullptr);
+    auto res = new_dmatrix(g, A->nrows, A->ncols, A->blk, new_pr, new_pc);
     for (int i = 0; i < n; ++i) {
       DeviceScope dev(g->ctx[i]);
       res->part[i] = new_sharded(g->ctx[i], make_layout(A->nrows, A->ncols, A->blk, new_pr, new_pc, i / new_pc, i % new_pc), false, true);
@@ -842,10 +864,8 @@ mr_status mr_dmatrix_repartition(mr_dmatrix* A, int32_t new_pr, int32_t new_pc, 
     if (n > 1) NCCL_CHECK(nccl_api().GroupStart());
     for (int64_t i = 0; i < nbr; ++i)
       for (int64_t j = 0; j < nbc; ++j) {
-        int from = -1;
-        for (int p = 0; p < n && from < 0; ++p)
-          if (src[p]->blocks.count({static_cast<int32_t>(i), static_cast<int32_t>(j)})) from = p;
-        if (from < 0) continue;
+        const int from = A->owner(static_cast<int32_t>(i), static_cast<int32_t>(j));
+        if (!src[from]->blocks.count({static_cast<int32_t>(i), static_cast<int32_t>(j)})) continue;
         const int to = static_cast<int>((i % new_pr) * new_pc + (j % new_pc));
         const Block& sb = src[from]->blocks.at({static_cast<int32_t>(i), static_cast<int32_t>(j)});
         const Block& db = res->part[to]->blocks.at({static_cast<int32_t>(i), static_cast<int32_t>(j)});
