@@ -74,7 +74,10 @@ typedef struct mr_options {
   void* stream;         /* cudaStream_t to run on; NULL = a stream owned by the context */
 } mr_options;
 
-/* ---- lifetime: replaces MatfastSession.builder().getOrCreate() (M/MatfastSession.scala:177-234) */
+/* ---- lifetime: replaces MatfastSession.builder().getOrCreate() (M/MatfastSession.scala:177-234).
+ * Destruction order: every mr_matrix / mr_dmatrix of a context must be freed BEFORE mr_shutdown (mr_grid_shutdown) of that
+ * context; handles are dangling afterwards.  mr_shutdown waits for all enqueued work, returns the memory the context's
+ * operators cached in the device's stream-ordered pool to the driver and restores the pool's release threshold. */
 MR_API mr_status mr_init(const mr_options* opts, mr_context** out);
 MR_API mr_status mr_shutdown(mr_context* ctx);
 MR_API mr_status mr_set_stream(mr_context* ctx, void* cuda_stream);
@@ -91,11 +94,18 @@ MR_API const char* mr_version(void);
 MR_API mr_status mr_matrix_create(mr_context* ctx, mr_matrix** out);
 MR_API mr_status mr_matrix_free(mr_matrix* m);
 /* Copies the block to the device (MLMatrixSerializer.deserialize, :50-69, incl. the ctor
- * `require`s of DenseMatrix :240 and SparseMatrix :533-542).  Host arrays stay caller-owned. */
+ * `require`s of DenseMatrix :240 and SparseMatrix :533-542).  Host arrays stay caller-owned.
+ * WHEN the host arrays may be reused: the copy is enqueued on the context's ingest stream.  From PAGEABLE memory (malloc, JVM
+ * heap staging, numpy) CUDA has staged the data when the call returns: the arrays are free at once.  From PAGE-LOCKED memory
+ * (cudaHostAlloc / cudaHostRegister) the copy engine reads the arrays asynchronously -- that is what lets a multiply overlap
+ * its own ingest -- so they must stay valid and unmodified until mr_matrix_wait_ingest(m) or mr_sync(ctx) has returned (or a
+ * mr_matrix_get_block of a result computed from this block has). */
 MR_API mr_status mr_matrix_put_block(mr_matrix* m, int32_t rid, int32_t cid, const mr_block_desc* blk);
 /* Batched mr_matrix_put_block: `count` blocks in one call (one ABI crossing per Seq[MatrixBlock], not per row). */
 MR_API mr_status mr_matrix_put_blocks(mr_matrix* m, int64_t count, const int32_t* rids, const int32_t* cids,
                                       const mr_block_desc* blks);
+/* Blocks the calling thread until every host->device copy of this dataset's blocks has completed (see mr_matrix_put_block). */
+MR_API mr_status mr_matrix_wait_ingest(mr_matrix* m);
 /* Adopts (borrows) a dense block already resident in device memory; not freed by the library. */
 MR_API mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int32_t numRows,
                                             int32_t numCols, const double* dvalues, uint8_t isTransposed);
@@ -120,6 +130,13 @@ MR_API mr_status mr_matrix_block_device_ptr(mr_matrix* m, int32_t rid, int32_t c
  * seed0 + rid*ceil(ncols/blk) + cid.  Used for synthetic benchmark inputs. */
 MR_API mr_status mr_matrix_rand(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize,
                                 int64_t seed0, mr_matrix** out);
+
+/* SparseMatrix.sprand(r, c, density, new java.util.Random(seed0 + rid * ceil(ncols / blk) + cid)) for every block
+ * (M/matrix/MLMatrix.scala:791-856: nnz = ceil(r * c * density) distinct coordinates drawn one by one, column-major order, values
+ * U(0,1) in storage order), generated on the device bit-identically to the JVM.  csr != 0: block (rid, cid) is the transpose of
+ * sprand(c, r, ...), i.e. CSR storage (isTransposed = true).  Power-of-two block dimensions, 0 < density < 0.34 (MR_ENOTSUP else). */
+MR_API mr_status mr_matrix_sprand(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize, double density, int64_t seed0,
+                                  uint8_t csr, mr_matrix** out);
 
 /* Same generator restricted to the blocks a rank of a pr x pc process grid owns
  * (rid % pr == r, RowPartitioner.scala:34; cid % pc == c, ColumnPartitioner.scala:34), written into a

@@ -91,7 +91,7 @@ _PP = C.POINTER(C.c_void_p)
 _i32, _i64, _f64 = C.c_int32, C.c_int64, C.c_double
 _BIN = [_P, _i64, _i64, _P, _i64, _i64, _i32, _PP]
 
-# name -> argtypes; every symbol include/matrel.h declares (tests/test_abi_symbols.py checks the two agree)
+# name -> argtypes; every symbol include/matrel.h declares (tests/test_abi_cpu.py checks the two agree)
 SIGNATURES = {
     "mr_init": [C.POINTER(mr_options), _PP],
     "mr_shutdown": [_P],
@@ -103,6 +103,7 @@ SIGNATURES = {
     "mr_matrix_free": [_P],
     "mr_matrix_put_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
     "mr_matrix_put_blocks": [_P, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(mr_block_desc)],
+    "mr_matrix_wait_ingest": [_P],
     "mr_matrix_put_block_device": [_P, _i32, _i32, _i32, _i32, _P, C.c_uint8],
     "mr_matrix_put_blocks_device": [_P, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_uint8)],
@@ -112,6 +113,7 @@ SIGNATURES = {
     "mr_matrix_get_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
     "mr_matrix_block_device_ptr": [_P, _i32, _i32, _PP],
     "mr_matrix_rand": [_P, _i64, _i64, _i32, _i64, _PP],
+    "mr_matrix_sprand": [_P, _i64, _i64, _i32, _f64, _i64, C.c_uint8, _PP],
     "mr_matrix_rand_partition": [_P, _i64, _i64, _i32, _i64, _i32, _i32, _i32, _i32, _P, _i64, _PP],
     "mr_matrix_multiply": _BIN,
     "mr_transpose": [_P, _PP],

@@ -321,6 +321,7 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
     // keep freed blocks in the pool: operators allocate result slabs on every call
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold_before));
     uint64_t thr = UINT64_MAX;
     CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     *out = ctx.release();
@@ -351,6 +352,14 @@ mr_status mr_shutdown(mr_context* ctx) {
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    {  // hand the cached operator memory back and undo the process-wide pool setting of mr_init
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold_before);
+        cudaMemPoolTrimTo(pool, 0);
+      }
+      (void)cudaGetLastError();
+    }
     delete ctx;
   });
 }
@@ -548,6 +557,20 @@ mr_status mr_matrix_put_blocks(mr_matrix* m, int64_t count, const int32_t* rids,
     if (st != MR_OK) return st;
   }
   return MR_OK;
+}
+
+mr_status mr_matrix_wait_ingest(mr_matrix* m) {
+  return guarded([&] {
+    MR_REQUIRE(m != nullptr, MR_EINVAL, "matrix is null");
+    DeviceScope dev(m->ctx);
+    std::vector<ReadyPtr> pending;
+    {
+      std::lock_guard<std::mutex> lock(m->ctx->mu);
+      for (auto& kv : m->blocks)
+        if (kv.second.ready) pending.push_back(kv.second.ready);
+    }
+    for (auto& r : pending) CUDA_CHECK(cudaEventSynchronize(r->ev));
+  });
 }
 
 mr_status mr_matrix_put_block_device(mr_matrix* m, int32_t rid, int32_t cid, int32_t numRows, int32_t numCols,
@@ -749,5 +772,94 @@ mr_status mr_matrix_rand_partition(mr_context* ctx, int64_t nrows, int64_t ncols
   });
 }
 
+// SparseMatrix.sprand(r, c, density, new java.util.Random(seed0 + rid * nbc + cid)) for every block of an nrows x ncols matrix
+// (M/matrix/MLMatrix.scala:791-856), generated on the device bit-identically to the JVM.  csr != 0: block (rid, cid) is
+// sprand(c, r, ...).transpose, i.e. the r x c block in CSR form (isTransposed = true) -- the BASELINE configs[4] operand.
+mr_status mr_matrix_sprand(mr_context* ctx, int64_t nrows, int64_t ncols, int32_t blkSize, double density, int64_t seed0, uint8_t csr,
+                           mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr && out != nullptr, MR_EINVAL, "ctx/out is null");
+    MR_REQUIRE(nrows > 0 && ncols > 0 && blkSize > 0, MR_EINVAL, "nrows, ncols, blkSize must be positive");
+    // genRandMatrix `require` (MLMatrix.scala:798-799)
+    MR_REQUIRE(density >= 0.0 && density <= 1.0, MR_EINVAL,
+               "density must be a double in the range 0.0 <= d <= 1.0. Currently, density: %g", density);
+    MR_REQUIRE(density > 0.0 && density < 0.34, MR_ENOTSUP, "device sprand restates the draw-by-draw branch (0 < density < 0.34), got %g", density);
+    DeviceScope dev(ctx);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const int64_t nbr = ceil_div(nrows, blkSize), nbc = ceil_div(ncols, blkSize);
+    struct Plan {
+      int32_t rid, cid, r, c, gr, gc;  // logical dims (r, c); generator dims (gr, gc)
+      int64_t nnz;
+      size_t off_ptr, off_idx, off_val;
+    };
+    std::vector<Plan> plans;
+    size_t total = 0;
+    int max_cols = 1;
+    for (int64_t i = 0; i < nbr; ++i)
+      for (int64_t j = 0; j < nbc; ++j) {
+        Plan p{};
+        p.rid = static_cast<int32_t>(i);
+        p.cid = static_cast<int32_t>(j);
+        p.r = static_cast<int32_t>(std::min<int64_t>(blkSize, nrows - i * blkSize));
+        p.c = static_cast<int32_t>(std::min<int64_t>(blkSize, ncols - j * blkSize));
+        p.gr = csr ? p.c : p.r;
+        p.gc = csr ? p.r : p.c;
+        MR_REQUIRE((p.gr & (p.gr - 1)) == 0 && (p.gc & (p.gc - 1)) == 0, MR_ENOTSUP,
+                   "device sprand needs power-of-two block dimensions (java.util.Random.nextInt consumes one draw per call only then); "
+                   "block (%d, %d) is %d x %d", p.rid, p.cid, p.r, p.c);
+        p.nnz = static_cast<int64_t>(std::ceil(static_cast<double>(p.gr) * p.gc * density));
+        MR_REQUIRE(sprand_draws(p.nnz) > 0, MR_ENOTSUP, "device sprand handles up to ~14000 non-zeros per block, block (%d, %d) needs %lld",
+                   p.rid, p.cid, (long long)p.nnz);
+        p.off_ptr = total;
+        total += align_up(static_cast<size_t>(p.gc + 1) * 4);
+        p.off_idx = total;
+        total += align_up(static_cast<size_t>(p.nnz) * 4);
+        p.off_val = total;
+        total += align_up(static_cast<size_t>(p.nnz) * 8);
+        max_cols = std::max(max_cols, p.gc);
+        plans.push_back(p);
+      }
+    Slab slab(ctx, total);
+    Buf status = std::make_shared<DevBuf>(ctx, sizeof(int));
+    CUDA_CHECK(cudaMemsetAsync(status->p, 0, sizeof(int), ctx->stream));
+    std::unique_ptr<mr_matrix> m(new_matrix(ctx));
+    std::vector<SprandDesc> descs;
+    for (const Plan& p : plans) {
+      Block b;
+      b.type = 0;
+      b.numRows = p.r;
+      b.numCols = p.c;
+      b.isT = csr != 0;
+      b.valuesLen = p.nnz;
+      b.colPtrsLen = p.gc + 1;
+      b.colPtrs = Span{slab.buf, p.off_ptr};
+      b.rowIndices = Span{slab.buf, p.off_idx};
+      b.values = Span{slab.buf, p.off_val};
+      SprandDesc d{};
+      d.rows = p.gr;
+      d.cols = p.gc;
+      d.nnz = static_cast<int32_t>(p.nnz);
+      d.draws = sprand_draws(p.nnz);
+      d.seed = seed0 + static_cast<int64_t>(p.rid) * nbc + p.cid;
+      d.colPtrs = b.colPtrs.ptr<int32_t>();
+      d.rowIndices = b.rowIndices.ptr<int32_t>();
+      d.values = b.values.ptr<double>();
+      d.status = static_cast<int*>(status->p);
+      descs.push_back(d);
+      m->blocks[{p.rid, p.cid}] = std::move(b);
+    }
+    for (size_t off = 0; off < descs.size(); off += 65535) {
+      std::vector<SprandDesc> chunk(descs.begin() + off, descs.begin() + std::min(descs.size(), off + 65535));
+      Buf d = upload(ctx, chunk);
+      CUDA_CHECK(launch_sprand(static_cast<const SprandDesc*>(d->p), static_cast<int>(chunk.size()), max_cols, ctx->stream));
+      note_launch(ctx);
+    }
+    int h_status = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h_status, status->p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (h_status) fail(MR_ECUDA, "device sprand ran out of draws before reaching the requested number of distinct coordinates");
+    *out = m.release();
+  });
+}
 
 }  // extern "C"

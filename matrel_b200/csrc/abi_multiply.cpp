@@ -316,16 +316,25 @@ struct Oz2Run {
       }
       return runs;
     };
+    // slots that start on even 128-row tiles let the cta_group::2 kernel run the tiles in vertically adjacent pairs
+    const bool paired = (ss % (2 * kOz2TileM)) == 0 && ctx->force_variant != 2;
     auto add_tiles = [&](Job& j, int rslot, int cslot, int m, int n) {
-      const int tm0 = rslot * ss / kOz2TileM, tm1 = (rslot * ss + m + kOz2TileM - 1) / kOz2TileM;
+      const int tm0 = rslot * ss / kOz2TileM;
+      int tm1 = (rslot * ss + m + kOz2TileM - 1) / kOz2TileM;
+      if (paired && ((tm1 - tm0) & 1)) ++tm1;  // the padding tile lies inside the slot: garbage rows, never stored
       const int tn0 = cslot * ss / kOz2TileN, tn1 = (cslot * ss + n + kOz2TileN - 1) / kOz2TileN;
       for (int a = tm0; a < tm1; ++a)
         for (int b = tn0; b < tn1; ++b) j.tiles.push_back(make_int2(a, b));
     };
     auto finish_tiles = [&](Job& j) {
-      std::sort(j.tiles.begin(), j.tiles.end(), [](const int2& x, const int2& y) {
+      std::sort(j.tiles.begin(), j.tiles.end(), [&](const int2& x, const int2& y) {
         const int bx = x.y / 8, by = y.y / 8;  // bands of 8 n-tiles: the resident CTAs share A row- and B column-panels in L2
         if (bx != by) return bx < by;
+        if (paired) {                          // (2a, b) directly followed by (2a + 1, b)
+          if ((x.x >> 1) != (y.x >> 1)) return x.x < y.x;
+          if (x.y != y.y) return x.y < y.y;
+          return x.x < y.x;
+        }
         if (x.x != y.x) return x.x < y.x;
         return x.y < y.y;
       });
@@ -400,12 +409,20 @@ struct Oz2Run {
     }
     if (jobs.empty()) return false;
     max_tiles = static_cast<int>(std::min<int64_t>(max_tiles, plane_cap_tiles));
+    max_tiles += max_tiles & 1;
     cudaError_t e = oz2_create(&eng, blk, K, T, cap_r, cap_c, max_tiles, guard ? 1 : 0, ctx->stream);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       eng = nullptr;
       jobs.clear();
       return false;  // e.g. out of memory for the scratch: the exact kernel needs none
+    }
+    oz2_set_paired(eng, paired);
+    if (paired && !oz2_paired(eng)) {  // cannot happen (ss % 256 == 0 makes Mpad a multiple of 256); stay on the safe side
+      oz2_destroy(eng, ctx->stream);
+      eng = nullptr;
+      jobs.clear();
+      return false;
     }
     return true;
   }

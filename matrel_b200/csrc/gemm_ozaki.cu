@@ -332,6 +332,180 @@ __global__ void __launch_bounds__(GEMM_THREADS_P, 1) ozaki_gemm_i8_kernel(const 
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_P) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same residue GEMM on CTA PAIRS (tcgen05 cta_group::2): a cluster of two CTAs (the two SMs of a TPC) computes a 256 x 256
+// tile.  Each CTA stages ITS 128 rows of A' and ITS 128 columns (rows of the K-major B') of the tile -- 32 KB per stage instead
+// of 48 KB -- and the pair's tensor cores share them, so per k-byte an SM writes 256 B and reads 256 B of shared memory instead
+// of 384 + 384: at kind::i8 rates the single-CTA kernel is bound by exactly that (ncu: tensor pipe 67 % = 128 / 192 of the
+// 128 B/clk shared-memory port).  Roles per CTA: warp 0 TMA producer (own halves; completion is signalled on the LEADER's full
+// barrier), warp 1 of the leader issues the M = 256 MMAs for both, warp 2 TMEM allocator (two 128 x 256 s32 accumulators per
+// CTA), warps 4..11 epilogue (own 128 rows -> residues -> compact planes).  Only used by the Ozaki-II engine: work item =
+// (modulus, pair of vertically adjacent 128-row tiles); the tile list holds the two halves at positions 2 t and 2 t + 1.
+// ------------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr int B2_BYTES = (BN / 2) * BKB, STAGE2_BYTES = A_BYTES + B2_BYTES;
+constexpr size_t SMEM2_BYTES = 1024 + STAGES2 * STAGE2_BYTES + (2 * STAGES2 + 4) * 8 + 16;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_P, 1) ozaki2_gemm_2sm_kernel(const OzakiGemmParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  // barriers: full[S] (used in the leader), empty[S] (per CTA), acc_full[2] (per CTA), acc_empty[2] (used in the leader)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const bool gated = p.gate != nullptr && *p.gate != 0;  // uniform over the grid: both CTAs of a pair take the same path
+  const int nk = p.nkc;
+  const int npairs_list = p.ntiles_list >> 1;             // pairs of 128-row tiles
+  const int nitems = gated ? 0 : npairs_list * p.nmod;
+  const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[STAGES2 + s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars[2 * STAGES2 + b]), 1);                  // acc_full: one multicast commit
+      mbar_init(smem_u32(&bars[2 * STAGES2 + 2 + b]), 2 * EPI_WARPS);  // acc_empty (leader): every epilogue warp of the pair
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS_P) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's 128 rows of A' and 128 of the tile's 256 rows of B' =====
+    if (lane == 0) {
+      int it = 0;
+      for (int w = cl; w < nitems; w += ncl) {
+        const int mi = w / npairs_list, t2 = w - mi * npairs_list;
+        const int2 tl = p.tile_list[2 * t2 + static_cast<int>(cta_rank)];
+        const int m0 = tl.x * BM, n0 = tl.y * BN + static_cast<int>(cta_rank) * (BN / 2);
+        const void* tmA = p.tmaps + static_cast<size_t>(mi) * 128;
+        const void* tmB = p.tmaps + static_cast<size_t>(2 * p.nmod + mi) * 128;  // the {128, 128}-box maps of B'
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int st = it % STAGES2;
+          const uint32_t ph = (it / STAGES2) & 1;
+          mbar_wait(smem_u32(&bars[STAGES2 + st]), ph ^ 1);                  // own empty barrier
+          const uint32_t full_leader = mapa_u32(smem_u32(&bars[st]), 0);     // the pair's full barrier lives in CTA 0
+          if (leader) mbar_arrive_expect_tx(smem_u32(&bars[st]), 2 * STAGE2_BYTES);
+          asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(smem_u32(smem + st * STAGE2_BYTES)), "l"(tmA), "r"(full_leader), "r"(kc * BKB), "r"(m0) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(smem_u32(smem + st * STAGE2_BYTES + A_BYTES)), "l"(tmB), "r"(full_leader), "r"(kc * BKB), "r"(n0) : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader's elected lane drives both tensor cores (M = 256 across the pair) =====
+    if (leader && lane == 0) {
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((2 * BM) >> 4) << 24);
+      int it = 0, lt = 0;
+      for (int w = cl; w < nitems; w += ncl, ++lt) {
+        const int buf = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(smem_u32(&bars[2 * STAGES2 + 2 + buf]), aph ^ 1);  // both CTAs' epilogues have drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int st = it % STAGES2;
+          const uint32_t ph = (it / STAGES2) & 1;
+          mbar_wait(smem_u32(&bars[st]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = smem_u32(smem + st * STAGE2_BYTES), b0 = a0 + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BKB / UMMA_K; ++k) {
+            const uint64_t da = umma_desc_k_sw128(a0 + k * UMMA_K), db = umma_desc_k_sw128(b0 + k * UMMA_K);
+            const uint32_t acc = (kc | k) != 0;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tacc),
+                         "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                         : "memory");
+          }
+          // the stage is free in BOTH CTAs once these MMAs retire
+          asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                           smem_u32(&bars[STAGES2 + st])),
+                       "h"(static_cast<uint16_t>(3))
+                       : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(&bars[2 * STAGES2 + buf])),
+                     "h"(static_cast<uint16_t>(3))
+                     : "memory");
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: own 128 TMEM lanes -> residues -> compact plane of this CTA's tile =====
+    const int ew = warp - 4;
+    const int q = ew & 3;
+    const int half = ew >> 2;
+    const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bars[2 * STAGES2 + 2]), 0);  // + 8 * buf
+    int lt = 0;
+    for (int w = cl; w < nitems; w += ncl, ++lt) {
+      const int mi = w / npairs_list, t2 = w - mi * npairs_list;
+      const int t = 2 * t2 + static_cast<int>(cta_rank);
+      const int buf = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      mbar_wait(smem_u32(&bars[2 * STAGES2 + buf]), aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tsrc = tmem_base + static_cast<uint32_t>(buf * BN) + (static_cast<uint32_t>(q * 32) << 16) + half * 128;
+      const int pm = p.mod_p[mi];
+      const double pinv = p.mod_inv[mi];
+      int8_t* dst_row = p.planes + static_cast<size_t>(mi) * p.plane_stride + static_cast<size_t>(t) * (BM * BN) +
+                        static_cast<size_t>(q * 32 + lane) * BN + half * 128;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t r[16];
+        TMEM_LD16(tsrc + c, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == 128 - 16) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * static_cast<uint32_t>(buf));
+        }
+        uint32_t packed[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t wv = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int v = static_cast<int32_t>(r[4 * g + j]);
+            int res = v - __double2int_rn(static_cast<double>(v) * pinv) * pm;
+            res += (res >> 31) & pm;
+            wv |= static_cast<uint32_t>(res) << (8 * j);
+          }
+          packed[g] = wv;
+        }
+        *reinterpret_cast<uint4*>(dst_row + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // nobody leaves while the peer may still signal / read
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS_P) : "memory");
+}
+
 // ---- pass 1: per-row / per-column maximum magnitude (as the IEEE bit pattern, which orders like the value) -------
 struct OzBlock {
   const double* v;
@@ -1043,6 +1217,7 @@ cudaError_t crt_constants(int* log2P) {
 // ------------------------------------------------------------------------------------------------
 struct Oz2Engine {
   int T = 0, alpha = 0, blk = 0, sstride = 0, cap_r = 0, cap_c = 0, max_tiles = 0, range_bits = 0;
+  bool paired = false;   // tile lists hold vertically adjacent 128-row tiles in pairs: the cta_group::2 kernel runs them
   int64_t K = 0, Kpad = 0, Mpad = 0, Npad = 0;
   size_t a_stride = 0, b_stride = 0, plane_stride = 0, smem_bytes = 0;
   int8_t *As = nullptr, *Bs = nullptr, *planes = nullptr;
@@ -1100,6 +1275,12 @@ cudaError_t oz2_create(Oz2Engine** out, int blk, int64_t K, int moduli, int cap_
   e->plane_stride = static_cast<size_t>(max_tiles) * (BM * BN);
   e->smem_bytes = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
   OZ_CHECK(configure_gemm_kernel(e->smem_bytes));
+  {
+    static PerDeviceOnce once2;
+    OZ_CHECK(once2.run([&] {
+      return cudaFuncSetAttribute(ozaki2_gemm_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM2_BYTES));
+    }));
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1124,10 +1305,12 @@ cudaError_t oz2_create(Oz2Engine** out, int blk, int64_t K, int moduli, int cap_
     for (int t = 0; t < T; ++t)
       OZ_CHECK(cudaMemsetAsync(e->Bs + e->b_stride * t + static_cast<size_t>(e->sstride) * cap_c * e->Kpad, 0,
                                static_cast<size_t>(e->Npad - static_cast<int64_t>(e->sstride) * cap_c) * e->Kpad, stream));
-  e->h_maps.resize(static_cast<size_t>(2 * T) * 128);
+  // tensor maps: A' (box 128 rows), B' (box 256 rows: single-CTA kernel), B' (box 128 rows: each CTA of a pair loads half)
+  e->h_maps.resize(static_cast<size_t>(3 * T) * 128);
   for (int t = 0; t < T; ++t) {
     if (!make_i8_map(&e->h_maps[static_cast<size_t>(t) * 128], e->As + e->a_stride * t, e->Kpad, e->Mpad, BM) ||
-        !make_i8_map(&e->h_maps[static_cast<size_t>(T + t) * 128], e->Bs + e->b_stride * t, e->Kpad, e->Npad, BN)) {
+        !make_i8_map(&e->h_maps[static_cast<size_t>(T + t) * 128], e->Bs + e->b_stride * t, e->Kpad, e->Npad, BN) ||
+        !make_i8_map(&e->h_maps[static_cast<size_t>(2 * T + t) * 128], e->Bs + e->b_stride * t, e->Kpad, e->Npad, BN / 2)) {
       Oz2Engine* raw = e.release();
       oz2_destroy(raw, stream);
       return cudaErrorInvalidValue;
@@ -1211,10 +1394,14 @@ cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, i
 // execution order, so the caller bands it for L2 reuse), written through d_ctab[rslot * cap_c + cslot] (nullptr = not part of
 // this job).  Lists longer than the plane capacity are processed in consecutive pieces.  ms_gemm (optional) accumulates the
 // tcgen05 launch time (events, synchronises): used for the roofline figure only.
+void oz2_set_paired(Oz2Engine* e, bool paired) { e->paired = paired && (e->max_tiles % 2 == 0) && (e->Mpad % (2 * BM) == 0); }
+bool oz2_paired(const Oz2Engine* e) { return e->paired; }
+
 cudaError_t oz2_multiply(Oz2Engine* e, const int2* d_tiles, int ntiles, double* const* d_ctab, cudaStream_t stream, double* ms_gemm,
                          cudaEvent_t ev0, cudaEvent_t ev1) {
   if (ntiles <= 0) return cudaSuccess;
   if (e->d_maps == nullptr) return cudaErrorInvalidValue;
+  if (e->paired && (ntiles & 1)) return cudaErrorInvalidValue;
   OzakiGemmParams p{};
   p.tmaps = e->d_maps;
   p.Kpad = static_cast<int32_t>(e->Kpad);
@@ -1239,7 +1426,13 @@ cudaError_t oz2_multiply(Oz2Engine* e, const int2* d_tiles, int ntiles, double* 
     p.ntiles_list = cnt;
     const int64_t nitems = static_cast<int64_t>(cnt) * e->T;
     if (ms_gemm) OZ_CHECK(cudaEventRecord(ev0, stream));
-    ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(nitems, e->sms)), GEMM_THREADS_P, e->smem_bytes, stream>>>(p);
+    if (e->paired) {  // cta_group::2: one cluster of two CTAs per (modulus, tile pair) work item
+      const int64_t npair_items = nitems / 2;
+      const unsigned clusters = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(npair_items, e->sms / 2)));
+      ozaki2_gemm_2sm_kernel<<<2 * clusters, GEMM_THREADS_P, SMEM2_BYTES, stream>>>(p);
+    } else {
+      ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(nitems, e->sms)), GEMM_THREADS_P, e->smem_bytes, stream>>>(p);
+    }
     OZ_CHECK(cudaGetLastError());
     if (ms_gemm) {
       OZ_CHECK(cudaEventRecord(ev1, stream));

@@ -100,6 +100,8 @@ void oz2_set_device_maps(Oz2Engine* e, const void* d_maps);     // ... and hande
 const int* oz2_flag(const Oz2Engine* e);
 int oz2_alpha(const Oz2Engine* e);
 int oz2_slot_stride(const Oz2Engine* e);
+void oz2_set_paired(Oz2Engine* e, bool paired);                  // tile lists come as (2a, b), (2a + 1, b) pairs: use the 2-SM kernel
+bool oz2_paired(const Oz2Engine* e);
 int oz2_launches(Oz2Engine* e);                                  // kernels launched since the last call
 cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, int nblocks, int max_rows, int max_cols, int slot0,
                         int nslots, const int32_t* d_dims, bool need_zero, cudaStream_t stream);
@@ -210,6 +212,17 @@ struct Spmm2Out {
 struct Spmm2Item {        // one CTA: 512 rows x 32 columns of one output block, all of its k-blocks
   int32_t out, strip, ctile, pad;
 };
+// SparseMatrix.sprand(rows, cols, density, new java.util.Random(seed)) on the device (power-of-two dims, draw-by-draw branch)
+struct SprandDesc {
+  int32_t rows, cols, nnz, draws;
+  int64_t seed;
+  int32_t* colPtrs;     // [cols + 1] out
+  int32_t* rowIndices;  // [nnz] out
+  double* values;       // [nnz] out
+  int* status;          // set to 1 when the draws did not yield nnz distinct coordinates
+};
+int sprand_draws(int64_t nnz);
+cudaError_t launch_sprand(const SprandDesc* d_descs, int nblocks, int max_cols, cudaStream_t stream);
 size_t spmm2_aux_bytes(int m, int kdim, int64_t nnz, size_t* ent_off, size_t* rp_off, size_t* seg_off);
 bool spmm2_encode_b_tmap(void* out128, const double* base, int64_t kdim, int64_t n, int64_t ld);
 cudaError_t launch_spmm2_prep(const Spmm2Prep* d_preps, int nblocks, int max_m, int max_kdim, cudaStream_t stream);

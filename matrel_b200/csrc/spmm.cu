@@ -274,6 +274,141 @@ __global__ void __launch_bounds__(THREADS, 1) spmm2_kernel(const Spmm2Item* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SparseMatrix.sprand on the device (M/matrix/MLMatrix.scala:791-856, the draw-by-draw branch, density < 0.34), bit-identical to
+// the JVM: draws (rng.nextInt(numRows), rng.nextInt(numCols)) into a set until it holds nnz = ceil(rows * cols * density)
+// distinct coordinates, sorts them column-major (fromCOO), then fills the values with rng.nextDouble() in storage order.
+// The sequential loop is restated in parallel: draw t is computed by jumping the 48-bit LCG to step 2t (power-of-two bounds
+// consume exactly one step per nextInt), duplicates are found by sorting (key, t), the cut t* is the draw at which the
+// number of first occurrences reaches nnz, and value e of the sorted list comes from LCG steps 2 (t* + 1) + 2 e + {1, 2}.
+// One CTA per block; everything lives in shared memory (up to 16384 draws).
+// ------------------------------------------------------------------------------------------------
+constexpr int SPR_MAX_T = 16384;
+constexpr uint64_t LCG_A = 0x5DEECE66Dull, LCG_C = 0xBull, LCG_MASK = (1ull << 48) - 1;
+__device__ __forceinline__ uint64_t lcg_jump(uint64_t s, uint64_t n) {
+  uint64_t a = LCG_A, c = LCG_C, A = 1, C = 0;
+  while (n) {
+    if (n & 1) {
+      A = (A * a) & LCG_MASK;
+      C = (C * a + c) & LCG_MASK;
+    }
+    c = (c * (a + 1)) & LCG_MASK;
+    a = (a * a) & LCG_MASK;
+    n >>= 1;
+  }
+  return (A * s + C) & LCG_MASK;
+}
+
+__global__ void __launch_bounds__(1024) sprand_kernel(const SprandDesc* __restrict__ descs) {
+  extern __shared__ unsigned char spr_smem[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(spr_smem);        // [SPR_MAX_T] (key << 32) | t
+  int32_t* cnt = reinterpret_cast<int32_t*>(spr_smem + SPR_MAX_T * 8);               // [SPR_MAX_T] flags / prefix sums
+  int32_t* colcnt = cnt + SPR_MAX_T;                                                  // [cols + 1]
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t s_tstar;
+  const SprandDesc d = descs[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = d.draws;                       // power of two >= nnz + slack, <= SPR_MAX_T
+  const int rbits = 31 - __clz(d.rows), cbits = 31 - __clz(d.cols);
+  const uint64_t s0 = (static_cast<uint64_t>(d.seed) ^ LCG_A) & LCG_MASK;
+  if (tid == 0) s_tstar = -1;
+  for (int t = tid; t < T; t += blockDim.x) {
+    const uint64_t s1 = lcg_jump(s0, 2ull * t + 1);
+    const uint64_t s2 = (s1 * LCG_A + LCG_C) & LCG_MASK;
+    const uint32_t i = static_cast<uint32_t>(s1 >> 17) >> (31 - rbits);   // nextInt(rows), rows = 2^rbits
+    const uint32_t j = static_cast<uint32_t>(s2 >> 17) >> (31 - cbits);   // nextInt(cols)
+    keys[t] = (static_cast<unsigned long long>(j * static_cast<uint32_t>(d.rows) + i) << 32) | static_cast<unsigned>(t);
+  }
+  for (int c = tid; c <= d.cols; c += blockDim.x) colcnt[c] = 0;
+  __syncthreads();
+  // bitonic sort of (key, t)
+  for (int k = 2; k <= T; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < T; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  // dup[t] = 1 when draw t repeats an earlier coordinate
+  for (int e = tid; e < T; e += blockDim.x) {
+    const bool first = e == 0 || (keys[e] >> 32) != (keys[e - 1] >> 32);
+    cnt[static_cast<uint32_t>(keys[e])] = first ? 1 : 0;   // indexed by draw number t
+  }
+  __syncthreads();
+  // inclusive scan over t of the first-occurrence flags; t* = first t whose count reaches nnz
+  auto block_scan = [&](int32_t* a, int n) {  // in place, inclusive
+    int carry = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int i = base + tid;
+      int x = i < n ? a[i] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) warp_tot[warp] = x;
+      __syncthreads();
+      if (warp == 0) {
+        int w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, w, o);
+          if (lane >= o) w += y;
+        }
+        warp_tot[lane] = w;
+      }
+      __syncthreads();
+      x += carry + (warp ? warp_tot[warp - 1] : 0);
+      if (i < n) a[i] = x;
+      const int tot = warp_tot[31];
+      __syncthreads();
+      carry += tot;
+    }
+  };
+  block_scan(cnt, T);
+  for (int t = tid; t < T; t += blockDim.x)
+    if (cnt[t] == d.nnz && (t == 0 || cnt[t - 1] < d.nnz)) s_tstar = t;
+  __syncthreads();
+  if (s_tstar < 0) {  // not enough distinct coordinates among T draws (cannot happen with the slack the host adds)
+    if (tid == 0) *d.status = 1;
+    return;
+  }
+  const int tstar = s_tstar;
+  __syncthreads();
+  // selected = first occurrence with t <= t*, in sorted (column-major) order
+  for (int e = tid; e < T; e += blockDim.x) {
+    const bool first = e == 0 || (keys[e] >> 32) != (keys[e - 1] >> 32);
+    cnt[e] = (first && static_cast<int>(static_cast<uint32_t>(keys[e])) <= tstar) ? 1 : 0;
+  }
+  __syncthreads();
+  block_scan(cnt, T);
+  const uint64_t sv = lcg_jump(s0, 2ull * (static_cast<uint64_t>(tstar) + 1));
+  for (int e = tid; e < T; e += blockDim.x) {
+    const int sel = cnt[e] - (e ? cnt[e - 1] : 0);
+    if (sel) {
+      const int pos = cnt[e] - 1;
+      const uint32_t key = static_cast<uint32_t>(keys[e] >> 32);
+      const uint32_t col = key / static_cast<uint32_t>(d.rows), row = key - col * static_cast<uint32_t>(d.rows);
+      d.rowIndices[pos] = static_cast<int32_t>(row);
+      atomicAdd(&colcnt[col + 1], 1);
+      const uint64_t a1 = lcg_jump(sv, 2ull * pos + 1);
+      const uint64_t a2 = (a1 * LCG_A + LCG_C) & LCG_MASK;
+      d.values[pos] = static_cast<double>(((a1 >> 22) << 27) + (a2 >> 21)) * (1.0 / 9007199254740992.0);
+    }
+  }
+  __syncthreads();
+  block_scan(colcnt, d.cols + 1);
+  for (int c = tid; c <= d.cols; c += blockDim.x) d.colPtrs[c] = colcnt[c];
+}
+
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -328,6 +463,24 @@ cudaError_t launch_spmm2_prep(const Spmm2Prep* d_preps, int nblocks, int max_m, 
   if (e != cudaSuccess) return e;
   if (smem > 64 * 1024) return cudaErrorInvalidValue;
   spmm2_prep_kernel<<<nblocks, 1024, smem, stream>>>(d_preps);
+  return cudaGetLastError();
+}
+
+int sprand_draws(int64_t nnz) {  // power-of-two number of draws with room for the expected duplicates; 0 = too many for one CTA
+  const int64_t need = nnz + std::max<int64_t>(512, nnz / 8);
+  int T = 1024;
+  while (T < need) T <<= 1;
+  return T <= SPR_MAX_T ? T : 0;
+}
+
+cudaError_t launch_sprand(const SprandDesc* d_descs, int nblocks, int max_cols, cudaStream_t stream) {
+  if (nblocks <= 0) return cudaSuccess;
+  const size_t smem = static_cast<size_t>(SPR_MAX_T) * 12 + static_cast<size_t>(max_cols + 1) * 4 + 16;
+  static PerDeviceOnce once;
+  cudaError_t e = once.run([&] { return cudaFuncSetAttribute(sprand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  if (e != cudaSuccess) return e;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  sprand_kernel<<<nblocks, 1024, smem, stream>>>(d_descs);
   return cudaGetLastError();
 }
 

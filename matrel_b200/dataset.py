@@ -100,6 +100,14 @@ class MatfastSession:
         return Dataset(self, h)
 
 
+def sprand(session: "MatfastSession", nrows: int, ncols: int, blkSize: int, density: float, seed0: int, csr: bool = True) -> "Dataset":
+    """Every block ``SparseMatrix.sprand(..., new java.util.Random(seed0 + rid*nbc + cid))`` (M/matrix/MLMatrix.scala:791-856),
+    generated on the device; ``csr`` presents each block in CSR form (the transpose of a sprand block)."""
+    h = C.c_void_p()
+    N.check(N.lib.mr_matrix_sprand(session._ctx, int(nrows), int(ncols), int(blkSize), float(density), int(seed0), 1 if csr else 0, C.byref(h)))
+    return Dataset(session, h)
+
+
 def rand_partition(session: "MatfastSession", nrows: int, ncols: int, blkSize: int, seed0: int, pr: int, pc: int,
                    r: int, c: int, slab_ptr: int, slot_elems: int) -> "Dataset":
     """The blocks rank (r, c) of a pr x pc grid owns, generated into a caller-owned device slab."""
@@ -222,6 +230,10 @@ class Dataset:
             else:
                 d.type = 1
         N.check(N.lib.mr_matrix_put_blocks(self._h, n, _i32p(rids), _i32p(cids), descs))
+
+    def wait_ingest(self) -> None:
+        """Host-blocking: every host->device copy of this dataset's blocks has completed (pinned sources may be reused)."""
+        N.check(N.lib.mr_matrix_wait_ingest(self._h))
 
     def put_block_device(self, rid: int, cid: int, numRows: int, numCols: int, device_ptr: int,
                          isTransposed: bool = False) -> None:

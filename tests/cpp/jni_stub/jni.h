@@ -18,17 +18,25 @@ class _jobject {};
 class _jclass : public _jobject {};
 class _jarray : public _jobject {};
 class _jintArray : public _jarray {};
+class _jlongArray : public _jarray {};
 class _jdoubleArray : public _jarray {};
 typedef _jobject* jobject;
 typedef _jclass* jclass;
 typedef _jarray* jarray;
 typedef _jintArray* jintArray;
+typedef _jlongArray* jlongArray;
 typedef _jdoubleArray* jdoubleArray;
 
 struct JNIEnv {
   jclass FindClass(const char* name);
   jint ThrowNew(jclass cls, const char* msg);
+  jboolean ExceptionCheck();
   jsize GetArrayLength(jarray a);
-  void* GetPrimitiveArrayCritical(jarray a, jboolean* is_copy);
-  void ReleasePrimitiveArrayCritical(jarray a, void* carray, jint mode);
+  jintArray NewIntArray(jsize n);
+  jlongArray NewLongArray(jsize n);
+  void GetIntArrayRegion(jintArray a, jsize start, jsize len, jint* buf);
+  void GetDoubleArrayRegion(jdoubleArray a, jsize start, jsize len, jdouble* buf);
+  void SetIntArrayRegion(jintArray a, jsize start, jsize len, const jint* buf);
+  void SetLongArrayRegion(jlongArray a, jsize start, jsize len, const jlong* buf);
+  void SetDoubleArrayRegion(jdoubleArray a, jsize start, jsize len, const jdouble* buf);
 };

@@ -100,3 +100,22 @@ def test_config5_blocks_from_sprand(session):
     want = O.matrix_multiply(A, n, n, B, n, n, blk)
     got = from_dataset(to_dataset(session, A).matrixMultiply(n, n, to_dataset(session, B), n, n, blk))
     assert_same_dataset(got, want, tol=1e-13)
+
+
+@pytest.mark.parametrize("nrows,ncols,blk,density,csr", [(2048, 2048, 1024, 0.01, True), (512, 1024, 256, 0.05, False),
+                                                           (1024, 512, 512, 0.002, True)])
+def test_device_sprand_is_bit_identical_to_the_jvm_stream(session, nrows, ncols, blk, density, csr):
+    """mr_matrix_sprand restates SparseMatrix.sprand (M/matrix/MLMatrix.scala:791-856) in parallel on the device: the same
+    coordinates (first nnz distinct draws of the java.util.Random stream, column-major) and the same U(0,1) values, bit for bit,
+    as the sequential oracle."""
+    from matrel_b200.dataset import sprand
+    ds = from_dataset(sprand(session, nrows, ncols, blk, density, 77, csr=csr))
+    nbc = -(-ncols // blk)
+    assert sorted(ds) == [(i, j) for i in range(-(-nrows // blk)) for j in range(nbc)]
+    for (i, j), got in ds.items():
+        r, c = min(blk, nrows - i * blk), min(blk, ncols - j * blk)
+        want = O.sprand(c, r, density, O.JavaRandom(77 + i * nbc + j)).transpose() if csr else O.sprand(r, c, density, O.JavaRandom(77 + i * nbc + j))
+        assert isinstance(got, mb.SparseMatrix) and (got.numRows, got.numCols, got.isTransposed) == (r, c, csr)
+        assert got.colPtrs.tolist() == want.colPtrs.tolist()
+        assert got.rowIndices.tolist() == want.rowIndices.tolist()
+        assert np.array_equal(got.values, want.values)
