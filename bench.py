@@ -566,6 +566,161 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# --workload cfg5: BASELINE configs[4] -- 32768^2 sparse(1 %) x dense fp64, CSR 1024-blocks, on 1 GPU or sharded over N GPUs
+# ------------------------------------------------------------------------------------------------
+def run_cfg5(args):
+    import numpy as np
+    import torch
+    import matrel_b200 as mb
+    from matrel_b200.dataset import grid_multiply_rows, memcpy_d2h, sprand
+    from matrel_b200.distributed import GridPlan, ShardedMatrix, stream_barrier
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    n, blk, density = args.n5, 1024, 0.01
+    nb = n // blk
+    plan = GridPlan(world, n, n, blk)
+    r, c = plan.coords(rank)
+
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    stream = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(stream):
+        s = mb.MatfastSession(device=local_rank, stream=stream.cuda_stream)
+        # A: every block SparseMatrix.sprand(1024, 1024, 0.01, new java.util.Random(seed)) in CSR form, generated on the device.
+        # The thin operand is replicated where it is needed (the reference's duplicateCrossPartitions): every rank generates the
+        # block rows it owns -- all k of them -- from the same seeds, so no sparse block crosses NVLink.
+        Afull = sprand(s, n, n, blk, density, 1000, csr=True)
+        A_rows = Afull.filter_blocks(plan.pr, r)
+        nnz_total = nb * nb * int(np.ceil(blk * blk * density))
+        B = ShardedMatrix.rand(s, plan, rank, 43, device)
+        s.sync()
+        peers = B.peer_slabs()
+        colB = [peers[plan.rank_of(rr, c)] for rr in range(plan.pr)]
+        barrier()
+        flops = 2.0 * nnz_total * n
+
+        def step():
+            return grid_multiply_rows(s, A_rows, n, n, B.sharded, colB)
+
+        for _ in range(args.warmup):
+            out = step()
+            del out
+        barrier()
+        s.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        sampler.mark()
+        e0.record(stream)
+        for _ in range(args.steps):
+            out = step()
+            del out
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms = allmax(e0.elapsed_time(e1) / args.steps)
+        st = s.stats()
+        s.set_option("time_kernels", 1)
+        s.reset_stats()
+        for _ in range(3):
+            out = step()
+            del out
+        kern_ms = allmax(s.stats()["gemm_ms_total"] / 3.0)
+        s.set_option("time_kernels", 0)
+        # correctness: one output block per rank against scipy on the host
+        import scipy.sparse as sp
+        dC = step()
+        mine = plan.owned(rank)
+        i, j = mine[len(mine) // 2]
+        want = np.zeros((blk, blk))
+        buf = np.empty(blk * blk)
+        for k in range(nb):
+            a = A_rows.get_block(i, k)                       # CSR: colPtrs = row pointers, rowIndices = column indices
+            csr = sp.csr_matrix((a.values, a.rowIndices, a.colPtrs), shape=(blk, blk))
+            memcpy_d2h(s, peers[plan.owner(k, j)] + plan.slot(k, j) * plan.slot_elems * 8, buf)
+            want += csr @ buf.reshape(blk, blk).T
+        got = dC.get_block(i, j).to_numpy()
+        err = allmax(float(np.max(np.abs(got - want)) / np.max(np.abs(want))))
+        del dC
+        # end to end: the dense operand and the result cross PCIe (A is 0.13 GB of CSR arrays, ingested once)
+        hostB = [(k, B.dataset.get_block(*k)) for k in B.dataset.block_ids()]
+        pB = [mb.MatrixBlock(i_, j_, mb.DenseMatrix(m.numRows, m.numCols, torch.from_numpy(m.values).pin_memory().numpy(), False)) for (i_, j_), m in hostB]
+        del hostB
+        outbuf = {k: torch.empty(blk * blk, dtype=torch.float64).pin_memory().numpy() for k in plan.owned(rank)}
+        eB = ShardedMatrix(plan, rank, torch.zeros_like(B.slab), None, s)
+        epeers = eB.peer_slabs()
+        ecolB = [epeers[plan.rank_of(rr, c)] for rr in range(plan.pr)]
+        barrier()
+
+        def e2e_step():
+            eB.sharded.put_blocks(pB)
+            s.wait_ingest()
+            stream_barrier(device)
+            dC_ = grid_multiply_rows(s, A_rows, n, n, eB.sharded, ecolB)
+            for k in sorted(dC_.block_ids()):
+                dC_.get_block(*k, out=outbuf[k])
+            stream_barrier(device)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        k_e2e = max(1, min(args.steps, 3))
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        e2e_ms = allmax((time.perf_counter() - t0) / k_e2e * 1e3)
+        h2d = sum(b.matrix.values.nbytes for b in pB) * world
+        d2h = sum(v.nbytes for v in outbuf.values()) * world
+        s.stop()
+    if rank == 0:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        alg_bytes = (12.0 * nnz_total + 4.0 * (n + nb) * nb + 2 * 8.0 * n * n) / world     # SURVEY 8d compulsory bytes, per rank
+        fma_roof = 148 * 16 * 2 * 1.9e9 / 1e12      # shared-memory port: 16 fp64 FMA / clk / SM at ~1.9 GHz
+        ach_tf = (flops / world) / (kern_ms * 1e-3) / 1e12
+        line = {"metric": "fp64 sparse(1%) x dense block-matmul GFLOP/s at N=%d" % n, "value": flops / (ms * 1e-3) / 1e9, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[4]: {n}x{n} sparse(1%) x dense fp64, CSR {blk}-blocks, {plan.pr}x{plan.pc} grid over {world}xB200",
+                           "inputs": "A blocks SparseMatrix.sprand(1024, 1024, 0.01, java.util.Random(1000 + rid*nb + cid)) as CSR, generated on the device; "
+                                     "B U(0,1) java.util.Random streams, column-major",
+                           "parallelism": "C-stationary grid; sparse block rows replicated where needed (duplicateCrossPartitions), dense B pulled from the grid column over NVLink",
+                           "nnz": nnz_total, "l2": "B panel per rank >> 126 MB L2"},
+                "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms, "steps": k_e2e},
+                "gpu_launches": int(st["kernel_launches"] * world), "gpu_launches_per_step_per_rank": st["kernel_launches"] / args.steps,
+                "roofline": {"bound": "hbm", "achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm, "traffic": None, "kernel": "spmm2_kernel", "kernel_ms": kern_ms,
+                             "algorithmic": f"{alg_bytes:.4g} compulsory bytes per rank per launch (12 nnz + 4 (rows + nb) nb + 16 N^2, SURVEY 8d) / world",
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                             "smem_port": {"achieved_tflops": ach_tf, "roof_tflops": fma_roof, "frac": ach_tf / fma_roof,
+                                           "note": "every FMA needs its own 8-byte B element from shared memory: 128 B/clk/SM = 16 FMA/clk/SM is the binding roof"}},
+                "clocks": clocks, "check": {"max_rel_err_vs_host_fp64": err, "blocks_checked": world}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -579,11 +734,18 @@ def main():
     ap.add_argument("--algo", type=int, default=0, choices=(0, 1, 2, 4),
                     help="gemm_algo of the headline: 0 = auto (tcgen05 Ozaki-II with the device-side guard), 1 = DMMA fp64")
     ap.add_argument("--crt-moduli", type=int, default=16)
+    ap.add_argument("--workload", default="metric", choices=("metric", "cfg5"), help="metric = BASELINE metric (dense N=16384); cfg5 = configs[4]")
+    ap.add_argument("--n5", type=int, default=32768, help="matrix size of --workload cfg5")
     ap.add_argument("--pull-chunks", type=int, default=4, help="N > 1: pieces the peer pull of A is cut into")
     ap.add_argument("--_cpu-worker", dest="cpu_worker", default=None, choices=("port", "f2j"), help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_worker:
         return _cpu_worker_main(args.cpu_worker, args.n, args.blk, args.steps, args.warmup, args.cpu_budget)
+    if args.workload == "cfg5":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the metric workload only (dense N=16384)"}))
+            return
+        return run_cfg5(args)
     if args.impl == "reference":
         run_reference(args)
     else:

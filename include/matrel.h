@@ -264,6 +264,14 @@ MR_API mr_status mr_memcpy_d2h(mr_context* ctx, const void* dptr, void* host, in
  * does it with events).  nchunks >= 1: pieces the pull of A is cut into (the multiply starts on the first).  *out is sharded. */
 MR_API mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
                                   int32_t nchunks, mr_matrix** out);
+/* The blocks a partition owns (rid % row_mod == row_rem, cid % col_mod == col_rem); shares the device arrays with `a`. */
+MR_API mr_status mr_matrix_filter_blocks(mr_matrix* a, int32_t row_mod, int32_t row_rem, int32_t col_mod, int32_t col_rem,
+                                         mr_matrix** out);
+/* The same with a left operand that is NOT sharded: A_rows holds every block A(i, k) -- sparse or dense -- of the block rows this
+ * rank owns (the thin / sparse operand is replicated where it is needed, the reference's duplicateCrossPartitions,
+ * MatfastExecutionHelper.scala:224-233); only the dense B is pulled from the grid column.  BASELINE configs[4]. */
+MR_API mr_status mr_grid_multiply_rows(mr_matrix* A_rows, int64_t leftRowNum, int64_t leftColNum, mr_matrix* B,
+                                       const double* const* slabsB_col, mr_matrix** out);
 
 /* ---- (2) one process, all GPUs.  Replaces MatfastSession + the executors (M/MatfastSession.scala:177-234). */
 MR_API mr_status mr_init_grid(const mr_options* opts, int32_t ngpus, mr_grid** out);  /* devices 0 .. ngpus-1, grid 1x1 / 1x2 / 2x2 / 2x4 */

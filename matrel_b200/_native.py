@@ -148,6 +148,8 @@ SIGNATURES = {
     "mr_ipc_close_all": [_P],
     "mr_memcpy_d2h": [_P, _P, _P, _i64],
     "mr_grid_multiply": [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32, _PP],
+    "mr_grid_multiply_rows": [_P, _i64, _i64, _P, C.POINTER(C.c_void_p), _PP],
+    "mr_matrix_filter_blocks": [_P, _i32, _i32, _i32, _i32, _PP],
     "mr_init_grid": [C.POINTER(mr_options), _i32, _PP],
     "mr_grid_shutdown": [_P],
     "mr_grid_info": [_P, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)],

@@ -335,6 +335,92 @@ mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slab
   });
 }
 
+// The blocks of a dataset that a partition owns: rid % row_mod == row_rem and cid % col_mod == col_rem (RowPartitioner /
+// ColumnPartitioner arithmetic); the result shares the device arrays with the source (no copy).
+mr_status mr_matrix_filter_blocks(mr_matrix* a, int32_t row_mod, int32_t row_rem, int32_t col_mod, int32_t col_rem, mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(a && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(row_mod >= 1 && col_mod >= 1 && row_rem >= 0 && row_rem < row_mod && col_rem >= 0 && col_rem < col_mod, MR_EINVAL,
+               "bad partition (%d mod %d, %d mod %d)", row_rem, row_mod, col_rem, col_mod);
+    std::lock_guard<std::mutex> lock(a->ctx->mu);
+    std::unique_ptr<mr_matrix> m(new_matrix(a->ctx));
+    for (auto& kv : a->blocks)
+      if (kv.first.first % row_mod == row_rem && kv.first.second % col_mod == col_rem) m->blocks[kv.first] = kv.second;
+    *out = m.release();
+  });
+}
+
+// The same with a LEFT operand that is not sharded: `A_rows` holds every block A(i, k) -- sparse or dense, any k -- of the block
+// rows i this rank owns (rid % pr == r).  This is how a thin / sparse operand travels: the reference replicates it with
+// duplicateCrossPartitions (MatfastExecutionHelper.scala:224-233); here the caller generates or ingests the block rows where they
+// are needed, and only the dense B is pulled from the grid column (BASELINE configs[4]: CSR blocks x dense on 4 GPUs).
+mr_status mr_grid_multiply_rows(mr_matrix* A_rows, int64_t leftRowNum, int64_t leftColNum, mr_matrix* B, const double* const* slabsB_col,
+                                mr_matrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(A_rows && B && out && slabsB_col, MR_EINVAL, "null argument");
+    MR_REQUIRE(B->shard, MR_EINVAL, "the right operand must be a sharded dataset (mr_matrix_create_sharded)");
+    MR_REQUIRE(A_rows->ctx == B->ctx, MR_EINVAL, "operands belong to different contexts");
+    const ShardLayout LB = B->shard->L;
+    MR_REQUIRE(leftColNum == LB.nrows, MR_EDIM, "Matrix dimension not match, leftColNum = %lld, rightRowNum = %lld",
+               (long long)leftColNum, (long long)LB.nrows);
+    MR_REQUIRE(!B->shard->isT, MR_ENOTSUP, "grid multiply of a flag-transposed sharded dataset: materialise it first");
+    mr_context* ctx = B->ctx;
+    DeviceScope dev(ctx);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const int pr = LB.pr, pc = LB.pc, r = LB.r, c = LB.c;
+    for (auto& kv : A_rows->blocks)
+      MR_REQUIRE(kv.first.first % pr == r, MR_EINVAL, "left block (%d, %d) is not in a block row of rank (%d, %d)", kv.first.first,
+                 kv.first.second, r, c);
+    const size_t slot_bytes = static_cast<size_t>(LB.slot_elems) * sizeof(double);
+    const size_t b_local = static_cast<size_t>(LB.local_slots()) * slot_bytes;
+    cudaStream_t ps = ctx->p2p_stream;
+    Buf panelB = pr > 1 ? std::make_shared<DevBuf>(ctx, b_local * (pr - 1)) : nullptr;
+    CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ps, ctx->ev_order, 0));
+    auto peer_index = [](int p, int self) { return p < self ? p : p - 1; };
+    ReadyPtr readyB;
+    if (pr > 1) {
+      for (int rr = 0; rr < pr; ++rr) {
+        if (rr == r) continue;
+        MR_REQUIRE(slabsB_col[rr] != nullptr, MR_EINVAL, "slabsB_col[%d] is null", rr);
+        CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(panelB->p) + b_local * peer_index(rr, r), slabsB_col[rr], b_local, cudaMemcpyDefault, ps));
+      }
+      readyB = std::make_shared<Ready>();
+      CUDA_CHECK(cudaEventRecord(readyB->ev, ps));
+      panelB->ready = readyB;
+      ctx->stats.p2p_bytes += static_cast<int64_t>(b_local * (pr - 1));
+    }
+    const uint64_t seqB = ++ctx->ingest_seq;
+    std::unique_ptr<mr_matrix> tB(new_matrix(ctx));
+    for (int64_t k = 0; k < LB.nbr; ++k) {
+      const int src = static_cast<int>(k % pr);
+      for (int64_t j = c; j < LB.nbc; j += pc) {
+        const int32_t br = static_cast<int32_t>(std::min<int64_t>(LB.blk, LB.nrows - k * LB.blk));
+        const int32_t bc = static_cast<int32_t>(std::min<int64_t>(LB.blk, LB.ncols - j * LB.blk));
+        const size_t slot_off = static_cast<size_t>((k / pr) * LB.slots_c + j / pc) * slot_bytes;
+        const std::pair<int32_t, int32_t> key{static_cast<int32_t>(k), static_cast<int32_t>(j)};
+        if (src == r) {
+          Block b = dense_block(br, bc, Span{B->shard->slab, slot_off}, false);
+          auto it = B->blocks.find(key);
+          if (it != B->blocks.end()) {
+            b.ready = it->second.ready;
+            b.seq = it->second.seq;
+            b.settled = it->second.settled;
+          }
+          tB->blocks[key] = std::move(b);
+        } else {
+          Block b = dense_block(br, bc, Span{panelB, b_local * peer_index(src, r) + slot_off}, false);
+          b.ready = readyB;
+          b.seq = seqB;
+          tB->blocks[key] = std::move(b);
+        }
+      }
+    }
+    const ShardLayout LC = make_layout(leftRowNum, LB.ncols, LB.blk, pr, pc, r, c);
+    *out = multiply_impl(ctx, A_rows, leftRowNum, leftColNum, tB.get(), LB.nrows, LB.ncols, LB.blk, &LC);
+  });
+}
+
 }  // extern "C"
 
 // =================================================================================================

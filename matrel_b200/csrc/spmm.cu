@@ -223,27 +223,60 @@ __global__ void __launch_bounds__(THREADS, 1) spmm2_kernel(const Spmm2Item* __re
         const int32_t* rp = reinterpret_cast<const int32_t*>(st + B_BYTES + ENT_BYTES);
         mbar_wait(smem_u32(&bars[s]), ph);
         const int seglen = rp[TM];
-        const Entry* ents = seglen <= E_CAP ? reinterpret_cast<const Entry*>(st + B_BYTES)
-                                            : reinterpret_cast<const Entry*>(pr.ent) + pr.segoff[item.strip * nchunks + q];
+        if (seglen <= E_CAP) {
+          // entries in shared memory.  One entry costs a 64-bit (value) and a 32-bit (k) shared load = 3 wavefronts for the
+          // warp (a 128-bit load is served per quarter-warp: 4 wavefronts even when the whole half-warp reads one address)
+          const uint32_t ebase = smem_u32(st + B_BYTES);
 #pragma unroll
-        for (int g = 0; g < TM / 128; ++g) {  // four rows of this half-warp at a time: four independent chains
-          int e[4], n[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int r = hw + 32 * (4 * g + t);
-            e[t] = rp[r];
-            n[t] = rp[r + 1] - e[t];
-          }
-          int maxn = max(max(n[0], n[1]), max(n[2], n[3]));
-          maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, 16));  // both half-warps of the warp run the same trip count
-          for (int i = 0; i < maxn; ++i) {
+          for (int g = 0; g < TM / 128; ++g) {  // four rows of this half-warp at a time: four independent chains
+            int e[4], n[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              if (i < n[t]) {
-                const Entry en = ents[e[t] + i];
-                const double* b = Bs + en.k * TN + l16;
-                acc[4 * g + t][0] = fma(en.a, b[0], acc[4 * g + t][0]);
-                acc[4 * g + t][1] = fma(en.a, b[16], acc[4 * g + t][1]);
+              const int r = hw + 32 * (4 * g + t);
+              e[t] = rp[r];
+              n[t] = rp[r + 1] - e[t];
+            }
+            int maxn = max(max(n[0], n[1]), max(n[2], n[3]));
+            maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, 16));  // both half-warps of the warp run the same trip count
+            for (int i = 0; i < maxn; ++i) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (i < n[t]) {
+                  const uint32_t ea = ebase + static_cast<uint32_t>(e[t] + i) * 16u;
+                  double a;
+                  int k;
+                  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(ea));
+                  asm volatile("ld.shared.s32 %0, [%1+8];" : "=r"(k) : "r"(ea));
+                  const double* b = Bs + k * TN + l16;
+                  acc[4 * g + t][0] = fma(a, b[0], acc[4 * g + t][0]);
+                  acc[4 * g + t][1] = fma(a, b[16], acc[4 * g + t][1]);
+                }
+              }
+            }
+          }
+        } else {
+          // a segment larger than the stage buffer (dense-ish blocks): its entries are read from global memory
+          const Entry* ents = reinterpret_cast<const Entry*>(pr.ent) + pr.segoff[item.strip * nchunks + q];
+#pragma unroll
+          for (int g = 0; g < TM / 128; ++g) {
+            int e[4], n[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int r = hw + 32 * (4 * g + t);
+              e[t] = rp[r];
+              n[t] = rp[r + 1] - e[t];
+            }
+            int maxn = max(max(n[0], n[1]), max(n[2], n[3]));
+            maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, 16));
+            for (int i = 0; i < maxn; ++i) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (i < n[t]) {
+                  const Entry en = ents[e[t] + i];
+                  const double* b = Bs + en.k * TN + l16;
+                  acc[4 * g + t][0] = fma(en.a, b[0], acc[4 * g + t][0]);
+                  acc[4 * g + t][1] = fma(en.a, b[16], acc[4 * g + t][1]);
+                }
               }
             }
           }
@@ -477,9 +510,10 @@ cudaError_t launch_sprand(const SprandDesc* d_descs, int nblocks, int max_cols, 
   if (nblocks <= 0) return cudaSuccess;
   const size_t smem = static_cast<size_t>(SPR_MAX_T) * 12 + static_cast<size_t>(max_cols + 1) * 4 + 16;
   static PerDeviceOnce once;
-  cudaError_t e = once.run([&] { return cudaFuncSetAttribute(sprand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  constexpr int kSprandSmemMax = 216 * 1024;  // dynamic part; the kernel's static shared variables come on top of it
+  cudaError_t e = once.run([&] { return cudaFuncSetAttribute(sprand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSprandSmemMax); });
   if (e != cudaSuccess) return e;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > static_cast<size_t>(kSprandSmemMax)) return cudaErrorInvalidValue;
   sprand_kernel<<<nblocks, 1024, smem, stream>>>(d_descs);
   return cudaGetLastError();
 }

@@ -167,6 +167,16 @@ def grid_multiply(session: "MatfastSession", A: "Dataset", B: "Dataset", slabsA_
     return Dataset(session, h)
 
 
+def grid_multiply_rows(session: "MatfastSession", A_rows: "Dataset", leftRowNum: int, leftColNum: int, B: "Dataset",
+                       slabsB_col: Sequence[int]) -> "Dataset":
+    """``mr_grid_multiply_rows``: the left operand holds the complete block rows this rank owns (sparse or dense, replicated by
+    the caller), only the sharded dense right operand is pulled from the grid column."""
+    pb = (C.c_void_p * len(slabsB_col))(*[int(x) for x in slabsB_col])
+    h = C.c_void_p()
+    N.check(N.lib.mr_grid_multiply_rows(A_rows._h, int(leftRowNum), int(leftColNum), B._h, pb, C.byref(h)))
+    return Dataset(session, h)
+
+
 class Dataset:
     """A bag of ``(rid, cid, block)`` rows resident in HBM (an ``mr_matrix`` handle)."""
 
@@ -253,6 +263,12 @@ class Dataset:
         if isTransposed is not None:
             flags = np.ascontiguousarray(isTransposed, dtype=np.uint8).ctypes.data_as(C.POINTER(C.c_uint8))
         N.check(N.lib.mr_matrix_put_blocks_device(self._h, n, _i32p(rids), _i32p(cids), _i32p(nr), _i32p(nc), ptrs, flags))
+
+    def filter_blocks(self, row_mod: int = 1, row_rem: int = 0, col_mod: int = 1, col_rem: int = 0) -> "Dataset":
+        """The blocks with rid % row_mod == row_rem and cid % col_mod == col_rem (a partition's share; no copy)."""
+        h = C.c_void_p()
+        N.check(N.lib.mr_matrix_filter_blocks(self._h, int(row_mod), int(row_rem), int(col_mod), int(col_rem), C.byref(h)))
+        return Dataset(self.matfastSession, h)
 
     def has_block(self, rid: int, cid: int) -> bool:
         out = C.c_int32()
