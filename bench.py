@@ -697,7 +697,7 @@ def run_cfg5(args):
         alg_bytes = (12.0 * nnz_total + 4.0 * (n + nb) * nb + 2 * 8.0 * n * n) / world     # SURVEY 8d compulsory bytes, per rank
         fma_roof = 148 * 16 * 2 * 1.9e9 / 1e12      # shared-memory port: 16 fp64 FMA / clk / SM at ~1.9 GHz
         ach_tf = (flops / world) / (kern_ms * 1e-3) / 1e12
-        line = {"metric": "fp64 sparse(1%) x dense block-matmul GFLOP/s at N=%d" % n, "value": flops / (ms * 1e-3) / 1e9, "unit": UNIT,
+        line = {"metric": f"fp64 sparse(1%) x dense block-matmul GFLOP/s at N={n}", "value": flops / (ms * 1e-3) / 1e9, "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"BASELINE configs[4]: {n}x{n} sparse(1%) x dense fp64, CSR {blk}-blocks, {plan.pr}x{plan.pc} grid over {world}xB200",
