@@ -86,6 +86,7 @@ MR_API mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value);
 MR_API mr_status mr_sync(mr_context* ctx);
 /* Orders the context stream (device side, no host wait) after every host->device block copy submitted so far. */
 MR_API mr_status mr_wait_ingest(mr_context* ctx);
+MR_API mr_status mr_wait_ingest_on(mr_context* ctx, void* cuda_stream);   /* the same for a caller-owned stream */
 MR_API const char* mr_last_error(void);
 MR_API const char* mr_version(void);
 
@@ -264,6 +265,10 @@ MR_API mr_status mr_memcpy_d2h(mr_context* ctx, const void* dptr, void* host, in
  * does it with events).  nchunks >= 1: pieces the pull of A is cut into (the multiply starts on the first).  *out is sharded. */
 MR_API mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
                                   int32_t nchunks, mr_matrix** out);
+/* mr_grid_multiply with one CUDA event (cudaEvent_t) per piece of the pull: gates[0] guards B, gates[1 + ch] piece ch of A
+ * (NULL = in place).  Lets every rank overlap its peers' host->device ingest with its own multiply. */
+MR_API mr_status mr_grid_multiply_gated(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
+                                        int32_t nchunks, const void* const* gates, mr_matrix** out);
 /* The blocks a partition owns (rid % row_mod == row_rem, cid % col_mod == col_rem); shares the device arrays with `a`. */
 MR_API mr_status mr_matrix_filter_blocks(mr_matrix* a, int32_t row_mod, int32_t row_rem, int32_t col_mod, int32_t col_rem,
                                          mr_matrix** out);

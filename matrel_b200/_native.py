@@ -99,6 +99,7 @@ SIGNATURES = {
     "mr_set_option": [_P, C.c_char_p, _i64],
     "mr_sync": [_P],
     "mr_wait_ingest": [_P],
+    "mr_wait_ingest_on": [_P, _P],
     "mr_matrix_create": [_P, _PP],
     "mr_matrix_free": [_P],
     "mr_matrix_put_block": [_P, _i32, _i32, C.POINTER(mr_block_desc)],
@@ -148,6 +149,7 @@ SIGNATURES = {
     "mr_ipc_close_all": [_P],
     "mr_memcpy_d2h": [_P, _P, _P, _i64],
     "mr_grid_multiply": [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32, _PP],
+    "mr_grid_multiply_gated": [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32, C.POINTER(C.c_void_p), _PP],
     "mr_grid_multiply_rows": [_P, _i64, _i64, _P, C.POINTER(C.c_void_p), _PP],
     "mr_matrix_filter_blocks": [_P, _i32, _i32, _i32, _i32, _PP],
     "mr_init_grid": [C.POINTER(mr_options), _i32, _PP],

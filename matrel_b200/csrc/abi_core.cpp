@@ -421,6 +421,17 @@ mr_status mr_wait_ingest(mr_context* ctx) {
   });
 }
 
+// The same for a caller-owned stream (e.g. the side stream a cross-process barrier runs on).
+mr_status mr_wait_ingest_on(mr_context* ctx, void* cuda_stream) {
+  return guarded([&] {
+    MR_REQUIRE(ctx != nullptr, MR_EINVAL, "ctx is null");
+    DeviceScope dev(ctx);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_CHECK(cudaEventRecord(ctx->ev_alloc, ctx->h2d_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(cuda_stream), ctx->ev_alloc, 0));
+  });
+}
+
 mr_status mr_get_stats(mr_context* ctx, mr_stats* out) {
   return guarded([&] {
     MR_REQUIRE(ctx != nullptr && out != nullptr, MR_EINVAL, "ctx/out is null");

@@ -211,8 +211,8 @@ mr_status mr_ipc_close_all(mr_context* ctx) {
 // IPC-opened).  The caller guarantees that the peers' slabs are complete and stay untouched until this rank's pulls have run
 // (one process per GPU: a barrier on the stream before, one after; mr_init_grid does it with events).  nchunks = number of pieces
 // the A pull is cut into along this rank's block rows (>= 1): the multiply starts on piece 0 while the others are on the wire.
-mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
-                           int32_t nchunks, mr_matrix** out) {
+static mr_status grid_multiply_impl(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
+                                    int32_t nchunks, const void* const* gates, mr_matrix** out) {
   return guarded([&] {
     MR_REQUIRE(A && B && out && slabsA_row && slabsB_col, MR_EINVAL, "null argument");
     MR_REQUIRE(A->shard && B->shard, MR_EINVAL, "operands must be sharded datasets (mr_matrix_create_sharded)");
@@ -237,8 +237,12 @@ mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slab
     CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
     CUDA_CHECK(cudaStreamWaitEvent(ps, ctx->ev_order, 0));
     auto peer_index = [](int p, int self) { return p < self ? p : p - 1; };  // position of peer p in the panel buffer
+    auto gate = [&](int idx) {  // caller-provided "the peers' data for this piece is in place" event
+      if (gates != nullptr && gates[idx] != nullptr) CUDA_CHECK(cudaStreamWaitEvent(ps, static_cast<cudaEvent_t>(const_cast<void*>(gates[idx])), 0));
+    };
     // ---- B: whole slabs of the grid column (every block of them is needed), one copy per peer
     ReadyPtr readyB;
+    gate(0);
     if (pr > 1) {
       for (int rr = 0; rr < pr; ++rr) {
         if (rr == r) continue;
@@ -258,6 +262,7 @@ mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slab
       for (int ch = 0; ch < nchunks; ++ch) {
         const int64_t lo = my_rows * ch / nchunks, hi = my_rows * (ch + 1) / nchunks;
         for (int64_t li = lo; li < hi; ++li) chunk_of_row[li] = ch;
+        gate(1 + ch);
         if (hi > lo) {
           const size_t off = static_cast<size_t>(lo) * LA.slots_c * slot_bytes, len = static_cast<size_t>(hi - lo) * LA.slots_c * slot_bytes;
           for (int cc = 0; cc < pc; ++cc) {
@@ -333,6 +338,20 @@ mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slab
     std::unique_ptr<mr_matrix> result(multiply_impl(ctx, tA.get(), LA.nrows, LA.ncols, tB.get(), LB.nrows, LB.ncols, LA.blk, &LC));
     *out = result.release();
   });
+}
+
+mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
+                           int32_t nchunks, mr_matrix** out) {
+  return grid_multiply_impl(A, B, slabsA_row, slabsB_col, nchunks, nullptr, out);
+}
+
+// The same with one caller-provided CUDA event per piece of the pull: gates[0] guards the pull of B, gates[1 + ch] the pull of
+// piece ch of A (ch < nchunks; the pieces are this rank's block rows [rows * ch / nchunks, rows * (ch + 1) / nchunks)).  A null
+// entry means "already in place".  This is how a multi-process caller overlaps its peers' host->device ingest with the multiply:
+// every rank uploads piece after piece, puts a stream barrier behind each, records an event, and hands the events in here.
+mr_status mr_grid_multiply_gated(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
+                                 int32_t nchunks, const void* const* gates, mr_matrix** out) {
+  return grid_multiply_impl(A, B, slabsA_row, slabsB_col, nchunks, gates, out);
 }
 
 // The blocks of a dataset that a partition owns: rid % row_mod == row_rem and cid % col_mod == col_rem (RowPartitioner /

@@ -66,6 +66,10 @@ class MatfastSession:
         """Device-side: the session stream waits for every host->device block copy submitted so far."""
         N.check(N.lib.mr_wait_ingest(self._ctx))
 
+    def wait_ingest_on(self, cuda_stream: int) -> None:
+        """Device-side: the given CUDA stream waits for every host->device block copy submitted so far."""
+        N.check(N.lib.mr_wait_ingest_on(self._ctx, C.c_void_p(cuda_stream)))
+
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         N.check(N.lib.mr_set_stream(self._ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
 
@@ -158,12 +162,19 @@ def memcpy_d2h(session: "MatfastSession", device_ptr: int, out: np.ndarray) -> n
 
 
 def grid_multiply(session: "MatfastSession", A: "Dataset", B: "Dataset", slabsA_row: Sequence[int], slabsB_col: Sequence[int],
-                  nchunks: int = 4) -> "Dataset":
-    """``mr_grid_multiply``: this rank's share of C = A B; the slab pointers are valid in this process (IPC-opened peers)."""
+                  nchunks: int = 4, gates: Optional[Sequence[Optional[int]]] = None) -> "Dataset":
+    """``mr_grid_multiply``: this rank's share of C = A B; the slab pointers are valid in this process (IPC-opened peers).
+    ``gates`` (optional, nchunks + 1 raw cudaEvent_t handles or None): gates[0] guards the pull of B, gates[1 + ch] the pull of
+    piece ch of A (``mr_grid_multiply_gated``)."""
     pa = (C.c_void_p * len(slabsA_row))(*[int(x) for x in slabsA_row])
     pb = (C.c_void_p * len(slabsB_col))(*[int(x) for x in slabsB_col])
     h = C.c_void_p()
-    N.check(N.lib.mr_grid_multiply(A._h, B._h, pa, pb, int(nchunks), C.byref(h)))
+    if gates is None:
+        N.check(N.lib.mr_grid_multiply(A._h, B._h, pa, pb, int(nchunks), C.byref(h)))
+    else:
+        assert len(gates) == nchunks + 1
+        pg = (C.c_void_p * len(gates))(*[int(g) if g else None for g in gates])
+        N.check(N.lib.mr_grid_multiply_gated(A._h, B._h, pa, pb, int(nchunks), pg, C.byref(h)))
     return Dataset(session, h)
 
 

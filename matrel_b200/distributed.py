@@ -184,7 +184,7 @@ class ShardedMatrix:
 
 
 def sharded_multiply(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMatrix, planA: GridPlan, planB: GridPlan,
-                     nchunks: int = 4):
+                     nchunks: int = 4, gates=None):
     """C = A * B, C-stationary on the process grid, through ``mr_grid_multiply``: this rank pulls A(i, :) of its block rows from
     the ranks of its grid row and B(:, j) of its block columns from its grid column out of their slabs (copy engines over
     NVLink, ``nchunks`` pieces along the block rows) while the multiply already runs on the pieces that have landed.
@@ -197,8 +197,16 @@ def sharded_multiply(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMa
     pa, pb = A.peer_slabs(), B.peer_slabs()
     rowA = [pa[planA.rank_of(r, cc)] for cc in range(planA.pc)]
     colB = [pb[planB.rank_of(rr, c)] for rr in range(planB.pr)]
-    dC = grid_multiply(session, A.sharded, B.sharded, rowA, colB, nchunks)
+    dC = grid_multiply(session, A.sharded, B.sharded, rowA, colB, nchunks, gates)
     return dC, (A, B)
+
+
+def pull_chunks(plan: GridPlan, rank: int, nchunks: int):
+    """The pieces ``mr_grid_multiply`` cuts this rank's block rows into: (effective nchunks, [list of global block-row ids])."""
+    r, _ = plan.coords(rank)
+    rows = list(range(r, plan.nbr, plan.pr))
+    nchunks = max(1, min(nchunks, max(len(rows), 1)))
+    return nchunks, [rows[len(rows) * ch // nchunks:len(rows) * (ch + 1) // nchunks] for ch in range(nchunks)]
 
 
 def stream_barrier(device):
@@ -579,13 +587,32 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
         torch.cuda.synchronize()
         dist.barrier()
 
+        side = torch.cuda.Stream(device=device)      # the cross-rank barriers run here, beside the multiply
+        nch, chunk_rows = pull_chunks(plan, rank, getattr(args, "pull_chunks", 4))
+        pA_by_chunk = [[b for b in pA if b.rid in set(rows)] for rows in chunk_rows]
+        tick = torch.zeros(1, device=device)
+
+        def gate_after_ingest():
+            """'Every rank's copies submitted so far have landed': the side stream waits for this rank's ingest, runs a one-element
+            all-reduce (complete only when every rank has got there), and the event recorded behind it gates the pulls."""
+            s.wait_ingest_on(side.cuda_stream)
+            with torch.cuda.stream(side):
+                if world > 1:
+                    dist.all_reduce(tick)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return ev
+
         def e2e_step():
+            # B first (every output block needs all of it), then A piece by piece; the multiply is called once and its pulls
+            # wait piece by piece for the peers' uploads, so ingest, NVLink pulls, tensor-core work and egress all overlap
             eB.sharded.put_blocks(pB)          # async copies on the ingest stream, one event per block
-            eA.sharded.put_blocks(pA)
-            s.wait_ingest()                    # device-side: the session stream follows the ingest ...
-            stream_barrier(device)             # ... so this barrier tells every peer "my slabs are in place"
-            dC, keep = sharded_multiply(s, groups, eA, eB, plan, plan, nchunks=getattr(args, "pull_chunks", 4))
-            for k in sorted(dC.block_ids()):   # block rows complete in order; egress overlaps the later chunks
+            evs = [gate_after_ingest()]
+            for blocks in pA_by_chunk:
+                eA.sharded.put_blocks(blocks)
+                evs.append(gate_after_ingest())
+            dC, keep = sharded_multiply(s, groups, eA, eB, plan, plan, nchunks=nch, gates=[e.cuda_event for e in evs])
+            for k in sorted(dC.block_ids()):   # block rows complete in order; egress overlaps the later pieces
                 dC.get_block(*k, out=outbuf[k])
             stream_barrier(device)             # nobody rewrites a slab while a peer may still be pulling from it
             return dC

@@ -33,7 +33,9 @@ def test_committed_bench_line(n_gpus):
     assert 0.5 < r["frac"] <= 1.0 and (r["traffic"] is None or r["traffic"] > 0)
     assert d["gpu_launches"] >= d["steps"]
     c = d["clocks"]
-    assert c["sm_mhz"] > 0.8 * c["sm_max_mhz"]
+    # clocks below max are only acceptable with the power cap as the stated reason (a dense int8 tensor-core kernel on a 1 kW part
+    # sits at ~1.45-1.65 GHz); a low clock with no reason would be a leftover clock lock
+    assert c["sm_mhz"] > 0.8 * c["sm_max_mhz"] or "sw_power_cap" in c["reasons"]
     assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     if n_gpus == 1:
         b = d["cpu_baseline"]
