@@ -106,7 +106,7 @@ def main():
             w = want[key]
             assert (g.numRows, g.numCols, g.isTransposed) == (w.numRows, w.numCols, False)
             err = float(np.max(np.abs(g.values - w.values)) / np.max(np.abs(w.values)))
-            assert err <= (5e-5 if algo == 3 else 1e-12), (key, err)      # algo 3 = fp32 results (3xTF32)
+            assert err <= (1e-5 if algo == 3 else 1e-12), (key, err)      # algo 3 = fp32 results (3xTF32)
         if algo == 2:
             assert s_launches >= 8, s_launches     # absmax/slice passes + one GEMM per diagonal: the tcgen05 path really ran
         if algo == 4:

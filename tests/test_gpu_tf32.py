@@ -1,8 +1,10 @@
 """GPU tests of the fp32 multiply on tcgen05 kind::tf32 (gemm_algo = 3, 3xTF32 split) -- BASELINE configs[3] shape.
 
 fp32 is not a reference feature (blocks are Array[Double]); parity is defined as: inputs rounded to fp32, oracle =
-fp64 product of those inputs, tolerance 5e-5 relative to max|C| (fp32 tensor-core accumulation inside each 4096-deep K
-chunk -- chunks are re-accumulated in fp64 -- plus the dropped lo*lo term; a single-pass TF32 product would be ~1e-3)."""
+fp64 product of those inputs, tolerance 1e-5 relative to max|C| (the north-star bar).  What makes it hold: the 3xTF32 split,
+K chunks of 4096 re-accumulated in fp64, and -- for operands fully covered by blocks -- mean-centring: the tensor core's fp32
+accumulation truncates, a bias that grows with K for same-signed data (1e-4 at K = 16384 on U(0,1) inputs); the operand means
+are removed before the split and put back in fp64 by the epilogue.  (A single-pass TF32 product would be ~1e-3.)"""
 import numpy as np
 import pytest
 
@@ -11,7 +13,7 @@ from oracle import matrel_oracle as O
 from tests.util import assert_same_dataset, from_dataset, random_block_dataset, rel_err, to_dataset
 
 pytestmark = pytest.mark.gpu
-TF32X3_TOL = 5e-5
+TF32X3_TOL = 1e-5
 
 
 def f32_round(ds):
@@ -42,12 +44,10 @@ def test_tf32x3_multiply(n, k, m, blk, pt):
     want = O.matrix_multiply(A, n, k, B, k, m, blk)
     with mb.MatfastSession(device=0, gemm_algo=3) as s:
         got = from_dataset(to_dataset(s, A).matrixMultiply(n, k, to_dataset(s, B), k, m, blk))
-        assert s.stats()["kernel_launches"] == 2 + -(-k // 4096)   # two slicing passes + one tcgen05 launch per K chunk
+        # (two sum passes when the operands are fully covered), two slicing passes, the correction kernel, one tcgen05 launch per K chunk
+        assert s.stats()["kernel_launches"] in (3 + -(-k // 4096), 5 + -(-k // 4096))
     assert_same_dataset(got, want, tol=TF32X3_TOL)          # ids / presence / shapes / flags exact
     full_g = O.assemble({k_: O.DenseMatrix(v.numRows, v.numCols, v.values) for k_, v in got.items()}, n, m, blk)
     err = rel_err(full_g, O.assemble(want, n, m, blk))
     assert err <= TF32X3_TOL, err
     assert err > 0                                           # it really is fp32 arithmetic
-    if k <= 4096:   # a single K chunk: every stored result is exactly an fp32 accumulator value
-        for v in got.values():
-            assert np.array_equal(v.values, v.values.astype(np.float32).astype(np.float64))
