@@ -900,22 +900,14 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
-// Sum of all elements of the blocks (for the operand mean), same tiling as the slicing pass.
-__global__ void __launch_bounds__(256) block_sum_kernel(const OzBlock* __restrict__ blocks, double* __restrict__ total, int tiles_c_max) {
+// Sum of all elements of the blocks (for the operand mean): the value arrays are summed in storage order (coalesced whatever
+// the block's orientation); blockIdx.x strides over 4096-element pieces, blockIdx.y = block.
+__global__ void __launch_bounds__(256) block_sum_kernel(const OzBlock* __restrict__ blocks, double* __restrict__ total) {
   __shared__ double part[8];
   const OzBlock b = blocks[blockIdx.y];
-  const int tr = blockIdx.x / tiles_c_max, tc = blockIdx.x % tiles_c_max;
-  const int r0 = tr * 32, c0 = tc * 128;
-  if (r0 >= b.rows || c0 >= b.cols) return;
-  // the block is read as its storage-order matrix (fast index first): sums do not care about orientation
-  const int fast_n = b.isT ? b.cols : b.rows, slow_n = b.isT ? b.rows : b.cols;
-  (void)fast_n;
-  (void)slow_n;
+  const size_t count = static_cast<size_t>(b.rows) * b.cols;
   double acc = 0.0;
-  for (int idx = threadIdx.x; idx < 32 * 128; idx += 256) {
-    const int r = r0 + idx / 128, c = c0 + idx % 128;
-    if (r < b.rows && c < b.cols) acc += blk_at(b, r, c);
-  }
+  for (size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x; i < count; i += static_cast<size_t>(gridDim.x) * 256) acc += b.v[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
@@ -1542,13 +1534,13 @@ cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand
   for (int i = 0; i < nb; ++i) area_b += static_cast<int64_t>(b_blocks[i].rows) * b_blocks[i].cols;
   const bool centre = area_a == M * K && area_b == K * N;
   if (centre) {
-    const int tc = (max_ac + 127) / 128, tr = (max_ar + 31) / 32;
+    const unsigned pieces_a = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, (static_cast<int64_t>(max_ar) * max_ac + 4095) / 4096)));
     OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
-      block_sum_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, totals, tc);
+      block_sum_kernel<<<dim3(pieces_a, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, totals);
     }));
-    const int tcb = (max_bc + 127) / 128, trb = (max_br + 31) / 32;
+    const unsigned pieces_b = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, (static_cast<int64_t>(max_br) * max_bc + 4095) / 4096)));
     OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
-      block_sum_kernel<<<dim3(trb * tcb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, totals + 1, tcb);
+      block_sum_kernel<<<dim3(pieces_b, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, totals + 1);
     }));
     *launches += 2;
   }
@@ -1614,10 +1606,11 @@ cudaError_t tf32x3_gemm(const OzakiOperand* a_blocks, int na, const OzakiOperand
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
-  // fp32 accumulation in the tensor core drifts with K (measured ~1e-4 at K = 16384 for all-positive data), so K is cut
-  // into chunks of 4096 whose fp32 tile sums are re-accumulated in fp64 by the epilogue (read-modify-write of C).
+  // fp32 accumulation in the tensor core truncates: besides the centring above (which removes the bias for same-signed data), K
+  // is cut into chunks of 2048 whose fp32 tile sums are re-accumulated in fp64 by the epilogue (read-modify-write of C), which
+  // keeps the random-walk part of the truncation error below 1e-5 of max|C| even for heavily cancelling data.
   const int stages_total = static_cast<int>(Kpad / 32);
-  const int chunk = 4096 / 32;
+  const int chunk = 2048 / 32;
   for (int kc = 0; kc < stages_total; kc += chunk) {
     p.kc0 = kc;
     p.nkc = std::min(chunk, stages_total - kc);

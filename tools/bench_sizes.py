@@ -100,7 +100,7 @@ if rank == 0:
     tflops = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
     line = {"config": f"{n}x{n} {'fp32' if algo == 3 else 'fp64'} dense multiply, {blk}-block, {plan.pr}x{plan.pc} grid over {world}xB200",
             "algo": {0: "auto: tcgen05 Ozaki-II (int8 residues + CRT), fp64-equivalent", 1: "fp64 DMMA (mma.sync m8n8k4)",
-                     3: "tcgen05 kind::tf32, 3xTF32 split, mean-centred, fp64 re-accumulation of 4096-deep K chunks"}.get(algo, str(algo)),
+                     3: "tcgen05 kind::tf32, 3xTF32 split, mean-centred, fp64 re-accumulation of 2048-deep K chunks"}.get(algo, str(algo)),
             "n_gpus": world, "ms_per_step": ms, "TFLOPs": tflops, "max_rel_err_sampled_blocks": err, "tc_path": bool(st["tc_gemm_launches"])}
     if algo == 3 and "tcgen05_tf32_sustained" in peaks:
         line["raw_tf32_TFLOPs"] = 3 * tflops
