@@ -71,8 +71,8 @@ def main():
             dG, keepG = sharded_multiply_allgather(s, groups, A, B, planA, planB)
             gotG = {(b.rid, b.cid): b.matrix for b in dG.collect()}
             assert sorted(gotG) == sorted(got)
-            for key in got:
-                assert np.array_equal(gotG[key].values, got[key].values), key
+            for key in got:   # (the fp32 path adds fp64 mean corrections accumulated with atomics: equal to rounding, not to the bit)
+                assert np.array_equal(gotG[key].values, got[key].values) if algo != 3 else np.allclose(gotG[key].values, got[key].values, rtol=1e-12, atol=1e-12), key
             # operands that arrive from the HOST into sharded datasets (put_block on the ingest stream), barrier, pull, multiply
             from matrel_b200.dataset import create_sharded
             Ah = O.rand_dense_dataset(n, k, blk, 42)
@@ -90,13 +90,13 @@ def main():
                 stream_barrier(device)
                 assert sorted(gotE) == sorted(got)
                 for key in got:
-                    assert np.array_equal(gotE[key].values, got[key].values), (rep, key)
+                    assert np.array_equal(gotE[key].values, got[key].values) if algo != 3 else np.allclose(gotE[key].values, got[key].values, rtol=1e-12, atol=1e-12), (rep, key)
             # the overlapped exchange (A gathered in chunks on a side stream) must give the same blocks
             outs, keep2 = sharded_multiply_overlapped(s, groups, A, B, planA, planB, torch.cuda.Stream(device=device), nchunks=3)
             got2 = {(b.rid, b.cid): b.matrix for d in outs for b in d.collect()}
             assert sorted(got2) == sorted(got)
             for key in got:
-                assert np.array_equal(got2[key].values, got[key].values), key
+                assert np.array_equal(got2[key].values, got[key].values) if algo != 3 else np.allclose(got2[key].values, got[key].values, rtol=1e-12, atol=1e-12), key
             if algo in (0, 1):
                 siblings(s, groups, A, planA, rank, device, n, k, blk)
             s.stop()
