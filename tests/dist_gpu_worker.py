@@ -15,6 +15,12 @@ from matrel_b200.distributed import (GridGroups, GridPlan, ShardedMatrix, sharde
 from oracle import matrel_oracle as O  # noqa: E402
 
 
+def same_fp32(a, b):
+    """Two runs of the fp32 path agree to fp32 rounding, not to the bit: the operand means (and with them the fp32 roundings of the
+    centred values) depend on which rows a call sees, and the fp64 corrections are accumulated with atomics."""
+    return float(np.max(np.abs(a - b))) <= 1e-5 * float(np.max(np.abs(b)))
+
+
 def siblings(s, groups, A, planA, rank, device, n, k, blk):
     """The multiply's siblings on the same grid: transpose (one packed P2P exchange, flag flip), co-partitioned element-wise
     ops (no communication), aggregates (local kernel + one O(N) all-reduce)."""
@@ -72,7 +78,7 @@ def main():
             gotG = {(b.rid, b.cid): b.matrix for b in dG.collect()}
             assert sorted(gotG) == sorted(got)
             for key in got:   # (the fp32 path adds fp64 mean corrections accumulated with atomics: equal to rounding, not to the bit)
-                assert np.array_equal(gotG[key].values, got[key].values) if algo != 3 else np.allclose(gotG[key].values, got[key].values, rtol=1e-12, atol=1e-12), key
+                assert np.array_equal(gotG[key].values, got[key].values) if algo != 3 else same_fp32(gotG[key].values, got[key].values), key
             # operands that arrive from the HOST into sharded datasets (put_block on the ingest stream), barrier, pull, multiply
             from matrel_b200.dataset import create_sharded
             Ah = O.rand_dense_dataset(n, k, blk, 42)
@@ -90,13 +96,13 @@ def main():
                 stream_barrier(device)
                 assert sorted(gotE) == sorted(got)
                 for key in got:
-                    assert np.array_equal(gotE[key].values, got[key].values) if algo != 3 else np.allclose(gotE[key].values, got[key].values, rtol=1e-12, atol=1e-12), (rep, key)
+                    assert np.array_equal(gotE[key].values, got[key].values) if algo != 3 else same_fp32(gotE[key].values, got[key].values), (rep, key)
             # the overlapped exchange (A gathered in chunks on a side stream) must give the same blocks
             outs, keep2 = sharded_multiply_overlapped(s, groups, A, B, planA, planB, torch.cuda.Stream(device=device), nchunks=3)
             got2 = {(b.rid, b.cid): b.matrix for d in outs for b in d.collect()}
             assert sorted(got2) == sorted(got)
             for key in got:
-                assert np.array_equal(got2[key].values, got[key].values) if algo != 3 else np.allclose(got2[key].values, got[key].values, rtol=1e-12, atol=1e-12), key
+                assert np.array_equal(got2[key].values, got[key].values) if algo != 3 else same_fp32(got2[key].values, got[key].values), key
             if algo in (0, 1):
                 siblings(s, groups, A, planA, rank, device, n, k, blk)
             s.stop()
