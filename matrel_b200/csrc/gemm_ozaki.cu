@@ -719,12 +719,13 @@ __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict_
   for (int l = warp; l < 32; l += 8) {
     if (l0 + l >= nlines) continue;
     const int e = line_exp[gl_base + l];
+    const double line_scale = scalbn(1.0, alpha - e);  // exact power of two
     uint32_t hi[4], lo[4];
-    int sgn[4];
+    float sgn[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const long long X = __double2ll_rn(scalbn(sm[l][lane * 4 + j], alpha - e));  // exact power-of-two scaling, |X| <= 2^alpha
-      sgn[j] = X < 0 ? -1 : 1;
+      const long long X = __double2ll_rn(sm[l][lane * 4 + j] * line_scale);  // exact scaling, |X| <= 2^alpha
+      sgn[j] = X < 0 ? -1.0f : 1.0f;
       const unsigned long long U = static_cast<unsigned long long>(X < 0 ? -X : X);
       hi[j] = static_cast<uint32_t>(U >> 32);
       lo[j] = static_cast<uint32_t>(U);
@@ -732,19 +733,27 @@ __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict_
     const int kq = k0 + lane * 4;
     const int gk = gk_base + lane * 4;
     const bool whole = kq + 3 < nks && (gk & 3) == 0;
+    // All arithmetic below stays on the FMA / ALU pipes (no int<->float conversion instructions, which run at a quarter rate):
+    //   x = sum_i byte_i (256^i mod p) < 2^19 (two dp4a), congruent to |X|;
+    //   float(x) by the exponent trick (x < 2^23): as_float(0x4B000000 | x) - 2^23;
+    //   q = rint(x / p) by the 1.5 * 2^23 magic add (the fp32 quotient is off by < 4e-4; for odd p a fractional part is never closer
+    //   than 1 / (2 p) >= 2e-3 to one half, so the rounding decision is exact; p = 256 has true ties, either neighbour is congruent);
+    //   r = x - q p exactly (|r| <= 128), signed, and its low byte read out of the mantissa of r * sgn + 1.5 * 2^23.
+    const float kMagic = 12582912.0f;
     for (int t = 0; t < T; ++t) {
-      const int pm = static_cast<int>(cc.p[t]);
+      const float pf = static_cast<float>(cc.p[t]);
       const uint32_t wl = cc.clo[t], wh = cc.chi[t];
       const float ip = cc.invpf[t];
-      uint32_t packed = 0;
+      uint32_t bytes[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        // |X| = sum_i byte_i 256^i  ->  x = sum_i byte_i (256^i mod p) < 2^19, congruent to |X| and exact in fp32
         const uint32_t x = __dp4a(lo[j], wl, __dp4a(hi[j], wh, 0u));
-        // nearest multiple of p: the fp32 quotient is off by < 5e-4, so |r| <= p/2 + 0.13 -> |r| <= 128 (p = 256), 127 (odd p)
-        const int r = (static_cast<int>(x) - __float2int_rn(__uint2float_rn(x) * ip) * pm) * sgn[j];
-        packed |= (static_cast<uint32_t>(r) & 0xffu) << (8 * j);  // +-128 (p = 256 only) wrap to the congruent -128
+        const float f = __uint_as_float(0x4B000000u | x) - 8388608.0f;
+        const float q = __fadd_rn(__fmaf_rn(f, ip, kMagic), -kMagic);
+        const float r = __fmaf_rn(-q, pf, f);
+        bytes[j] = __float_as_uint(__fmaf_rn(r, sgn[j], kMagic));   // low byte = r * sgn in two's complement (+-128 wrap to -128: p = 256 only)
       }
+      const uint32_t packed = __byte_perm(__byte_perm(bytes[0], bytes[1], 0x0040), __byte_perm(bytes[2], bytes[3], 0x0040), 0x5410);
       int8_t* dst = out + static_cast<size_t>(t) * slice_stride + static_cast<size_t>(gl_base + l) * Kpad + gk;
       if (whole) {
         *reinterpret_cast<uint32_t*>(dst) = packed;
