@@ -24,6 +24,12 @@ namespace mrhost {
 
 thread_local std::string g_last_error;
 
+// release threshold of each device's default memory pool before the first context on it raised it (restored by the last one)
+constexpr int kMaxPoolDevices = 64;
+std::mutex g_pool_mu;
+int g_pool_users[kMaxPoolDevices] = {};
+uint64_t g_pool_threshold_before[kMaxPoolDevices] = {};
+
 [[noreturn]] void fail(mr_status code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -321,7 +327,11 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
     // keep freed blocks in the pool: operators allocate result slabs on every call
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
-    CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold_before));
+    {  // the pool setting is per device, shared by every context on it: the first context saves it, the last one restores it
+      std::lock_guard<std::mutex> g(g_pool_mu);
+      if (dev < kMaxPoolDevices && g_pool_users[dev]++ == 0)
+        CUDA_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &g_pool_threshold_before[dev]));
+    }
     uint64_t thr = UINT64_MAX;
     CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     *out = ctx.release();
@@ -352,10 +362,11 @@ mr_status mr_shutdown(mr_context* ctx) {
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-    {  // hand the cached operator memory back and undo the process-wide pool setting of mr_init
+    {  // the last context on the device hands the cached operator memory back and undoes the pool setting of mr_init
+      std::lock_guard<std::mutex> g(g_pool_mu);
       cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold_before);
+      if (ctx->device < kMaxPoolDevices && --g_pool_users[ctx->device] == 0 && cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &g_pool_threshold_before[ctx->device]);
         cudaMemPoolTrimTo(pool, 0);
       }
       (void)cudaGetLastError();

@@ -103,7 +103,6 @@ struct mr_context {
   char* stage_dev = nullptr;
   size_t stage_cap = 0, stage_off = 0;
   int pipeline = 1;
-  uint64_t pool_threshold_before = 0;            // release threshold of the device's default mempool before mr_init raised it
   cudaStream_t p2p_stream = nullptr;             // pulls of peers' blocks over NVLink (copy engines), see abi_grid.cpp
   std::map<std::string, void*> ipc_open;         // CUDA IPC handles opened by this context (handle bytes -> mapped base)
   mr_stats stats{};

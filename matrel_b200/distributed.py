@@ -313,6 +313,74 @@ def sharded_elementwise(op: str, A: ShardedMatrix, B: ShardedMatrix, plan: GridP
     return getattr(A.dataset, fn)(plan.nrows, plan.ncols, B.dataset, plan.nrows, plan.ncols, plan.blk)
 
 
+def repartition_routes(src: GridPlan, dst: GridPlan, rank: int):
+    """Block moves of repartitionWithTargetPartitioner (M/execution/MatfastExecutionHelper.scala:34-44) between two placement grids
+    of the same ranks (e.g. (P, 1) = RowPartitioner, (1, P) = ColumnPartitioner, (pr, pc) = the multiply's grid): block (i, j) moves
+    from src.owner(i, j) to dst.owner(i, j).  Returns (sends, recvs): sends[peer] = [(src_slot, dst_slot)], recvs[peer] = [dst_slot],
+    both ordered by block id so that one packed message per peer suffices."""
+    assert (src.world, src.nrows, src.ncols, src.blk) == (dst.world, dst.nrows, dst.ncols, dst.blk)
+    sends: Dict[int, list] = {}
+    recvs: Dict[int, list] = {}
+    for (i, j) in sorted(src.owned(rank)):
+        sends.setdefault(dst.owner(i, j), []).append((src.slot(i, j), dst.slot(i, j)))
+    for (i, j) in sorted(dst.owned(rank)):
+        recvs.setdefault(src.owner(i, j), []).append(dst.slot(i, j))
+    return sends, recvs
+
+
+def exchange_repartition(slab, src: GridPlan, dst: GridPlan, rank: int):
+    """The all-to-all permutation that replaces the reference's ShuffledRDD: every block travels once, untouched, to its owner
+    under `dst` (point-to-point, one packed message per peer; CPU tensors over gloo, device tensors over NCCL)."""
+    import torch
+    import torch.distributed as dist
+    out = torch.zeros((dst.local_slots, dst.slot_elems), dtype=slab.dtype, device=slab.device)
+    sends, recvs = repartition_routes(src, dst, rank)
+    ops, staged, inbox = [], [], []
+    for peer, moves in sorted(sends.items()):
+        src_idx = torch.tensor([m_[0] for m_ in moves], dtype=torch.long, device=slab.device)
+        if peer == rank:
+            out[torch.tensor([m_[1] for m_ in moves], dtype=torch.long, device=slab.device)] = slab[src_idx]
+        else:
+            buf = slab[src_idx].contiguous()
+            staged.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, peer))
+    for peer, slots in sorted(recvs.items()):
+        if peer == rank:
+            continue
+        buf = torch.empty((len(slots), dst.slot_elems), dtype=slab.dtype, device=slab.device)
+        inbox.append((buf, slots))
+        ops.append(dist.P2POp(dist.irecv, buf, peer))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for buf, slots in inbox:
+        out[torch.tensor(slots, dtype=torch.long, device=slab.device)] = buf
+    return out
+
+
+def sharded_repartition(session, A: ShardedMatrix, dst: GridPlan) -> ShardedMatrix:
+    """A on another placement grid of the same ranks (collective)."""
+    slab = exchange_repartition(A.slab, A.plan, dst, A.rank)
+    esz = slab.element_size()
+    ds = session.emptyDataset()
+    blocks = dst.owned(A.rank)
+    shapes = [dst.block_shape(i, j) for i, j in blocks]
+    if blocks:
+        ds.put_blocks_device([b[0] for b in blocks], [b[1] for b in blocks], [sh[0] for sh in shapes], [sh[1] for sh in shapes],
+                             [slab.data_ptr() + dst.slot(i, j) * dst.slot_elems * esz for i, j in blocks],
+                             [1 if A.transposed else 0] * len(blocks))
+    return ShardedMatrix(dst, A.rank, slab, ds, session, transposed=A.transposed)
+
+
+def sharded_elementwise_any(op: str, session, A: ShardedMatrix, B: ShardedMatrix):
+    """add / mul / div of two sharded matrices that may live on DIFFERENT placement grids: the right operand is first re-partitioned
+    to the left one's grid (MatrixElementAddExecution picks the left partitioner, MatfastExecution.scala:590-606), then the
+    co-partitioned kernel runs.  Returns (local result Dataset, keep-alive)."""
+    if (B.plan.pr, B.plan.pc) != (A.plan.pr, A.plan.pc):
+        B = sharded_repartition(session, B, GridPlan(A.plan.world, B.plan.nrows, B.plan.ncols, B.plan.blk, A.plan.pr, A.plan.pc))
+    return sharded_elementwise(op, A, B, A.plan), B
+
+
 def transpose_plan(plan: GridPlan) -> GridPlan:
     return GridPlan(plan.world, plan.ncols, plan.nrows, plan.blk, plan.pr, plan.pc)
 

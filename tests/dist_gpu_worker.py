@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import matrel_b200 as mb  # noqa: E402
 from matrel_b200.distributed import (GridGroups, GridPlan, ShardedMatrix, sharded_aggregate,  # noqa: E402
-                                     sharded_elementwise, sharded_multiply, sharded_multiply_allgather, sharded_multiply_overlapped,
-                                     sharded_transpose, stream_barrier)
+                                     sharded_elementwise, sharded_elementwise_any, sharded_multiply, sharded_multiply_allgather,
+                                     sharded_multiply_overlapped, sharded_repartition, sharded_transpose, stream_barrier)
 from oracle import matrel_oracle as O  # noqa: E402
 
 
@@ -41,6 +41,18 @@ def siblings(s, groups, A, planA, rank, device, n, k, blk):
         assert sorted(g) == sorted(planA.owned(rank))
         for key, m in g.items():
             assert np.allclose(m.to_numpy(), w[key].to_numpy(), rtol=1e-14, atol=0), (op, key)
+    # operands that start on DIFFERENT placement grids: A2 arrives in the RowPartitioner layout (world x 1); the element-wise
+    # operator re-partitions it to A's grid (NCCL point-to-point all-to-all) and must give the co-partitioned result bit for bit
+    world = planA.world
+    A2_rows = sharded_repartition(s, A2, GridPlan(world, n, k, blk, world, 1))
+    assert sorted(A2_rows.dataset.block_ids()) == sorted(A2_rows.plan.owned(rank))
+    for op, fn in (("add", O.add_element), ("div", O.divide_element)):
+        w = fn(Af, n, k, A2f, n, k, blk)
+        res, keep_b = sharded_elementwise_any(op, s, A, A2_rows)
+        g = {(b.rid, b.cid): b.matrix for b in res.collect()}
+        assert sorted(g) == sorted(planA.owned(rank))
+        for key, m in g.items():
+            assert np.allclose(m.to_numpy(), w[key].to_numpy(), rtol=1e-14, atol=0), ("repartitioned", op, key)
     r, c = planA.coords(rank)
     rows = np.concatenate([np.arange(i * blk, min(n, (i + 1) * blk)) for i in range(r, planA.nbr, planA.pr)])
     cols = np.concatenate([np.arange(j * blk, min(k, (j + 1) * blk)) for j in range(c, planA.nbc, planA.pc)])

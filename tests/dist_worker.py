@@ -11,8 +11,8 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from matrel_b200.distributed import (GridGroups, GridPlan, exchange_transpose, gather_panels, panel_blocks_A,  # noqa: E402
-                                     panel_blocks_B, transpose_routes)
+from matrel_b200.distributed import (GridGroups, GridPlan, exchange_repartition, exchange_transpose, gather_panels,  # noqa: E402
+                                     panel_blocks_A, panel_blocks_B, repartition_routes, transpose_routes)
 from oracle import matrel_oracle as O  # noqa: E402
 
 
@@ -66,6 +66,22 @@ def main():
     sends, recvs = transpose_routes(planA, rank)
     assert sum(len(v) for v in sends.values()) == len(planA.owned(rank))
     assert sum(len(v) for v in recvs.values()) == len(planT.owned(rank))
+    # re-partitioning (repartitionWithTargetPartitioner): grid -> RowPartitioner layout (P x 1) -> ColumnPartitioner layout (1 x P) -> grid;
+    # every block arrives untouched at its owner under each layout, and the round trip is the identity
+    slab0 = local_slab(A, planA)
+    cur, cur_plan = slab0, planA
+    for (pr_, pc_) in [(world, 1), (1, world), (planA.pr, planA.pc)]:
+        nxt_plan = GridPlan(world, n, k, blk, pr_, pc_)
+        sends, recvs = repartition_routes(cur_plan, nxt_plan, rank)
+        assert sum(len(v) for v in sends.values()) == len(cur_plan.owned(rank))
+        assert sum(len(v) for v in recvs.values()) == len(nxt_plan.owned(rank))
+        nxt = exchange_repartition(cur, cur_plan, nxt_plan, rank)
+        for (i, j) in nxt_plan.owned(rank):
+            assert nxt_plan.coords(rank) == (i % pr_, j % pc_)
+            v = A[(i, j)].values
+            assert np.array_equal(nxt[nxt_plan.slot(i, j), :v.size].numpy(), v), ("repartition", pr_, pc_, i, j)
+        cur, cur_plan = nxt, nxt_plan
+    assert torch.equal(cur, slab0)
     dist.barrier()
     if rank == 0:
         print(f"OK world={world} grid={planA.pr}x{planA.pc} blocks={len(full)}")
