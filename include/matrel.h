@@ -69,7 +69,8 @@ typedef struct mr_options {
                            and small products take the exact DMMA kernel instead;
                            1 = DMMA fp64 tensor-core kernel (mma.sync m8n8k4 f64), always;
                            2 = Ozaki-I int8 tcgen05 kernel (digit slices); 3 = 3xTF32 tcgen05 kernel (fp32 results);
-                           4 = Ozaki-II without the range guard (mr_set_option "crt_moduli" 6..16, default 16) */
+                           4 = Ozaki-II without the range guard.  mr_set_option "crt_moduli": 6..16 residue moduli, 0 (default) = chosen
+                              from K so that the operand truncation stays below half the fp64 dot-product bound K 2^-53 (14) */
   int32_t ozaki_slices; /* number of int8 slices for gemm_algo 2 (0 = default) */
   void* stream;         /* cudaStream_t to run on; NULL = a stream owned by the context */
 } mr_options;
@@ -318,6 +319,7 @@ typedef struct mr_stats {
   int64_t tc_gemm_launches; /* multiplies that ran on the tcgen05 path since reset */
   int64_t tc_int8_ops;      /* int8 multiply-add operations (x 2) of the most recent tcgen05 multiply */
   int64_t p2p_bytes;        /* bytes pulled from peer GPUs over NVLink by this context (grid multiply) */
+  int64_t tc_moduli;        /* residue moduli of the most recent tcgen05 (Ozaki-II) multiply */
 } mr_stats;
 MR_API mr_status mr_get_stats(mr_context* ctx, mr_stats* out);
 MR_API mr_status mr_reset_stats(mr_context* ctx);

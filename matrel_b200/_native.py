@@ -71,6 +71,7 @@ class mr_stats(C.Structure):
         ("tc_gemm_launches", C.c_int64),
         ("tc_int8_ops", C.c_int64),
         ("p2p_bytes", C.c_int64),
+        ("tc_moduli", C.c_int64),
     ]
 
 

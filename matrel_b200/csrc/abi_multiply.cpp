@@ -218,7 +218,7 @@ struct Oz2Run {
             std::vector<int>& group_of, int& ngroups, int32_t blk, int64_t M, int64_t K, int64_t N, bool outer, bool guard) {
     ctx = c;
     if (M <= 0 || K <= 0 || N <= 0 || K >= (1 << 17) || out_plan.empty()) return false;
-    const int T = ctx->crt_moduli > 0 ? ctx->crt_moduli : 16;
+    const int T = oz2_moduli_for(K, ctx->crt_moduli);
     const int ss = (blk + kOz2TileM - 1) / kOz2TileM * kOz2TileM;
     std::map<int32_t, int> crow, ccol;
     for (size_t oi : out_plan) {
@@ -783,6 +783,7 @@ void run_multiply(mr_context* ctx, std::vector<OutPlan>& plans, MultiplyPlanner&
     if (use_oz2) {
       oz2.upload_tables();
       ctx->stats.tc_int8_ops = oz2.int8_ops;
+      ctx->stats.tc_moduli = oz2_moduli(oz2.eng);
       ctx->stats.tc_gemm_launches += 1;
     }
     if (ctx->time_kernels) CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));

@@ -522,65 +522,97 @@ __device__ __forceinline__ double blk_at(const OzBlock& b, int r, int c) {
   return b.isT ? b.v[c + static_cast<size_t>(b.cols) * r] : b.v[r + static_cast<size_t>(b.rows) * c];
 }
 
-// by_row = true: out[row0 + r] = max_c |b(r,c)|; false: out[col0 + c] = max_r |b(r,c)|.  32x32 tiles, 256 threads;
-// tx runs along the block's contiguous dimension (rows for column-major, columns for row-major blocks).
+// by_row = true: out[row0 + r] = max_c |b(r,c)|; false: out[col0 + c] = max_r |b(r,c)|.  One CTA sweeps a tile of AM_FAST
+// elements along the block's contiguous index (rows of a column-major block, columns of a row-major one) x AM_SLOW along the
+// strided one: a warp reads eight 256-byte runs per strided index, so 8 x 8 independent loads are in flight per thread.
 // minout (optional): the smallest NON-ZERO magnitude of the same line (initialised to all-ones by the caller); the Ozaki-II
-// auto-selection uses it to bound the dynamic range inside a row / column.
+// auto-selection uses it to bound the dynamic range inside a row / column.  grid.x = fast tiles x tiles_s_max.
+constexpr int AM_FAST = 256, AM_SLOW = 64;
 __global__ void __launch_bounds__(256) absmax_kernel(const OzBlock* __restrict__ blocks, unsigned long long* __restrict__ out,
-                                                     unsigned long long* __restrict__ minout, int by_row, int tiles_c_max) {
-  __shared__ unsigned long long sm[8][32];
-  __shared__ unsigned long long sn[8][32];
+                                                     unsigned long long* __restrict__ minout, int by_row, int tiles_s_max) {
+  __shared__ unsigned long long sm[8][AM_FAST];
+  __shared__ unsigned long long sn[8][AM_FAST];
   const OzBlock b = blocks[blockIdx.y];
-  const int tr = blockIdx.x / tiles_c_max, tc = blockIdx.x % tiles_c_max;
-  const int r0 = tr * 32, c0 = tc * 32;
-  if (r0 >= b.rows || c0 >= b.cols) return;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const bool kept_is_fast = (by_row != 0) == (b.isT == 0);  // kept index == the one tx runs along
-  unsigned long long best = 0, least = ~0ull;
+  const int fastdim = b.isT ? b.cols : b.rows, slowdim = b.isT ? b.rows : b.cols;
+  const int f0 = (blockIdx.x / tiles_s_max) * AM_FAST, s0 = (blockIdx.x % tiles_s_max) * AM_SLOW;
+  if (f0 >= fastdim || s0 >= slowdim) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool kept_is_fast = (by_row != 0) == (b.isT == 0);  // the kept index is the contiguous one
+  const int line0 = by_row ? b.row0 : b.col0;
+  const bool want_min = minout != nullptr;
+  if (kept_is_fast) {
+    unsigned long long best[8], least[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int r = b.isT ? r0 + ty + 8 * j : r0 + tx;
-    const int c = b.isT ? c0 + tx : c0 + ty + 8 * j;
-    unsigned long long bits = 0;
-    if (r < b.rows && c < b.cols) bits = static_cast<unsigned long long>(__double_as_longlong(fabs(blk_at(b, r, c))));
-    unsigned long long nz = bits ? bits : ~0ull;
-    if (kept_is_fast) {
-      best = max(best, bits);  // reduce over the slow index: per-thread, then across ty below
-      least = min(least, nz);
-    } else {
-      // reduce over the fast index (the 32 lanes of this warp share one slow index)
+    for (int i = 0; i < 8; ++i) {
+      best[i] = 0ull;
+      least[i] = ~0ull;
+    }
+#pragma unroll 2
+    for (int j = 0; j < AM_SLOW / 8; ++j) {
+      const int sidx = s0 + warp + 8 * j;
+      if (sidx >= slowdim) break;
+      const double* src = b.v + static_cast<size_t>(fastdim) * sidx + f0 + lane;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
-        nz = min(nz, __shfl_xor_sync(0xffffffffu, nz, o));
-      }
-      const int slow = by_row ? r : c;
-      const int lim = by_row ? b.rows : b.cols;
-      if (tx == 0 && slow < lim) {
-        atomicMax(&out[(by_row ? b.row0 : b.col0) + slow], bits);
-        if (minout != nullptr && nz != ~0ull) atomicMin(&minout[(by_row ? b.row0 : b.col0) + slow], nz);
+      for (int i = 0; i < 8; ++i) {
+        unsigned long long bits = 0ull;
+        if (f0 + lane + 32 * i < fastdim) bits = static_cast<unsigned long long>(__double_as_longlong(fabs(src[32 * i])));
+        best[i] = max(best[i], bits);
+        least[i] = min(least[i], bits ? bits : ~0ull);
       }
     }
-  }
-  if (kept_is_fast) {
-    sm[ty][tx] = best;
-    sn[ty][tx] = least;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sm[warp][lane + 32 * i] = best[i];
+      sn[warp][lane + 32 * i] = least[i];
+    }
     __syncthreads();
-    if (ty == 0) {
+    const int f = f0 + threadIdx.x;
+    if (f < fastdim) {
+      unsigned long long m = sm[0][threadIdx.x], n = sn[0][threadIdx.x];
 #pragma unroll
       for (int k = 1; k < 8; ++k) {
-        best = max(best, sm[k][tx]);
-        least = min(least, sn[k][tx]);
+        m = max(m, sm[k][threadIdx.x]);
+        n = min(n, sn[k][threadIdx.x]);
       }
-      const int kept = (by_row ? r0 : c0) + tx;
-      const int lim = by_row ? b.rows : b.cols;
-      if (kept < lim) {
-        atomicMax(&out[(by_row ? b.row0 : b.col0) + kept], best);
-        if (minout != nullptr && least != ~0ull) atomicMin(&minout[(by_row ? b.row0 : b.col0) + kept], least);
+      if (m != 0ull) atomicMax(&out[line0 + f], m);
+      if (want_min && n != ~0ull) atomicMin(&minout[line0 + f], n);
+    }
+  } else {
+#pragma unroll 2
+    for (int j = 0; j < AM_SLOW / 8; ++j) {
+      const int sidx = s0 + warp + 8 * j;
+      if (sidx >= slowdim) break;  // warp-uniform
+      const double* src = b.v + static_cast<size_t>(fastdim) * sidx + f0 + lane;
+      unsigned long long m = 0ull, n = ~0ull;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        unsigned long long bits = 0ull;
+        if (f0 + lane + 32 * i < fastdim) bits = static_cast<unsigned long long>(__double_as_longlong(fabs(src[32 * i])));
+        m = max(m, bits);
+        n = min(n, bits ? bits : ~0ull);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (want_min) n = min(n, __shfl_xor_sync(0xffffffffu, n, o));
+      }
+      if (lane == 0) {
+        if (m != 0ull) atomicMax(&out[line0 + sidx], m);
+        if (want_min && n != ~0ull) atomicMin(&minout[line0 + sidx], n);
       }
     }
   }
 }
+
+// grid of absmax_kernel for blocks of at most max_rows x max_cols (either orientation)
+struct AbsmaxGrid {
+  int ts, tiles;
+  AbsmaxGrid(int max_rows, int max_cols) {
+    const int d = max_rows > max_cols ? max_rows : max_cols;
+    ts = (d + AM_SLOW - 1) / AM_SLOW;
+    tiles = ((d + AM_FAST - 1) / AM_FAST) * ts;
+  }
+};
 
 // exponent table: e = ilogb(max) + 1 (so |x| * 2^-e < 1), 0 for all-zero lines; flags non-finite input.
 // range_bits > 0 (Ozaki-II auto-selection): also flags a line whose smallest non-zero magnitude lies more than range_bits
@@ -684,12 +716,24 @@ struct CrtConst {
   uint32_t clo[CRT_MAX_T];     // bytes (256^0, 256^1, 256^2, 256^3) mod p
   uint32_t chi[CRT_MAX_T];     // bytes (256^4, 256^5, 256^6, 256^7) mod p
   float invpf[CRT_MAX_T];      // 1 / p
-  uint32_t w[CRT_MAX_T][4];    // CRT weight (P / p_t) * ((P / p_t)^-1 mod p_t) < P, little-endian 32-bit limbs
-  uint32_t P[4], Phalf[4];     // P and floor(P / 2)
-  double invP;                 // 1 / P (rounded)
   int32_t T, pad;
 };
 __constant__ CrtConst c_crt[CRT_MAX_T + 1];  // indexed by T, filled once on first use
+// the same CRT weights and P as exact fp64 chunks of CRT_CHUNK_BITS bits (little-endian; the top chunk takes the rest)
+constexpr int CRT_CHUNK_BITS = 40;
+struct CrtF {
+  double w[CRT_MAX_T][4];
+  double P[4];
+  double invP;
+  int32_t nch, pad;
+  // three chunks cover P < 2^120 (top chunk < 2^40); four are needed above (T = 16: P ~ 2^125.4, top chunk < 2^6)
+  static int nch_for(unsigned __int128 P) { return (P >> (3 * CRT_CHUNK_BITS)) == 0 ? 3 : 4; }
+  static double chunk(unsigned __int128 x, int i, int nch) {
+    const unsigned __int128 sh = x >> (CRT_CHUNK_BITS * i);
+    return static_cast<double>(static_cast<uint64_t>(i + 1 < nch ? sh & ((static_cast<unsigned __int128>(1) << CRT_CHUNK_BITS) - 1) : sh));
+  }
+};
+__constant__ CrtF c_crtf[CRT_MAX_T + 1];
 
 // out_t[line * Kpad + k] = symmetric residue of a'(line, k) mod p_t, same tiling / staging as slice_kernel
 __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict__ blocks, const int32_t* __restrict__ line_exp,
@@ -767,10 +811,30 @@ __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict_
 }
 
 // CRT reconstruction: one CTA = 32 rows x 128 columns of one 128 x 256 tile of the job (8 CTAs per tile).  Thread (row, 4 columns)
-// reads its T residue quads (coalesced along the compact plane rows), accumulates sum_t r_t w_t in 32-bit limbs (IMAD.WIDE into
-// 64-bit lanes), reduces modulo P to the symmetric range, converts to fp64 and scales by 2^(e_i + f_j - 2 alpha); the tile is
-// transposed through shared memory so the stores follow the column-major output blocks.  Buffer rows / columns are organised
-// in slots of `sstride` lines (one block row / block column each); ctab[rslot * ncslots + cslot] is the output block or nullptr.
+// reads its T residue quads (coalesced along the compact plane rows) and accumulates S = sum_t r_t w_t in fp64, EXACTLY: every
+// weight is split into 40-bit chunks (c_crtf), so each chunk sum stays an integer below 2^52 (r < 2^8, T <= 2^4).  With
+// q = rint(S / P) the chunk differences D_i = S_i - q P_i are again exact (one FMA each, |q P_i| < 2^52) and represent the
+// symmetric residue C' = S - q P, |C'| <= P / 2; a carry pass makes the chunks non-overlapping signed digits, so the top-down
+// Horner sum rounds once per step and is exact whenever C' fits 53 bits (integer data give the exact integer product).  The
+// scaling by 2^(e_i + f_j - 2 alpha) is a multiplication by a constructed power of two.  The tile is transposed through shared
+// memory so the stores follow the column-major output blocks.  Buffer rows / columns are organised in slots of `sstride` lines
+// (one block row / block column each); ctab[rslot * ncslots + cslot] is the output block or nullptr.
+__device__ __forceinline__ double pow2_double(int n) {  // 2^n, -1022 <= n <= 1023
+  return __hiloint2double((n + 1023) << 20, 0);
+}
+__device__ __forceinline__ double scale_by_pow2(double x, int n) {
+  const int n1 = max(-1022, min(1023, n));
+  x *= pow2_double(n1);
+  n -= n1;
+  while (n != 0) {  // beyond the normal exponent range (sub-normal or overflowing results): continue in steps
+    const int n2 = max(-1022, min(1023, n));
+    x *= pow2_double(n2);
+    n -= n2;
+  }
+  return x;
+}
+
+template <int NCH>
 __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ planes, size_t plane_stride, int T,
                                                   const int2* __restrict__ tiles, const int32_t* __restrict__ row_exp,
                                                   const int32_t* __restrict__ col_exp, int two_alpha, double* const* __restrict__ ctab,
@@ -778,7 +842,7 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
                                                   int ncslots, const int* __restrict__ gate) {
   __shared__ double tile[128][33];
   if (gate != nullptr && *gate != 0) return;
-  const CrtConst& cc = c_crt[T];
+  const CrtF& cf = c_crtf[T];
   const int t_idx = blockIdx.x >> 3, sub = blockIdx.x & 7;
   const int2 tl = tiles[t_idx];
   const int r0t = (sub >> 1) * 32, c0t = (sub & 1) * 128;  // inside the tile
@@ -786,101 +850,49 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
   const int tid = threadIdx.x;
   const int lr = tid >> 5, lc = (tid & 31) * 4;  // 8 rows per pass, 4 passes
   const int8_t* tbase = planes + static_cast<size_t>(t_idx) * (BM * BN);
+  constexpr double kTwo52 = 4503599627370496.0, kMagic = 6755399441055744.0;  // 2^52, 1.5 * 2^52
+  constexpr double kUp = 1099511627776.0, kDown = 1.0 / 1099511627776.0;        // 2^40, 2^-40
+#pragma unroll 1
   for (int pass = 0; pass < 4; ++pass) {
     const int row = r0 + pass * 8 + lr;
-    unsigned long long acc[4][4];
+    double S[4][NCH];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = 0ull;
+      for (int i = 0; i < NCH; ++i) S[j][i] = 0.0;
     const int8_t* src = tbase + static_cast<size_t>(r0t + pass * 8 + lr) * BN + c0t + lc;
+#pragma unroll 4
     for (int t = 0; t < T; ++t) {
       const uint32_t quad = *reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(t) * plane_stride);
-      const uint32_t w0 = cc.w[t][0], w1 = cc.w[t][1], w2 = cc.w[t][2], w3 = cc.w[t][3];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t ru = (quad >> (8 * j)) & 0xffu;
-        acc[j][0] += static_cast<unsigned long long>(ru) * w0;
-        acc[j][1] += static_cast<unsigned long long>(ru) * w1;
-        acc[j][2] += static_cast<unsigned long long>(ru) * w2;
-        acc[j][3] += static_cast<unsigned long long>(ru) * w3;
+        // byte j as a double: 2^52 + r has r in its low mantissa bits
+        const double x = __hiloint2double(0x43300000, static_cast<int>(__byte_perm(quad, 0u, 0x4440u + j))) - kTwo52;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) S[j][i] = fma(x, cf.w[t][i], S[j][i]);
       }
     }
     const int er = row_exp[row];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      // carry-normalise to five 32-bit limbs (value < T * 256 * P < 2^140)
-      uint32_t l[5];
-      unsigned long long c = acc[j][0];
-      l[0] = static_cast<uint32_t>(c);
-      c = (c >> 32) + acc[j][1];
-      l[1] = static_cast<uint32_t>(c);
-      c = (c >> 32) + acc[j][2];
-      l[2] = static_cast<uint32_t>(c);
-      c = (c >> 32) + acc[j][3];
-      l[3] = static_cast<uint32_t>(c);
-      l[4] = static_cast<uint32_t>(c >> 32);
-      // quotient estimate from the top limbs (relative error 2^-52 on a quotient < 2^13): one below, then fix up
-      const double top = (static_cast<double>((static_cast<unsigned long long>(l[4]) << 32) | l[3]) * 4294967296.0 + static_cast<double>(l[2])) *
-                         18446744073709551616.0;  // * 2^64
-      const double qd = floor(top * cc.invP);
-      const uint32_t qq = qd >= 1.0 ? static_cast<uint32_t>(qd) - 1u : 0u;
-      {
-        unsigned long long m = 0;
-        long long bw = 0;
+      double v = S[j][NCH - 1];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          if (i < 4) m += static_cast<unsigned long long>(qq) * cc.P[i];
-          const long long d = static_cast<long long>(l[i]) - static_cast<long long>(static_cast<uint32_t>(m)) + bw;
-          l[i] = static_cast<uint32_t>(d);
-          bw = d >> 32;
-          m >>= 32;
-        }
+      for (int i = NCH - 2; i >= 0; --i) v = fma(v, kUp, S[j][i]);
+      const double q = fma(v, cf.invP, kMagic) - kMagic;  // rint(S / P), < 2^12
+      double D[NCH];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) D[i] = fma(-q, cf.P[i], S[j][i]);
+#pragma unroll
+      for (int i = 0; i + 1 < NCH; ++i) {
+        const double c = fma(D[i], kDown, kMagic) - kMagic;  // nearest multiple of 2^40 carried upwards
+        D[i] = fma(-c, kUp, D[i]);
+        D[i + 1] += c;
       }
-#pragma unroll 1
-      for (int it = 0; it < 3; ++it) {  // remainder is in [0, 3P): at most two subtractions
-        bool ge = l[4] != 0;
-        if (!ge) {
-          ge = true;
+      double x = D[NCH - 1];
 #pragma unroll
-          for (int i = 3; i >= 0; --i) {
-            if (l[i] != cc.P[i]) {
-              ge = l[i] > cc.P[i];
-              break;
-            }
-          }
-        }
-        if (!ge) break;
-        long long bw = 0;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const long long d = static_cast<long long>(l[i]) - (i < 4 ? static_cast<long long>(cc.P[i]) : 0ll) + bw;
-          l[i] = static_cast<uint32_t>(d);
-          bw = d >> 32;
-        }
-      }
-      // symmetric range: x > floor(P / 2)  ->  x - P (store the magnitude P - x)
-      bool gt = false;
-#pragma unroll
-      for (int i = 3; i >= 0; --i) {
-        if (l[i] != cc.Phalf[i]) {
-          gt = l[i] > cc.Phalf[i];
-          break;
-        }
-      }
-      if (gt) {
-        long long bw = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const long long d = static_cast<long long>(cc.P[i]) - static_cast<long long>(l[i]) + bw;
-          l[i] = static_cast<uint32_t>(d);
-          bw = d >> 32;
-        }
-      }
-      const double mag = static_cast<double>((static_cast<unsigned long long>(l[3]) << 32) | l[2]) * 18446744073709551616.0 +
-                         static_cast<double>((static_cast<unsigned long long>(l[1]) << 32) | l[0]);
+      for (int i = NCH - 2; i >= 0; --i) x = fma(x, kUp, D[i]);
       const int ec = col_exp[c0 + lc + j];
-      tile[lc + j][pass * 8 + lr] = scalbn(gt ? -mag : mag, er + ec - two_alpha);
+      tile[lc + j][pass * 8 + lr] = scale_by_pow2(x, er + ec - two_alpha);
     }
   }
   __syncthreads();
@@ -1112,13 +1124,12 @@ cudaError_t ozaki_gemm_f64(const OzakiOperand* a_blocks, int na, const OzakiOper
   int32_t* col_exp = row_exp + Mpad;
   // pass 1
   {
-    const int tc = (max_ac + 31) / 32, tr = (max_ar + 31) / 32;
+    const AbsmaxGrid ga(max_ar, max_ac), gb(max_br, max_bc);
     OZ_CHECK(for_block_chunks(na, [&](int off, int cnt) {
-      absmax_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, rowmax, nullptr, 1, tc);
+      absmax_kernel<<<dim3(ga.tiles, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_ab.p) + off, rowmax, nullptr, 1, ga.ts);
     }));
-    const int tcb = (max_bc + 31) / 32, trb = (max_br + 31) / 32;
     OZ_CHECK(for_block_chunks(nb, [&](int off, int cnt) {
-      absmax_kernel<<<dim3(trb * tcb, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, colmax, nullptr, 0, tcb);
+      absmax_kernel<<<dim3(gb.tiles, cnt), 256, 0, stream>>>(static_cast<const OzBlock*>(d_bb.p) + off, colmax, nullptr, 0, gb.ts);
     }));
     exp_kernel<<<static_cast<unsigned>((Mpad + Npad + 255) / 256), 256, 0, stream>>>(rowmax, nullptr, row_exp, static_cast<double*>(d_scale.p),
                                                                                       static_cast<int>(Mpad + Npad), 0, static_cast<int*>(d_bad.p));
@@ -1211,15 +1222,18 @@ namespace {
 const int kCrtModuli[CRT_MAX_T] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};  // pairwise coprime
 
 // fills c_crt[T] for every supported T once; returns floor(log2 P) per T through log2P
-cudaError_t crt_constants(int* log2P) {
+cudaError_t crt_constants(int* log2P, bool upload = true) {
   static PerDeviceOnce uploaded;
   static std::once_flag built;
   static int l2[CRT_MAX_T + 1];
   static std::vector<CrtConst> all(CRT_MAX_T + 1);
+  static std::vector<CrtF> allf(CRT_MAX_T + 1);
   std::call_once(built, [&] {
     for (int T = CRT_MIN_T; T <= CRT_MAX_T; ++T) {
       CrtConst& c = all[T];
+      CrtF& f = allf[T];
       memset(&c, 0, sizeof(c));
+      memset(&f, 0, sizeof(f));
       unsigned __int128 P = 1;
       for (int t = 0; t < T; ++t) P *= static_cast<unsigned>(kCrtModuli[t]);
       for (int t = 0; t < T; ++t) {
@@ -1236,15 +1250,12 @@ cudaError_t crt_constants(int* log2P) {
         const unsigned mr = static_cast<unsigned>(Mt % pm);
         unsigned inv = 1;
         while ((mr * inv) % pm != 1u) ++inv;  // Mt is coprime to pm, the inverse exists below pm
-        const unsigned __int128 w = Mt * inv;
-        for (int i = 0; i < 4; ++i) c.w[t][i] = static_cast<uint32_t>(w >> (32 * i));
+        const unsigned __int128 w = Mt * inv;  // CRT weight (P / p_t) * ((P / p_t)^-1 mod p_t) < P
+        for (int i = 0; i < f.nch_for(P); ++i) f.w[t][i] = CrtF::chunk(w, i, f.nch_for(P));
       }
-      const unsigned __int128 H = P >> 1;
-      for (int i = 0; i < 4; ++i) {
-        c.P[i] = static_cast<uint32_t>(P >> (32 * i));
-        c.Phalf[i] = static_cast<uint32_t>(H >> (32 * i));
-      }
-      c.invP = 1.0 / static_cast<double>(P);
+      f.nch = f.nch_for(P);
+      for (int i = 0; i < f.nch; ++i) f.P[i] = CrtF::chunk(P, i, f.nch);
+      f.invP = 1.0 / static_cast<double>(P);
       c.T = T;
       int lg = 0;
       while ((P >> (lg + 1)) != 0) ++lg;
@@ -1252,7 +1263,11 @@ cudaError_t crt_constants(int* log2P) {
     }
   });
   for (int T = 0; T <= CRT_MAX_T; ++T) log2P[T] = l2[T];
-  return uploaded.run([&] { return cudaMemcpyToSymbol(c_crt, all.data(), sizeof(CrtConst) * (CRT_MAX_T + 1)); });
+  if (!upload) return cudaSuccess;
+  return uploaded.run([&] {
+    const cudaError_t e1 = cudaMemcpyToSymbol(c_crt, all.data(), sizeof(CrtConst) * (CRT_MAX_T + 1));
+    return e1 != cudaSuccess ? e1 : cudaMemcpyToSymbol(c_crtf, allf.data(), sizeof(CrtF) * (CRT_MAX_T + 1));
+  });
 }
 }  // namespace
 
@@ -1270,7 +1285,7 @@ cudaError_t crt_constants(int* log2P) {
 // and un-gates the exact DMMA launch the caller enqueues behind every job.
 // ------------------------------------------------------------------------------------------------
 struct Oz2Engine {
-  int T = 0, alpha = 0, blk = 0, sstride = 0, cap_r = 0, cap_c = 0, max_tiles = 0, range_bits = 0;
+  int T = 0, alpha = 0, crt_chunks = 4, blk = 0, sstride = 0, cap_r = 0, cap_c = 0, max_tiles = 0, range_bits = 0;
   bool paired = false;   // tile lists hold vertically adjacent 128-row tiles in pairs: the cta_group::2 kernel runs them
   int64_t K = 0, Kpad = 0, Mpad = 0, Npad = 0;
   size_t a_stride = 0, b_stride = 0, plane_stride = 0, smem_bytes = 0;
@@ -1283,6 +1298,29 @@ struct Oz2Engine {
   int sms = 148;
   int launches = 0;
 };
+
+// K * (2^alpha)^2 <= 2^(floor(log2 P) - 1) < P / 2: the exact integer product is recovered from its residues
+static int crt_alpha(int log2P, int64_t K) {
+  int lgK = 0;
+  while ((1ll << lgK) < K) ++lgK;
+  const int alpha = (log2P - 1 - lgK) / 2;
+  return alpha > 62 ? 62 : alpha;
+}
+
+// Number of moduli for an inner dimension K.  requested > 0: that many (clamped to the supported range).  requested <= 0: the
+// smallest count whose operand truncation 2^-alpha (relative to the line maxima), grown by sqrt(K) over a dot product of
+// length K, stays below half the classical fp64 rounding bound K 2^-53 of the same dot product: alpha >= 54 - ceil(lg K / 2).
+int oz2_moduli_for(int64_t K, int requested) {
+  if (requested > 0) return requested < CRT_MIN_T ? CRT_MIN_T : (requested > CRT_MAX_T ? CRT_MAX_T : requested);
+  int log2P[CRT_MAX_T + 1];
+  crt_constants(log2P, false);
+  int lgK = 0;
+  while ((1ll << lgK) < K) ++lgK;
+  const int want = 54 - (lgK + 1) / 2;
+  for (int T = CRT_MIN_T; T <= CRT_MAX_T; ++T)
+    if (crt_alpha(log2P[T], K) >= want) return T;
+  return CRT_MAX_T;
+}
 
 size_t oz2_scratch_bytes(int blk, int64_t K, int T, int cap_r, int cap_c, int max_tiles) {
   const int64_t sstride = (blk + BM - 1) / BM * BM;
@@ -1300,17 +1338,15 @@ int oz2_tiles_per_block(int blk) {
 cudaError_t oz2_create(Oz2Engine** out, int blk, int64_t K, int moduli, int cap_r, int cap_c, int max_tiles, int guard_range,
                        cudaStream_t stream) {
   *out = nullptr;
-  const int T = moduli < CRT_MIN_T ? CRT_MIN_T : (moduli > CRT_MAX_T ? CRT_MAX_T : moduli);
+  const int T = oz2_moduli_for(K, moduli);
   int log2P[CRT_MAX_T + 1];
   OZ_CHECK(crt_constants(log2P));
-  int lgK = 0;
-  while ((1ll << lgK) < K) ++lgK;
-  int alpha = (log2P[T] - 1 - lgK) / 2;  // K * (2^alpha)^2 <= 2^(floor(log2 P) - 1) < P / 2
-  if (alpha > 62) alpha = 62;
+  int alpha = crt_alpha(log2P[T], K);
   if (alpha < 8 || K >= (1 << 17) || cap_r <= 0 || cap_c <= 0 || max_tiles <= 0) return cudaErrorInvalidValue;
   std::unique_ptr<Oz2Engine> e(new Oz2Engine);
   e->T = T;
   e->alpha = alpha;
+  e->crt_chunks = log2P[T] < 3 * CRT_CHUNK_BITS ? 3 : 4;
   e->blk = blk;
   e->sstride = (blk + BM - 1) / BM * BM;
   e->cap_r = cap_r;
@@ -1389,6 +1425,7 @@ const void* oz2_host_maps(const Oz2Engine* e, size_t* bytes) {
 void oz2_set_device_maps(Oz2Engine* e, const void* d_maps) { e->d_maps = static_cast<const unsigned char*>(d_maps); }
 const int* oz2_flag(const Oz2Engine* e) { return e->bad; }
 int oz2_alpha(const Oz2Engine* e) { return e->alpha; }
+int oz2_moduli(const Oz2Engine* e) { return e->T; }
 int oz2_slot_stride(const Oz2Engine* e) { return e->sstride; }
 int oz2_launches(Oz2Engine* e) {
   const int n = e->launches;
@@ -1420,9 +1457,9 @@ cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, i
     for (int t = 0; t < e->T; ++t)
       OZ_CHECK(cudaMemsetAsync(res + stride * t + static_cast<size_t>(slot0) * e->sstride * e->Kpad, 0, nlines * e->Kpad, stream));
   if (nblocks > 0) {
-    const int tc = (max_cols + 31) / 32, tr = (max_rows + 31) / 32;
+    const AbsmaxGrid g(max_rows, max_cols);
     OZ_CHECK(for_block_chunks(nblocks, [&](int off, int cnt) {
-      absmax_kernel<<<dim3(tr * tc, cnt), 256, 0, stream>>>(blocks + off, maxb, e->range_bits ? minb : nullptr, is_a ? 1 : 0, tc);
+      absmax_kernel<<<dim3(g.tiles, cnt), 256, 0, stream>>>(blocks + off, maxb, e->range_bits ? minb : nullptr, is_a ? 1 : 0, g.ts);
     }));
     e->launches += 1;
   }
@@ -1495,9 +1532,10 @@ cudaError_t oz2_multiply(Oz2Engine* e, const int2* d_tiles, int ntiles, double* 
       OZ_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
       *ms_gemm += ms;
     }
-    crt_kernel<<<static_cast<unsigned>(cnt) * 8u, 256, 0, stream>>>(e->planes, e->plane_stride, e->T, d_tiles + off, e->exps,
-                                                                      e->exps + e->Mpad, 2 * e->alpha, d_ctab, e->dims,
-                                                                      e->dims + e->cap_r, e->sstride, e->cap_c, e->bad);
+    auto crt = e->crt_chunks == 3 ? crt_kernel<3> : crt_kernel<4>;
+    crt<<<static_cast<unsigned>(cnt) * 8u, 256, 0, stream>>>(e->planes, e->plane_stride, e->T, d_tiles + off, e->exps, e->exps + e->Mpad,
+                                                              2 * e->alpha, d_ctab, e->dims, e->dims + e->cap_r, e->sstride, e->cap_c,
+                                                              e->bad);
     OZ_CHECK(cudaGetLastError());
     e->launches += 2;
   }

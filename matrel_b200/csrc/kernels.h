@@ -99,6 +99,8 @@ const void* oz2_host_maps(const Oz2Engine* e, size_t* bytes);   // 2 * moduli CU
 void oz2_set_device_maps(Oz2Engine* e, const void* d_maps);     // ... and handed back as a device pointer
 const int* oz2_flag(const Oz2Engine* e);
 int oz2_alpha(const Oz2Engine* e);
+int oz2_moduli(const Oz2Engine* e);
+int oz2_moduli_for(int64_t K, int requested);  // requested <= 0: chosen from K (see gemm_ozaki.cu)
 int oz2_slot_stride(const Oz2Engine* e);
 void oz2_set_paired(Oz2Engine* e, bool paired);                  // tile lists come as (2a, b), (2a + 1, b) pairs: use the 2-SM kernel
 bool oz2_paired(const Oz2Engine* e);

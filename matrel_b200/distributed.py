@@ -518,7 +518,7 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
     with torch.cuda.stream(stream):
         s = MatfastSession(device=local_rank, stream=stream.cuda_stream)
         s.set_option("gemm_algo", algo)
-        s.set_option("crt_moduli", getattr(args, "crt_moduli", 16))
+        s.set_option("crt_moduli", getattr(args, "crt_moduli", 0))
         A = ShardedMatrix.rand(s, plan, rank, 42, device)
         B = ShardedMatrix.rand(s, plan, rank, 43, device)
         s.sync()
@@ -574,8 +574,8 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
             ach = st2["tc_int8_ops"] / (kern_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": ipeak, "unit": "TFLOP/s", "frac": ach / ipeak, "traffic": None,
                         "op": "int8 multiply-add x 2 (TOPS) on tcgen05.mma kind::i8, per rank",
-                        "kernel": "ozaki_gemm_i8_kernel", "kernel_ms": kern_ms,
-                        "algorithmic": f"{st2['tc_int8_ops']:.4g} int8 ops per rank per step (moduli x 2 M_loc N_loc K; max-over-ranks kernel time)",
+                        "kernel": "ozaki2_gemm_2sm_kernel", "kernel_ms": kern_ms,
+                        "algorithmic": f"{st2['tc_int8_ops']:.4g} int8 ops per rank per step ({st2['tc_moduli']} moduli x 2 M_loc N_loc K; max-over-ranks kernel time)",
                         "peak_source": ipeak_src,
                         "fp64_equivalent": {"achieved": flops / (ms_max * 1e-3) / 1e12, "dmma_peak": world * dpeak,
                                             "x_dmma_roof": flops / (ms_max * 1e-3) / 1e12 / (world * dpeak)}}

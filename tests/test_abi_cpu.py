@@ -35,6 +35,23 @@ def test_header_symbols_exported_and_bound():
     assert N.lib.mr_version().startswith(b"matrel-b200")
 
 
+def test_library_is_not_older_than_its_sources():
+    """The in-tree .so is what travels to the GPU box: a source or header edited after the last build would ship a stale ABI."""
+    import glob
+    import matrel_b200._native as N
+    srcs = glob.glob(os.path.join(ROOT, "matrel_b200", "csrc", "*")) + [os.path.join(ROOT, "include", "matrel.h")]
+    newest = max(srcs, key=os.path.getmtime)
+    assert os.path.getmtime(N.LIB_PATH) >= os.path.getmtime(newest), f"{newest} is newer than the built library: run __graft_entry__.build()"
+
+
+def test_stats_struct_matches_the_header():
+    import matrel_b200._native as N
+    src = open(os.path.join(ROOT, "include", "matrel.h")).read()
+    body = re.search(r"typedef struct mr_stats \{(.*?)\} mr_stats;", src, re.S).group(1)
+    fields = re.findall(r"^\s*(int64_t|double)\s+(\w+);", body, re.M)
+    assert [(n, {"int64_t": C.c_int64, "double": C.c_double}[t]) for t, n in fields] == list(N.mr_stats._fields_)
+
+
 def test_so_contains_blackwell_native_sass():
     """UBLKCP = TMA bulk copy, DMMA = fp64 tensor pipe, SYNCS = mbarrier (B200_PROFILING.md table)."""
     import matrel_b200._native as N

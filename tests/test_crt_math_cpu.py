@@ -38,28 +38,100 @@ def test_alpha_rule_keeps_the_integer_product_inside_the_crt_range():
             assert 2 * K * (1 << a) ** 2 < P, (T, K, a)
             assert a >= 8
     assert alpha_of(16, 16384)[0] == 55 and alpha_of(14, 16384)[0] == 47 and alpha_of(16, (1 << 17) - 1)[0] >= 53
-    assert math.prod(MODULI) < 1 << 126                           # the kernel's four 32-bit limbs hold P and the weights
+    assert math.prod(MODULI) < 1 << 126                           # four 40-bit fp64 chunks hold P and the weights (top chunk < 2^6)
 
 
 def test_s32_accumulator_bound():
     assert ((1 << 17) - 1) * 128 * 128 < 1 << 31                   # K < 2^17 residue products of magnitude <= 2^14
 
 
-def test_crt_weights_reconstruct_every_residue_vector():
-    rng = np.random.default_rng(0)
-    for T in (T_MIN, 9, T_MAX):
-        mods = MODULI[:T]
-        P = math.prod(mods)
-        w = [(P // p) * pow((P // p) % p, -1, p) for p in mods]
-        assert all(0 < wi < P for wi in w)
-        for _ in range(200):
-            x = int(rng.integers(-(1 << 62), 1 << 62)) * int(rng.integers(1, 1 << 40)) % P
-            x = x - P if x > P // 2 else x
-            acc = sum((x % p) * wi for p, wi in zip(mods, w))      # non-negative residues, as the planes store them
-            assert acc < T * 256 * P < 1 << 140                    # five 32-bit limbs after carry normalisation
-            y = acc % P
-            y = y - P if y > P // 2 else y
-            assert y == x
+CHUNK = int(re.search(r"CRT_CHUNK_BITS = (\d+)", SRC).group(1))
+
+
+def crt_tables(T):
+    """c_crtf[T] as crt_constants() builds it: the weights and P in CHUNK-bit fp64 chunks (three below 2^120, else four)."""
+    mods = MODULI[:T]
+    P = math.prod(mods)
+    nch = 3 if P < 1 << (3 * CHUNK) else 4
+    mask = (1 << CHUNK) - 1
+
+    def chunks(x):
+        return [float((x >> (CHUNK * i)) & mask) if i + 1 < nch else float(x >> (CHUNK * i)) for i in range(nch)]
+    w = [(P // p) * pow((P // p) % p, -1, p) for p in mods]
+    assert all(0 < wi < P for wi in w)
+    return P, nch, np.array([chunks(wi) for wi in w]), np.array(chunks(P))
+
+
+def crt_fp64(res, P, nch, W, Pc):
+    """crt_kernel<NCH>, operation by operation, in numpy float64 (an FMA whose exact result fits 53 bits equals the two-step form)."""
+    up, down, magic = np.float64(2.0 ** CHUNK), np.float64(2.0 ** -CHUNK), np.float64(1.5 * 2.0 ** 52)
+    S = np.zeros(nch)
+    for t, r in enumerate(res):
+        S = S + np.float64(r) * W[t]
+    assert np.all(S < 2.0 ** 52) and np.all(S == np.floor(S))      # exact integer chunk sums
+    v = S[nch - 1]
+    for i in range(nch - 2, -1, -1):
+        v = v * up + S[i]
+    q = (v * (np.float64(1.0) / np.float64(P)) + magic) - magic
+    assert 0 <= q < 1 << 12 and np.all(q * Pc < 2.0 ** 52)
+    D = list(S - q * Pc)
+    for i in range(nch - 1):
+        c = (D[i] * down + magic) - magic
+        D[i] = D[i] - c * up
+        D[i + 1] = D[i + 1] + c
+        assert abs(D[i]) <= 2.0 ** (CHUNK - 1)
+    x = D[nch - 1]
+    for i in range(nch - 2, -1, -1):
+        x = x * up + D[i]
+    return float(x)
+
+
+def test_fp64_crt_reconstructs_the_symmetric_residue():
+    """The fp64 chunk arithmetic of crt_kernel returns the integer |c| <= 2^(floor(log2 P) - 1) its residues encode: exactly when
+    c fits 53 bits (integer data give the exact product), else within one rounding (< 1 ulp) of it."""
+    import random
+    from fractions import Fraction
+    random.seed(3)
+    assert CHUNK == 40
+    for T in range(T_MIN, T_MAX + 1):
+        P, nch, W, Pc = crt_tables(T)
+        lg = P.bit_length() - 1
+        assert W[:, nch - 1].max() * T * 255 < 2.0 ** 52            # the top chunk sums stay exact as well
+        bound = 1 << (lg - 1)
+        assert bound * (1 + 2.0 ** -30) < P / 2                     # margin that keeps rint(S / P) on the right representative
+        for trial in range(600):
+            kind = trial % 6
+            if kind == 0:
+                c = random.randint(-bound, bound)
+            elif kind == 1:
+                c = random.choice([-1, 1]) * bound
+            elif kind == 2:
+                sh = random.randint(0, max(0, lg - 55))
+                mb = min(53, lg - 1 - sh)
+                c = random.randint(-(1 << mb), 1 << mb) << sh        # representable in fp64
+            elif kind == 3:
+                c = random.randint(-1000, 1000)
+            elif kind == 4:
+                c = random.choice([-1, 1]) * (bound - random.randint(0, 1000))
+            else:
+                c = random.randint(-bound, bound) >> random.randint(0, lg)
+            x = crt_fp64([c % p for p in MODULI[:T]], P, nch, W, Pc)  # non-negative residues, as the planes store them
+            if kind in (2, 3):
+                assert x == float(c), (T, c, x)
+            elif c:
+                assert abs(Fraction(x) - c) < Fraction(math.ulp(float(c))), (T, c, x)
+
+
+def test_auto_moduli_rule():
+    """oz2_moduli_for(K, 0): the smallest T with alpha >= 54 - ceil(lg K / 2), i.e. sqrt(K) 2^-alpha <= K 2^-54."""
+    for K in (256, 1000, 4096, 16384, 65536, (1 << 17) - 1):
+        lgK = 0
+        while (1 << lgK) < K:
+            lgK += 1
+        want = 54 - (lgK + 1) // 2
+        T = next(t for t in range(T_MIN, T_MAX + 1) if alpha_of(t, K)[0] >= want)
+        assert T == 14, (K, T)
+        assert math.sqrt(K) * 2.0 ** -alpha_of(T, K)[0] <= K * 2.0 ** -54 * 1.5
 
 
 def test_dp4a_fp32_residue_is_congruent_and_fits_int8():

@@ -2,8 +2,10 @@
 
 The integer product of the scaled operands is recovered EXACTLY, so (a) integer-valued inputs give bit-exact
 results, and (b) the only error is the rounding of the operands to alpha bits relative to their row / column
-maximum plus one final rounding: with 16 moduli (alpha >= 53 for K <= 2^16) the result is at least as accurate
-as an fp64 dgemm for U(-1,1) data.  Bars: bit-exact for integer data; 1e-14 relative to |A||B| at 16 moduli."""
+maximum plus one final rounding.  The number of moduli follows the inner dimension (crt_moduli = 0, the default:
+14 moduli, alpha = 54 - ceil(lg K / 2) or better, so sqrt(K) 2^-alpha stays below half the fp64 dot-product bound
+K 2^-53); 16 moduli (alpha >= 53 for K <= 2^16) can be requested.  Bars: bit-exact for integer data; 1e-14
+relative to |A||B| at the default and at 16 moduli."""
 import numpy as np
 import pytest
 
@@ -80,6 +82,22 @@ def test_crt_error_scales_with_moduli(moduli, bound):
         s.set_option("crt_moduli", moduli)
         got = full(from_dataset(to_dataset(s, A).matrixMultiply(n, n, to_dataset(s, B), n, n, blk)), n, n, blk)
     assert rel_err(got, want) <= bound, rel_err(got, want)
+
+
+def test_default_moduli_follow_the_inner_dimension(oz2):
+    rng = np.random.default_rng(41)
+    n, blk = 1024, 256
+    Af, Bf = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+    want, scale = Af @ Bf, np.abs(Af) @ np.abs(Bf)
+    errs = {}
+    for moduli in (0, 16):
+        with mb.MatfastSession(device=0, gemm_algo=4) as s:
+            s.set_option("crt_moduli", moduli)
+            got = full(from_dataset(to_dataset(s, blocks_of(Af, blk)).matrixMultiply(n, n, to_dataset(s, blocks_of(Bf, blk)), n, n, blk)), n, n, blk)
+            assert s.stats()["tc_moduli"] == (moduli or 14)
+            errs[moduli] = float(np.max(np.abs(got - want) / scale))
+    # both sit at the rounding level of the fp64 reference product itself (|A||B|-relative)
+    assert errs[16] <= 5e-16 and errs[0] <= 1e-15, errs
 
 
 def test_crt_wide_dynamic_range_rows_and_columns(oz2):
