@@ -186,15 +186,15 @@ struct SpmmOut {
 constexpr int kSpmmMaxDim = 1024;   // m and kdim limit of the shared-memory kernel
 cudaError_t launch_spmm_fused(const SpmmOut* d_outs, int nouts, const SpmmPair* d_pairs, int max_n, cudaStream_t stream);
 
-// ---- the pipelined CSR x dense kernel (spmm.cu): 512-row x 32-column tiles, row-major B staged by TMA, packed CSR segments.
-constexpr int kSpmm2StripRows = 512, kSpmm2TileCols = 32, kSpmm2ChunkK = 256;
+// ---- the pipelined CSR x dense kernel (spmm.cu): 256-row x 64-column tiles, row-major B staged by TMA, packed CSR segments.
+constexpr int kSpmm2StripRows = 256, kSpmm2TileCols = 64, kSpmm2ChunkK = 128;
 struct Spmm2Prep {        // one sparse (CSR) block to re-pack
   const int32_t* ptrs;    // CSR row pointers (m + 1)
   const int32_t* idx;     // column indices
   const double* vals;
   int32_t m, kdim;
-  unsigned char* ent;     // out: packed entries (16 bytes each: value, k inside its 256-wide chunk), segment after segment
-  int32_t* rp;            // out: [strips * chunks][516] row pointers relative to the segment (+ its length at [512 ..])
+  unsigned char* ent;     // out: packed entries (16 bytes each: value, byte offset of its B row inside the staged chunk), segment after segment
+  int32_t* rp;            // out: [strips * chunks][TM + 4] row pointers relative to the segment (+ its length at [TM ..])
   int32_t* segoff;        // out: [strips * chunks + 1] first entry of every (strip, chunk) segment
 };
 struct Spmm2Pair {        // A(i,k) (prepared) x B(k,j) (row-major, through its tensor map)
@@ -211,7 +211,7 @@ struct Spmm2Out {
   int32_t accumulate;     // 1: C already holds the dense-pair sum
   int32_t pad;
 };
-struct Spmm2Item {        // one CTA: 512 rows x 32 columns of one output block, all of its k-blocks
+struct Spmm2Item {        // one CTA: 256 rows x 64 columns of one output block, all of its k-blocks
   int32_t out, strip, ctile, pad;
 };
 // SparseMatrix.sprand(rows, cols, density, new java.util.Random(seed)) on the device (power-of-two dims, draw-by-draw branch)

@@ -6,17 +6,19 @@
 //
 // What bounds it: every multiply-add needs its own 8-byte B element at a data-dependent row, so the shared-memory port
 // (128 B/clk/SM = 16 fp64 FMA/clk/SM, ~9 TFLOP/s) is the algorithmic roof, not the fp64 pipe.  The kernel is organised around
-// spending as few shared-memory wavefronts per FMA as the format allows:
-//   * B is staged ROW-major ([k][32 columns], 256-byte rows, TMA tensor copies of a {32, KC} box), so the 16 lanes of a half-warp
-//     read 16 consecutive doubles of row k: one conflict-free 128-byte wavefront feeds 16 FMAs.  (Column-major B blocks are
-//     transposed once per multiply by the host layer -- 2 x 8 bytes per element of HBM traffic against ~10 uses per element.)
-//   * a half-warp owns a row; each lane accumulates 2 columns (c, c + 16), so one CSR entry costs one broadcast 16-byte read
-//     (value + k packed by the preparation pass) and two B wavefronts for 32 FMAs: 5 wavefronts per 64 FMAs for the warp.
-//   * the CSR entries of a (512-row strip, 256-wide k chunk) are re-packed by a preparation pass into one contiguous segment
-//     that the producer warp brings in with ONE bulk copy per pipeline stage, together with its row-pointer table; four rows
-//     are walked concurrently per half-warp so that four independent load->FMA chains are in flight.
-//   * producer warp + 16 consumer warps, 2-stage full/empty mbarrier ring; the 512 x 32 result tile is transposed through the
-//     (by then idle) stage buffers so that C is written as 256-byte coalesced column runs.
+// spending as few shared-memory wavefronts AND as few issue slots per FMA as the format allows:
+//   * B is staged ROW-major ([k][64 columns], 512-byte rows, TMA tensor copies of a {64, KC} box), and a whole WARP owns a row of
+//     A: lane l accumulates columns 2l and 2l + 1, so one CSR entry costs one warp-uniform 16-byte read (value + byte offset of
+//     its B row, packed by the preparation pass) and one 128-bit load per lane (four conflict-free wavefronts) for 64 FMAs.
+//     No lane is ever predicated off: rows of different length cost different trip counts of a warp-uniform loop, not idle lanes.
+//     (Column-major B blocks are transposed once per multiply by the host layer -- 2 x 8 bytes per element of HBM traffic against
+//     ~10 uses per element.)
+//   * the CSR entries of a (256-row strip, 128-wide k chunk) are re-packed by a preparation pass into one contiguous segment
+//     that the producer warp brings in with ONE bulk copy per pipeline stage, together with its row-pointer table; a warp owns
+//     16 CONSECUTIVE rows, reads their 17 row pointers with one load and hands them round by shuffles.
+//   * producer warp + 16 consumer warps, 3-stage full/empty mbarrier ring (a fast warp runs up to two stages ahead of a slow
+//     one); the 256 x 64 result tile is transposed through the (by then idle) stage buffers so that C is written as coalesced
+//     column runs.
 #include <cuda.h>
 
 #include <algorithm>
@@ -31,23 +33,27 @@ namespace {
 constexpr int TM = kSpmm2StripRows;   // rows per CTA
 constexpr int TN = kSpmm2TileCols;    // columns per CTA
 constexpr int KC = kSpmm2ChunkK;      // k extent of one pipeline stage
+constexpr int NSTAGE = 3;
 constexpr int RP_PAD = TM + 4;        // row-pointer table entries per (strip, chunk): TM + 1, padded to a 16-byte multiple
-constexpr int E_CAP = 2816;           // entries per stage held in shared memory (larger segments are read from global memory)
+constexpr int E_CAP = 664;            // entries per stage held in shared memory (larger segments are read from global memory)
 constexpr int NCW = 16;               // consumer warps
+constexpr int RPW = TM / NCW;         // rows per consumer warp
 constexpr int THREADS = (NCW + 1) * 32;
 constexpr int B_BYTES = KC * TN * 8;                 // 65536
-constexpr int RP_BYTES = RP_PAD * 4;                 // 2064
-constexpr int ENT_BYTES = E_CAP * 16;                // 45056
-constexpr int STAGE_BYTES = B_BYTES + ENT_BYTES + RP_BYTES + 48;  // + pad to keep 128-byte alignment of the next stage
+constexpr int RP_BYTES = RP_PAD * 4;                 // 1040
+constexpr int ENT_BYTES = E_CAP * 16;                // 10624
+constexpr int STAGE_BYTES = B_BYTES + ENT_BYTES + RP_BYTES;
 constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
-constexpr int SMEM_BYTES = 128 + 2 * STAGE_STRIDE + 64;
-constexpr int CS_LD = TM + 1;                        // result tile in shared memory: [32 columns][TM + 1] doubles
-static_assert(CS_LD * TN * 8 <= 2 * STAGE_STRIDE, "result tile must fit the stage buffers");
+constexpr int SMEM_BYTES = 128 + NSTAGE * STAGE_STRIDE + 64;
+constexpr int CS_LD = TM + 1;                        // result tile in shared memory: [64 columns][TM + 1] doubles
+static_assert(TN == 64 && RPW == 16, "lane <-> column pair and lane <-> row pointer mappings");
+static_assert(CS_LD * TN * 8 <= NSTAGE * STAGE_STRIDE, "result tile must fit the stage buffers");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct __align__(16) Entry {
   double a;
-  int32_t k;     // column index inside the chunk
-  int32_t pad;
+  uint32_t boff;  // byte offset of B row k inside the stage's B tile: (k - chunk start) * TN * 8
+  uint32_t pad;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(1024) spmm2_prep_kernel(const Spmm2Prep* __res
       const int pos = cnt[slot(row, q)]++;
       Entry en;
       en.a = p.vals[e];
-      en.k = col - q * KC;
+      en.boff = static_cast<uint32_t>(col - q * KC) * (TN * 8);
       en.pad = 0;
       ent[pos] = en;
     }
@@ -161,20 +167,36 @@ __global__ void __launch_bounds__(1024) spmm2_prep_kernel(const Spmm2Prep* __res
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
+// shared-memory accesses by 32-bit shared address (plain C++ through the dynamically aligned base pointer compiles to generic loads)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lds_entry(uint32_t addr, double& a, uint32_t& boff) {
+  uint32_t lo, hi, pad;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(boff), "=r"(pad) : "r"(addr));
+  a = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+}
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+
 __global__ void __launch_bounds__(THREADS, 1) spmm2_kernel(const Spmm2Item* __restrict__ items, const Spmm2Out* __restrict__ outs,
                                                            const Spmm2Pair* __restrict__ pairs, const unsigned char* __restrict__ tmaps) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_STRIDE);  // full[2], empty[2]
+  const uint32_t smem_a = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_STRIDE);  // full[NSTAGE], empty[NSTAGE]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Spmm2Item item = items[blockIdx.x];
   const Spmm2Out out = outs[item.out];
   const int row0 = item.strip * TM, col0 = item.ctile * TN;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(smem_u32(&bars[s]), 1);
-      mbar_init(smem_u32(&bars[2 + s]), NCW);
+      mbar_init(smem_u32(&bars[NSTAGE + s]), NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -183,120 +205,118 @@ __global__ void __launch_bounds__(THREADS, 1) spmm2_kernel(const Spmm2Item* __re
   if (warp == NCW) {
     // ===================== producer warp (one elected lane) =====================
     if (lane == 0) {
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int p = 0; p < out.pair_count; ++p) {
         const Spmm2Pair pr = pairs[out.pair_begin + p];
         const int nchunks = (pr.kdim + KC - 1) / KC;
         const void* tm = tmaps + static_cast<size_t>(pr.tmB) * 128;
-        for (int q = 0; q < nchunks; ++q, ++it) {
-          const int s = it & 1;
-          const uint32_t ph = (it >> 1) & 1;
-          mbar_wait(smem_u32(&bars[2 + s]), ph ^ 1);
-          unsigned char* st = smem + s * STAGE_STRIDE;
+        for (int q = 0; q < nchunks; ++q) {
+          mbar_wait(smem_u32(&bars[NSTAGE + s]), ph ^ 1);
+          const uint32_t st = smem_a + s * STAGE_STRIDE;
           const int sg = item.strip * nchunks + q;
           const int e0 = pr.segoff[sg], len = pr.segoff[sg + 1] - e0;
           const uint32_t full = smem_u32(&bars[s]);
           const uint32_t ent_bytes = len <= E_CAP ? static_cast<uint32_t>(len) * 16u : 0u;
           mbar_arrive_expect_tx(full, B_BYTES + RP_BYTES + ent_bytes);
-          tma_2d(smem_u32(st), tm, col0, q * KC, full);
-          tma_bulk_g2s(smem_u32(st + B_BYTES + ENT_BYTES), pr.rp + static_cast<size_t>(sg) * RP_PAD, RP_BYTES, full);
-          if (ent_bytes) tma_bulk_g2s(smem_u32(st + B_BYTES), pr.ent + static_cast<size_t>(e0) * 16, ent_bytes, full);
+          tma_2d(st, tm, col0, q * KC, full);
+          tma_bulk_g2s(st + B_BYTES + ENT_BYTES, pr.rp + static_cast<size_t>(sg) * RP_PAD, RP_BYTES, full);
+          if (ent_bytes) tma_bulk_g2s(st + B_BYTES, pr.ent + static_cast<size_t>(e0) * 16, ent_bytes, full);
+          if (++s == NSTAGE) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
   } else {
-    // ===================== consumer warps =====================
-    const int hw = warp * 2 + (lane >> 4);  // half-warp 0..31 owns rows hw, hw + 32, ... of the strip
-    const int l16 = lane & 15;
-    double acc[TM / 32][2];
+    // ===================== consumer warps: warp w owns rows [16 w, 16 w + 16) of the strip, lane l columns 2l, 2l + 1 =====================
+    double acc[RPW][2];
 #pragma unroll
-    for (int i = 0; i < TM / 32; ++i) acc[i][0] = acc[i][1] = 0.0;
-    int it = 0;
+    for (int i = 0; i < RPW; ++i) acc[i][0] = acc[i][1] = 0.0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int p = 0; p < out.pair_count; ++p) {
       const Spmm2Pair pr = pairs[out.pair_begin + p];
       const int nchunks = (pr.kdim + KC - 1) / KC;
-      for (int q = 0; q < nchunks; ++q, ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        const unsigned char* st = smem + s * STAGE_STRIDE;
-        const double* Bs = reinterpret_cast<const double*>(st);
-        const int32_t* rp = reinterpret_cast<const int32_t*>(st + B_BYTES + ENT_BYTES);
+      for (int q = 0; q < nchunks; ++q) {
+        const uint32_t st = smem_a + s * STAGE_STRIDE;
+        const uint32_t rp_a = st + B_BYTES + ENT_BYTES;
+        const uint32_t bl = st + lane * 16;  // this lane's column pair inside a B row
         mbar_wait(smem_u32(&bars[s]), ph);
-        const int seglen = rp[TM];
+        const int rpv = static_cast<int>(lds_u32(rp_a + (warp * RPW + (lane < RPW ? lane : RPW)) * 4));  // lanes 0 .. 16: rp[16 w + lane]
+        const int seglen = static_cast<int>(lds_u32(rp_a + TM * 4));
         if (seglen <= E_CAP) {
-          // entries in shared memory: one broadcast 128-bit load per entry (measured faster than a 64-bit + a 32-bit load)
-          const Entry* ents = reinterpret_cast<const Entry*>(st + B_BYTES);
+          int ev[RPW + 1];  // the 17 row pointers of this warp's rows, warp-uniform
 #pragma unroll
-          for (int g = 0; g < TM / 128; ++g) {  // four rows of this half-warp at a time: four independent chains
-            int e[4], n[4];
+          for (int r = 0; r <= RPW; ++r) ev[r] = __shfl_sync(0xffffffffu, rpv, r);
+          const uint32_t ents = st + B_BYTES;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int r = hw + 32 * (4 * g + t);
-              e[t] = rp[r];
-              n[t] = rp[r + 1] - e[t];
-            }
-            int maxn = max(max(n[0], n[1]), max(n[2], n[3]));
-            maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, 16));  // both half-warps of the warp run the same trip count
-            for (int i = 0; i < maxn; ++i) {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                if (i < n[t]) {
-                  const Entry en = ents[e[t] + i];
-                  const double* b = Bs + en.k * TN + l16;
-                  acc[4 * g + t][0] = fma(en.a, b[0], acc[4 * g + t][0]);
-                  acc[4 * g + t][1] = fma(en.a, b[16], acc[4 * g + t][1]);
-                }
-              }
+          for (int r = 0; r < RPW; ++r) {
+            uint32_t ea = ents + static_cast<uint32_t>(ev[r]) * 16u;
+            const uint32_t ee = ents + static_cast<uint32_t>(ev[r + 1]) * 16u;
+#pragma unroll 1
+            for (; ea < ee; ea += 16) {  // warp-uniform trip count, 1.3 on average at 1 % density: not worth unrolling
+              double a, b0, b1;
+              uint32_t boff;
+              lds_entry(ea, a, boff);
+              lds_f64x2(bl + boff, b0, b1);
+              acc[r][0] = fma(a, b0, acc[r][0]);
+              acc[r][1] = fma(a, b1, acc[r][1]);
             }
           }
         } else {
-          // a segment larger than the stage buffer (dense-ish blocks): its entries are read from global memory
-          const Entry* ents = reinterpret_cast<const Entry*>(pr.ent) + pr.segoff[item.strip * nchunks + q];
+          // a segment larger than the stage buffer (denser blocks): the warp's entries (one contiguous run, rows ascending) are
+          // fetched from global memory 32 at a time, one coalesced 16-byte load per lane, and handed round by shuffles
+          const uint4* gents = reinterpret_cast<const uint4*>(pr.ent) + pr.segoff[item.strip * nchunks + q];
+          const int eend = __shfl_sync(0xffffffffu, rpv, RPW);
+          int e = __shfl_sync(0xffffffffu, rpv, 0), bb = e;
+          uint4 mine = bb + lane < eend ? __ldg(gents + bb + lane) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-          for (int g = 0; g < TM / 128; ++g) {
-            int e[4], n[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int r = hw + 32 * (4 * g + t);
-              e[t] = rp[r];
-              n[t] = rp[r + 1] - e[t];
-            }
-            int maxn = max(max(n[0], n[1]), max(n[2], n[3]));
-            maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, 16));
-            for (int i = 0; i < maxn; ++i) {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                if (i < n[t]) {
-                  const Entry en = ents[e[t] + i];
-                  const double* b = Bs + en.k * TN + l16;
-                  acc[4 * g + t][0] = fma(en.a, b[0], acc[4 * g + t][0]);
-                  acc[4 * g + t][1] = fma(en.a, b[16], acc[4 * g + t][1]);
-                }
+          for (int r = 0; r < RPW; ++r) {
+            const int e1 = __shfl_sync(0xffffffffu, rpv, r + 1);
+#pragma unroll 1
+            for (; e < e1; ++e) {
+              if (e - bb == 32) {
+                bb = e;
+                mine = bb + lane < eend ? __ldg(gents + bb + lane) : make_uint4(0u, 0u, 0u, 0u);
               }
+              const int j = e - bb;
+              const double a = __hiloint2double(static_cast<int>(__shfl_sync(0xffffffffu, mine.y, j)),
+                                                static_cast<int>(__shfl_sync(0xffffffffu, mine.x, j)));
+              const uint32_t boff = __shfl_sync(0xffffffffu, mine.z, j);
+              double b0, b1;
+              lds_f64x2(bl + boff, b0, b1);
+              acc[r][0] = fma(a, b0, acc[r][0]);
+              acc[r][1] = fma(a, b1, acc[r][1]);
             }
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars[2 + s]));
+        if (lane == 0) mbar_arrive(smem_u32(&bars[NSTAGE + s]));
+        if (++s == NSTAGE) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
     // ---- epilogue: registers -> shared memory [column][row] -> coalesced column runs of the column-major output block
     asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");  // every consumer has finished reading the stage buffers
     double* Cs = reinterpret_cast<double*>(smem);
 #pragma unroll
-    for (int i = 0; i < TM / 32; ++i) {
-      const int r = hw + 32 * i;
-      Cs[l16 * CS_LD + r] = acc[i][0];
-      Cs[(l16 + 16) * CS_LD + r] = acc[i][1];
+    for (int i = 0; i < RPW; ++i) {
+      const int r = warp * RPW + i;
+      Cs[(2 * lane) * CS_LD + r] = acc[i][0];
+      Cs[(2 * lane + 1) * CS_LD + r] = acc[i][1];
     }
     asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");
     const int rows = min(TM, out.m - row0), cols = min(TN, out.n - col0);
-    const int ctid = threadIdx.x;  // 0 .. 511
-    for (int c = 0; c < cols; ++c) {
-      double* dst = out.C + static_cast<size_t>(out.m) * (col0 + c) + row0;
-      for (int r = ctid; r < rows; r += NCW * 32) {
+    for (int idx = threadIdx.x; idx < cols * TM; idx += NCW * 32) {
+      const int c = idx / TM, r = idx % TM;
+      if (r < rows) {
+        double* dst = out.C + static_cast<size_t>(out.m) * (col0 + c) + row0 + r;
         const double v = Cs[c * CS_LD + r];
-        dst[r] = out.accumulate ? dst[r] + v : v;
+        *dst = out.accumulate ? *dst + v : v;
       }
     }
   }
@@ -465,7 +485,7 @@ size_t spmm2_aux_bytes(int m, int kdim, int64_t nnz, size_t* ent_off, size_t* rp
   return off;
 }
 
-// Row-major dense operand (kdim rows x n columns, line stride ld doubles): box {32 columns, KC rows}, no swizzle.
+// Row-major dense operand (kdim rows x n columns, line stride ld doubles): box {TN columns, KC rows}, no swizzle.
 bool spmm2_encode_b_tmap(void* out128, const double* base, int64_t kdim, int64_t n, int64_t ld) {
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 1) != 0 || kdim <= 0 || n <= 0) return false;
   EncodeFn fn = spmm_encode_fn();
