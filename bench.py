@@ -511,6 +511,16 @@ def run_ours(args):
             return (time.perf_counter() - t0) / k_ * 1e3, k_
 
         e2e_ms, e2e_steps = e2e_time()
+        # the PCIe floor of the step on this box: the same uploads alone
+        t0 = time.perf_counter()
+        for _ in range(2):
+            dA, dB = s.emptyDataset(), s.emptyDataset()
+            dA.put_blocks(pA)
+            dB.put_blocks(pB)
+            dA.wait_ingest()               # host-blocking
+            dB.wait_ingest()
+            del dA, dB
+        ingest_only_ms = (time.perf_counter() - t0) / 2 * 1e3
         checksum = float(outbuf[(0, 0)][0])
         e2e_blk = outbuf[(nb // 2, nb // 3)].copy()
         if isinstance(check, dict) and "error" not in check:
@@ -555,7 +565,8 @@ def run_ours(args):
                    "l2": f"inputs 2 x {n * n * 8 / 2**30:.0f} GiB + output {n * n * 8 / 2**30:.0f} GiB >> 126 MB L2; no flush needed",
                    "gemm_algo": algo_name, "wall_ms_per_step": t_wall / args.steps * 1e3, "c00": checksum},
         "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "steps": e2e_steps},
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "ingest_only_ms": ingest_only_ms,
+                "note": "ingest_only_ms = the step's host->device copies alone on this box: the PCIe floor of the step"},
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "gpu_launches_per_step": launches_per_step,
         "roofline": roofline,
@@ -734,6 +745,7 @@ def main():
     ap.add_argument("--ozaki-slices", type=int, default=7)
     ap.add_argument("--algo", type=int, default=0, choices=(0, 1, 2, 4),
                     help="gemm_algo of the headline: 0 = auto (tcgen05 Ozaki-II with the device-side guard), 1 = DMMA fp64")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="N > 1: pieces of block rows / block columns the pipelined end-to-end step uploads and pulls")
     ap.add_argument("--crt-moduli", type=int, default=0, help="Ozaki-II residue moduli (6..16); 0 = chosen by the library from K")
     ap.add_argument("--workload", default="metric", choices=("metric", "cfg5"), help="metric = BASELINE metric (dense N=16384); cfg5 = configs[4]")
     ap.add_argument("--n5", type=int, default=32768, help="matrix size of --workload cfg5")

@@ -263,11 +263,14 @@ MR_API mr_status mr_memcpy_d2h(mr_context* ctx, const void* dptr, void* host, in
  * slabsA_row[c'] (c' = 0 .. pc-1) / slabsB_col[r'] (r' = 0 .. pr-1): slab base pointers of the ranks of this rank's grid row / grid
  * column, valid in this process (own slab, peer-mapped, or mr_ipc_open'ed).  The caller makes sure the peers' slabs are complete
  * before the call and stay untouched until every rank's call has run on the device (a stream barrier before and after; mr_dmatrix
- * does it with events).  nchunks >= 1: pieces the pull of A is cut into (the multiply starts on the first).  *out is sharded. */
+ * does it with events).  nchunks >= 1 (<= 64): the pull is cut into nchunks pieces of A's block rows and nchunks pieces of B's block
+ * columns, fetched alternately (A0, B0, A1, B1, ...); the multiply starts on the corner of C the first pair unlocks and grows it
+ * piece by piece.  *out is sharded. */
 MR_API mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
                                   int32_t nchunks, mr_matrix** out);
-/* mr_grid_multiply with one CUDA event (cudaEvent_t) per piece of the pull: gates[0] guards B, gates[1 + ch] piece ch of A
- * (NULL = in place).  Lets every rank overlap its peers' host->device ingest with its own multiply. */
+/* mr_grid_multiply with one CUDA event (cudaEvent_t) per piece of the pull, 2 * nchunks of them: gates[2 ch] guards piece ch of A
+ * (this rank's block rows [rows ch / nchunks, rows (ch + 1) / nchunks)), gates[2 ch + 1] piece ch of B (its block columns, cut the
+ * same way); NULL = in place.  Lets every rank overlap its peers' host->device ingest with its own multiply. */
 MR_API mr_status mr_grid_multiply_gated(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
                                         int32_t nchunks, const void* const* gates, mr_matrix** out);
 /* The blocks a partition owns (rid % row_mod == row_rem, cid % col_mod == col_rem); shares the device arrays with `a`. */

@@ -240,30 +240,24 @@ static mr_status grid_multiply_impl(mr_matrix* A, mr_matrix* B, const double* co
     auto gate = [&](int idx) {  // caller-provided "the peers' data for this piece is in place" event
       if (gates != nullptr && gates[idx] != nullptr) CUDA_CHECK(cudaStreamWaitEvent(ps, static_cast<cudaEvent_t>(const_cast<void*>(gates[idx])), 0));
     };
-    // ---- B: whole slabs of the grid column (every block of them is needed), one copy per peer
-    ReadyPtr readyB;
-    gate(0);
-    if (pr > 1) {
-      for (int rr = 0; rr < pr; ++rr) {
-        if (rr == r) continue;
-        MR_REQUIRE(slabsB_col[rr] != nullptr, MR_EINVAL, "slabsB_col[%d] is null", rr);
-        CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(panelB->p) + b_local * peer_index(rr, r), slabsB_col[rr], b_local, cudaMemcpyDefault, ps));
-      }
-      readyB = std::make_shared<Ready>();
-      CUDA_CHECK(cudaEventRecord(readyB->ev, ps));
-      panelB->ready = readyB;
-    }
-    // ---- A: block row by block row (the k-blocks a peer owns of one block row are contiguous in its slab)
+    // ---- pulls, piece by piece: block rows [rows * ch / n, rows * (ch + 1) / n) of A from the grid row, then block columns
+    //      [cols * ch / n, cols * (ch + 1) / n) of B from the grid column, ch = 0 .. n - 1.  Alternating the two operands lets the
+    //      multiply start on the leading (1 / n) x (1 / n) corner of C and grow it piece by piece, instead of waiting for all of B.
+    //      The k-blocks a peer owns of one block row are contiguous in its slab (one copy per peer and piece of A); a piece of B is
+    //      one run per local k-row.  Pulled blocks carry the event of their piece and an ingest sequence number in pull order,
+    //      which is what the multiply groups its launches by; own blocks keep whatever event / number their host ingest gave them.
     const int64_t my_rows = LA.slots_r_of(r);
-    nchunks = static_cast<int32_t>(std::max<int64_t>(1, std::min<int64_t>(nchunks, std::max<int64_t>(my_rows, 1))));
-    std::vector<ReadyPtr> readyA(nchunks);
-    std::vector<int> chunk_of_row(static_cast<size_t>(std::max<int64_t>(my_rows, 1)), 0);
-    if (pc > 1) {
-      for (int ch = 0; ch < nchunks; ++ch) {
+    const int64_t my_cols = LB.nbc > c ? (LB.nbc - c + pc - 1) / pc : 0;
+    nchunks = static_cast<int32_t>(std::max<int32_t>(1, std::min<int32_t>(nchunks, 64)));
+    std::vector<ReadyPtr> readyA(nchunks), readyB(nchunks);
+    std::vector<uint64_t> seqA(nchunks), seqB(nchunks);
+    std::vector<int> chunk_of_row(static_cast<size_t>(std::max<int64_t>(my_rows, 1)), 0), chunk_of_col(static_cast<size_t>(std::max<int64_t>(my_cols, 1)), 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      {
         const int64_t lo = my_rows * ch / nchunks, hi = my_rows * (ch + 1) / nchunks;
         for (int64_t li = lo; li < hi; ++li) chunk_of_row[li] = ch;
-        gate(1 + ch);
-        if (hi > lo) {
+        gate(2 * ch);
+        if (pc > 1 && hi > lo) {
           const size_t off = static_cast<size_t>(lo) * LA.slots_c * slot_bytes, len = static_cast<size_t>(hi - lo) * LA.slots_c * slot_bytes;
           for (int cc = 0; cc < pc; ++cc) {
             if (cc == c) continue;
@@ -274,16 +268,32 @@ static mr_status grid_multiply_impl(mr_matrix* A, mr_matrix* B, const double* co
         }
         readyA[ch] = std::make_shared<Ready>();
         CUDA_CHECK(cudaEventRecord(readyA[ch]->ev, ps));
+        seqA[ch] = ++ctx->ingest_seq;
       }
-      panelA->ready = readyA[nchunks - 1];
+      {
+        const int64_t lo = my_cols * ch / nchunks, hi = my_cols * (ch + 1) / nchunks;
+        for (int64_t lj = lo; lj < hi; ++lj) chunk_of_col[lj] = ch;
+        gate(2 * ch + 1);
+        if (pr > 1 && hi > lo) {
+          const size_t len = static_cast<size_t>(hi - lo) * slot_bytes;
+          for (int rr = 0; rr < pr; ++rr) {
+            if (rr == r) continue;
+            MR_REQUIRE(slabsB_col[rr] != nullptr, MR_EINVAL, "slabsB_col[%d] is null", rr);
+            for (int64_t lk = 0; lk < LB.slots_r_of(rr); ++lk) {
+              const size_t off = static_cast<size_t>(lk * LB.slots_c + lo) * slot_bytes;
+              CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(panelB->p) + b_local * peer_index(rr, r) + off,
+                                         reinterpret_cast<const char*>(slabsB_col[rr]) + off, len, cudaMemcpyDefault, ps));
+            }
+          }
+        }
+        readyB[ch] = std::make_shared<Ready>();
+        CUDA_CHECK(cudaEventRecord(readyB[ch]->ev, ps));
+        seqB[ch] = ++ctx->ingest_seq;
+      }
     }
+    if (panelA) panelA->ready = readyA[nchunks - 1];
+    if (panelB) panelB->ready = readyB[nchunks - 1];
     ctx->stats.p2p_bytes += static_cast<int64_t>((pc > 1 ? a_local * (pc - 1) : 0) + (pr > 1 ? b_local * (pr - 1) : 0));
-    // ---- the operands as this rank sees them: A(i, :) for my block rows, B(:, j) for my block columns.  Pulled blocks carry
-    //      the event of their chunk and an ingest sequence number in pull order (B, then the A chunks), which is what the
-    //      multiply groups its launches by; own blocks keep whatever event / number their host ingest gave them.
-    const uint64_t seqB = ++ctx->ingest_seq;
-    std::vector<uint64_t> chunk_seq(nchunks);
-    for (int ch = 0; ch < nchunks; ++ch) chunk_seq[ch] = ++ctx->ingest_seq;
     std::unique_ptr<mr_matrix> tA(new_matrix(ctx)), tB(new_matrix(ctx));
     for (int64_t i = r; i < LA.nbr; i += pr) {
       const int64_t li = i / pr;
@@ -296,16 +306,16 @@ static mr_status grid_multiply_impl(mr_matrix* A, mr_matrix* B, const double* co
         if (src == c) {
           Block b = dense_block(br, bc, Span{A->shard->slab, slot_off}, false);
           auto it = A->blocks.find(key);
-          if (it != A->blocks.end()) {  // own block possibly still being ingested from the host
-            b.ready = it->second.ready;
-            b.seq = it->second.seq;
+          if (it != A->blocks.end()) {  // own block possibly still being ingested from the host: it keeps its own event, and
+            b.ready = it->second.ready;  // counts as part of its piece for the order the multiply works in (a gated caller
+            b.seq = seqA[chunk_of_row[li]];  // uploads piece by piece in pull order, so the piece number is its arrival order)
             b.settled = it->second.settled;
           }
           tA->blocks[key] = std::move(b);
         } else {
           Block b = dense_block(br, bc, Span{panelA, a_local * peer_index(src, c) + slot_off}, false);
           b.ready = readyA[chunk_of_row[li]];
-          b.seq = chunk_seq[chunk_of_row[li]];
+          b.seq = seqA[chunk_of_row[li]];
           tA->blocks[key] = std::move(b);
         }
       }
@@ -322,14 +332,14 @@ static mr_status grid_multiply_impl(mr_matrix* A, mr_matrix* B, const double* co
           auto it = B->blocks.find(key);
           if (it != B->blocks.end()) {
             b.ready = it->second.ready;
-            b.seq = it->second.seq;
+            b.seq = seqB[chunk_of_col[j / pc]];
             b.settled = it->second.settled;
           }
           tB->blocks[key] = std::move(b);
         } else {
           Block b = dense_block(br, bc, Span{panelB, b_local * peer_index(src, r) + slot_off}, false);
-          b.ready = readyB;
-          b.seq = seqB;
+          b.ready = readyB[chunk_of_col[j / pc]];
+          b.seq = seqB[chunk_of_col[j / pc]];
           tB->blocks[key] = std::move(b);
         }
       }
@@ -345,9 +355,9 @@ mr_status mr_grid_multiply(mr_matrix* A, mr_matrix* B, const double* const* slab
   return grid_multiply_impl(A, B, slabsA_row, slabsB_col, nchunks, nullptr, out);
 }
 
-// The same with one caller-provided CUDA event per piece of the pull: gates[0] guards the pull of B, gates[1 + ch] the pull of
-// piece ch of A (ch < nchunks; the pieces are this rank's block rows [rows * ch / nchunks, rows * (ch + 1) / nchunks)).  A null
-// entry means "already in place".  This is how a multi-process caller overlaps its peers' host->device ingest with the multiply:
+// The same with one caller-provided CUDA event per piece of the pull, 2 * nchunks of them: gates[2 ch] guards the pull of piece
+// ch of A (this rank's block rows [rows * ch / nchunks, rows * (ch + 1) / nchunks)), gates[2 ch + 1] the pull of piece ch of B (its
+// block columns [cols * ch / nchunks, cols * (ch + 1) / nchunks)); pieces may be empty.  A null entry means "already in place".  This is how a multi-process caller overlaps its peers' host->device ingest with the multiply:
 // every rank uploads piece after piece, puts a stream barrier behind each, records an event, and hands the events in here.
 mr_status mr_grid_multiply_gated(mr_matrix* A, mr_matrix* B, const double* const* slabsA_row, const double* const* slabsB_col,
                                  int32_t nchunks, const void* const* gates, mr_matrix** out) {

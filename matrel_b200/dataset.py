@@ -164,15 +164,15 @@ def memcpy_d2h(session: "MatfastSession", device_ptr: int, out: np.ndarray) -> n
 def grid_multiply(session: "MatfastSession", A: "Dataset", B: "Dataset", slabsA_row: Sequence[int], slabsB_col: Sequence[int],
                   nchunks: int = 4, gates: Optional[Sequence[Optional[int]]] = None) -> "Dataset":
     """``mr_grid_multiply``: this rank's share of C = A B; the slab pointers are valid in this process (IPC-opened peers).
-    ``gates`` (optional, nchunks + 1 raw cudaEvent_t handles or None): gates[0] guards the pull of B, gates[1 + ch] the pull of
-    piece ch of A (``mr_grid_multiply_gated``)."""
+    ``gates`` (optional, 2 * nchunks raw cudaEvent_t handles or None): gates[2 ch] guards the pull of piece ch of A (block rows),
+    gates[2 ch + 1] the pull of piece ch of B (block columns) (``mr_grid_multiply_gated``)."""
     pa = (C.c_void_p * len(slabsA_row))(*[int(x) for x in slabsA_row])
     pb = (C.c_void_p * len(slabsB_col))(*[int(x) for x in slabsB_col])
     h = C.c_void_p()
     if gates is None:
         N.check(N.lib.mr_grid_multiply(A._h, B._h, pa, pb, int(nchunks), C.byref(h)))
     else:
-        assert len(gates) == nchunks + 1
+        assert len(gates) == 2 * nchunks
         pg = (C.c_void_p * len(gates))(*[int(g) if g else None for g in gates])
         N.check(N.lib.mr_grid_multiply_gated(A._h, B._h, pa, pb, int(nchunks), pg, C.byref(h)))
     return Dataset(session, h)

@@ -187,7 +187,8 @@ def sharded_multiply(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMa
                      nchunks: int = 4, gates=None):
     """C = A * B, C-stationary on the process grid, through ``mr_grid_multiply``: this rank pulls A(i, :) of its block rows from
     the ranks of its grid row and B(:, j) of its block columns from its grid column out of their slabs (copy engines over
-    NVLink, ``nchunks`` pieces along the block rows) while the multiply already runs on the pieces that have landed.
+    NVLink, ``nchunks`` pieces of A's block rows and of B's block columns, fetched alternately) while the multiply already runs
+    on the corner of C that the pieces landed so far unlock.
     The peers' slabs must be complete when the pulls run and stay untouched until every rank's multiply has consumed them:
     callers that rewrite slabs between steps put a stream barrier around the call (``stream_barrier``).
     Returns (local C Dataset -- a sharded dataset --, keep-alive objects)."""
@@ -201,12 +202,30 @@ def sharded_multiply(session, groups: GridGroups, A: ShardedMatrix, B: ShardedMa
     return dC, (A, B)
 
 
-def pull_chunks(plan: GridPlan, rank: int, nchunks: int):
-    """The pieces ``mr_grid_multiply`` cuts this rank's block rows into: (effective nchunks, [list of global block-row ids])."""
-    r, _ = plan.coords(rank)
-    rows = list(range(r, plan.nbr, plan.pr))
-    nchunks = max(1, min(nchunks, max(len(rows), 1)))
-    return nchunks, [rows[len(rows) * ch // nchunks:len(rows) * (ch + 1) // nchunks] for ch in range(nchunks)]
+def pull_chunks(planA: GridPlan, planB: GridPlan, rank: int, nchunks: int):
+    """The pieces ``mr_grid_multiply`` cuts this rank's pull into: (nchunks, [global block-row ids of A per piece], [global
+    block-column ids of B per piece]); piece ch of A is fetched before piece ch of B, pieces may be empty."""
+    r, c = planA.coords(rank)
+    rows = list(range(r, planA.nbr, planA.pr))
+    cols = list(range(c, planB.nbc, planB.pc))
+    nchunks = max(1, min(nchunks, 64))
+    cut = lambda v: [v[len(v) * ch // nchunks:len(v) * (ch + 1) // nchunks] for ch in range(nchunks)]  # noqa: E731
+    return nchunks, cut(rows), cut(cols)
+
+
+def ingest_gate(session, side, tick):
+    """'Every rank's host->device copies submitted so far have landed', as a CUDA event: the side stream waits for this rank's
+    ingest, runs a one-element all-reduce (complete only when every rank has got there), and the event recorded behind it is
+    what ``mr_grid_multiply_gated`` lets the pull of a piece wait for.  No host synchronisation."""
+    import torch
+    import torch.distributed as dist
+    session.wait_ingest_on(side.cuda_stream)
+    with torch.cuda.stream(side):
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(tick)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return ev
 
 
 def stream_barrier(device):
@@ -656,31 +675,28 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
         dist.barrier()
 
         side = torch.cuda.Stream(device=device)      # the cross-rank barriers run here, beside the multiply
-        nch, chunk_rows = pull_chunks(plan, rank, getattr(args, "pull_chunks", 4))
+        nch, chunk_rows, chunk_cols = pull_chunks(plan, plan, rank, getattr(args, "e2e_chunks", 8))
         pA_by_chunk = [[b for b in pA if b.rid in set(rows)] for rows in chunk_rows]
+        pB_by_chunk = [[b for b in pB if b.cid in set(cols)] for cols in chunk_cols]
+        piece_of_row = {i: ch for ch, rows in enumerate(chunk_rows) for i in rows}
+        piece_of_col = {j: ch for ch, cols in enumerate(chunk_cols) for j in cols}
         tick = torch.zeros(1, device=device)
 
         def gate_after_ingest():
-            """'Every rank's copies submitted so far have landed': the side stream waits for this rank's ingest, runs a one-element
-            all-reduce (complete only when every rank has got there), and the event recorded behind it gates the pulls."""
-            s.wait_ingest_on(side.cuda_stream)
-            with torch.cuda.stream(side):
-                if world > 1:
-                    dist.all_reduce(tick)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            return ev
+            return ingest_gate(s, side, tick)
 
         def e2e_step():
-            # B first (every output block needs all of it), then A piece by piece; the multiply is called once and its pulls
-            # wait piece by piece for the peers' uploads, so ingest, NVLink pulls, tensor-core work and egress all overlap
-            eB.sharded.put_blocks(pB)          # async copies on the ingest stream, one event per block
-            evs = [gate_after_ingest()]
-            for blocks in pA_by_chunk:
-                eA.sharded.put_blocks(blocks)
+            # block rows of A and block columns of B are uploaded alternately, piece by piece (async copies on the ingest stream,
+            # one event per block); the multiply is called once and its pulls wait piece by piece for the peers' uploads, so the
+            # corner of C that the pieces landed so far unlock is multiplied and read back while the rest is still on the wire
+            evs = []
+            for ch in range(nch):
+                eA.sharded.put_blocks(pA_by_chunk[ch])
+                evs.append(gate_after_ingest())
+                eB.sharded.put_blocks(pB_by_chunk[ch])
                 evs.append(gate_after_ingest())
             dC, keep = sharded_multiply(s, groups, eA, eB, plan, plan, nchunks=nch, gates=[e.cuda_event for e in evs])
-            for k in sorted(dC.block_ids()):   # block rows complete in order; egress overlaps the later pieces
+            for k in sorted(dC.block_ids(), key=lambda ij: (max(piece_of_row[ij[0]], piece_of_col[ij[1]]), ij)):   # completion order
                 dC.get_block(*k, out=outbuf[k])
             stream_barrier(device)             # nobody rewrites a slab while a peer may still be pulling from it
             return dC
@@ -689,6 +705,15 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
             e2e_step()
         torch.cuda.synchronize()
         dist.barrier()
+        # the PCIe floor of the step on this box: the same uploads alone (all ranks at once), nothing else running
+        t0 = time.perf_counter()
+        for _ in range(2):
+            eA.sharded.put_blocks(pA)
+            eB.sharded.put_blocks(pB)
+            eA.sharded.wait_ingest()       # host-blocking
+            eB.sharded.wait_ingest()
+        dist.barrier()
+        ingest_only_ms = allmax((time.perf_counter() - t0) / 2 * 1e3)
         e2e_steps = max(1, min(args.steps, 5))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -720,7 +745,9 @@ def bench_main(args, METRIC, UNIT, fp64_peak_tflops, ClockSampler, cpu_reference
                        "gemm_algo": "auto -> Ozaki-II on tcgen05 on every rank" if on_tc else "dmma_fp64",
                        "p2p_bytes_per_step": p2p},
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
-                    "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "ingest_only_ms": ingest_only_ms, "pieces": nch,
+                    "note": "ingest_only_ms = the step's host->device copies alone on this box (max over ranks): the PCIe floor of the step"},
             "gpu_launches": int(launches), "gpu_launches_per_step_per_rank": st["kernel_launches"] / args.steps,
             "roofline": roofline,
             "clocks": clocks,

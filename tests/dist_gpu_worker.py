@@ -9,7 +9,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import matrel_b200 as mb  # noqa: E402
-from matrel_b200.distributed import (GridGroups, GridPlan, ShardedMatrix, sharded_aggregate,  # noqa: E402
+from matrel_b200.distributed import (GridGroups, GridPlan, ShardedMatrix, ingest_gate, pull_chunks, sharded_aggregate,  # noqa: E402
                                      sharded_elementwise, sharded_elementwise_any, sharded_multiply, sharded_multiply_allgather,
                                      sharded_multiply_overlapped, sharded_repartition, sharded_transpose, stream_barrier)
 from oracle import matrel_oracle as O  # noqa: E402
@@ -98,12 +98,24 @@ def main():
             eA = ShardedMatrix(planA, rank, torch.zeros_like(A.slab), None, s)
             eB = ShardedMatrix(planB, rank, torch.zeros_like(B.slab), None, s)
             eA.peer_slabs(); eB.peer_slabs()
-            for rep in range(2):
-                eA.sharded.put_blocks(mb.MatrixBlock(i, j, mb.DenseMatrix(Ah[(i, j)].numRows, Ah[(i, j)].numCols, Ah[(i, j)].values)) for (i, j) in planA.owned(rank))
-                eB.sharded.put_blocks(mb.MatrixBlock(i, j, mb.DenseMatrix(Bh[(i, j)].numRows, Bh[(i, j)].numCols, Bh[(i, j)].values)) for (i, j) in planB.owned(rank))
-                s.wait_ingest()
-                stream_barrier(device)
-                dE, keepE = sharded_multiply(s, groups, eA, eB, planA, planB, nchunks=2)
+            mk = lambda H, i, j: mb.MatrixBlock(i, j, mb.DenseMatrix(H[(i, j)].numRows, H[(i, j)].numCols, H[(i, j)].values))  # noqa: E731
+            side, tick = torch.cuda.Stream(device=device), torch.zeros(1, device=device)
+            for rep in range(3):
+                if rep < 2:     # upload everything, wait, barrier, multiply
+                    eA.sharded.put_blocks(mk(Ah, i, j) for (i, j) in planA.owned(rank))
+                    eB.sharded.put_blocks(mk(Bh, i, j) for (i, j) in planB.owned(rank))
+                    s.wait_ingest()
+                    stream_barrier(device)
+                    dE, keepE = sharded_multiply(s, groups, eA, eB, planA, planB, nchunks=2)
+                else:           # pipelined: pieces of A's block rows and B's block columns uploaded alternately, one gate event each
+                    nch, crow, ccol = pull_chunks(planA, planB, rank, 3)
+                    evs = []
+                    for ch in range(nch):
+                        eA.sharded.put_blocks(mk(Ah, i, j) for (i, j) in planA.owned(rank) if i in crow[ch])
+                        evs.append(ingest_gate(s, side, tick))
+                        eB.sharded.put_blocks(mk(Bh, i, j) for (i, j) in planB.owned(rank) if j in ccol[ch])
+                        evs.append(ingest_gate(s, side, tick))
+                    dE, keepE = sharded_multiply(s, groups, eA, eB, planA, planB, nchunks=nch, gates=[e.cuda_event for e in evs])
                 gotE = {(b.rid, b.cid): b.matrix for b in dE.collect()}
                 stream_barrier(device)
                 assert sorted(gotE) == sorted(got)
