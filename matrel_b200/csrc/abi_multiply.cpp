@@ -195,7 +195,9 @@ struct Oz2Run {
     std::vector<Prep> preps;
     std::vector<int2> tiles;
     std::vector<double*> ctab;
-    Buf d_tiles, d_ctab;
+    std::vector<Oz2FixOut> fouts;   // auto mode: the job's output blocks and their operand pairs, for the exact products of
+    std::vector<Oz2FixSrc> fsrcs;   // elements the residue scheme leaves out (oz2_fixup)
+    Buf d_tiles, d_ctab, d_fouts, d_fsrcs;
   };
   mr_context* ctx = nullptr;
   Oz2Engine* eng = nullptr;
@@ -342,6 +344,14 @@ struct Oz2Run {
                     j.tiles.end());
       int8_ops += static_cast<int64_t>(j.tiles.size()) * T * 2ll * kOz2TileM * kOz2TileN * Kpad;
     };
+    auto add_fix = [&](Job& j, const OutPlan& o, double* C, int rslot, int cslot) {
+      if (!guard) return;
+      Oz2FixOut fo{C, o.m, o.n, rslot, cslot, static_cast<int32_t>(j.fsrcs.size()), static_cast<int32_t>(o.src.size())};
+      for (const GemmSrc& g : o.src)
+        j.fsrcs.push_back(Oz2FixSrc{g.a->values.ptr<double>(), g.b->values.ptr<double>(), outer ? 0 : g.k * blk, g.a->numCols, g.a->numRows,
+                                    g.b->numCols, static_cast<uint8_t>(g.a->isT), static_cast<uint8_t>(g.b->isT), {0}});
+      j.fouts.push_back(fo);
+    };
     int max_tiles = 1;
     if (resident) {
       std::vector<char> rprep(nr, 0), cprep(nc, 0);
@@ -364,6 +374,7 @@ struct Oz2Run {
           }
           j.ctab[static_cast<size_t>(cr) * cap_c + cc] = cptr[out_plan[t]];
           add_tiles(j, cr, cc, o.m, o.n);
+          add_fix(j, o, cptr[out_plan[t]], cr, cc);
         }
         if (j.tiles.empty()) continue;
         for (auto& run : runs_of(newr)) j.preps.push_back(make_prep(true, run, run.front()));
@@ -390,6 +401,7 @@ struct Oz2Run {
               const OutPlan& o = plans[out_plan[it->second]];
               j.ctab[static_cast<size_t>(cr - r0) * cap_c + (cc - c0)] = cptr[out_plan[it->second]];
               add_tiles(j, cr - r0, cc - c0, o.m, o.n);
+              add_fix(j, o, cptr[out_plan[it->second]], cr - r0, cc - c0);
             }
           if (j.tiles.empty()) continue;
           if (!row_prepared) {
@@ -439,6 +451,10 @@ struct Oz2Run {
       }
       j.d_tiles = upload(ctx, j.tiles);
       j.d_ctab = upload(ctx, j.ctab);
+      if (!j.fouts.empty()) {
+        j.d_fouts = upload(ctx, j.fouts);
+        j.d_fsrcs = upload(ctx, j.fsrcs);
+      }
     }
   }
 
@@ -452,6 +468,9 @@ struct Oz2Run {
                                p.max_rows, p.max_cols, p.slot0, p.nslots, static_cast<const int32_t*>(p.d_dims->p), p.need_zero, cs));
       CUDA_CHECK(oz2_multiply(eng, static_cast<const int2*>(j.d_tiles->p), static_cast<int>(j.tiles.size()),
                               static_cast<double* const*>(j.d_ctab->p), cs, timed ? &ms : nullptr, ctx->ev2, ctx->ev3));
+      if (!j.fouts.empty())
+        CUDA_CHECK(oz2_fixup(eng, static_cast<const Oz2FixOut*>(j.d_fouts->p), static_cast<int>(j.fouts.size()),
+                             static_cast<const Oz2FixSrc*>(j.d_fsrcs->p), cs));
     }
     note_launch(ctx, oz2_launches(eng));
     if (timed) ctx->stats.tc_gemm_ms_total += ms;

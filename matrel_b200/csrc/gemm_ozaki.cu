@@ -735,10 +735,23 @@ struct CrtF {
 };
 __constant__ CrtF c_crtf[CRT_MAX_T + 1];
 
-// out_t[line * Kpad + k] = symmetric residue of a'(line, k) mod p_t, same tiling / staging as slice_kernel
+// An element too far below the maximum of its line to keep enough significand bits after the per-line scaling.  It is left out
+// of the residues (treated as zero) and its products are added exactly, in fp64, by oz2_fixup_kernel after the CRT pass.
+struct OutlierRec {
+  int32_t line;  // buffer line (row of A' / row of B') of the side it belongs to
+  int32_t k;     // inner index
+  double v;      // the element
+};
+constexpr int OZ2_REC_CAP = 64;  // records per slot (block row / block column); more than that raises the fallback flag
+__device__ __forceinline__ int exponent_of(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }  // ilogb for normal x
+
+// out_t[line * Kpad + k] = symmetric residue of a'(line, k) mod p_t, same tiling / staging as slice_kernel.
+// range_bits > 0: non-zero elements more than range_bits binary orders below their line maximum become OutlierRecs of their
+// slot (recs / rec_cnt are the tables of this side, sstride lines per slot); a full slot table raises *gate.
 __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict__ blocks, const int32_t* __restrict__ line_exp,
                                                       int8_t* __restrict__ out, size_t slice_stride, int Kpad, int T, int alpha,
-                                                      int lines_are_rows, int tiles_k_max, const int* __restrict__ gate) {
+                                                      int lines_are_rows, int tiles_k_max, int* __restrict__ gate, int range_bits,
+                                                      OutlierRec* __restrict__ recs, int* __restrict__ rec_cnt, int sstride) {
   __shared__ double sm[32][129];
   if (gate != nullptr && *gate != 0) return;
   const OzBlock b = blocks[blockIdx.y];
@@ -768,7 +781,15 @@ __global__ void __launch_bounds__(256) residue_kernel(const OzBlock* __restrict_
     float sgn[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const long long X = __double2ll_rn(sm[l][lane * 4 + j] * line_scale);  // exact scaling, |X| <= 2^alpha
+      double xv = sm[l][lane * 4 + j];
+      if (range_bits > 0 && xv != 0.0 && exponent_of(xv) < e - 1 - range_bits) {
+        const int slot = (gl_base + l) / sstride;
+        const int at = atomicAdd(&rec_cnt[slot], 1);
+        if (at < OZ2_REC_CAP) recs[static_cast<size_t>(slot) * OZ2_REC_CAP + at] = OutlierRec{gl_base + l, gk_base + lane * 4 + j, xv};
+        else *gate = 1;
+        xv = 0.0;
+      }
+      const long long X = __double2ll_rn(xv * line_scale);  // exact scaling, |X| <= 2^alpha
       sgn[j] = X < 0 ? -1.0f : 1.0f;
       const unsigned long long U = static_cast<unsigned long long>(X < 0 ? -X : X);
       hi[j] = static_cast<uint32_t>(U >> 32);
@@ -911,6 +932,54 @@ __global__ void __launch_bounds__(256) crt_kernel(const int8_t* __restrict__ pla
     if (lcol >= cdims[cslot]) continue;
     double* blkp = ctab[static_cast<size_t>(rslot) * ncslots + cslot];
     if (blkp != nullptr) blkp[lrow + static_cast<size_t>(brows) * lcol] = tile[cidx][lane];
+  }
+}
+
+// Exact products of the outlier elements (see OutlierRec), added to the C blocks of a job after its CRT pass.  One CTA per output
+// block: first the outliers of its block row of A (C(i, :) += a_ik B(k, :), thread = column), then those of its block column of
+// B (C(:, j) += A(:, k) b_kj, thread = row; an a_ik that is an outlier itself was already paired with the original b_kj in the
+// first phase and is skipped).  Operand values come from the original fp64 blocks.
+__global__ void __launch_bounds__(256) oz2_fixup_kernel(const Oz2FixOut* __restrict__ outs, const Oz2FixSrc* __restrict__ srcs,
+                                                        const OutlierRec* __restrict__ recs, const int* __restrict__ rec_cnt, int cap_r,
+                                                        int sstride, const int32_t* __restrict__ row_exp, int range_bits,
+                                                        const int* __restrict__ gate) {
+  if (*gate != 0) return;
+  const Oz2FixOut o = outs[blockIdx.x];
+  const int nA = min(rec_cnt[o.rslot], OZ2_REC_CAP), nB = min(rec_cnt[cap_r + o.cslot], OZ2_REC_CAP);
+  if (nA == 0 && nB == 0) return;
+  const OutlierRec* ra = recs + static_cast<size_t>(o.rslot) * OZ2_REC_CAP;
+  const OutlierRec* rb = recs + static_cast<size_t>(cap_r + o.cslot) * OZ2_REC_CAP;
+  for (int q = 0; q < nA; ++q) {
+    const OutlierRec r = ra[q];
+    const int i = r.line - o.rslot * sstride;
+    if (i < 0 || i >= o.m) continue;
+    for (int t = 0; t < o.src_count; ++t) {
+      const Oz2FixSrc sc = srcs[o.src_begin + t];
+      if (r.k < sc.k0 || r.k >= sc.k0 + sc.kdim) continue;
+      const int kk = r.k - sc.k0;
+      for (int j = threadIdx.x; j < o.n; j += blockDim.x) {
+        const double b = sc.bT ? sc.B[static_cast<size_t>(kk) * sc.b_cols + j] : sc.B[kk + static_cast<size_t>(sc.kdim) * j];
+        o.C[i + static_cast<size_t>(o.m) * j] += r.v * b;
+      }
+      break;
+    }
+  }
+  __syncthreads();
+  for (int q = 0; q < nB; ++q) {
+    const OutlierRec r = rb[q];
+    const int j = r.line - o.cslot * sstride;
+    if (j < 0 || j >= o.n) continue;
+    for (int t = 0; t < o.src_count; ++t) {
+      const Oz2FixSrc sc = srcs[o.src_begin + t];
+      if (r.k < sc.k0 || r.k >= sc.k0 + sc.kdim) continue;
+      const int kk = r.k - sc.k0;
+      for (int i = threadIdx.x; i < o.m; i += blockDim.x) {
+        const double a = sc.aT ? sc.A[static_cast<size_t>(i) * sc.kdim + kk] : sc.A[i + static_cast<size_t>(sc.a_rows) * kk];
+        if (a == 0.0 || exponent_of(a) < row_exp[o.rslot * sstride + i] - 1 - range_bits) continue;
+        o.C[i + static_cast<size_t>(o.m) * j] += a * r.v;
+      }
+      break;
+    }
   }
 }
 
@@ -1290,9 +1359,11 @@ struct Oz2Engine {
   int64_t K = 0, Kpad = 0, Mpad = 0, Npad = 0;
   size_t a_stride = 0, b_stride = 0, plane_stride = 0, smem_bytes = 0;
   int8_t *As = nullptr, *Bs = nullptr, *planes = nullptr;
-  unsigned long long *maxb = nullptr, *minb = nullptr;
+  unsigned long long* maxb = nullptr;
   int32_t *exps = nullptr, *dims = nullptr;   // exps: [Mpad + Npad]; dims: rows per row slot [cap_r] then columns per column slot [cap_c]
   int* bad = nullptr;
+  OutlierRec* recs = nullptr;                 // [cap_r + cap_c][OZ2_REC_CAP]: A slots first, then B slots
+  int* rec_cnt = nullptr;                     // [cap_r + cap_c]
   const unsigned char* d_maps = nullptr;      // uploaded by the caller (oz2_host_maps)
   std::vector<unsigned char> h_maps;
   int sms = 148;
@@ -1381,15 +1452,17 @@ cudaError_t oz2_create(Oz2Engine** out, int blk, int64_t K, int moduli, int cap_
       (err = alloc(reinterpret_cast<void**>(&e->Bs), e->b_stride * T)) != cudaSuccess ||
       (err = alloc(reinterpret_cast<void**>(&e->planes), e->plane_stride * T)) != cudaSuccess ||
       (err = alloc(reinterpret_cast<void**>(&e->maxb), lines * 8)) != cudaSuccess ||
-      (err = alloc(reinterpret_cast<void**>(&e->minb), lines * 8)) != cudaSuccess ||
       (err = alloc(reinterpret_cast<void**>(&e->exps), lines * 4)) != cudaSuccess ||
       (err = alloc(reinterpret_cast<void**>(&e->dims), static_cast<size_t>(cap_r + cap_c) * 4)) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->recs), static_cast<size_t>(cap_r + cap_c) * OZ2_REC_CAP * sizeof(OutlierRec))) != cudaSuccess ||
+      (err = alloc(reinterpret_cast<void**>(&e->rec_cnt), static_cast<size_t>(cap_r + cap_c) * sizeof(int))) != cudaSuccess ||
       (err = alloc(reinterpret_cast<void**>(&e->bad), sizeof(int))) != cudaSuccess) {
     Oz2Engine* raw = e.release();
     oz2_destroy(raw, stream);
     return err;
   }
   OZ_CHECK(cudaMemsetAsync(e->bad, 0, sizeof(int), stream));
+  OZ_CHECK(cudaMemsetAsync(e->rec_cnt, 0, static_cast<size_t>(cap_r + cap_c) * sizeof(int), stream));
   // B' rows beyond the last column slot (Npad rounding to the 256-wide tile) are read by the last tile: keep them defined
   if (e->Npad > static_cast<int64_t>(e->sstride) * cap_c)
     for (int t = 0; t < T; ++t)
@@ -1412,7 +1485,7 @@ cudaError_t oz2_create(Oz2Engine** out, int blk, int64_t K, int moduli, int cap_
 
 void oz2_destroy(Oz2Engine* e, cudaStream_t stream) {
   if (!e) return;
-  void* ptrs[] = {e->As, e->Bs, e->planes, e->maxb, e->minb, e->exps, e->dims, e->bad};
+  void* ptrs[] = {e->As, e->Bs, e->planes, e->maxb, e->exps, e->dims, e->bad, e->recs, e->rec_cnt};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, stream);
   delete e;
@@ -1446,10 +1519,9 @@ cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, i
   const size_t nlines = static_cast<size_t>(nslots) * e->sstride;
   // the tables are indexed by buffer line: A lines first, then B lines
   unsigned long long* maxb = e->maxb + (is_a ? 0 : e->Mpad);
-  unsigned long long* minb = e->minb + (is_a ? 0 : e->Mpad);
   int32_t* exps = e->exps + (is_a ? 0 : e->Mpad);
   OZ_CHECK(cudaMemsetAsync(e->maxb + line0, 0, nlines * 8, stream));
-  OZ_CHECK(cudaMemsetAsync(e->minb + line0, 0xff, nlines * 8, stream));
+  OZ_CHECK(cudaMemsetAsync(e->rec_cnt + (is_a ? 0 : e->cap_r) + slot0, 0, static_cast<size_t>(nslots) * sizeof(int), stream));
   OZ_CHECK(cudaMemcpyAsync(e->dims + (is_a ? 0 : e->cap_r) + slot0, d_dims, static_cast<size_t>(nslots) * 4, cudaMemcpyDeviceToDevice, stream));
   int8_t* res = is_a ? e->As : e->Bs;
   const size_t stride = is_a ? e->a_stride : e->b_stride;
@@ -1459,13 +1531,13 @@ cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, i
   if (nblocks > 0) {
     const AbsmaxGrid g(max_rows, max_cols);
     OZ_CHECK(for_block_chunks(nblocks, [&](int off, int cnt) {
-      absmax_kernel<<<dim3(g.tiles, cnt), 256, 0, stream>>>(blocks + off, maxb, e->range_bits ? minb : nullptr, is_a ? 1 : 0, g.ts);
+      absmax_kernel<<<dim3(g.tiles, cnt), 256, 0, stream>>>(blocks + off, maxb, nullptr, is_a ? 1 : 0, g.ts);
     }));
     e->launches += 1;
   }
-  exp_kernel<<<static_cast<unsigned>((nlines + 255) / 256), 256, 0, stream>>>(e->maxb + line0, e->range_bits ? e->minb + line0 : nullptr,
-                                                                               e->exps + line0, nullptr, static_cast<int>(nlines),
-                                                                               e->range_bits, e->bad);
+  // the exponent pass flags non-finite lines only; elements too far below their line maximum are handled one by one (OutlierRec)
+  exp_kernel<<<static_cast<unsigned>((nlines + 255) / 256), 256, 0, stream>>>(e->maxb + line0, nullptr, e->exps + line0, nullptr,
+                                                                               static_cast<int>(nlines), 0, e->bad);
   OZ_CHECK(cudaGetLastError());
   e->launches += 1;
   if (nblocks > 0) {
@@ -1474,7 +1546,9 @@ cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, i
     const int tk = (max_k + 127) / 128, tl = (max_l + 31) / 32;
     OZ_CHECK(for_block_chunks(nblocks, [&](int off, int cnt) {
       residue_kernel<<<dim3(tl * tk, cnt), 256, 0, stream>>>(blocks + off, exps, res, stride, static_cast<int>(e->Kpad), e->T, e->alpha,
-                                                             is_a ? 1 : 0, tk, e->bad);
+                                                             is_a ? 1 : 0, tk, e->bad, e->range_bits,
+                                                             e->recs + static_cast<size_t>(is_a ? 0 : e->cap_r) * OZ2_REC_CAP,
+                                                             e->rec_cnt + (is_a ? 0 : e->cap_r), e->sstride);
     }));
     e->launches += 1;
   }
@@ -1539,6 +1613,16 @@ cudaError_t oz2_multiply(Oz2Engine* e, const int2* d_tiles, int ntiles, double* 
     OZ_CHECK(cudaGetLastError());
     e->launches += 2;
   }
+  return cudaSuccess;
+}
+
+// Adds the exact products of the outlier elements recorded while the slots were prepared to the output blocks of a job (to be
+// called behind oz2_multiply of the same job, on the same stream).  No-op for an engine without the range guard.
+cudaError_t oz2_fixup(Oz2Engine* e, const Oz2FixOut* d_outs, int nouts, const Oz2FixSrc* d_srcs, cudaStream_t stream) {
+  if (nouts <= 0 || e->range_bits <= 0) return cudaSuccess;
+  oz2_fixup_kernel<<<nouts, 256, 0, stream>>>(d_outs, d_srcs, e->recs, e->rec_cnt, e->cap_r, e->sstride, e->exps, e->range_bits, e->bad);
+  OZ_CHECK(cudaGetLastError());
+  e->launches += 1;
   return cudaSuccess;
 }
 

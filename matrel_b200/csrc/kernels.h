@@ -98,6 +98,22 @@ void oz2_destroy(Oz2Engine* e, cudaStream_t stream);
 const void* oz2_host_maps(const Oz2Engine* e, size_t* bytes);   // 2 * moduli CUtensorMaps to be uploaded by the caller ...
 void oz2_set_device_maps(Oz2Engine* e, const void* d_maps);     // ... and handed back as a device pointer
 const int* oz2_flag(const Oz2Engine* e);
+// Operand blocks of an output block, for the exact fp64 products of elements the residue scheme leaves out (oz2_fixup)
+struct Oz2FixSrc {
+  const double* A;      // a_rows x kdim, column-major, row-major if aT
+  const double* B;      // kdim x b_cols, column-major, row-major if bT
+  int32_t k0, kdim;     // inner-index range [k0, k0 + kdim) this pair covers
+  int32_t a_rows, b_cols;
+  uint8_t aT, bT;
+  uint8_t pad[6];
+};
+struct Oz2FixOut {
+  double* C;            // m x n, column-major
+  int32_t m, n;
+  int32_t rslot, cslot; // the engine slots its block row of A / block column of B were prepared into
+  int32_t src_begin, src_count;
+};
+cudaError_t oz2_fixup(Oz2Engine* e, const Oz2FixOut* d_outs, int nouts, const Oz2FixSrc* d_srcs, cudaStream_t stream);
 int oz2_alpha(const Oz2Engine* e);
 int oz2_moduli(const Oz2Engine* e);
 int oz2_moduli_for(int64_t K, int requested);  // requested <= 0: chosen from K (see gemm_ozaki.cu)

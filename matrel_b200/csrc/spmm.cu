@@ -176,6 +176,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 __device__ __forceinline__ void lds_entry(uint32_t addr, double& a, uint32_t& boff) {
   uint32_t lo, hi, pad;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(boff), "=r"(pad) : "r"(addr));
+  (void)pad;
   a = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
 }
 __device__ __forceinline__ void lds_f64x2(uint32_t addr, double& x, double& y) {

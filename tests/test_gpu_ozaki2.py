@@ -243,6 +243,41 @@ def test_auto_selection_guards_in_row_dynamic_range():
         assert np.max(np.abs(got - want) / scale) > 1e-2
 
 
+def test_auto_selection_corrects_isolated_tiny_elements_exactly():
+    """A handful of elements far below their row / column maximum (what any large random matrix contains by chance) do not send
+    the multiply to the fallback: the residue pass leaves them out and their products are added exactly in fp64 afterwards.
+    Here they are placed where they matter -- C(i0, j0) consists of nothing but such a product -- and every other element of
+    the result must be bit-identical to the unguarded tcgen05 run (proof that the tensor-core path was kept)."""
+    rng = np.random.default_rng(19)
+    n, blk = 2048, 256
+    Af, Bf = rng.uniform(1.0, 2.0, (n, n)), rng.uniform(1.0, 2.0, (n, n))
+    spots = [(5, 700, 33), (5, 1900, 33), (300, 12, 1500), (1999, 2047, 0), (1024, 1024, 1024)]   # (i0, k0, j0)
+    for (i0, k0, j0) in spots:
+        Af[i0, k0] = 2.0 ** -45 * rng.uniform(1.0, 2.0)             # tiny element of row i0 of A ...
+    for j0 in {j for _, _, j in spots}:
+        ks = [k for _, k, j in spots if j == j0]
+        Bf[:, j0] = 0.0
+        Bf[ks, j0] = rng.uniform(1.0, 2.0, len(ks))                  # ... facing the only non-zeros of column j0 of B
+    Bf[77, 900] = 2.0 ** -50                                         # and a tiny element of B (column 900 is ordinary)
+    Bf[700, 33] *= 2.0 ** -48                                        # a tiny b facing a tiny a: the pair must be counted once
+    want, scale = Af @ Bf, np.abs(Af) @ np.abs(Bf)
+    res = {}
+    for algo in (0, 4):
+        with mb.MatfastSession(device=0, gemm_algo=algo) as s:
+            res[algo] = full(from_dataset(to_dataset(s, blocks_of(Af, blk)).matrixMultiply(n, n, to_dataset(s, blocks_of(Bf, blk)), n, n, blk)), n, n, blk)
+            assert s.stats()["tc_gemm_launches"] == 1
+    err0 = np.abs(res[0] - want) / scale
+    err4 = np.abs(res[4] - want) / scale
+    assert np.max(err0) <= 1e-13, np.max(err0)                      # exact where only the tiny products contribute
+    assert np.max(err4) > 1e-3                                       # the unguarded run loses them
+    touched = np.zeros((n, n), dtype=bool)
+    for (i0, _, _) in spots:
+        touched[i0, :] = True                                        # rows with a tiny a: C(i0, :) += a B(k0, :)
+    touched[:, 900] = True                                           # column with the tiny b
+    touched[:, 33] = True
+    assert np.array_equal(res[0][~touched], res[4][~touched])
+
+
 def test_auto_selection_small_products_stay_on_dmma(session):
     n, blk = 512, 128
     A, B = session.rand(n, n, blk, 1), session.rand(n, n, blk, 2)
