@@ -64,9 +64,11 @@ typedef struct mr_options {
   int32_t device;       /* CUDA device ordinal; -1 = current device */
   int32_t compat_bugs;  /* 1 = reproduce reference defects B3/B4; 0 = intended math */
   int32_t gemm_algo;    /* 0 = auto: large regular dense products run on the tcgen05 tensor cores (Ozaki-II: int8 residue GEMMs +
-                           CRT, fp64-exact to 1e-14 on data of ordinary range), guarded on the device: Inf / NaN operands, a
-                           dynamic range of more than ~2^37 inside one row of A / column of B, K >= 2^17, irregular block grids
-                           and small products take the exact DMMA kernel instead;
+                           CRT, fp64-exact to 1e-14 on data of ordinary range), guarded on the device: isolated elements more than
+                           alpha - 18 binary orders (29 at K = 16384) below the maximum of their row of A / column of B are left out
+                           of the residues and their products added exactly in fp64; Inf / NaN operands, more than 64 such elements
+                           in one block row / block column, K >= 2^17, irregular block grids and small products take the exact DMMA
+                           kernel instead;
                            1 = DMMA fp64 tensor-core kernel (mma.sync m8n8k4 f64), always;
                            2 = Ozaki-I int8 tcgen05 kernel (digit slices); 3 = 3xTF32 tcgen05 kernel (fp32 results);
                            4 = Ozaki-II without the range guard.  mr_set_option "crt_moduli": 6..16 residue moduli, 0 (default) = chosen
