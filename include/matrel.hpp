@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <tuple>
 #include <vector>
 
 #include "matrel.h"
@@ -150,12 +151,44 @@ class Dataset {
   Dataset addScalar(double alpha) const { return unary(mr_add_scalar, alpha); }
   Dataset multiplyScalar(double alpha) const { return unary(mr_multiply_scalar, alpha); }
   Dataset power(double alpha) const { return unary(mr_power, alpha); }
+  // aggregates and slicing (Dataset.scala:38-87)
+  Dataset rowSum(int64_t nrows, int64_t ncols) const { return shaped(mr_row_sum, nrows, ncols); }
+  Dataset colSum(int64_t nrows, int64_t ncols) const { return shaped(mr_col_sum, nrows, ncols); }
+  Dataset sum(int64_t nrows, int64_t ncols) const { return shaped(mr_sum, nrows, ncols); }
+  Dataset trace(int64_t nrows, int64_t ncols) const { return shaped(mr_trace, nrows, ncols); }
+  Dataset project(int64_t nrows, int64_t ncols, int32_t blkSize, bool rowOrCol, int64_t index) const {
+    mr_matrix* o = nullptr;
+    check(mr_project(h_.get(), nrows, ncols, blkSize, rowOrCol ? 1 : 0, index, &o));
+    return Dataset(*session_, o);
+  }
+  Dataset selection(int64_t nrows, int64_t ncols, int32_t blkSize, int64_t rowIdx, int64_t colIdx) const {
+    mr_matrix* o = nullptr;
+    check(mr_selection(h_.get(), nrows, ncols, blkSize, rowIdx, colIdx, &o));
+    return Dataset(*session_, o);
+  }
+  Dataset vec(int64_t nrows, int64_t ncols, int32_t blkSize) const {
+    mr_matrix* o = nullptr;
+    check(mr_vec(h_.get(), nrows, ncols, blkSize, &o));
+    return Dataset(*session_, o);
+  }
+  // Dataset.collect(): every dense block as (rid, cid, matrix); sparse results go through the two-call mr_matrix_get_block protocol
+  std::vector<std::tuple<int32_t, int32_t, DenseMatrix>> collect() const {
+    std::vector<std::tuple<int32_t, int32_t, DenseMatrix>> out;
+    for (const auto& id : blockIds()) out.emplace_back(id.first, id.second, getDenseBlock(id.first, id.second));
+    return out;
+  }
   mr_matrix* raw() const { return h_.get(); }
 
  private:
   Dataset(MatfastSession& s, mr_matrix* h) : session_(&s), h_(h, [](mr_matrix* m) { mr_matrix_free(m); }) {}
   using BinFn = mr_status (*)(mr_matrix*, int64_t, int64_t, mr_matrix*, int64_t, int64_t, int32_t, mr_matrix**);
   using UnFn = mr_status (*)(mr_matrix*, double, mr_matrix**);
+  using ShapedFn = mr_status (*)(mr_matrix*, int64_t, int64_t, mr_matrix**);
+  Dataset shaped(ShapedFn f, int64_t nrows, int64_t ncols) const {
+    mr_matrix* o = nullptr;
+    check(f(h_.get(), nrows, ncols, &o));
+    return Dataset(*session_, o);
+  }
   Dataset binary(BinFn f, int64_t lr, int64_t lc, const Dataset& right, int64_t rr, int64_t rc, int32_t blk) const {
     mr_matrix* o = nullptr;
     check(f(h_.get(), lr, lc, right.h_.get(), rr, rc, blk, &o));
@@ -168,6 +201,113 @@ class Dataset {
   }
   MatfastSession* session_;
   std::shared_ptr<mr_matrix> h_;
+};
+
+// ---- one process, all GPUs of the box (mr_init_grid): the placement grid replaces the Spark cluster --------------------------
+class GridSession {
+ public:
+  explicit GridSession(int32_t ngpus, bool compat_bugs = true) {
+    mr_options o{};
+    o.device = -1;
+    o.compat_bugs = compat_bugs ? 1 : 0;
+    check(mr_init_grid(&o, ngpus, &g_));
+  }
+  ~GridSession() {
+    if (g_) mr_grid_shutdown(g_);
+  }
+  GridSession(const GridSession&) = delete;
+  GridSession& operator=(const GridSession&) = delete;
+  void sync() { check(mr_grid_sync(g_)); }
+  int32_t gpus() const {
+    int32_t n = 0, pr = 0, pc = 0, nccl = 0;
+    check(mr_grid_info(g_, &n, &pr, &pc, &nccl));
+    return n;
+  }
+  mr_grid* raw() const { return g_; }
+
+ private:
+  mr_grid* g_ = nullptr;
+};
+
+// A Dataset whose blocks live on the GPUs of a GridSession (rank (rid % pr, cid % pc) owns block (rid, cid)).
+class DistributedDataset {
+ public:
+  DistributedDataset(GridSession& g, int64_t nrows, int64_t ncols, int32_t blkSize) : grid_(&g) {
+    mr_dmatrix* h = nullptr;
+    check(mr_dmatrix_create(g.raw(), nrows, ncols, blkSize, &h));
+    h_.reset(h, [](mr_dmatrix* m) { mr_dmatrix_free(m); });
+  }
+  // per-block java.util.Random(seed0 + rid * nbc + cid) streams, generated where the blocks live
+  static DistributedDataset rand(GridSession& g, int64_t nrows, int64_t ncols, int32_t blkSize, int64_t seed0) {
+    mr_dmatrix* h = nullptr;
+    check(mr_dmatrix_rand(g.raw(), nrows, ncols, blkSize, seed0, &h));
+    return DistributedDataset(g, h);
+  }
+  void putBlock(int32_t rid, int32_t cid, const DenseMatrix& m) {  // routed to the owner
+    mr_block_desc d{};
+    d.type = 1;
+    d.numRows = m.numRows;
+    d.numCols = m.numCols;
+    d.values = const_cast<double*>(m.values.data());
+    d.valuesLen = static_cast<int64_t>(m.values.size());
+    d.isTransposed = m.isTransposed;
+    check(mr_dmatrix_put_block(h_.get(), rid, cid, &d));
+  }
+  bool hasBlock(int32_t rid, int32_t cid) const {
+    int32_t present = 0;
+    check(mr_dmatrix_has_block(h_.get(), rid, cid, &present));
+    return present != 0;
+  }
+  DenseMatrix getDenseBlock(int32_t rid, int32_t cid) const {
+    mr_block_desc d{};
+    check(mr_dmatrix_get_block(h_.get(), rid, cid, &d));
+    DenseMatrix m;
+    m.numRows = d.numRows;
+    m.numCols = d.numCols;
+    m.isTransposed = d.isTransposed != 0;
+    m.values.resize(static_cast<size_t>(d.valuesLen));
+    d.values = m.values.data();
+    check(mr_dmatrix_get_block(h_.get(), rid, cid, &d));
+    return m;
+  }
+  int32_t owner(int32_t rid, int32_t cid) const {
+    int32_t rank = 0;
+    check(mr_dmatrix_owner(h_.get(), rid, cid, &rank));
+    return rank;
+  }
+  // Dataset.matrixMultiply :134-142 on the grid: peers' blocks are pulled over NVLink, no reduction
+  DistributedDataset matrixMultiply(const DistributedDataset& right) const {
+    mr_dmatrix* o = nullptr;
+    check(mr_dmatrix_multiply(h_.get(), right.h_.get(), &o));
+    return DistributedDataset(*grid_, o);
+  }
+  DistributedDataset addElement(const DistributedDataset& right) const { return elementwise(0, right); }
+  DistributedDataset multiplyElement(const DistributedDataset& right) const { return elementwise(1, right); }
+  DistributedDataset divideElement(const DistributedDataset& right) const { return elementwise(2, right); }
+  double sum() const { return reduce(0); }
+  double trace() const { return reduce(1); }
+  // repartitionWithTargetPartitioner: (P, 1) = RowPartitioner, (1, P) = ColumnPartitioner
+  DistributedDataset repartition(int32_t new_pr, int32_t new_pc) const {
+    mr_dmatrix* o = nullptr;
+    check(mr_dmatrix_repartition(h_.get(), new_pr, new_pc, &o));
+    return DistributedDataset(*grid_, o);
+  }
+  mr_dmatrix* raw() const { return h_.get(); }
+
+ private:
+  DistributedDataset(GridSession& g, mr_dmatrix* h) : grid_(&g), h_(h, [](mr_dmatrix* m) { mr_dmatrix_free(m); }) {}
+  DistributedDataset elementwise(int32_t op, const DistributedDataset& right) const {
+    mr_dmatrix* o = nullptr;
+    check(mr_dmatrix_elementwise(op, h_.get(), right.h_.get(), &o));
+    return DistributedDataset(*grid_, o);
+  }
+  double reduce(int32_t what) const {
+    double v = 0.0;
+    check(mr_dmatrix_reduce_scalar(h_.get(), what, &v));
+    return v;
+  }
+  GridSession* grid_;
+  std::shared_ptr<mr_dmatrix> h_;
 };
 
 }  // namespace matfast

@@ -76,6 +76,43 @@ int main() {
           worst = std::fmax(worst, std::fabs(m.values[r + blk * c] - 2.0 * (C[(i * blk + r) * n + j * blk + c] + 1.0)));
     }
   if (worst > 1e-12) return fail("random product");
+  // aggregates, slicing and collect() on the same product: trace / sum of A B against the triple loop
+  {
+    Dataset P = dA.matrixMultiply(n, n, dB, n, n, blk);
+    double tr = 0.0, sm = 0.0;
+    for (int i = 0; i < n; ++i) {
+      tr += C[i * n + i];
+      for (int j = 0; j < n; ++j) sm += C[i * n + j];
+    }
+    const double gtr = P.trace(n, n).getDenseBlock(0, 0).values[0], gsm = P.sum(n, n).getDenseBlock(0, 0).values[0];
+    if (std::fabs(gtr - tr) > 1e-10 || std::fabs(gsm - sm) > 1e-9) return fail("trace / sum");
+    if (std::fabs(P.selection(n, n, blk, 57, 101).getDenseBlock(0, 0).values[0] - C[57 * n + 101]) > 1e-12) return fail("selection");
+    DenseMatrix row = P.project(n, n, blk, true, 77).getDenseBlock(0, 1);   // row 77, columns 50 .. 99
+    for (int c = 0; c < blk; ++c)
+      if (std::fabs(row.values[c] - C[77 * n + blk + c]) > 1e-12) return fail("project");
+    if (P.collect().size() != static_cast<size_t>(nb * nb)) return fail("collect");
+    if (P.rowSum(n, n).blockIds().size() != static_cast<size_t>(nb) || P.colSum(n, n).blockIds().size() != static_cast<size_t>(nb))
+      return fail("rowSum / colSum shapes");
+  }
+  // the single-process grid classes on one GPU (tests/cpp/grid_smoke.cpp drives several GPUs through the C ABI directly)
+  {
+    GridSession g(1);
+    DistributedDataset gA(g, n, n, blk), gB(g, n, n, blk);
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j < nb; ++j) {
+        gA.putBlock(i, j, dA.getDenseBlock(i, j));
+        gB.putBlock(i, j, dB.getDenseBlock(i, j));
+      }
+    DistributedDataset gC = gA.matrixMultiply(gB);
+    double tr = 0.0;
+    for (int i = 0; i < n; ++i) tr += C[i * n + i];
+    if (std::fabs(gC.trace() - tr) > 1e-10) return fail("grid trace");
+    DenseMatrix m = gC.getDenseBlock(2, 1);
+    for (int r = 0; r < blk; ++r)
+      for (int c = 0; c < blk; ++c)
+        if (std::fabs(m.values[r + blk * c] - C[(2 * blk + r) * n + blk + c]) > 1e-12) return fail("grid product");
+    if (gC.owner(1, 2) != 0 || g.gpus() != 1) return fail("grid placement");
+  }
   std::printf("OK facade_smoke worst=%.3e\n", worst);
   return 0;
 }
