@@ -98,11 +98,26 @@ int main() {
   {
     GridSession g(1);
     DistributedDataset gA(g, n, n, blk), gB(g, n, n, blk);
+    // a sharded dataset keeps ONE isTransposed flag for all of its blocks (column-major here): dA's row-major blocks are
+    // re-laid out on the host before they are routed to their owner (mr_dmatrix_put_block rejects a differing flag)
+    auto columnMajor = [](const DenseMatrix& m) {
+      if (!m.isTransposed) return m;
+      DenseMatrix o{m.numRows, m.numCols, std::vector<double>(m.values.size()), false};
+      for (int r = 0; r < m.numRows; ++r)
+        for (int c = 0; c < m.numCols; ++c) o.values[r + static_cast<size_t>(m.numRows) * c] = m.values[c + static_cast<size_t>(m.numCols) * r];
+      return o;
+    };
     for (int i = 0; i < nb; ++i)
       for (int j = 0; j < nb; ++j) {
-        gA.putBlock(i, j, dA.getDenseBlock(i, j));
-        gB.putBlock(i, j, dB.getDenseBlock(i, j));
+        gA.putBlock(i, j, columnMajor(dA.getDenseBlock(i, j)));
+        gB.putBlock(i, j, columnMajor(dB.getDenseBlock(i, j)));
       }
+    try {  // the rejected case carries its explanation across the ABI
+      gA.putBlock(0, 0, dA.getDenseBlock(0, 0));
+      return fail("row-major block accepted by a column-major sharded dataset");
+    } catch (const MatrelError& e) {
+      if (std::string(e.what()).find("isTransposed differs") == std::string::npos) return fail(e.what());
+    }
     DistributedDataset gC = gA.matrixMultiply(gB);
     double tr = 0.0;
     for (int i = 0; i < n; ++i) tr += C[i * n + i];

@@ -11,7 +11,7 @@ run() {  # tool, tag, pytest -k expression
 run memcheck dmma    "multiply_dense_vs_oracle and (131 or 300 or 40-40)"
 run memcheck ozaki   "ozaki_multiply_vs_oracle and (131 or 300)"
 run memcheck crt     "crt_multiply_vs_oracle and (131 or 300 or 1024) or crt_is_bit_exact"          # engine: 1-SM (blk 64/128) and CTA-pair (blk 256) kernels
-run memcheck crtjobs "crt_pipelined or crt_panelled"                                                # pipelined groups, panelled scratch
+run memcheck crtjobs "crt_pipelined or crt_panelled or corrects_isolated"           # + outlier records and the fix-up kernel                                                # pipelined groups, panelled scratch
 run memcheck tf32    "tf32x3_multiply and (300 or 512)"
 run memcheck sparse  "sparse_blocks or sparse_op_sparse or aggregates or project"
 run memcheck spsp    "sparse_times_sparse"
