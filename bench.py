@@ -57,6 +57,19 @@ def dram_traffic_per_launch(n: int):
         return None
 
 
+def tc_traffic_per_launch(n: int, moduli: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one ozaki2_gemm_2sm_kernel launch at this N and moduli count, from the
+    committed `ncu --set full` capture (profiles/gemm_traffic_r02.json), or None when no capture exists for this configuration.
+    Algorithmic bytes of the launch: the int8 residues of both operands read once (2 x T x N^2) + the residue planes written (T x N^2)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r02.json")))
+        e = d.get(f"{n}x{moduli}")
+        return None if e is None else {"bytes": e["dram_read_bytes"] + e["dram_write_bytes"], "algorithmic_bytes": 3 * moduli * n * n,
+                                       "unit": "bytes per launch", "source": e.get("source", "ncu")}
+    except (OSError, ValueError, KeyError, TypeError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -394,7 +407,9 @@ def run_ours(args):
             kern_ms = st2["tc_gemm_ms_total"] / reps
             ipeak, ipeak_src = int8_peak_tops()
             ach = st2["tc_int8_ops"] / (kern_ms * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "achieved": ach, "peak": ipeak, "unit": "TFLOP/s", "frac": ach / ipeak, "traffic": None,
+            tct = tc_traffic_per_launch(n, moduli_used)
+            roofline = {"bound": "tensor", "achieved": ach, "peak": ipeak, "unit": "TFLOP/s", "frac": ach / ipeak,
+                        "traffic": (tct or {}).get("bytes"), "traffic_detail": tct,
                         "op": "int8 multiply-add x 2 (TOPS) on tcgen05.mma kind::i8, s32 accumulators in TMEM",
                         "kernel": "ozaki2_gemm_2sm_kernel (persistent CTA pairs, TMA -> 6-stage smem ring -> UTCIMMA cta_group::2 256x256x32 -> TMEM -> residue epilogue)",
                         "kernel_ms": kern_ms, "launches_per_step": 1.0,

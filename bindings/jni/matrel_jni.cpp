@@ -307,6 +307,31 @@ MR_JNI(jlong, dmatrixRepartition)(JNIEnv* env, jclass, jlong a, jint newPr, jint
   if (throw_if(env, mr_dmatrix_repartition(ptr<mr_dmatrix>(a), newPr, newPc, &out))) return 0;
   return reinterpret_cast<jlong>(out);
 }
+MR_JNI(jlong, dmatrixTranspose)(JNIEnv* env, jclass, jlong a) {
+  mr_dmatrix* out = nullptr;
+  if (throw_if(env, mr_dmatrix_transpose(ptr<mr_dmatrix>(a), &out))) return 0;
+  return reinterpret_cast<jlong>(out);
+}
+MR_JNI(jlong, dmatrixAxisSum)(JNIEnv* env, jclass, jlong a, jint axis) {  // 0 rowSum, 1 colSum
+  mr_dmatrix* out = nullptr;
+  if (throw_if(env, mr_dmatrix_axis_sum(ptr<mr_dmatrix>(a), axis, &out))) return 0;
+  return reinterpret_cast<jlong>(out);
+}
+MR_JNI(jlong, dmatrixProject)(JNIEnv* env, jclass, jlong a, jboolean rowOrCol, jlong index) {
+  mr_dmatrix* out = nullptr;
+  if (throw_if(env, mr_dmatrix_project(ptr<mr_dmatrix>(a), rowOrCol ? 1 : 0, index, &out))) return 0;
+  return reinterpret_cast<jlong>(out);
+}
+MR_JNI(jlong, dmatrixSelection)(JNIEnv* env, jclass, jlong a, jlong rowIdx, jlong colIdx) {
+  mr_dmatrix* out = nullptr;
+  if (throw_if(env, mr_dmatrix_selection(ptr<mr_dmatrix>(a), rowIdx, colIdx, &out))) return 0;
+  return reinterpret_cast<jlong>(out);
+}
+MR_JNI(jlong, dmatrixScalar)(JNIEnv* env, jclass, jint op, jlong a, jdouble alpha) {  // 0 addScalar, 1 multiplyScalar, 2 power
+  mr_dmatrix* out = nullptr;
+  if (throw_if(env, mr_dmatrix_scalar(op, ptr<mr_dmatrix>(a), alpha, &out))) return 0;
+  return reinterpret_cast<jlong>(out);
+}
 
 }  // extern "C"
 #endif  // __has_include(<jni.h>)

@@ -59,6 +59,11 @@ private[b200] object Native {
   @native def dmatrixElementwise(op: Int, a: Long, b: Long): Long
   @native def dmatrixReduceScalar(a: Long, what: Int): Double
   @native def dmatrixRepartition(a: Long, newPr: Int, newPc: Int): Long
+  @native def dmatrixTranspose(a: Long): Long
+  @native def dmatrixScalar(op: Int, a: Long, alpha: Double): Long
+  @native def dmatrixAxisSum(a: Long, axis: Int): Long
+  @native def dmatrixProject(a: Long, rowOrCol: Boolean, index: Long): Long
+  @native def dmatrixSelection(a: Long, rowIdx: Long, colIdx: Long): Long
 
   /** MLMatrixSerializer.deserialize (util/MLMatrixSerializer.scala:50-69) from the two-call protocol. */
   def readBlock(meta: Array[Long], fill: (Array[Int], Array[Int], Array[Double]) => Unit): MLMatrix = {
@@ -185,5 +190,19 @@ class B200GridDataset private[b200](val session: B200GridSession, private[b200] 
   def trace(): Double = Native.dmatrixReduceScalar(h, 1)
   /** repartitionWithTargetPartitioner (MatfastExecutionHelper.scala:34-44): (P, 1) = RowPartitioner, (1, P) = ColumnPartitioner */
   def repartition(newPr: Int, newPc: Int): B200GridDataset = wrap(Native.dmatrixRepartition(h, newPr, newPc), nrows, ncols)
+  /** Dataset.t / transpose (:57-61): blocks swap ids and move to their new owners; payloads untouched, isTransposed flipped */
+  def t(): B200GridDataset = transpose()
+  def transpose(): B200GridDataset = wrap(Native.dmatrixTranspose(h), ncols, nrows)
+  /** Dataset.addScalar / multiplyScalar / power (:89-103): a map over the blocks each GPU owns */
+  def addScalar(alpha: Double): B200GridDataset = wrap(Native.dmatrixScalar(0, h, alpha), nrows, ncols)
+  def multiplyScalar(alpha: Double): B200GridDataset = wrap(Native.dmatrixScalar(1, h, alpha), nrows, ncols)
+  def power(alpha: Double): B200GridDataset = wrap(Native.dmatrixScalar(2, h, alpha), nrows, ncols)
+  /** Dataset.rowSum / colSum (:63-72): local line sums + one ncclAllReduce; the result is nrows x 1 / 1 x ncols */
+  def rowSum(): B200GridDataset = wrap(Native.dmatrixAxisSum(h, 0), nrows, 1L)
+  def colSum(): B200GridDataset = wrap(Native.dmatrixAxisSum(h, 1), 1L, ncols)
+  /** Dataset.project (:38-47) / selection (:49-55); dimensions and block size travel with the handle */
+  def project(rowOrCol: Boolean, index: Long): B200GridDataset =
+    if (rowOrCol) wrap(Native.dmatrixProject(h, true, index), 1L, ncols) else wrap(Native.dmatrixProject(h, false, index), nrows, 1L)
+  def selection(rowIdx: Long, colIdx: Long): B200GridDataset = wrap(Native.dmatrixSelection(h, rowIdx, colIdx), 1L, 1L)
   override def finalize(): Unit = Native.dmatrixFree(h)
 }

@@ -310,6 +310,19 @@ MR_API mr_status mr_dmatrix_reduce_scalar(mr_dmatrix* A, int32_t what, double* v
 /* repartitionWithTargetPartitioner (MatfastExecutionHelper.scala:34-44): the blocks move to their owners under a new_pr x new_pc
  * grid of the same GPUs ((P, 1) = RowPartitioner, (1, P) = ColumnPartitioner) as grouped ncclSend / ncclRecv between the slabs. */
 MR_API mr_status mr_dmatrix_repartition(mr_dmatrix* A, int32_t new_pr, int32_t new_pc, mr_dmatrix** out);
+/* Dataset.t / transpose :57-61 (MatrixTransposeExecution, MatfastExecution.scala:215-236): block (i, j) becomes block (j, i) on
+ * the same placement function and moves to its new owner (grouped ncclSend / ncclRecv); payloads are untouched, the result's
+ * blocks carry isTransposed = 1, exactly as the reference's flag flip (MLMatrix.scala:312). */
+MR_API mr_status mr_dmatrix_transpose(mr_dmatrix* A, mr_dmatrix** out);
+/* Dataset.addScalar / multiplyScalar / power :89-103 (op 0 / 1 / 2): every GPU maps the blocks it owns, no block moves */
+MR_API mr_status mr_dmatrix_scalar(int32_t op, mr_dmatrix* A, double alpha, mr_dmatrix** out);
+/* Dataset.rowSum / colSum :63-72 (axis 0 / 1; RowSum / ColumnSumDirectExecution + reduceByKey(add), MatfastExecution.scala:239-370):
+ * local line-sum kernels, ONE ncclAllReduce of a vector covering the axis, result blocks (i, 0) / (0, j) registered at their owners */
+MR_API mr_status mr_dmatrix_axis_sum(mr_dmatrix* A, int32_t axis, mr_dmatrix** out);
+/* Dataset.project :38-47 (rowOrCol != 0: row `index` as 1 x ncols, else column `index` as nrows x 1) and Dataset.selection :49-55
+ * (entry (rowIdx, colIdx) as a 1 x 1 dataset): the owners extract their pieces, the same vector all-reduce re-keys and places them */
+MR_API mr_status mr_dmatrix_project(mr_dmatrix* A, int32_t rowOrCol, int64_t index, mr_dmatrix** out);
+MR_API mr_status mr_dmatrix_selection(mr_dmatrix* A, int64_t rowIdx, int64_t colIdx, mr_dmatrix** out);
 
 /* ---- introspection used by bench/tests (not part of the reference surface) */
 typedef struct mr_stats {

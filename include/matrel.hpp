@@ -292,9 +292,44 @@ class DistributedDataset {
     check(mr_dmatrix_repartition(h_.get(), new_pr, new_pc, &o));
     return DistributedDataset(*grid_, o);
   }
+  // Dataset.t / transpose :57-61: blocks swap ids and move to their new owners; payloads untouched, isTransposed flipped
+  DistributedDataset t() const { return transpose(); }
+  DistributedDataset transpose() const {
+    mr_dmatrix* o = nullptr;
+    check(mr_dmatrix_transpose(h_.get(), &o));
+    return DistributedDataset(*grid_, o);
+  }
+  // Dataset.addScalar / multiplyScalar / power :89-103: a map over the blocks each GPU owns
+  DistributedDataset addScalar(double alpha) const { return scalar(0, alpha); }
+  DistributedDataset multiplyScalar(double alpha) const { return scalar(1, alpha); }
+  DistributedDataset power(double alpha) const { return scalar(2, alpha); }
+  // Dataset.rowSum / colSum :63-72: local line sums + one ncclAllReduce; the result is nrows x 1 / 1 x ncols on the same grid
+  DistributedDataset rowSum() const { return axisSum(0); }
+  DistributedDataset colSum() const { return axisSum(1); }
+  // Dataset.project :38-47 / selection :49-55; dimensions and block size travel with the handle
+  DistributedDataset project(bool rowOrCol, int64_t index) const {
+    mr_dmatrix* o = nullptr;
+    check(mr_dmatrix_project(h_.get(), rowOrCol ? 1 : 0, index, &o));
+    return DistributedDataset(*grid_, o);
+  }
+  DistributedDataset selection(int64_t rowIdx, int64_t colIdx) const {
+    mr_dmatrix* o = nullptr;
+    check(mr_dmatrix_selection(h_.get(), rowIdx, colIdx, &o));
+    return DistributedDataset(*grid_, o);
+  }
   mr_dmatrix* raw() const { return h_.get(); }
 
  private:
+  DistributedDataset axisSum(int32_t axis) const {
+    mr_dmatrix* o = nullptr;
+    check(mr_dmatrix_axis_sum(h_.get(), axis, &o));
+    return DistributedDataset(*grid_, o);
+  }
+  DistributedDataset scalar(int32_t op, double alpha) const {
+    mr_dmatrix* o = nullptr;
+    check(mr_dmatrix_scalar(op, h_.get(), alpha, &o));
+    return DistributedDataset(*grid_, o);
+  }
   DistributedDataset(GridSession& g, mr_dmatrix* h) : grid_(&g), h_(h, [](mr_dmatrix* m) { mr_dmatrix_free(m); }) {}
   DistributedDataset elementwise(int32_t op, const DistributedDataset& right) const {
     mr_dmatrix* o = nullptr;

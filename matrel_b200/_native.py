@@ -172,6 +172,11 @@ SIGNATURES = {
     "mr_dmatrix_elementwise": [_i32, _P, _P, _PP],
     "mr_dmatrix_reduce_scalar": [_P, _i32, C.POINTER(_f64)],
     "mr_dmatrix_repartition": [_P, _i32, _i32, _PP],
+    "mr_dmatrix_transpose": [_P, _PP],
+    "mr_dmatrix_scalar": [_i32, _P, _f64, _PP],
+    "mr_dmatrix_axis_sum": [_P, _i32, _PP],
+    "mr_dmatrix_project": [_P, _i32, _i64, _PP],
+    "mr_dmatrix_selection": [_P, _i64, _i64, _PP],
     "mr_get_stats": [_P, C.POINTER(mr_stats)],
     "mr_reset_stats": [_P],
 }

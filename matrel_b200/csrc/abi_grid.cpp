@@ -62,10 +62,11 @@ void register_owned_blocks(mr_matrix* m) {
     }
 }
 
-mr_matrix* new_sharded(mr_context* ctx, const ShardLayout& L, bool ipc_capable, bool zero) {
+mr_matrix* new_sharded(mr_context* ctx, const ShardLayout& L, bool ipc_capable, bool zero, bool isT) {
   std::unique_ptr<mr_matrix> m(new_matrix(ctx));
   auto sh = std::make_shared<ShardInfo>();
   sh->L = L;
+  sh->isT = isT;
   const size_t bytes = std::max<size_t>(static_cast<size_t>(L.local_slots()) * L.slot_elems * sizeof(double), 16);
   sh->slab = ipc_capable ? std::make_shared<DevBuf>(ctx, bytes, DevBuf::SyncAlloc{}) : std::make_shared<DevBuf>(ctx, bytes);
   sh->ipc_capable = ipc_capable;
@@ -616,6 +617,110 @@ mr_matrix* ensure_sharded(mr_matrix* part, const ShardLayout& L, std::unique_ptr
   return keep.get();
 }
 
+
+// Moves every block of `A` into the slab of its owner in `res` (same GPUs, `res` carries its own dims and placement): block
+// (i, j) keeps its id (re-partitioning) or becomes block (j, i) (transpose; the payload is reinterpreted, not rewritten, and the
+// result's shared layout flag is set).  Blocks that stay on their GPU are copied on its stream; the others travel as one
+// ncclSend / ncclRecv pair per block inside ONE group, each on its endpoint's context stream.
+void move_blocks(mr_dmatrix* A, mr_dmatrix* res, bool swap_ids) {
+  mr_grid* g = A->g;
+  const int n = g->n;
+  if (n > 1 && g->comms.empty()) fail(MR_ENCCL, "NCCL is not available (libnccl.so.2 could not be loaded or ncclCommInitAll failed)");
+  std::vector<std::unique_ptr<mr_matrix>> keep(n);
+  std::vector<mr_matrix*> src(n);
+  for (int i = 0; i < n; ++i) {   // sources as column-major slabs
+    DeviceScope dev(g->ctx[i]);
+    std::lock_guard<std::mutex> lock(g->ctx[i]->mu);
+    src[i] = ensure_sharded(A->part[i], A->part[i]->shard ? A->part[i]->shard->L : layout_of(A, i), keep[i]);
+    wait_ready_all(g->ctx[i], src[i]);
+  }
+  for (int i = 0; i < n; ++i) {
+    DeviceScope dev(g->ctx[i]);
+    res->part[i] = new_sharded(g->ctx[i], layout_of(res, i), false, true, /*isT=*/swap_ids);
+  }
+  const int64_t nbr = ceil_div(A->nrows, A->blk), nbc = ceil_div(A->ncols, A->blk);
+  if (n > 1) NCCL_CHECK(nccl_api().GroupStart());
+  for (int64_t i = 0; i < nbr; ++i)
+    for (int64_t j = 0; j < nbc; ++j) {
+      const std::pair<int32_t, int32_t> sid{static_cast<int32_t>(i), static_cast<int32_t>(j)};
+      const std::pair<int32_t, int32_t> did = swap_ids ? std::make_pair(sid.second, sid.first) : sid;
+      const int from = A->owner(sid.first, sid.second);
+      if (!src[from]->blocks.count(sid)) continue;
+      const int to = res->owner(did.first, did.second);
+      const Block& sb = src[from]->blocks.at(sid);
+      const Block& db = res->part[to]->blocks.at(did);
+      const size_t cnt = static_cast<size_t>(sb.numRows) * sb.numCols;
+      if (from == to) {
+        DeviceScope dev(g->ctx[to]);
+        CUDA_CHECK(cudaMemcpyAsync(db.values.ptr<double>(), sb.values.ptr<double>(), cnt * sizeof(double), cudaMemcpyDeviceToDevice, g->ctx[to]->stream));
+      } else {
+        NCCL_CHECK(nccl_api().Send(sb.values.ptr<double>(), cnt, ncclDouble, to, g->comms[from], g->ctx[from]->stream));
+        NCCL_CHECK(nccl_api().Recv(db.values.ptr<double>(), cnt, ncclDouble, from, g->comms[to], g->ctx[to]->stream));
+      }
+    }
+  if (n > 1) NCCL_CHECK(nccl_api().GroupEnd());
+  // the sources' temporaries (keep) are released stream-ordered behind the copies / sends enqueued above
+}
+
+// The common shape of rowSum / colSum / project / selection on the grid: a per-GPU operator yields pieces keyed (line, 0) (axis 0:
+// the result is len x 1) or (0, line) (axis 1: 1 x len); pieces with the same key are ADDED across the GPUs and the sum becomes
+// result block (line, 0) / (0, line) at its owner under A's placement.  Every GPU writes its pieces into a zeroed vector covering
+// the axis (one 256-byte aligned segment per block line), ONE ncclAllReduce adds the vectors, and each owner registers its
+// segments as blocks (zero-copy windows of the vector).  A line without a piece on any GPU produces no block, as in the reference.
+template <typename LocalOp>
+std::unique_ptr<mr_dmatrix> collect_lines(mr_dmatrix* A, int axis, int64_t len, LocalOp&& local) {
+  mr_grid* g = A->g;
+  const int n = g->n;
+  if (n > 1 && g->comms.empty()) fail(MR_ENCCL, "NCCL is not available (libnccl.so.2 could not be loaded or ncclCommInitAll failed)");
+  const int64_t nlines = ceil_div(len, A->blk);
+  const int64_t seg = static_cast<int64_t>(align_up(static_cast<size_t>(A->blk) * sizeof(double)) / sizeof(double));  // doubles per segment
+  const size_t bytes = static_cast<size_t>(nlines) * seg * sizeof(double);
+  std::vector<Buf> vec(n);
+  std::vector<char> present(static_cast<size_t>(nlines), 0);
+  for (int i = 0; i < n; ++i) {
+    mr_context* ctx = g->ctx[i];
+    DeviceScope dev(ctx);
+    mr_matrix* s = nullptr;
+    const mr_status st = local(A->part[i], &s);
+    if (st != MR_OK) throw MrError{st, g_last_error};
+    std::unique_ptr<mr_matrix> hold(s);
+    vec[i] = std::make_shared<DevBuf>(ctx, std::max<size_t>(bytes, 16));
+    CUDA_CHECK(cudaMemsetAsync(vec[i]->p, 0, bytes, ctx->stream));
+    for (auto& kv : s->blocks) {
+      const int64_t line = axis == 0 ? kv.first.first : kv.first.second;
+      const int64_t cnt = static_cast<int64_t>(kv.second.numRows) * kv.second.numCols;
+      MR_REQUIRE(line >= 0 && line < nlines && cnt == std::min<int64_t>(A->blk, len - line * A->blk), MR_EDIM,
+                 "piece (%d, %d) holds %lld elements, the %lld x %lld matrix in %d-blocks expects %lld", kv.first.first, kv.first.second,
+                 (long long)cnt, (long long)A->nrows, (long long)A->ncols, A->blk, (long long)std::min<int64_t>(A->blk, len - line * A->blk));
+      present[static_cast<size_t>(line)] = 1;
+      wait_ready(ctx, kv.second);
+      CUDA_CHECK(cudaMemcpyAsync(static_cast<double*>(vec[i]->p) + line * seg, kv.second.values.ptr<double>(),
+                                 static_cast<size_t>(cnt) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  if (n > 1) {
+    NCCL_CHECK(nccl_api().GroupStart());
+    for (int i = 0; i < n; ++i)
+      NCCL_CHECK(nccl_api().AllReduce(vec[i]->p, vec[i]->p, static_cast<size_t>(nlines * seg), ncclDouble, ncclSum, g->comms[i], g->ctx[i]->stream));
+    NCCL_CHECK(nccl_api().GroupEnd());
+  }
+  auto res = new_dmatrix(g, axis == 0 ? len : 1, axis == 0 ? 1 : len, A->blk, A->pr, A->pc);
+  for (int i = 0; i < n; ++i) {
+    DeviceScope dev(g->ctx[i]);
+    std::unique_ptr<mr_matrix> p(new_matrix(g->ctx[i]));
+    for (int64_t line = 0; line < nlines; ++line) {
+      if (!present[static_cast<size_t>(line)]) continue;
+      const int32_t rid = axis == 0 ? static_cast<int32_t>(line) : 0, cid = axis == 0 ? 0 : static_cast<int32_t>(line);
+      if (res->owner(rid, cid) != i) continue;
+      const int32_t cnt = static_cast<int32_t>(std::min<int64_t>(A->blk, len - line * A->blk));
+      Span sp{vec[i], static_cast<size_t>(line * seg) * sizeof(double)};
+      p->blocks[{rid, cid}] = axis == 0 ? dense_block(cnt, 1, sp) : dense_block(1, cnt, sp);
+    }
+    res->part[i] = p.release();
+  }
+  return res;
+}
+
 }  // namespace
 
 extern "C" {
@@ -949,6 +1054,43 @@ mr_status mr_dmatrix_reduce_scalar(mr_dmatrix* A, int32_t what /* 0 = sum, 1 = t
   });
 }
 
+// Dataset.rowSum / colSum (M/Dataset.scala:63-72; RowSumDirectExecution / ColumnSumDirectExecution, M/execution/MatfastExecution.scala
+// :239-370: per-block line sums, then reduceByKey(add) over the block row / block column): axis 0 = rowSum (nrows x 1), 1 = colSum
+// (1 x ncols).  collect_lines() does the work: local kernels, ONE ncclAllReduce of a vector -- the shuffle of the reference.
+mr_status mr_dmatrix_axis_sum(mr_dmatrix* A, int32_t axis, mr_dmatrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(A && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(axis == 0 || axis == 1, MR_EINVAL, "axis must be 0 (rowSum) or 1 (colSum), got %d", axis);
+    *out = collect_lines(A, axis, axis == 0 ? A->nrows : A->ncols, [&](mr_matrix* part, mr_matrix** o) {
+             return axis == 0 ? mr_row_sum(part, A->nrows, A->ncols, o) : mr_col_sum(part, A->nrows, A->ncols, o);
+           }).release();
+  });
+}
+
+// Dataset.project (M/Dataset.scala:38-47; ProjectRow / ProjectColumnDirectExecution, M/execution/MatfastExecution.scala:31-169): row
+// `index` as a 1 x ncols dataset (rowOrCol != 0) or column `index` as nrows x 1.  The GPUs that own blocks of the block row /
+// block column extract their pieces; the same vector all-reduce brings every piece to the owner of its result block (the other
+// GPUs contribute zeros), which is the re-keying to (0, cid) / (rid, 0) plus the shuffle the reference's next operator would do.
+mr_status mr_dmatrix_project(mr_dmatrix* A, int32_t rowOrCol, int64_t index, mr_dmatrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(A && out, MR_EINVAL, "null argument");
+    *out = collect_lines(A, rowOrCol ? 1 : 0, rowOrCol ? A->ncols : A->nrows, [&](mr_matrix* part, mr_matrix** o) {
+             return mr_project(part, A->nrows, A->ncols, A->blk, rowOrCol, index, o);
+           }).release();
+  });
+}
+
+// Dataset.selection (M/Dataset.scala:49-55; SelectDirectExecution, M/execution/MatfastExecution.scala:171-213): entry (rowIdx, colIdx)
+// as a 1 x 1 dataset whose block (0, 0) lives on rank 0.
+mr_status mr_dmatrix_selection(mr_dmatrix* A, int64_t rowIdx, int64_t colIdx, mr_dmatrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(A && out, MR_EINVAL, "null argument");
+    *out = collect_lines(A, 0, 1, [&](mr_matrix* part, mr_matrix** o) {
+             return mr_selection(part, A->nrows, A->ncols, A->blk, rowIdx, colIdx, o);
+           }).release();
+  });
+}
+
 // repartitionWithTargetPartitioner (M/execution/MatfastExecutionHelper.scala:34-44) between two grids of the same GPUs: every
 // block moves from its owner under (pr, pc) to its owner under (new_pr, new_pc) -- the all-to-all permutation that replaces the
 // reference's ShuffledRDD, as grouped ncclSend / ncclRecv straight between the slabs (one message per block).  new_pr x new_pc
@@ -959,42 +1101,43 @@ mr_status mr_dmatrix_repartition(mr_dmatrix* A, int32_t new_pr, int32_t new_pc, 
     mr_grid* g = A->g;
     MR_REQUIRE(new_pr > 0 && new_pc > 0 && new_pr * new_pc == g->n, MR_EINVAL, "%d x %d does not cover the %d GPUs of the grid", new_pr,
                new_pc, g->n);
-    const int n = g->n;
-    if (n > 1 && g->comms.empty()) fail(MR_ENCCL, "NCCL is not available (libnccl.so.2 could not be loaded or ncclCommInitAll failed)");
-    std::vector<std::unique_ptr<mr_matrix>> keep(n);
-    std::vector<mr_matrix*> src(n);
-    for (int i = 0; i < n; ++i) {
-      DeviceScope dev(g->ctx[i]);
-      std::lock_guard<std::mutex> lock(g->ctx[i]->mu);
-      src[i] = ensure_sharded(A->part[i], A->part[i]->shard ? A->part[i]->shard->L : layout_of(A, i), keep[i]);
-      wait_ready_all(g->ctx[i], src[i]);
-    }
     auto res = new_dmatrix(g, A->nrows, A->ncols, A->blk, new_pr, new_pc);
-    for (int i = 0; i < n; ++i) {
-      DeviceScope dev(g->ctx[i]);
-      res->part[i] = new_sharded(g->ctx[i], make_layout(A->nrows, A->ncols, A->blk, new_pr, new_pc, i / new_pc, i % new_pc), false, true);
+    move_blocks(A, res.get(), /*swap_ids=*/false);
+    *out = res.release();
+  });
+}
+
+// Dataset.t / transpose (M/Dataset.scala:57-61; MatrixTransposeExecution, M/execution/MatfastExecution.scala:215-236: a key swap
+// (rid, cid) -> (cid, rid) plus the isTransposed flag flip of MLMatrix.scala:312) on the grid: block (i, j) of A becomes block
+// (j, i) of the result on the SAME placement function, i.e. it moves from rank (i % pr, j % pc) to rank (j % pr, i % pc) -- the
+// re-placement the reference's next shuffle would do -- as grouped ncclSend / ncclRecv between the slabs.  Payloads are not
+// touched: a column-major block IS the row-major block of the transpose, so the result is a sharded dataset whose shared
+// isTransposed flag is set (operators that need column-major slabs normalise it on the device, ensure_sharded).
+mr_status mr_dmatrix_transpose(mr_dmatrix* A, mr_dmatrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(A && out, MR_EINVAL, "null argument");
+    auto res = new_dmatrix(A->g, A->ncols, A->nrows, A->blk, A->pr, A->pc);
+    move_blocks(A, res.get(), /*swap_ids=*/true);
+    *out = res.release();
+  });
+}
+
+// Dataset.addScalar / multiplyScalar / power (M/Dataset.scala:89-103; MatrixScalar{Add,Multiply}Execution, MatrixPowerExecution,
+// M/execution/MatfastExecution.scala:465-532: a map over the blocks, no shuffle): op 0 = add, 1 = multiply, 2 = power.  Every
+// GPU maps the blocks it owns; placement, layout flags and sparsity structure are preserved (LocalMatrix.scala:411-426,931-980).
+mr_status mr_dmatrix_scalar(int32_t op, mr_dmatrix* A, double alpha, mr_dmatrix** out) {
+  return guarded([&] {
+    MR_REQUIRE(A && out, MR_EINVAL, "null argument");
+    MR_REQUIRE(op >= 0 && op <= 2, MR_EINVAL, "unknown scalar op %d", op);
+    auto res = new_dmatrix(A->g, A->nrows, A->ncols, A->blk, A->pr, A->pc);
+    for (int i = 0; i < A->g->n; ++i) {
+      DeviceScope dev(A->g->ctx[i]);
+      mr_matrix* o = nullptr;
+      auto fn = op == 0 ? mr_add_scalar : (op == 1 ? mr_multiply_scalar : mr_power);
+      const mr_status st = fn(A->part[i], alpha, &o);
+      if (st != MR_OK) throw MrError{st, g_last_error};
+      res->part[i] = o;
     }
-    const int64_t nbr = ceil_div(A->nrows, A->blk), nbc = ceil_div(A->ncols, A->blk);
-    const size_t slot_elems = static_cast<size_t>(A->blk) * A->blk;
-    if (n > 1) NCCL_CHECK(nccl_api().GroupStart());
-    for (int64_t i = 0; i < nbr; ++i)
-      for (int64_t j = 0; j < nbc; ++j) {
-        const int from = A->owner(static_cast<int32_t>(i), static_cast<int32_t>(j));
-        if (!src[from]->blocks.count({static_cast<int32_t>(i), static_cast<int32_t>(j)})) continue;
-        const int to = static_cast<int>((i % new_pr) * new_pc + (j % new_pc));
-        const Block& sb = src[from]->blocks.at({static_cast<int32_t>(i), static_cast<int32_t>(j)});
-        const Block& db = res->part[to]->blocks.at({static_cast<int32_t>(i), static_cast<int32_t>(j)});
-        const size_t cnt = static_cast<size_t>(sb.numRows) * sb.numCols;
-        (void)slot_elems;
-        if (from == to) {
-          DeviceScope dev(g->ctx[to]);
-          CUDA_CHECK(cudaMemcpyAsync(db.values.ptr<double>(), sb.values.ptr<double>(), cnt * sizeof(double), cudaMemcpyDeviceToDevice, g->ctx[to]->stream));
-        } else {
-          NCCL_CHECK(nccl_api().Send(sb.values.ptr<double>(), cnt, ncclDouble, to, g->comms[from], g->ctx[from]->stream));
-          NCCL_CHECK(nccl_api().Recv(db.values.ptr<double>(), cnt, ncclDouble, from, g->comms[to], g->ctx[to]->stream));
-        }
-      }
-    if (n > 1) NCCL_CHECK(nccl_api().GroupEnd());
     *out = res.release();
   });
 }

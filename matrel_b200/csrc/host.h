@@ -238,7 +238,7 @@ struct DeviceScope {
   DeviceScope& operator=(const DeviceScope&) = delete;
 };
 ShardLayout make_layout(int64_t nrows, int64_t ncols, int32_t blk, int32_t pr, int32_t pc, int32_t r, int32_t c);
-mr_matrix* new_sharded(mr_context* ctx, const ShardLayout& L, bool ipc_capable, bool zero);
+mr_matrix* new_sharded(mr_context* ctx, const ShardLayout& L, bool ipc_capable, bool zero, bool isT = false);
 // The body of mr_matrix_multiply (abi_multiply.cpp).  out_layout != nullptr: the result is a sharded dataset in that layout
 // (its blocks are windows of one slab at their slots) instead of a packed one.  The caller holds ctx->mu.
 mr_matrix* multiply_impl(mr_context* ctx, mr_matrix* left, int64_t leftRowNum, int64_t leftColNum, mr_matrix* right, int64_t rightRowNum,

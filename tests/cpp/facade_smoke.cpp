@@ -127,6 +127,16 @@ int main() {
       for (int c = 0; c < blk; ++c)
         if (std::fabs(m.values[r + blk * c] - C[(2 * blk + r) * n + blk + c]) > 1e-12) return fail("grid product");
     if (gC.owner(1, 2) != 0 || g.gpus() != 1) return fail("grid placement");
+    // t(): block (1, 2) of C^T is block (2, 1) of C with the flag flipped; scalar maps keep ids and layout
+    DistributedDataset gT = gC.t();
+    if (std::fabs(gT.trace() - tr) > 1e-10) return fail("grid transpose trace");
+    DenseMatrix mt = gT.getDenseBlock(1, 2), ms = gC.multiplyScalar(2.0).addScalar(1.0).getDenseBlock(2, 1);
+    if (!mt.isTransposed || ms.isTransposed) return fail("grid transpose / scalar flags");
+    for (int r = 0; r < blk; ++r)
+      for (int c = 0; c < blk; ++c) {
+        if (mt.values[c + blk * r] != m.values[c + blk * r]) return fail("grid transpose payload");   // same array, other reading
+        if (std::fabs(ms.values[r + blk * c] - (2.0 * C[(2 * blk + r) * n + blk + c] + 1.0)) > 1e-12) return fail("grid scalar ops");
+      }
   }
   std::printf("OK facade_smoke worst=%.3e\n", worst);
   return 0;

@@ -115,3 +115,96 @@ def test_sharded_put_block_rejects_foreign_blocks(session):
         ds.put_block(0, 0, mb.DenseMatrix(64, 64, np.zeros(4096)))
     with pytest.raises(mb.IllegalArgumentException, match="layout expects"):
         ds.put_block(1, 0, mb.DenseMatrix(32, 64, np.zeros(2048)))
+
+
+def _get_any(dm, rid, cid):
+    """(numRows, numCols, isTransposed, values) of a block, whatever its layout flag."""
+    d = N.mr_block_desc()
+    N.check(N.lib.mr_dmatrix_get_block(dm, rid, cid, C.byref(d)))
+    v = np.empty(d.valuesLen)
+    d.values = v.ctypes.data_as(C.POINTER(C.c_double))
+    N.check(N.lib.mr_dmatrix_get_block(dm, rid, cid, C.byref(d)))
+    assert d.type == 1
+    return d.numRows, d.numCols, bool(d.isTransposed), v
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_grid_transpose_and_scalar_ops_match_oracle(world):
+    """Dataset.t and the scalar maps on the single-process grid against the oracle (O.transpose = key swap + flag flip,
+    MatfastExecution.scala:215-236): ids, shapes, flags and payloads exactly; the owner of block (j, i) of A^T is the reference's
+    Row x ColumnPartitioner arithmetic on the same grid; a transposed operand feeds the multiply."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n, m, blk = 5 * 64 - 3, 3 * 64 + 10, 64
+    rng = np.random.default_rng(7 + world)
+    Ao = {(i, j): O.DenseMatrix(min(blk, n - i * blk), min(blk, m - j * blk), rng.uniform(-1, 1, min(blk, n - i * blk) * min(blk, m - j * blk)))
+          for i in range(-(-n // blk)) for j in range(-(-m // blk))}
+    opts = N.mr_options(-1, 1, 1, 0, None)
+    g = C.c_void_p()
+    N.check(N.lib.mr_init_grid(C.byref(opts), world, C.byref(g)))
+    try:
+        pr, pc = C.c_int32(), C.c_int32()
+        N.check(N.lib.mr_grid_info(g, None, C.byref(pr), C.byref(pc), None))
+        A, At, G, S = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        N.check(N.lib.mr_dmatrix_create(g, n, m, blk, C.byref(A)))
+        for (i, j), b in Ao.items():
+            _put(A, i, j, b)
+        N.check(N.lib.mr_dmatrix_transpose(A, C.byref(At)))
+        want = O.transpose(Ao)
+        for (i, j), w in want.items():
+            nr, nc, isT, v = _get_any(At, i, j)
+            assert (nr, nc, isT) == (w.numRows, w.numCols, w.isTransposed) and np.array_equal(v, w.values)
+            owner = C.c_int32()
+            N.check(N.lib.mr_dmatrix_owner(At, i, j, C.byref(owner)))
+            assert owner.value == (i % pr.value) * pc.value + (j % pc.value)
+        nblocks = C.c_int64()
+        N.check(N.lib.mr_dmatrix_num_blocks(At, C.byref(nblocks)))
+        assert nblocks.value == len(want)
+        # A^T A through the grid multiply (the row-major slabs are normalised on the device)
+        N.check(N.lib.mr_dmatrix_multiply(At, A, C.byref(G)))
+        wantG = O.assemble(O.matrix_multiply(want, m, n, Ao, n, m, blk), m, m, blk)
+        assert np.max(np.abs(_assemble(G, m, m, blk) - wantG)) <= 1e-12 * np.max(np.abs(wantG))
+        # scalar maps keep ids, placement and layout flags: (A^T * 3 + 0.25) ^ 2
+        T1, T2 = C.c_void_p(), C.c_void_p()
+        N.check(N.lib.mr_dmatrix_scalar(1, At, 3.0, C.byref(T1)))
+        N.check(N.lib.mr_dmatrix_scalar(0, T1, 0.25, C.byref(T2)))
+        N.check(N.lib.mr_dmatrix_scalar(2, T2, 2.0, C.byref(S)))
+        wantS = O.power(O.add_scalar(O.multiply_scalar(want, 3.0), 0.25), 2.0)
+        for (i, j), w in wantS.items():
+            nr, nc, isT, v = _get_any(S, i, j)
+            assert (nr, nc, isT) == (w.numRows, w.numCols, w.isTransposed)
+            np.testing.assert_allclose(v, w.values, rtol=1e-14, atol=0)
+        # rowSum / colSum: block ids (i, 0) / (0, j), shapes and values against the oracle; owners under the operand's placement
+        Rs, Cs = C.c_void_p(), C.c_void_p()
+        N.check(N.lib.mr_dmatrix_axis_sum(A, 0, C.byref(Rs)))
+        N.check(N.lib.mr_dmatrix_axis_sum(At, 1, C.byref(Cs)))      # colSum of A^T = (rowSum of A)^T, from row-major blocks
+        wr, wc = O.row_sum(Ao, n, m), O.col_sum(want, m, n)
+        for dm, w in ((Rs, wr), (Cs, wc)):
+            N.check(N.lib.mr_dmatrix_num_blocks(dm, C.byref(nblocks)))
+            assert nblocks.value == len(w)
+            for (i, j), blkm in w.items():
+                nr, nc, isT, v = _get_any(dm, i, j)
+                assert (nr, nc) == (blkm.numRows, blkm.numCols)
+                np.testing.assert_allclose(v, blkm.values, rtol=0, atol=1e-12 * m)
+                owner = C.c_int32()
+                N.check(N.lib.mr_dmatrix_owner(dm, i, j, C.byref(owner)))
+                assert owner.value == (i % pr.value) * pc.value + (j % pc.value)
+        # project / selection re-key the pieces to (0, cid) / (rid, 0) / (0, 0) and place them at their owners
+        Pr, Pc, Se = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        N.check(N.lib.mr_dmatrix_project(A, 1, 130, C.byref(Pr)))
+        N.check(N.lib.mr_dmatrix_project(At, 0, 131, C.byref(Pc)))   # column 131 of A^T = row 131 of A, from row-major blocks
+        N.check(N.lib.mr_dmatrix_selection(A, n - 1, m - 1, C.byref(Se)))
+        for dm, w in ((Pr, O.project(Ao, n, m, blk, True, 130)), (Pc, O.project(want, m, n, blk, False, 131)),
+                      (Se, O.selection(Ao, n, m, blk, n - 1, m - 1))):
+            N.check(N.lib.mr_dmatrix_num_blocks(dm, C.byref(nblocks)))
+            assert nblocks.value == len(w) > 0
+            for (i, j), blkm in w.items():
+                nr, nc, isT, v = _get_any(dm, i, j)
+                assert (nr, nc) == (blkm.numRows, blkm.numCols) and np.array_equal(v, blkm.to_numpy().ravel(order="F"))
+        bad = C.c_void_p()
+        assert N.lib.mr_dmatrix_project(A, 0, m, C.byref(bad)) == N.MR_EINVAL
+        assert "col index should be smaller than #cols" in N.last_error()
+        for h in (A, At, G, S, T1, T2, Rs, Cs, Pr, Pc, Se):
+            N.check(N.lib.mr_dmatrix_free(h))
+    finally:
+        N.check(N.lib.mr_grid_shutdown(g))
