@@ -590,7 +590,8 @@ def run_ours(args):
         "config": {"workload": f"{n}x{n} fp64 dense multiply, {blk}-block, 1xB200 (BASELINE metric size)",
                    "inputs": "U(0,1) java.util.Random streams, every block present, column-major",
                    "l2": f"inputs 2 x {n * n * 8 / 2**30:.0f} GiB + output {n * n * 8 / 2**30:.0f} GiB >> 126 MB L2; no flush needed",
-                   "gemm_algo": algo_name, "wall_ms_per_step": t_wall / args.steps * 1e3, "c00": checksum},
+                   "gemm_algo": algo_name, "wall_ms_per_step": t_wall / args.steps * 1e3, "c00": checksum,
+                   "oz2_ksplit_env": os.environ.get("MATREL_OZ2_KSPLIT")},
         "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "ingest_only_ms": ingest_only_ms,
                 "note": "ingest_only_ms = the step's host->device copies alone on this box: the PCIe floor of the step"},

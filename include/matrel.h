@@ -84,7 +84,10 @@ typedef struct mr_options {
 MR_API mr_status mr_init(const mr_options* opts, mr_context** out);
 MR_API mr_status mr_shutdown(mr_context* ctx);
 MR_API mr_status mr_set_stream(mr_context* ctx, void* cuda_stream);
-/* keys: "compat_bugs", "gemm_algo", "ozaki_slices", "crt_moduli", "ozaki_scratch_mb", "spmm_algo", "pipeline", "time_kernels", "gemm_variant" */
+/* keys: "compat_bugs", "gemm_algo", "ozaki_slices", "crt_moduli", "ozaki_scratch_mb", "spmm_algo", "pipeline", "time_kernels", "gemm_variant",
+ *       "oz2_ksplit" (the CTA-pair tcgen05 GEMM walks (modulus, K half, tile pair) work items -- half the L2 footprint of the
+ *       residue panels in flight, bit-identical results: 1 = for long tile lists and K >= 8192 only, 2 = whenever possible; default 0,
+ *       or the environment variable MATREL_OZ2_KSPLIT at mr_init) */
 MR_API mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value);
 MR_API mr_status mr_sync(mr_context* ctx);
 /* Orders the context stream (device side, no host wait) after every host->device block copy submitted so far. */

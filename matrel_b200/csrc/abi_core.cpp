@@ -15,6 +15,8 @@
 // device-resident block table; every arithmetic step is a CUDA kernel (gemm_f64.cu, ew.cu).
 // There is no CPU compute path in this file: host code only validates, builds descriptor tables
 // and launches.
+#include <cstdlib>
+
 #include "host.h"
 
 using namespace matrel;
@@ -290,6 +292,7 @@ mr_status mr_init(const mr_options* opts, mr_context** out) {
       ctx->gemm_algo = opts->gemm_algo;
       ctx->ozaki_slices = opts->ozaki_slices;
     }
+    if (const char* ks = std::getenv("MATREL_OZ2_KSPLIT")) ctx->oz2_ksplit = std::atoi(ks);  // A/B switch for measurements; option "oz2_ksplit"
     if (opts && opts->stream) {
       ctx->stream = static_cast<cudaStream_t>(opts->stream);
     } else {
@@ -404,6 +407,7 @@ mr_status mr_set_option(mr_context* ctx, const char* key, int64_t value) {
     else if (k == "spmm_algo") ctx->spmm_algo = static_cast<int>(value);
     else if (k == "time_kernels") ctx->time_kernels = static_cast<int>(value);
     else if (k == "gemm_variant") ctx->force_variant = static_cast<int>(value);
+    else if (k == "oz2_ksplit") ctx->oz2_ksplit = static_cast<int>(value);
     else if (k == "pipeline") ctx->pipeline = static_cast<int>(value);
     else fail(MR_EINVAL, "unknown option '%s'", key);
   });

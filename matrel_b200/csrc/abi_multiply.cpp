@@ -430,6 +430,7 @@ struct Oz2Run {
       return false;  // e.g. out of memory for the scratch: the exact kernel needs none
     }
     oz2_set_paired(eng, paired);
+    oz2_set_ksplit(eng, ctx->oz2_ksplit);
     if (paired && !oz2_paired(eng)) {  // cannot happen (ss % 256 == 0 makes Mpad a multiple of 256); stay on the safe side
       oz2_destroy(eng, ctx->stream);
       eng = nullptr;

@@ -358,6 +358,59 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// The work items of ONE CTA pair in execution order; the producer, the MMA issuer and the epilogue warps walk identical copies.
+//   KSPLIT = false: item = (modulus, tile pair), flat index w = cl, cl + ncl, ... over nmod x npairs, the whole K per item.
+//   KSPLIT = true : item = (modulus, K half, tile pair).  The pair that owns tile pair t2 of modulus mi runs BOTH halves (first
+//                   the lower half of all its tiles of the modulus, then the upper half), so the thread that stored a residue byte
+//                   of the lower half is the one that adds the upper half to it -- no cross-CTA ordering is needed.  The CTA pairs
+//                   in flight then share panels of K / 2 residue bytes: half the L2 footprint of the unsplit order (at K = 16384,
+//                   72 MiB -> 36 MiB for 74 pairs), which is what decides whether the panels survive in L2 once the pairs have
+//                   drifted apart in k.  The leftover tile pairs of a sweep (npairs % ncl) rotate over the CTA pairs from one
+//                   modulus to the next, so the load stays balanced over the launch.
+template <bool KSPLIT>
+struct Oz2Items {
+  int npairs, ncl, cl, nmod, nk, rot, w, cur_mi, cur_kh, cur_t2;
+  __device__ __forceinline__ int first_of(int mi) const { return (cl + ncl - (mi * rot) % ncl) % ncl; }
+  __device__ __forceinline__ Oz2Items(int npairs_, int ncl_, int cl_, int nmod_, int nk_)
+      : npairs(npairs_), ncl(ncl_), cl(cl_), nmod(nmod_), nk(nk_), rot(npairs_ % ncl_), w(cl_), cur_mi(0), cur_kh(0), cur_t2(0) {
+    cur_t2 = first_of(0);
+  }
+  // next item: modulus mi, tile pair t2, k-chunks [kc0, kc0 + kcn), add = the epilogue adds the residue byte already stored
+  __device__ __forceinline__ bool next(int& mi, int& t2, int& kc0, int& kcn, bool& add) {
+    if constexpr (!KSPLIT) {
+      if (w >= npairs * nmod) return false;
+      mi = w / npairs;
+      t2 = w - mi * npairs;
+      kc0 = 0;
+      kcn = nk;
+      add = false;
+      w += ncl;
+      return true;
+    } else {
+      while (cur_mi < nmod) {
+        if (cur_t2 < npairs) {
+          mi = cur_mi;
+          t2 = cur_t2;
+          kcn = nk >> 1;
+          kc0 = cur_kh * kcn;
+          add = cur_kh != 0;
+          cur_t2 += ncl;
+          return true;
+        }
+        if (cur_kh == 0) {
+          cur_kh = 1;
+        } else {
+          cur_kh = 0;
+          ++cur_mi;
+        }
+        cur_t2 = first_of(cur_mi);
+      }
+      return false;
+    }
+  }
+};
+
+template <bool KSPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_P, 1) ozaki2_gemm_2sm_kernel(const OzakiGemmParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -371,7 +424,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_P, 1) o
   const bool gated = p.gate != nullptr && *p.gate != 0;  // uniform over the grid: both CTAs of a pair take the same path
   const int nk = p.nkc;
   const int npairs_list = p.ntiles_list >> 1;             // pairs of 128-row tiles
-  const int nitems = gated ? 0 : npairs_list * p.nmod;
+  const int nmod_run = gated ? 0 : p.nmod;
   const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
 
   if (threadIdx.x == 0) {
@@ -400,13 +453,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_P, 1) o
     // ===== TMA producer: this CTA's 128 rows of A' and 128 of the tile's 256 rows of B' =====
     if (lane == 0) {
       int it = 0;
-      for (int w = cl; w < nitems; w += ncl) {
-        const int mi = w / npairs_list, t2 = w - mi * npairs_list;
+      Oz2Items<KSPLIT> items(npairs_list, ncl, cl, nmod_run, nk);
+      int mi, t2, kc0, kcn;
+      bool add;
+      while (items.next(mi, t2, kc0, kcn, add)) {
         const int2 tl = p.tile_list[2 * t2 + static_cast<int>(cta_rank)];
         const int m0 = tl.x * BM, n0 = tl.y * BN + static_cast<int>(cta_rank) * (BN / 2);
         const void* tmA = p.tmaps + static_cast<size_t>(mi) * 128;
         const void* tmB = p.tmaps + static_cast<size_t>(2 * p.nmod + mi) * 128;  // the {128, 128}-box maps of B'
-        for (int kc = 0; kc < nk; ++kc, ++it) {
+        for (int kc = kc0; kc < kc0 + kcn; ++kc, ++it) {
           const int st = it % STAGES2;
           const uint32_t ph = (it / STAGES2) & 1;
           mbar_wait(smem_u32(&bars[STAGES2 + st]), ph ^ 1);                  // own empty barrier
@@ -424,13 +479,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_P, 1) o
     if (leader && lane == 0) {
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((2 * BM) >> 4) << 24);
       int it = 0, lt = 0;
-      for (int w = cl; w < nitems; w += ncl, ++lt) {
+      Oz2Items<KSPLIT> items(npairs_list, ncl, cl, nmod_run, nk);
+      int mi, t2, kc0, kcn;
+      bool add;
+      for (; items.next(mi, t2, kc0, kcn, add); ++lt) {
         const int buf = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(smem_u32(&bars[2 * STAGES2 + 2 + buf]), aph ^ 1);  // both CTAs' epilogues have drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf * BN);
-        for (int kc = 0; kc < nk; ++kc, ++it) {
+        for (int kc = 0; kc < kcn; ++kc, ++it) {   // kc counts within the item: the first MMA of an item overwrites the accumulator
           const int st = it % STAGES2;
           const uint32_t ph = (it / STAGES2) & 1;
           mbar_wait(smem_u32(&bars[st]), ph);
@@ -463,8 +521,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_P, 1) o
     const int half = ew >> 2;
     const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bars[2 * STAGES2 + 2]), 0);  // + 8 * buf
     int lt = 0;
-    for (int w = cl; w < nitems; w += ncl, ++lt) {
-      const int mi = w / npairs_list, t2 = w - mi * npairs_list;
+    Oz2Items<KSPLIT> items(npairs_list, ncl, cl, nmod_run, nk);
+    int mi, t2, kc0, kcn;
+    bool add;
+    for (; items.next(mi, t2, kc0, kcn, add); ++lt) {
       const int t = 2 * t2 + static_cast<int>(cta_rank);
       const int buf = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
@@ -485,13 +545,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_P, 1) o
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * static_cast<uint32_t>(buf));
         }
+        uint32_t prev[4] = {0u, 0u, 0u, 0u};
+        if constexpr (KSPLIT) {
+          // upper K half: the residue this SAME thread stored for the lower half joins the sum before the reduction
+          // ((x mod p) + y) mod p = (x + y) mod p; |y| <= K/2 * 2^14 and x < 256 keep the sum far inside int32
+          if (add) {
+            const uint4 pv = *reinterpret_cast<const uint4*>(dst_row + c);
+            prev[0] = pv.x;
+            prev[1] = pv.y;
+            prev[2] = pv.z;
+            prev[3] = pv.w;
+          }
+        }
         uint32_t packed[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t wv = 0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int v = static_cast<int32_t>(r[4 * g + j]);
+            int v = static_cast<int32_t>(r[4 * g + j]);
+            if constexpr (KSPLIT) v += static_cast<int>((prev[g] >> (8 * j)) & 0xffu);
             int res = v - __double2int_rn(static_cast<double>(v) * pinv) * pm;
             res += (res >> 31) & pm;
             wv |= static_cast<uint32_t>(res) << (8 * j);
@@ -1355,6 +1428,8 @@ cudaError_t crt_constants(int* log2P, bool upload = true) {
 // ------------------------------------------------------------------------------------------------
 struct Oz2Engine {
   int T = 0, alpha = 0, crt_chunks = 4, blk = 0, sstride = 0, cap_r = 0, cap_c = 0, max_tiles = 0, range_bits = 0;
+  int ksplit = 0;  // CTA-pair kernel walks (modulus, K half, tile pair) items (half the L2 footprint of the panels in flight): 1 = for
+                   // long tile lists and deep K only, 2 = whenever K has an even number of chunks (tests)
   bool paired = false;   // tile lists hold vertically adjacent 128-row tiles in pairs: the cta_group::2 kernel runs them
   int64_t K = 0, Kpad = 0, Mpad = 0, Npad = 0;
   size_t a_stride = 0, b_stride = 0, plane_stride = 0, smem_bytes = 0;
@@ -1439,7 +1514,9 @@ cudaError_t oz2_create(Oz2Engine** out, int blk, int64_t K, int moduli, int cap_
   {
     static PerDeviceOnce once2;
     OZ_CHECK(once2.run([&] {
-      return cudaFuncSetAttribute(ozaki2_gemm_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM2_BYTES));
+      cudaError_t e1 = cudaFuncSetAttribute(ozaki2_gemm_2sm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM2_BYTES));
+      if (e1 != cudaSuccess) return e1;
+      return cudaFuncSetAttribute(ozaki2_gemm_2sm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM2_BYTES));
     }));
   }
   int dev = 0;
@@ -1559,6 +1636,7 @@ cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, i
 // execution order, so the caller bands it for L2 reuse), written through d_ctab[rslot * cap_c + cslot] (nullptr = not part of
 // this job).  Lists longer than the plane capacity are processed in consecutive pieces.  ms_gemm (optional) accumulates the
 // tcgen05 launch time (events, synchronises): used for the roofline figure only.
+void oz2_set_ksplit(Oz2Engine* e, int level) { e->ksplit = level; }
 void oz2_set_paired(Oz2Engine* e, bool paired) { e->paired = paired && (e->max_tiles % 2 == 0) && (e->Mpad % (2 * BM) == 0); }
 bool oz2_paired(const Oz2Engine* e) { return e->paired; }
 
@@ -1594,7 +1672,10 @@ cudaError_t oz2_multiply(Oz2Engine* e, const int2* d_tiles, int ntiles, double* 
     if (e->paired) {  // cta_group::2: one cluster of two CTAs per (modulus, tile pair) work item
       const int64_t npair_items = nitems / 2;
       const unsigned clusters = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(npair_items, e->sms / 2)));
-      ozaki2_gemm_2sm_kernel<<<2 * clusters, GEMM_THREADS_P, SMEM2_BYTES, stream>>>(p);
+      // K-split order (opt-in, oz2_set_ksplit): only for lists long enough that every CTA pair sweeps several tiles per (modulus, half)
+      const bool ks = (p.nkc % 2 == 0) && (e->ksplit >= 2 || (e->ksplit == 1 && p.nkc >= 64 && (cnt / 2) >= 4 * static_cast<int>(clusters)));
+      if (ks) ozaki2_gemm_2sm_kernel<true><<<2 * clusters, GEMM_THREADS_P, SMEM2_BYTES, stream>>>(p);
+      else ozaki2_gemm_2sm_kernel<false><<<2 * clusters, GEMM_THREADS_P, SMEM2_BYTES, stream>>>(p);
     } else {
       ozaki_gemm_i8_kernel<<<static_cast<unsigned>(std::min<int64_t>(nitems, e->sms)), GEMM_THREADS_P, e->smem_bytes, stream>>>(p);
     }

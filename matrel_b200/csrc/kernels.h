@@ -120,6 +120,7 @@ int oz2_moduli_for(int64_t K, int requested);  // requested <= 0: chosen from K 
 int oz2_slot_stride(const Oz2Engine* e);
 void oz2_set_paired(Oz2Engine* e, bool paired);                  // tile lists come as (2a, b), (2a + 1, b) pairs: use the 2-SM kernel
 bool oz2_paired(const Oz2Engine* e);
+void oz2_set_ksplit(Oz2Engine* e, int level);                    // CTA-pair kernel: (modulus, K half, tile pair) work items (see Oz2Items); 1 = large jobs, 2 = always
 int oz2_launches(Oz2Engine* e);                                  // kernels launched since the last call
 cudaError_t oz2_prepare(Oz2Engine* e, bool is_a, const OzakiOperand* d_blocks, int nblocks, int max_rows, int max_cols, int slot0,
                         int nslots, const int32_t* d_dims, bool need_zero, cudaStream_t stream);
