@@ -175,3 +175,33 @@ def test_header_is_plain_c():
     r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-x", "c", os.path.join(ROOT, "include", "matrel.h")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_scala_native_declarations_match_the_jni_shim():
+    """Neither side of the JVM binding can be compiled here (no JDK, no scalac), so the two files are checked against each other:
+    every `@native def` of bindings/scala/Dataset.scala has exactly one Java_..._Native_<name> in bindings/jni/matrel_jni.cpp with the
+    same arity and the JNI type of every parameter and of the result, and the shim exports nothing the facade does not declare."""
+    import re
+    scala = open(os.path.join(ROOT, "bindings", "scala", "Dataset.scala")).read()
+    jni = open(os.path.join(ROOT, "bindings", "jni", "matrel_jni.cpp")).read()
+    to_jni = {"Long": "jlong", "Int": "jint", "Double": "jdouble", "Boolean": "jboolean", "Byte": "jbyte", "Unit": "void",
+              "Array[Int]": "jintArray", "Array[Double]": "jdoubleArray", "Array[Long]": "jlongArray"}
+    natives = {}
+    for m in re.finditer(r"@native def (\w+)\(([^)]*)\)\s*:\s*([\w\[\]]+)", scala, re.S):
+        params = [p.split(":")[1].strip() for p in m.group(2).split(",") if p.strip()]
+        natives[m.group(1)] = ([to_jni[p] for p in params], to_jni[m.group(3)])
+    # the shim generates some functions with macros: look at what the preprocessor makes of it (stand-in <jni.h> of tests/cpp/jni_stub)
+    r = subprocess.run(["g++", "-std=c++17", "-E", "-P", "-I", os.path.join(ROOT, "tests", "cpp", "jni_stub"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "bindings", "jni", "matrel_jni.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    shim = {}
+    for m in re.finditer(r"(\w+)\s+Java_org_apache_spark_sql_matfast_b200_Native_(\w+)\s*\(\s*JNIEnv\s*\*\s*\w*\s*,\s*jclass\s*((?:,[^)]*)?)\)\s*\{",
+                         r.stdout, re.S):
+        args = [a.strip().rsplit(" ", 1)[0].strip() for a in m.group(3).split(",") if a.strip()]
+        assert m.group(2) not in shim, f"{m.group(2)} defined twice in the shim"
+        shim[m.group(2)] = (args, m.group(1))
+    assert len(natives) >= 45 and set(natives) == set(shim), (sorted(set(natives) - set(shim)), sorted(set(shim) - set(natives)))
+    for name, sig in natives.items():
+        assert sig == shim[name], (name, sig, shim[name])
+    # the package path of the exported symbols is the one the facade's `object Native` lives in
+    assert "Java_org_apache_spark_sql_matfast_b200_Native_##NAME" in jni and "package org.apache.spark.sql.matfast.b200" in scala
