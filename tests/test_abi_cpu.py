@@ -205,3 +205,31 @@ def test_scala_native_declarations_match_the_jni_shim():
         assert sig == shim[name], (name, sig, shim[name])
     # the package path of the exported symbols is the one the facade's `object Native` lives in
     assert "Java_org_apache_spark_sql_matfast_b200_Native_##NAME" in jni and "package org.apache.spark.sql.matfast.b200" in scala
+
+
+REFERENCE_DATASET_METHODS = ["project", "selection", "t", "transpose", "rowSum", "colSum", "sum", "trace", "vec", "addScalar",
+                             "multiplyScalar", "power", "addElement", "multiplyElement", "divideElement", "matrixMultiply",
+                             "matrixRankOneUpdate"]   # M/Dataset.scala:38-152, in source order
+
+
+def test_facades_expose_the_reference_operator_names():
+    """The three host-side mirrors of the reference's Dataset (Python, C++, Scala) carry every public operator name of
+    M/Dataset.scala:38-152; the grid classes carry all but vec / matrixRankOneUpdate."""
+    import re
+    import matrel_b200 as mb
+    for name in REFERENCE_DATASET_METHODS:
+        assert callable(getattr(mb.Dataset, name)), name
+    hpp = open(os.path.join(ROOT, "include", "matrel.hpp")).read()
+    scala = open(os.path.join(ROOT, "bindings", "scala", "Dataset.scala")).read()
+    cls_hpp = hpp[hpp.index("class Dataset {"):hpp.index("class GridSession")]
+    grid_hpp = hpp[hpp.index("class DistributedDataset {"):]
+    cls_scala = scala[scala.index("class B200Dataset"):scala.index("class B200GridSession")]
+    grid_scala = scala[scala.index("class B200GridDataset"):]
+    for name in REFERENCE_DATASET_METHODS:
+        assert re.search(r"\b%s\(" % name, cls_hpp), f"matrel.hpp Dataset lacks {name}"
+        assert re.search(r"def %s\(" % name, cls_scala), f"B200Dataset lacks {name}"
+        if name not in ("vec", "matrixRankOneUpdate"):
+            assert re.search(r"\b%s\(" % name, grid_hpp), f"matrel.hpp DistributedDataset lacks {name}"
+            assert re.search(r"def %s\(" % name, grid_scala), f"B200GridDataset lacks {name}"
+    for extra in ("collect", "getBlock"):
+        assert re.search(r"def %s\(" % extra, cls_scala) and re.search(r"def %s\(" % extra, grid_scala), extra
